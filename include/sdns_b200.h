@@ -1,0 +1,148 @@
+/* sdns_b200.h -- C ABI of libsdns_b200.so: the B200-native replacement for the hot path of
+ * spectralDNS (triply periodic pseudo-spectral RHS + RK4 step of the NS / VV / MHD solvers).
+ *
+ * The reference has no FFI of its own for this path: its "native" layer is Cython modules
+ * called with numpy arrays (spectralDNS/optimization/cython_{maths,solvers,integrators}.in) plus
+ * the FFTW/MPI calls that shenfun / mpi4py-fft make underneath T.forward / T.backward.  Each
+ * entry point below names the reference interface it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes binding a maintainer adds to solvers/NS.py etc.
+ *
+ * Conventions
+ *   - plain C linkage, plain pointers and sizes; no C++/torch types cross the boundary;
+ *   - every function returns 0 on success or a negative sdns_status; sdns_last_error() returns
+ *     a thread-local message for the last failure;
+ *   - device pointers are BORROWED (the caller -- PyTorch in the shipped host layer -- owns
+ *     the allocations and keeps them alive); a plan is not thread-safe;
+ *   - all work is enqueued on the plan's CUDA stream (sdns_plan_set_stream; default stream 0)
+ *     and is asynchronous unless stated otherwise;
+ *   - spectral arrays: C order (ncomp, N0, N1/P, N2/2+1) complex<real>, physical arrays
+ *     (ncomp, M0/P, M1, M2) real, exactly the local shapes of the reference's Function(VT) /
+ *     Array(VT) (solvers/NS.py:51-63, spectralDNS3D_short.py:28-29).
+ *   - there is NO CPU fallback: every entry point fails with SDNS_ERR_CUDA when no device is
+ *     present.
+ */
+#ifndef SDNS_B200_H
+#define SDNS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDNS_ABI_VERSION 1
+
+typedef enum {
+    SDNS_OK = 0,
+    SDNS_ERR_ARG = -1,        /* invalid argument / unsupported configuration */
+    SDNS_ERR_SIZE = -2,       /* grid size without a compiled transform */
+    SDNS_ERR_CUDA = -3,       /* CUDA runtime error (message has the cudaError string) */
+    SDNS_ERR_WORKSPACE = -4,  /* workspace missing or too small */
+    SDNS_ERR_STATE = -5       /* call order violation */
+} sdns_status;
+
+enum { SDNS_SINGLE = 0, SDNS_DOUBLE = 1 };                         /* config.py:166-167  --precision   */
+enum { SDNS_DEALIAS_NONE = 0, SDNS_DEALIAS_23 = 1, SDNS_DEALIAS_32 = 2 }; /* config.py:190-192 --dealias */
+enum { SDNS_NS = 0, SDNS_VV = 1, SDNS_MHD = 2 };                   /* config.py:228-233 solver sub-command */
+enum { SDNS_CONV_VORTEX = 0, SDNS_CONV_DIVERGENCE = 1,
+       SDNS_CONV_STANDARD = 2, SDNS_CONV_SKEWED = 3 };             /* config.py:214-216 --convection   */
+enum { SDNS_SLAB = 0, SDNS_PENCIL = 1 };                           /* config.py:194-195 --decomposition */
+enum { SDNS_SPACE_T = 0, SDNS_SPACE_TP = 1 };                      /* solvers/NS.py:21-32  T/VT vs Tp/VTp */
+
+typedef struct sdns_config {
+    int32_t abi_version;      /* SDNS_ABI_VERSION */
+    int32_t N[3];             /* params.N  (config.py:115-118) */
+    double  L[3];             /* params.L  (config.py:141-145) */
+    int32_t precision;        /* SDNS_SINGLE | SDNS_DOUBLE */
+    int32_t dealias;          /* SDNS_DEALIAS_* (solvers/NS.py:29-31) */
+    int32_t solver;           /* SDNS_NS | SDNS_VV | SDNS_MHD */
+    int32_t convection;       /* SDNS_CONV_* (NS.getConvection, solvers/NS.py:164-201) */
+    int32_t mask_nyquist;     /* params.mask_nyquist (config.py:207-209, NS.py:34) */
+    int32_t decomposition;    /* SDNS_SLAB | SDNS_PENCIL */
+    int32_t kcut[3];          /* 2/3-rule: largest kept |k| per axis; <0 = default
+                                 ceil(2/3*(N/2+1))-1  (spectralDNS3D_short.py:44-46) */
+    int32_t prune;            /* 1: skip transform lines that the truncation zeroes (same result) */
+    int32_t rank, nranks;     /* slab position of this process (solvers/spectralinit.py:19-21) */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t reserved[8];
+} sdns_config;
+
+typedef struct sdns_plan sdns_plan;
+
+/* version / diagnostics */
+int         sdns_abi_version(void);
+const char* sdns_last_error(void);
+/* 0 if a transform of length n is compiled in for the precision, else SDNS_ERR_SIZE */
+int         sdns_size_supported(int n, int precision);
+
+/* plan lifetime: replaces get_context()'s FunctionSpace/TensorProductSpace/get_dealiased setup
+ * (solvers/NS.py:12-48, MHD.py:13-50): spaces, wavenumbers K, K2, K_over_K2, Nyquist mask. */
+int sdns_plan_create(sdns_plan** plan, const sdns_config* cfg);
+int sdns_plan_destroy(sdns_plan* plan);
+/* scratch the caller must provide (device bytes), then hand over with set_workspace.  Replaces
+ * the reference's work = CachedArrayDict() arrays and u_dealias / ZZ_hat (NS.py:57-64, MHD.py:59-60) */
+int sdns_workspace_bytes(const sdns_plan* plan, size_t* bytes);
+int sdns_plan_set_workspace(sdns_plan* plan, void* device_ptr, size_t bytes);
+int sdns_plan_set_stream(sdns_plan* plan, void* cuda_stream);
+int sdns_sync(sdns_plan* plan);                          /* cudaStreamSynchronize on the plan stream */
+
+/* local array extents of this rank (T.shape(True), T.shape(False), Tp.shape(False)) */
+int sdns_local_shapes(const sdns_plan* plan, int32_t spectral[3], int32_t physical[3], int32_t padded[3]);
+
+/* T.forward / VT.forward (space = SDNS_SPACE_T) and Tp.forward / VTp.forward (SDNS_SPACE_TP):
+ * rfftn/prod(M) incl. 3/2-rule truncation.  Call sites NS.py:103,135; MHD.py:107. */
+int sdns_forward(sdns_plan* plan, int space, int ncomp, const void* real_in, void* cplx_out);
+/* T.backward / VT.backward / Tp.backward / VTp.backward: irfftn*prod(M) incl. the 2/3-rule
+ * truncation of the input or the 3/2-rule zero padding.  Call sites NS.py:93,98,128; MHD.py:121. */
+int sdns_backward(sdns_plan* plan, int space, int ncomp, const void* cplx_in, void* real_out);
+
+/* solver.ComputeRHS(rhs, u_hat, solver, **context)  (NS.py:219-261, VV.py:112-146, MHD.py:151-176)
+ * including conv (getConvection), mask_nyquist, add_pressure_diffusion / add_linear, +Source.
+ * source and p_hat may be NULL.  nu/eta as in params (config.py:123-127: cast to the precision). */
+int sdns_compute_rhs(sdns_plan* plan, void* rhs, const void* u_hat, double nu, double eta,
+                     const void* source, void* p_hat);
+
+/* integrate() for params.integrator == 'RK4'  (maths/integrators.py:150-159,177-191;
+ * cython_integrators.in:8-52): four ComputeRHS evaluations with the stage updates fused into the
+ * last transform pass.  u_hat is updated in place; u1, u2 are the integrator's work arrays
+ * (u0.copy() at integrators.py:181,187). */
+int sdns_rk4_step(sdns_plan* plan, void* u_hat, void* u1, void* u2, double dt, double nu, double eta,
+                  const void* source);
+
+/* ForwardEuler and AB2 (maths/integrators.py:161-175): rhs is the caller's dU array. */
+int sdns_euler_step(sdns_plan* plan, void* u_hat, void* rhs, double dt, double nu, double eta,
+                    const void* source);
+int sdns_ab2_step(sdns_plan* plan, void* u_hat, void* u1, void* rhs, double dt, int tstep,
+                  double nu, double eta, const void* source);
+
+/* cross2(c, K, b) / cross2(c, K_over_K2, b): c = 1j*(K x b)  (maths/cross.py:30-35,
+ * cython_maths.in:32-86).  over_k2 != 0 selects K_over_K2 (VV.py:64). */
+int sdns_cross2(sdns_plan* plan, void* c, const void* b, int over_k2);
+
+/* shenfun.fourier.energy_fourier(u_hat, T) of ncomp components (tests/TG.py:101,
+ * demo/Isotropic.py:67,167-182): Hermitian-weighted sum |u_hat|^2 of the LOCAL block.
+ * Synchronous (returns the value). */
+int sdns_energy(sdns_plan* plan, const void* u_hat, int ncomp, double* out);
+
+/* Host-buffer variant of integrate(): copies the state from (pinned) host memory, runs nsteps RK4
+ * steps, copies it back.  This is the call a host-array caller (the reference's numpy context)
+ * makes; bench.py's e2e number is measured through it. */
+int sdns_rk4_steps_host(sdns_plan* plan, void* host_u_hat, void* dev_u_hat, void* dev_u1, void* dev_u2,
+                        int nsteps, double dt, double nu, double eta);
+
+/* number of kernels this plan has launched since creation (bench.py's gpu_launches) */
+int sdns_launch_count(const sdns_plan* plan, long long* count);
+
+/* Measurement aid (no reference counterpart; the reference's own metric is Timer, utilities/__init__.py:18-68):
+ * with profiling on, every kernel launch is bracketed by CUDA events on the plan stream.
+ * sdns_profile_read returns, per kernel family (0 plain fwd c2c, 1 plain bwd c2c, 2 NS B0, 3 VV B0,
+ * 4 NS F0, 5 VV F0, 6 MHD F0, 7 c2r, 8 r2c, 9 fused z cross, 10 fused z MHD), the summed device
+ * time, the launch count and the summed algorithmic HBM bytes since sdns_profile_enable. */
+int sdns_profile_enable(sdns_plan* plan, int on);
+int sdns_profile_read(sdns_plan* plan, int family, double* total_ms, long long* launches, double* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDNS_B200_H */

@@ -1,0 +1,89 @@
+"""Build libsdns_b200.so in-tree with nvcc for sm_100a.
+
+    python -m spectraldns_b200.build [--force] [--jobs N]
+
+Every (kernel family, precision) pair of csrc/inst.cu is its own object file so the build
+parallelises over the host cores; csrc/sdns_api.cu holds the plan and the C ABI.  The shared
+object lands next to this file (git-ignored, but it travels to the GPU box with the tree).
+"""
+import os
+import subprocess
+import sys
+import hashlib
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OBJ = os.path.join(HERE, 'build')
+LIB = os.path.join(HERE, 'libsdns_b200.so')
+NFAM = 11
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+
+
+def _nvcc():
+    for c in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError('nvcc not found')
+
+
+def _sources_digest(extra=''):
+    h = hashlib.sha1()
+    for f in sorted(os.listdir(CSRC)) + ['../../include/sdns_b200.h']:
+        with open(os.path.join(CSRC, f), 'rb') as fh:
+            h.update(fh.read())
+    h.update(extra.encode())
+    return h.hexdigest()
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('command failed: %s\n%s' % (' '.join(cmd), r.stdout))
+    return r.stdout
+
+
+def build(force=False, jobs=None, verbose=False, sizes=None):
+    """Compile every CUDA translation unit for sm_100a and link libsdns_b200.so."""
+    os.makedirs(OBJ, exist_ok=True)
+    extra = []
+    if sizes:
+        extra = ['-DSDNS_SIZES(X)=' + ' '.join('X(%d)' % s for s in sizes)]
+    digest = _sources_digest(' '.join(extra))
+    stamp = os.path.join(OBJ, 'stamp')
+    if (not force and os.path.exists(LIB) and os.path.exists(stamp)
+            and open(stamp).read().strip() == digest):
+        return LIB
+    nvcc = _nvcc()
+    jobs = jobs or os.cpu_count() or 4
+    units = []
+    for fam in range(NFAM):
+        for prec in (32, 64):
+            o = os.path.join(OBJ, 'inst_%d_f%d.o' % (fam, prec))
+            units.append((o, [nvcc] + ARCH + FLAGS + extra +
+                          ['-DSDNS_FAMILY=%d' % fam, '-DSDNS_PREC=%d' % prec,
+                           '-c', os.path.join(CSRC, 'inst.cu'), '-o', o]))
+    o_api = os.path.join(OBJ, 'sdns_api.o')
+    units.append((o_api, [nvcc] + ARCH + FLAGS + extra + ['-c', os.path.join(CSRC, 'sdns_api.cu'), '-o', o_api]))
+    with ThreadPoolExecutor(max_workers=jobs) as ex:
+        outs = list(ex.map(lambda u: _run(u[1]), units))
+    if verbose:
+        for o in outs:
+            if o.strip():
+                print(o)
+    _run([nvcc] + ARCH + ['-shared', '-o', LIB] + [u[0] for u in units])
+    with open(stamp, 'w') as f:
+        f.write(digest)
+    return LIB
+
+
+if __name__ == '__main__':
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--force', action='store_true')
+    ap.add_argument('--jobs', type=int, default=None)
+    ap.add_argument('--verbose', action='store_true')
+    ap.add_argument('--sizes', type=int, nargs='*', default=None)
+    a = ap.parse_args()
+    print(build(a.force, a.jobs, a.verbose, a.sizes))

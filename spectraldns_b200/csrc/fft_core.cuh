@@ -1,0 +1,220 @@
+// fft_core.cuh -- register-resident mixed-radix Stockham line FFT for sm_100a.
+//
+// One FFT line of length N is owned by P = N/E threads; thread t holds the E elements
+// x[q] = line[t + q*P].  Every stage (radix R | E, R in {8,4,2,3,5}) reads exactly that
+// element set, so the global load pattern (t + q*P, coalesced over t or over the column
+// index) is the same for every N, and the last stage leaves the result in natural order in
+// the same register slots.  Between stages the line is exchanged through shared memory.
+//
+// This replaces the serial FFTW plans that shenfun / mpi4py-fft run underneath the
+// reference's T.forward / T.backward (call sites solvers/NS.py:93,98,103,128,135).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdns {
+
+template <typename T> struct C2;
+template <> struct C2<float>  { typedef float2  type; };
+template <> struct C2<double> { typedef double2 type; };
+
+template <typename T> __device__ __forceinline__ typename C2<T>::type mk(T x, T y) {
+    typename C2<T>::type r; r.x = x; r.y = y; return r;
+}
+template <typename V> __device__ __forceinline__ V cadd(V a, V b) { a.x += b.x; a.y += b.y; return a; }
+template <typename V> __device__ __forceinline__ V csub(V a, V b) { a.x -= b.x; a.y -= b.y; return a; }
+template <typename V> __device__ __forceinline__ V cmul(V a, V b) {
+    V r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+template <typename V> __device__ __forceinline__ V cconj(V a) { a.y = -a.y; return a; }
+// multiply by -i*DIRSIGN... mul_mi: a * (-i) ; mul_pi: a * (+i)
+template <typename V> __device__ __forceinline__ V mul_mi(V a) { V r; r.x = a.y; r.y = -a.x; return r; }
+template <typename V> __device__ __forceinline__ V mul_pi(V a) { V r; r.x = -a.y; r.y = a.x; return r; }
+// rotate by -i for the forward transform (DIR=-1), +i for the backward one (DIR=+1)
+template <int DIR, typename V> __device__ __forceinline__ V rot90(V a) {
+    return DIR < 0 ? mul_mi(a) : mul_pi(a);
+}
+
+// ---------------------------------------------------------------------------------------
+// small DFTs, natural-order in/out, exponent sign DIR (-1 forward, +1 backward)
+// ---------------------------------------------------------------------------------------
+template <int DIR, typename V>
+__device__ __forceinline__ void dft2(V& a, V& b) {
+    V t = a; a = cadd(t, b); b = csub(t, b);
+}
+
+template <int DIR, typename V>
+__device__ __forceinline__ void dft4(V& a0, V& a1, V& a2, V& a3) {
+    V t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    V t2 = cadd(a1, a3), t3 = rot90<DIR>(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2);
+    a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+
+template <int DIR, typename T, typename V>
+__device__ __forceinline__ void dft8(V& a0, V& a1, V& a2, V& a3, V& a4, V& a5, V& a6, V& a7) {
+    const T h = (T)0.70710678118654752440084436210485L;
+    // radix-2 split: evens (a0,a2,a4,a6), odds (a1,a3,a5,a7)
+    V e0 = a0, e1 = a2, e2 = a4, e3 = a6;
+    V o0 = a1, o1 = a3, o2 = a5, o3 = a7;
+    dft4<DIR>(e0, e1, e2, e3);
+    dft4<DIR>(o0, o1, o2, o3);
+    // twiddles W8^k, k=1..3 with sign DIR:  W8^1 = (1 + DIR*i)/sqrt2 ; W8^2 = DIR*i ; W8^3 = (-1 + DIR*i)/sqrt2
+    V w1, w3;
+    if (DIR < 0) { w1 = mk<T>(h * (o1.x + o1.y), h * (o1.y - o1.x));
+                   w3 = mk<T>(h * (o3.y - o3.x), -h * (o3.x + o3.y)); }
+    else         { w1 = mk<T>(h * (o1.x - o1.y), h * (o1.y + o1.x));
+                   w3 = mk<T>(-h * (o3.x + o3.y), h * (o3.x - o3.y)); }
+    V w2 = rot90<DIR>(o2);
+    a0 = cadd(e0, o0); a4 = csub(e0, o0);
+    a1 = cadd(e1, w1); a5 = csub(e1, w1);
+    a2 = cadd(e2, w2); a6 = csub(e2, w2);
+    a3 = cadd(e3, w3); a7 = csub(e3, w3);
+}
+
+template <int DIR, typename T, typename V>
+__device__ __forceinline__ void dft3(V& a0, V& a1, V& a2) {
+    const T s = (T)0.86602540378443864676372317075294L;   // sin(pi/3)
+    V t1 = cadd(a1, a2);
+    V t2 = mk<T>(a0.x - (T)0.5 * t1.x, a0.y - (T)0.5 * t1.y);
+    V d = csub(a1, a2);
+    // forward: X1 = t2 - i*s*d ; backward: X1 = t2 + i*s*d
+    V r = rot90<DIR>(mk<T>(s * d.x, s * d.y));
+    a0 = cadd(a0, t1);
+    a1 = cadd(t2, r);
+    a2 = csub(t2, r);
+}
+
+template <int DIR, typename T, typename V>
+__device__ __forceinline__ void dft5(V& a0, V& a1, V& a2, V& a3, V& a4) {
+    const T c1 = (T)0.30901699437494742410229341718282L;   // cos(2pi/5)
+    const T c2 = (T)-0.80901699437494742410229341718282L;  // cos(4pi/5)
+    const T s1 = (T)0.95105651629515357211643933337938L;   // sin(2pi/5)
+    const T s2 = (T)0.58778525229247312916870595463907L;   // sin(4pi/5)
+    V p1 = cadd(a1, a4), m1 = csub(a1, a4);
+    V p2 = cadd(a2, a3), m2 = csub(a2, a3);
+    V b1 = mk<T>(a0.x + c1 * p1.x + c2 * p2.x, a0.y + c1 * p1.y + c2 * p2.y);
+    V b2 = mk<T>(a0.x + c2 * p1.x + c1 * p2.x, a0.y + c2 * p1.y + c1 * p2.y);
+    V r1 = rot90<DIR>(mk<T>(s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y));
+    V r2 = rot90<DIR>(mk<T>(s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y));
+    a0 = mk<T>(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
+    a1 = cadd(b1, r1); a4 = csub(b1, r1);
+    a2 = cadd(b2, r2); a3 = csub(b2, r2);
+}
+
+// ---------------------------------------------------------------------------------------
+// radix plan: largest radix in {8,4,2,3,5} dividing both what is left of N and E
+// ---------------------------------------------------------------------------------------
+__host__ __device__ constexpr int pick_radix(int rem, int E) {
+    return (rem % 8 == 0 && E % 8 == 0) ? 8 :
+           (rem % 4 == 0 && E % 4 == 0) ? 4 :
+           (rem % 2 == 0 && E % 2 == 0) ? 2 :
+           (rem % 3 == 0 && E % 3 == 0) ? 3 :
+           (rem % 5 == 0 && E % 5 == 0) ? 5 : 0;
+}
+__host__ __device__ constexpr bool plan_ok(int N, int E) {
+    int ns = 1;
+    while (ns < N) { int r = pick_radix(N / ns, E); if (r == 0) return false; ns *= r; }
+    return ns == N && N % E == 0;
+}
+__host__ __device__ constexpr int num_stages(int N, int E) {
+    int ns = 1, s = 0;
+    while (ns < N) { int r = pick_radix(N / ns, E); if (r == 0) return -1; ns *= r; ++s; }
+    return s;
+}
+
+// Shared-memory addressing of one line during an exchange.
+//   contiguous-line kernels: addr = base + idx + idx/PADW   (PADW elements = 128 bytes)
+//   strided (column-tile) kernels: addr = idx*TCOLS + column  (a quarter/half warp touches
+//   TCOLS contiguous elements = 128 bytes: conflict free for every stage)
+template <int MUL, int PADW>
+struct SmemLine {
+    int base;
+    __device__ __forceinline__ int operator()(int idx) const {
+        if constexpr (PADW > 0) return base + idx + idx / PADW;
+        else return base + idx * MUL;
+    }
+};
+
+// SYNC: 0 = __syncthreads (line spans warps), 1 = __syncwarp (line lives inside one warp)
+template <int SYNC> __device__ __forceinline__ void line_sync() {
+    if (SYNC == 1) __syncwarp(); else __syncthreads();
+}
+
+template <typename T, int N, int E, int DIR, int Ns, int R, typename V>
+__device__ __forceinline__ void fft_stage(V (&x)[E], int t, const V* __restrict__ tw) {
+    constexpr int P = N / E;
+    constexpr int NB = E / R;          // butterflies per thread
+    constexpr int TS = N / (Ns * R);   // twiddle table stride
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        if (Ns > 1) {
+            const int jm = (t + m * P) % Ns;
+#pragma unroll
+            for (int k = 1; k < R; ++k) {
+                V w = __ldg(&tw[(jm * k) * TS]);
+                if (DIR > 0) w.y = -w.y;
+                x[m + k * NB] = cmul(x[m + k * NB], w);
+            }
+        }
+        if (R == 2) dft2<DIR>(x[m], x[m + NB]);
+        else if (R == 4) dft4<DIR>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB]);
+        else if (R == 8) dft8<DIR, T>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB],
+                                      x[m + 4 * NB], x[m + 5 * NB], x[m + 6 * NB], x[m + 7 * NB]);
+        else if (R == 3) dft3<DIR, T>(x[m], x[m + NB], x[m + 2 * NB]);
+        else if (R == 5) dft5<DIR, T>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB], x[m + 4 * NB]);
+    }
+}
+
+template <typename T, int N, int E, int Ns, int R, typename V, typename SM>
+__device__ __forceinline__ void fft_scatter(const V (&x)[E], int t, V* sm, const SM& map) {
+    constexpr int P = N / E;
+    constexpr int NB = E / R;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * P;
+        const int o = (j / Ns) * (Ns * R) + (j % Ns);
+#pragma unroll
+        for (int k = 0; k < R; ++k) sm[map(o + k * Ns)] = x[m + k * NB];
+    }
+}
+
+template <typename T, int N, int E, typename V, typename SM>
+__device__ __forceinline__ void fft_gather(V (&x)[E], int t, const V* sm, const SM& map) {
+    constexpr int P = N / E;
+#pragma unroll
+    for (int q = 0; q < E; ++q) x[q] = sm[map(t + q * P)];
+}
+
+// Full line transform.  sm points at this CTA's exchange region; `map` places this line in it.
+// NBUF = 2: ping-pong between two regions `bufstride` elements apart (one sync per exchange);
+// NBUF = 1: single region, two syncs per exchange.  `phase` must be CTA-uniform.
+template <typename T, int N, int E, int DIR, int SYNC, int NBUF, int Ns, typename V, typename SM>
+__device__ __forceinline__ void fft_stages(V (&x)[E], int t, const V* __restrict__ tw,
+                                           V* sm, const SM& map, int bufstride, int& phase) {
+    if constexpr (Ns < N) {
+        constexpr int R = pick_radix(N / Ns, E);
+        static_assert(R > 0, "unsupported FFT length for this E");
+        fft_stage<T, N, E, DIR, Ns, R>(x, t, tw);
+        if constexpr (Ns * R < N) {
+            V* b = sm + (NBUF == 2 ? phase * bufstride : 0);
+            if (NBUF == 1) line_sync<SYNC>();
+            fft_scatter<T, N, E, Ns, R>(x, t, b, map);
+            line_sync<SYNC>();
+            fft_gather<T, N, E>(x, t, b, map);
+            if (NBUF == 2) phase ^= 1;
+            fft_stages<T, N, E, DIR, SYNC, NBUF, Ns * R>(x, t, tw, sm, map, bufstride, phase);
+        }
+    }
+}
+
+template <typename T, int N, int E, int DIR, int SYNC, int NBUF, typename V, typename SM>
+__device__ __forceinline__ void fft_line(V (&x)[E], int t, const V* __restrict__ tw,
+                                         V* sm, const SM& map, int bufstride, int& phase) {
+    fft_stages<T, N, E, DIR, SYNC, NBUF, 1>(x, t, tw, sm, map, bufstride, phase);
+}
+
+// wavenumber (integer) of memory index i on a c2c axis of length n (numpy.fft.fftfreq order)
+__device__ __forceinline__ int wavenum(int i, int n) { return i < (n + 1) / 2 ? i : i - n; }
+
+}  // namespace sdns

@@ -1,0 +1,89 @@
+// inst.cu -- one instantiation unit: compile with -DSDNS_FAMILY=<0..10> -DSDNS_PREC=<32|64>.
+// Defines sdns_launch_<family>_f<prec>(n, args, stream): picks the kernel compiled for transform
+// length n and launches it.
+#include "launch.cuh"
+
+#ifndef SDNS_FAMILY
+#error "compile with -DSDNS_FAMILY=n"
+#endif
+#if SDNS_PREC == 32
+typedef float real_t;
+#define SDNS_FN2(f) sdns_launch_##f##_f32
+#else
+typedef double real_t;
+#define SDNS_FN2(f) sdns_launch_##f##_f64
+#endif
+#define SDNS_FN1(f) SDNS_FN2(f)
+#define SDNS_FN SDNS_FN1(SDNS_FAMILY)
+
+namespace sdns {
+
+template <typename T, int N, int MODE, int DIR>
+static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
+    typedef SCfg<T, N, MODE> C;
+    static_assert(plan_ok(N, C::E), "no radix plan");
+    auto kern = strided_kernel<T, N, C::E, C::TC, DIR, MODE, C::NBUF>;
+    static bool once = false;
+    if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
+    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC), MODE == S_PLAIN ? a.nfields : 1);
+    kern<<<grid, C::P * C::TC, C::smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int N>
+static int run_mhd_f0(const StridedArgs<T>& a, cudaStream_t st) {
+    typedef MCfg<T, N> C;
+    static_assert(plan_ok(N, C::E), "no radix plan");
+    auto kern = mhd_f0_kernel<T, N, C::E, C::TC, C::NBUF>;
+    static bool once = false;
+    if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
+    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC));
+    kern<<<grid, C::P * C::TC, C::smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int M, int MODE>
+static int run_z(const ZArgs<T>& a, cudaStream_t st) {
+    typedef ZCfg<T, M, MODE> C;
+    static_assert(plan_ok(M, C::E), "no radix plan");
+    auto kern = z_kernel<T, M, C::E, C::LPC, MODE, C::SYNC, C::NBUF>;
+    static bool once = false;
+    if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
+    dim3 grid((unsigned)((a.nlines + C::LPC - 1) / C::LPC));
+    kern<<<grid, C::P * C::LPC, C::smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int SDNS_FN(int n, const void* args, cudaStream_t st) {
+    typedef real_t T;
+    switch (n) {
+#if SDNS_FAMILY == 0
+#define X(N) case N: return run_strided<T, N, S_PLAIN, -1>(*(const StridedArgs<T>*)args, st);
+#elif SDNS_FAMILY == 1
+#define X(N) case N: return run_strided<T, N, S_PLAIN, +1>(*(const StridedArgs<T>*)args, st);
+#elif SDNS_FAMILY == 2
+#define X(N) case N: return run_strided<T, N, S_NS_B0, +1>(*(const StridedArgs<T>*)args, st);
+#elif SDNS_FAMILY == 3
+#define X(N) case N: return run_strided<T, N, S_VV_B0, +1>(*(const StridedArgs<T>*)args, st);
+#elif SDNS_FAMILY == 4
+#define X(N) case N: return run_strided<T, N, S_NS_F0, -1>(*(const StridedArgs<T>*)args, st);
+#elif SDNS_FAMILY == 5
+#define X(N) case N: return run_strided<T, N, S_VV_F0, -1>(*(const StridedArgs<T>*)args, st);
+#elif SDNS_FAMILY == 6
+#define X(N) case N: return run_mhd_f0<T, N>(*(const StridedArgs<T>*)args, st);
+#elif SDNS_FAMILY == 7
+#define X(N) case N: return run_z<T, N, Z_C2R>(*(const ZArgs<T>*)args, st);
+#elif SDNS_FAMILY == 8
+#define X(N) case N: return run_z<T, N, Z_R2C>(*(const ZArgs<T>*)args, st);
+#elif SDNS_FAMILY == 9
+#define X(N) case N: return run_z<T, N, Z_CROSS>(*(const ZArgs<T>*)args, st);
+#elif SDNS_FAMILY == 10
+#define X(N) case N: return run_z<T, N, Z_MHD>(*(const ZArgs<T>*)args, st);
+#endif
+        SDNS_SIZES(X)
+#undef X
+        default: return -1000;
+    }
+}
+
+}  // namespace sdns

@@ -1,0 +1,552 @@
+// passes.cuh -- the axis passes of the pseudo-spectral right-hand side, sm_100a.
+//
+// A scalar 3-D transform is three axis passes (SURVEY.md section 8d "three-pass model").  All
+// pointwise work of the reference's hot path is fused into them:
+//   B0  axis-0 inverse c2c.  Load functor: 2/3 truncation or 3/2 zero padding (shenfun Tp,
+//       solvers/NS.py:29-31), curl_hat = i k x u_hat (cross2, maths/cross.py:30-35,
+//       optimization/cython_maths.in:62-86) or u_hat = i k x w_hat / k^2 (VV.py:52-67).
+//   B1  axis-1 inverse c2c.
+//   Z   axis-2: c2r of all fields, the real-space product (cross1 maths/cross.py:16-28 /
+//       Elsasser products MHD.py:99-110), r2c of the products -- one kernel, the real fields
+//       never touch HBM.
+//   F1  axis-1 forward c2c (+ 3/2 truncation).
+//   F0  axis-0 forward c2c.  Epilogue: Nyquist mask (NS.py:253-254), pressure projection +
+//       viscous term (add_pressure_diffusion, NS.py:203-217, cython_solvers.in:44-80), Source
+//       (NS.py:259), VV/MHD variants (VV.py:99-110, MHD.py:89-97,132-149) and the RK4 stage
+//       update (maths/integrators.py:150-159, cython_integrators.in:8-52).
+#pragma once
+#include "fft_core.cuh"
+
+namespace sdns {
+
+// transform index j in [0, M)  <->  memory index along the same axis (or -1: not stored)
+struct AxisMap { int nlo, nhi, shift; };
+__device__ __forceinline__ int axis_mem(const AxisMap& a, int M, int j) {
+    return j < a.nlo ? j : (j >= M - a.nhi ? j - a.shift : -1);
+}
+
+enum StridedMode { S_PLAIN = 0, S_NS_B0 = 1, S_VV_B0 = 2, S_NS_F0 = 3, S_VV_F0 = 4, S_MHD_F0 = 5 };
+enum ZMode { Z_C2R = 0, Z_R2C = 1, Z_CROSS = 2, Z_MHD = 3 };
+enum OutMode { OUT_RHS = 0, OUT_STAGE = 1 };
+
+template <typename T>
+struct StridedArgs {
+    typedef typename C2<T>::type V;
+    const V* in; V* out;
+    long long in_fs, out_fs;      // field strides (elements)
+    long long in_ls, out_ls;      // stride along the transform line
+    long long in_os, out_os;      // stride between column runs
+    int cw;                       // columns per run (contiguous in memory)
+    long long ncols;              // total columns
+    int col_nlo, col_gap;         // run index -> memory run index (pruned axis-1 set on B0 input)
+    AxisMap imap, omap;
+    const V* tw;
+    T scale;
+    int nfields;
+    // functor data
+    const T* kx; const T* ky; const T* kz;      // scaled wavenumbers K[0],K[1],K[2] (NS.py:38-41)
+    int N0, N1, N2;                             // logical (unpadded) grid
+    int mask_nyquist;
+    // epilogue (F0 modes)
+    int out_mode;                 // OutMode
+    const V* u_hat;               // stage input u0 (viscous term)   [may alias u0]
+    V* rhs;                       // OUT_RHS target
+    V* u0; V* u1; V* u2;          // OUT_STAGE state
+    const V* source;              // optional
+    V* p_hat;                     // optional (NS OUT_RHS)
+    long long st_fs;              // field stride of the dense state arrays (= N0*N1*Nh)
+    T nu, eta, adt, bdt;
+    int rk;
+};
+
+template <typename V> __device__ __forceinline__ V czero() { V z; z.x = 0; z.y = 0; return z; }
+template <typename T, typename V> __device__ __forceinline__ V cscale(V a, T s) { a.x *= s; a.y *= s; return a; }
+
+// i*(ka*b - kb*a) for real ka,kb, complex a,b   (one component of cross2)
+template <typename T, typename V>
+__device__ __forceinline__ V icross(T ka, V b, T kb, V a) {
+    // (ka*b - kb*a) * i = ( -(ka*b.y - kb*a.y), ka*b.x - kb*a.x )
+    V r; r.x = -(ka * b.y - kb * a.y); r.y = ka * b.x - kb * a.x; return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Strided c2c pass over a tile of TC adjacent columns (TC*sizeof(V) = 128 bytes -> every
+// global access of a warp covers whole 128-byte lines; thread index = column + TC*t).
+// ---------------------------------------------------------------------------------------
+template <typename T, int N, int E, int TC, int DIR, int MODE, int NBUF>
+__global__ void __launch_bounds__((N / E) * TC)
+strided_kernel(const StridedArgs<T> a) {
+    typedef typename C2<T>::type V;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    V* sm = reinterpret_cast<V*>(smraw);
+    constexpr int P = N / E;
+    const int c = threadIdx.x % TC;
+    const int t = threadIdx.x / TC;
+    const long long col = (long long)blockIdx.x * TC + c;
+    const bool valid = col < a.ncols;
+    const int c1 = valid ? (int)(col / a.cw) : 0;
+    const int c2 = valid ? (int)(col % a.cw) : 0;
+    const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
+    const long long ibase = (long long)c1m * a.in_os + c2;
+    const long long obase = (long long)c1 * a.out_os + c2;
+    SmemLine<TC, 0> map; map.base = c;
+    int phase = 0;
+    constexpr int BUFSTRIDE = N * TC;
+
+    if (MODE == S_PLAIN) {
+        const int f = blockIdx.y;
+        V x[E];
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int i = axis_mem(a.imap, N, t + q * P);
+            x[q] = (valid && i >= 0) ? a.in[f * a.in_fs + (long long)i * a.in_ls + ibase] : czero<V>();
+        }
+        fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int i = axis_mem(a.omap, N, t + q * P);
+            if (valid && i >= 0) a.out[f * a.out_fs + (long long)i * a.out_ls + obase] = cscale<T>(x[q], a.scale);
+        }
+    } else if (MODE == S_NS_B0 || MODE == S_VV_B0) {
+        // in: 3 dense spectral fields.  out: 6 fields (NS: u_hat, i k x u_hat ; VV: i k x w_hat / k^2, w_hat)
+        const T k1 = valid ? a.ky[c1m] : (T)0;
+        const T k2 = valid ? a.kz[c2] : (T)0;
+#pragma unroll 1
+        for (int f = 0; f < 6; ++f) {
+            V x[E];
+            const bool direct = (MODE == S_NS_B0) ? (f < 3) : (f >= 3);
+            const int g = f % 3;               // component
+            const int ga = (g + 1) % 3, gb = (g + 2) % 3;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const int i = axis_mem(a.imap, N, t + q * P);
+                V v = czero<V>();
+                if (valid && i >= 0) {
+                    const long long off = (long long)i * a.in_ls + ibase;
+                    if (direct) {
+                        v = a.in[g * a.in_fs + off];
+                    } else {
+                        // component g of i*(K x b) = i*(K[ga]*b[gb] - K[gb]*b[ga])
+                        const T k0 = a.kx[i];
+                        T ka = ga == 0 ? k0 : (ga == 1 ? k1 : k2);
+                        T kb = gb == 0 ? k0 : (gb == 1 ? k1 : k2);
+                        if (MODE == S_VV_B0) {
+                            T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;   // NS.py:42-44
+                            if (ksq == (T)0) ksq = (T)1;                        // NS.py:46-48
+                            ka = ka / ksq; kb = kb / ksq;                       // K_over_K2
+                        }
+                        const V bb = a.in[gb * a.in_fs + off];
+                        const V ba = a.in[ga * a.in_fs + off];
+                        v = icross<T, V>(ka, bb, kb, ba);
+                    }
+                }
+                x[q] = v;
+            }
+            fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const int i = axis_mem(a.omap, N, t + q * P);
+                if (valid && i >= 0) a.out[f * a.out_fs + (long long)i * a.out_ls + obase] = x[q];
+            }
+        }
+    } else if (MODE == S_NS_F0 || MODE == S_VV_F0) {
+        V r[3][E];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const int i = axis_mem(a.imap, N, t + q * P);
+                r[f][q] = (valid && i >= 0) ? a.in[f * a.in_fs + (long long)i * a.in_ls + ibase] : czero<V>();
+            }
+            fft_line<T, N, E, DIR, 0, NBUF>(r[f], t, a.tw, sm, map, BUFSTRIDE, phase);
+        }
+        if (!valid) return;
+        const int i1 = c1, i2 = c2;
+        const T k1 = a.ky[i1], k2 = a.kz[i2];
+        const bool nyq12 = a.mask_nyquist && ((2 * i1 == a.N1) || (2 * i2 == a.N2));
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int i0 = axis_mem(a.omap, N, t + q * P);
+            if (i0 < 0) continue;
+            const long long off = (long long)i0 * a.out_ls + obase;
+            const T k0 = a.kx[i0];
+            T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;
+            V d0 = cscale<T>(r[0][q], a.scale), d1 = cscale<T>(r[1][q], a.scale), d2 = cscale<T>(r[2][q], a.scale);
+            if (MODE == S_VV_F0) {
+                // rhs = i*(K x v_hat)   (VV.py:99)
+                V e0 = icross<T, V>(k1, d2, k2, d1);
+                V e1 = icross<T, V>(k2, d0, k0, d2);
+                V e2 = icross<T, V>(k0, d1, k1, d0);
+                d0 = e0; d1 = e1; d2 = e2;
+            }
+            if (nyq12 || (a.mask_nyquist && 2 * i0 == a.N0)) { d0 = czero<V>(); d1 = czero<V>(); d2 = czero<V>(); }
+            const V w0 = a.u_hat[off], w1 = a.u_hat[a.st_fs + off], w2 = a.u_hat[2 * a.st_fs + off];
+            const T z = a.nu * ksq;
+            if (MODE == S_NS_F0) {
+                const T ks = ksq == (T)0 ? (T)1 : ksq;
+                const T q0 = k0 / ks, q1 = k1 / ks, q2 = k2 / ks;       // K_over_K2 (NS.py:46-48)
+                V p;
+                p.x = d0.x * q0 + d1.x * q1; p.x += d2.x * q2;
+                p.y = d0.y * q0 + d1.y * q1; p.y += d2.y * q2;
+                if (a.p_hat) a.p_hat[off] = p;
+                d0.x -= p.x * k0; d0.y -= p.y * k0;
+                d1.x -= p.x * k1; d1.y -= p.y * k1;
+                d2.x -= p.x * k2; d2.y -= p.y * k2;
+            }
+            d0.x -= z * w0.x; d0.y -= z * w0.y;
+            d1.x -= z * w1.x; d1.y -= z * w1.y;
+            d2.x -= z * w2.x; d2.y -= z * w2.y;
+            if (a.source) {
+                d0 = cadd(d0, a.source[off]); d1 = cadd(d1, a.source[a.st_fs + off]);
+                d2 = cadd(d2, a.source[2 * a.st_fs + off]);
+            }
+            V dd[3] = {d0, d1, d2};
+            V ww[3] = {w0, w1, w2};
+            if (a.out_mode == OUT_RHS) {
+#pragma unroll
+                for (int f = 0; f < 3; ++f) a.rhs[f * a.st_fs + off] = dd[f];
+            } else {
+                // RK4 stage rk (integrators.py:150-159): u1 = u2 = u0 at rk 0;
+                // u0 = u1 + b*dt*rhs (rk<3); u2 += a*dt*rhs; u0 = u2 after rk 3.
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    const long long o = f * a.st_fs + off;
+                    V b1, b2;
+                    if (a.rk == 0) { b1 = ww[f]; b2 = ww[f]; a.u1[o] = b1; }
+                    else { b2 = a.u2[o]; if (a.rk < 3) b1 = a.u1[o]; }
+                    b2.x += a.adt * dd[f].x; b2.y += a.adt * dd[f].y;
+                    if (a.rk < 3) {
+                        a.u2[o] = b2;
+                        V n; n.x = b1.x + a.bdt * dd[f].x; n.y = b1.y + a.bdt * dd[f].y;
+                        a.u0[o] = n;
+                    } else {
+                        a.u0[o] = b2;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// MHD F0: 9 Elsasser product fields ZZ[i][j] -> 6 rhs components (MHD.py:89-97), Nyquist mask,
+// pressure projection on the first three, -nu k^2 u, -eta k^2 b (MHD.py:132-149), RK4 stage.
+// Register budget: six accumulators of EH = E elements; the transforms stream through one
+// work array, so E is chosen smaller than for the NS epilogue.
+// ---------------------------------------------------------------------------------------
+template <typename T, int N, int E, int TC, int NBUF>
+__global__ void __launch_bounds__((N / E) * TC)
+mhd_f0_kernel(const StridedArgs<T> a) {
+    typedef typename C2<T>::type V;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    V* sm = reinterpret_cast<V*>(smraw);
+    constexpr int P = N / E;
+    const int c = threadIdx.x % TC;
+    const int t = threadIdx.x / TC;
+    const long long col = (long long)blockIdx.x * TC + c;
+    const bool valid = col < a.ncols;
+    const int c1 = valid ? (int)(col / a.cw) : 0;
+    const int c2 = valid ? (int)(col % a.cw) : 0;
+    const long long ibase = (long long)c1 * a.in_os + c2;
+    const long long obase = (long long)c1 * a.out_os + c2;
+    SmemLine<TC, 0> map; map.base = c;
+    int phase = 0;
+    constexpr int BUFSTRIDE = N * TC;
+    const T k1 = valid ? a.ky[c1] : (T)0, k2 = valid ? a.kz[c2] : (T)0;
+
+    V acc[6][E];
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+#pragma unroll
+        for (int q = 0; q < E; ++q) acc[f][q] = czero<V>();
+
+    // R_ij = FFT0(ZZ[i][j]); S_a = sum_b K_b (R_ab + R_ba) ; D_a = sum_b K_b (R_ba - R_ab)
+    // R_ij contributes  K_j*R_ij to S_i,  K_i*R_ij to S_j,  K_i*R_ij to D_j,  -K_j*R_ij to D_i
+#pragma unroll
+    for (int ij = 0; ij < 9; ++ij) {
+        const int i = ij / 3, j = ij % 3;
+        V x[E];
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int m = axis_mem(a.imap, N, t + q * P);
+            x[q] = (valid && m >= 0) ? a.in[ij * a.in_fs + (long long)m * a.in_ls + ibase] : czero<V>();
+        }
+        fft_line<T, N, E, -1, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int i0 = axis_mem(a.omap, N, t + q * P);
+            const T k0 = i0 >= 0 ? a.kx[i0] : (T)0;
+            const T kk[3] = {k0, k1, k2};
+            const T ki = kk[i], kj = kk[j];
+            acc[i][q].x += kj * x[q].x;     acc[i][q].y += kj * x[q].y;
+            acc[j][q].x += ki * x[q].x;     acc[j][q].y += ki * x[q].y;
+            acc[3 + j][q].x += ki * x[q].x; acc[3 + j][q].y += ki * x[q].y;
+            acc[3 + i][q].x -= kj * x[q].x; acc[3 + i][q].y -= kj * x[q].y;
+        }
+    }
+    if (!valid) return;
+    const int i1 = c1, i2 = c2;
+    const bool nyq12 = a.mask_nyquist && ((2 * i1 == a.N1) || (2 * i2 == a.N2));
+    const T hs = (T)0.5 * a.scale;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int i0 = axis_mem(a.omap, N, t + q * P);
+        if (i0 < 0) continue;
+        const long long off = (long long)i0 * a.out_ls + obase;
+        const T k0 = a.kx[i0];
+        T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;
+        V d[6];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            // rhs[:3] = -i/2 * S ; rhs[3:] = +i/2 * D
+            d[f].x = hs * acc[f][q].y;      d[f].y = -hs * acc[f][q].x;
+            d[3 + f].x = -hs * acc[3 + f][q].y; d[3 + f].y = hs * acc[3 + f][q].x;
+        }
+        if (nyq12 || (a.mask_nyquist && 2 * i0 == a.N0)) {
+#pragma unroll
+            for (int f = 0; f < 6; ++f) d[f] = czero<V>();
+        }
+        const T ks = ksq == (T)0 ? (T)1 : ksq;
+        const T q0 = k0 / ks, q1 = k1 / ks, q2 = k2 / ks;
+        V p;
+        p.x = d[0].x * q0 + d[1].x * q1; p.x += d[2].x * q2;
+        p.y = d[0].y * q0 + d[1].y * q1; p.y += d[2].y * q2;
+        if (a.p_hat) a.p_hat[off] = p;
+        d[0].x -= p.x * k0; d[0].y -= p.y * k0;
+        d[1].x -= p.x * k1; d[1].y -= p.y * k1;
+        d[2].x -= p.x * k2; d[2].y -= p.y * k2;
+        const T zu = a.nu * ksq, zb = a.eta * ksq;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+            const long long o = f * a.st_fs + off;
+            const V w = a.u_hat[o];
+            const T z = f < 3 ? zu : zb;
+            V dd = d[f];
+            dd.x -= z * w.x; dd.y -= z * w.y;
+            if (a.source) dd = cadd(dd, a.source[o]);
+            if (a.out_mode == OUT_RHS) {
+                a.rhs[o] = dd;
+            } else {
+                V b1, b2;
+                if (a.rk == 0) { b1 = w; b2 = w; a.u1[o] = b1; }
+                else { b2 = a.u2[o]; if (a.rk < 3) b1 = a.u1[o]; }
+                b2.x += a.adt * dd.x; b2.y += a.adt * dd.y;
+                if (a.rk < 3) {
+                    a.u2[o] = b2;
+                    V n; n.x = b1.x + a.bdt * dd.x; n.y = b1.y + a.bdt * dd.y;
+                    a.u0[o] = n;
+                } else {
+                    a.u0[o] = b2;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Contiguous-axis pass.  Lines of one CTA: LPC; thread index = t + P*line.
+// Two real lines ride on one complex transform of length M (a + i b).
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct ZArgs {
+    typedef typename C2<T>::type V;
+    const void* in; void* out;
+    long long in_fs, out_fs;      // field strides (elements of the respective type)
+    long long in_ls, out_ls;      // line pitch
+    long long nlines;
+    int nin_keep;                 // spectral modes present on input (c2r side)
+    int nout_keep;                // spectral modes stored on output (r2c side)
+    int nf;                       // fields for Z_C2R / Z_R2C
+    const V* tw;
+    T scale;                      // applied on the r2c side (and Z_C2R output)
+};
+
+template <typename T, int M, int E, typename V>
+__device__ __forceinline__ void load_pair(V (&x)[E], const V* __restrict__ A, const V* __restrict__ B,
+                                          int t, int nkeep) {
+    constexpr int P = M / E;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int k = t + q * P;
+        const int kk = (2 * k <= M) ? k : M - k;
+        V va = czero<V>(), vb = czero<V>();
+        if (kk < nkeep) { va = A[kk]; if (B) vb = B[kk]; }
+        if (2 * k > M) { va.y = -va.y; vb.y = -vb.y; }
+        if (k == 0 || 2 * k == M) { va.y = 0; vb.y = 0; }     // c2r ignores Im of DC / Nyquist
+        x[q].x = va.x - vb.y; x[q].y = va.y + vb.x;
+    }
+}
+
+// x = FFT(c + i d).  Writes C[k], D[k], k < nkeep (<= M/2+1) scaled by s.  D may be null.
+// The mirror exchange is one more step of the ping-pong sequence used by fft_line.
+template <typename T, int M, int E, int SYNC, int NBUF, typename V, typename SM>
+__device__ __forceinline__ void unpack_store_pair(const V (&x)[E], V* __restrict__ C, V* __restrict__ D,
+                                                  int t, int nkeep, T s, V* sm, const SM& map,
+                                                  int bufstride, int& phase) {
+    constexpr int P = M / E;
+    V* b = sm + (NBUF == 2 ? phase * bufstride : 0);
+    if (NBUF == 1) line_sync<SYNC>();
+#pragma unroll
+    for (int q = 0; q < E; ++q) b[map(t + q * P)] = x[q];
+    line_sync<SYNC>();
+    if (NBUF == 2) phase ^= 1;
+    const T h = (T)0.5 * s;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int k = t + q * P;
+        if (k < nkeep) {
+            const V zm = b[map(k == 0 ? 0 : M - k)];
+            V c, d;
+            c.x = h * (x[q].x + zm.x); c.y = h * (x[q].y - zm.y);
+            // d = -i/2 * (z - conj(zm))
+            d.x = h * (x[q].y + zm.y); d.y = -h * (x[q].x - zm.x);
+            C[k] = c;
+            if (D) D[k] = d;
+        }
+    }
+}
+
+template <typename T, int M, int E, int LPC, int MODE, int SYNC, int NBUF>
+__global__ void __launch_bounds__((M / E) * LPC)
+z_kernel(const ZArgs<T> a) {
+    typedef typename C2<T>::type V;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    V* sm = reinterpret_cast<V*>(smraw);
+    constexpr int P = M / E;
+    constexpr int PADW = 128 / (int)sizeof(V);
+    constexpr int LP = M + M / PADW + 1;            // padded line length in shared memory
+    constexpr int BUFSTRIDE = LP * LPC;
+    const int t = threadIdx.x % P;
+    const int ln = threadIdx.x / P;
+    long long line = (long long)blockIdx.x * LPC + ln;
+    const bool valid = line < a.nlines;
+    if (!valid) line = a.nlines - 1;               // keep all threads alive for the barriers
+    SmemLine<1, PADW> map; map.base = ln * LP;
+    int phase = 0;
+
+    if (MODE == Z_C2R) {
+        // nf complex lines -> nf real lines (plain backward, diagnostics path NS.py:86-99)
+        const V* in = reinterpret_cast<const V*>(a.in);
+        T* out = reinterpret_cast<T*>(a.out);
+        for (int f = 0; f < a.nf; f += 2) {
+            const bool two = f + 1 < a.nf;
+            V x[E];
+            load_pair<T, M, E>(x, in + f * a.in_fs + line * a.in_ls,
+                               two ? in + (f + 1) * a.in_fs + line * a.in_ls : nullptr, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    out[f * a.out_fs + line * a.out_ls + t + q * P] = x[q].x * a.scale;
+                    if (two) out[(f + 1) * a.out_fs + line * a.out_ls + t + q * P] = x[q].y * a.scale;
+                }
+            }
+        }
+    } else if (MODE == Z_R2C) {
+        const T* in = reinterpret_cast<const T*>(a.in);
+        V* out = reinterpret_cast<V*>(a.out);
+        for (int f = 0; f < a.nf; f += 2) {
+            const bool two = f + 1 < a.nf;
+            V x[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                x[q].x = in[f * a.in_fs + line * a.in_ls + t + q * P];
+                x[q].y = two ? in[(f + 1) * a.in_fs + line * a.in_ls + t + q * P] : (T)0;
+            }
+            fft_line<T, M, E, -1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+            V* C = out + f * a.out_fs + line * a.out_ls;
+            V* D = two ? out + (f + 1) * a.out_fs + line * a.out_ls : nullptr;
+            unpack_store_pair<T, M, E, SYNC, NBUF>(x, C, D, t, valid ? a.nout_keep : 0, a.scale, sm, map, BUFSTRIDE, phase);
+        }
+    } else {
+        // fused: 6 spectral lines -> real space -> products -> spectral lines
+        const V* in = reinterpret_cast<const V*>(a.in);
+        V* out = reinterpret_cast<V*>(a.out);
+        V p01[E], p23[E], p45[E];
+        load_pair<T, M, E>(p01, in + 0 * a.in_fs + line * a.in_ls, in + 1 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+        fft_line<T, M, E, +1, SYNC, NBUF>(p01, t, a.tw, sm, map, BUFSTRIDE, phase);
+        load_pair<T, M, E>(p23, in + 2 * a.in_fs + line * a.in_ls, in + 3 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+        fft_line<T, M, E, +1, SYNC, NBUF>(p23, t, a.tw, sm, map, BUFSTRIDE, phase);
+        load_pair<T, M, E>(p45, in + 4 * a.in_fs + line * a.in_ls, in + 5 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+        fft_line<T, M, E, +1, SYNC, NBUF>(p45, t, a.tw, sm, map, BUFSTRIDE, phase);
+        const int nk = valid ? a.nout_keep : 0;
+        if (MODE == Z_CROSS) {
+            // fields: a = (p01.x, p01.y, p23.x), b = (p23.y, p45.x, p45.y); c = a x b (cross1)
+            V x[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const T a0 = p01[q].x, a1 = p01[q].y, a2 = p23[q].x;
+                const T b0 = p23[q].y, b1 = p45[q].x, b2 = p45[q].y;
+                x[q].x = a1 * b2 - a2 * b1;
+                x[q].y = a2 * b0 - a0 * b2;
+                p01[q].x = a0 * b1 - a1 * b0;      // third component kept for the second transform
+                p01[q].y = (T)0;
+            }
+            fft_line<T, M, E, -1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+            unpack_store_pair<T, M, E, SYNC, NBUF>(x, out + 0 * a.out_fs + line * a.out_ls,
+                                                   out + 1 * a.out_fs + line * a.out_ls, t, nk, a.scale, sm, map,
+                                                   BUFSTRIDE, phase);
+            fft_line<T, M, E, -1, SYNC, NBUF>(p01, t, a.tw, sm, map, BUFSTRIDE, phase);
+            if (valid) {
+                V* C = out + 2 * a.out_fs + line * a.out_ls;
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    const int k = t + q * P;
+                    if (k < nk) C[k] = cscale<T>(p01[q], a.scale);
+                }
+            }
+        } else {
+            // MHD (MHD.py:119-127, 99-110): u = (p01.x,p01.y,p23.x), b = (p23.y,p45.x,p45.y)
+            // z0 = u + b, z1 = u - b ; ZZ[i][j] = F(z0_i * z1_j)
+            T z0[3][E], z1[3][E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const T u0 = p01[q].x, u1 = p01[q].y, u2 = p23[q].x;
+                const T b0 = p23[q].y, b1 = p45[q].x, b2 = p45[q].y;
+                z0[0][q] = u0 + b0; z0[1][q] = u1 + b1; z0[2][q] = u2 + b2;
+                z1[0][q] = u0 - b0; z1[1][q] = u1 - b1; z1[2][q] = u2 - b2;
+            }
+#pragma unroll
+            for (int pr = 0; pr < 5; ++pr) {
+                const int fa = 2 * pr, fb = 2 * pr + 1;
+                V x[E];
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    x[q].x = z0[fa / 3][q] * z1[fa % 3][q];
+                    x[q].y = fb < 9 ? z0[fb / 3][q] * z1[fb % 3][q] : (T)0;
+                }
+                fft_line<T, M, E, -1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+                unpack_store_pair<T, M, E, SYNC, NBUF>(x, out + fa * a.out_fs + line * a.out_ls,
+                                                       fb < 9 ? out + fb * a.out_fs + line * a.out_ls : nullptr,
+                                                       t, nk, a.scale, sm, map, BUFSTRIDE, phase);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Hermitian-weighted sum |u_hat|^2 (shenfun.fourier.energy_fourier as used by tests/TG.py:101)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void energy_kernel(const typename C2<T>::type* __restrict__ u, long long n, int Nh, int N2,
+                              double* __restrict__ out) {
+    double s = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k2 = (int)(i % Nh);
+        const typename C2<T>::type v = u[i];
+        const double w = (k2 == 0 || 2 * k2 == N2) ? 1.0 : 2.0;
+        s += w * ((double)v.x * v.x + (double)v.y * v.y);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double ws[32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[blockIdx.x] = s;
+    }
+}
+
+}  // namespace sdns

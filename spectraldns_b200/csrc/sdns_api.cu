@@ -1,0 +1,625 @@
+// sdns_api.cu -- plan object and C ABI of libsdns_b200.so (see include/sdns_b200.h).
+//
+// Host-side equivalent of the reference's get_context() setup (solvers/NS.py:12-72) and of the
+// call sequence ComputeRHS -> conv -> transforms (NS.py:191-261, VV.py:92-146, MHD.py:119-176),
+// re-expressed as five kernel launches per right-hand side (B0, B1, Z, F1, F0).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/sdns_b200.h"
+#include "launch.cuh"
+
+using namespace sdns;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+    return fail(SDNS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+typedef int (*launch_fn)(int, const void*, cudaStream_t);
+static launch_fn g_launch[FAM_COUNT][2] = {
+#define ROW(f) { sdns_launch_##f##_f32, sdns_launch_##f##_f64 },
+    ROW(0) ROW(1) ROW(2) ROW(3) ROW(4) ROW(5) ROW(6) ROW(7) ROW(8) ROW(9) ROW(10)
+#undef ROW
+};
+
+static bool size_ok(int n) {
+    switch (n) {
+#define X(N) case N: return true;
+        SDNS_SIZES(X)
+#undef X
+        default: return false;
+    }
+}
+
+// geometry of one function space (T or Tp)
+struct Space {
+    int M[3];              // transform lengths (physical shape)
+    AxisMap bmap[3];       // backward-input map per axis (transform index -> memory index)
+    AxisMap fmap[2];       // forward-output map, axes 0,1
+    int K1n;               // axis-1 modes entering the backward transform (compact count)
+    int col_nlo, col_gap;  // compact axis-1 index -> memory index
+    int K2n, K2p;          // axis-2 modes entering the backward transform, padded pitch
+    double scale;          // 1/prod(M)
+};
+
+struct sdns_plan {
+    sdns_config cfg;
+    int N[3], Nh, Nhp;
+    int prec;               // 0 f32, 1 f64
+    size_t rs, cs;          // sizeof real / complex
+    Space sp[2];            // SDNS_SPACE_T, SDNS_SPACE_TP
+    cudaStream_t stream;
+    // workspace carving (byte offsets)
+    size_t ws_need, off_tab, off_A, off_B, off_red, bytes_A, bytes_B;
+    char* ws; size_t ws_bytes;
+    std::vector<char> host_tables;                 // image of the table region
+    std::map<int, size_t> tw_off;                  // transform length -> offset of its twiddles
+    size_t kx_off, ky_off, kz_off;
+    long long launches;
+    int red_blocks;
+    // optional per-family profiling (bench.py roofline): CUDA events around every launch
+    bool prof;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used;
+    struct Rec { int fam; cudaEvent_t a, b; double bytes; };
+    std::vector<Rec> recs;
+    double prof_ms[FAM_COUNT]; double prof_bytes[FAM_COUNT]; long long prof_n[FAM_COUNT];
+};
+
+static AxisMap all_map(int n) { AxisMap m; m.nlo = n; m.nhi = 0; m.shift = 0; return m; }
+
+static int default_kcut(int n) { return (int)ceil(2.0 / 3.0 * (n / 2 + 1)) - 1; }
+
+static void build_spaces(sdns_plan* p) {
+    const int* N = p->N;
+    // T: plain space
+    Space& t = p->sp[SDNS_SPACE_T];
+    for (int i = 0; i < 3; ++i) { t.M[i] = N[i]; t.bmap[i] = all_map(i < 2 ? N[i] : p->Nh); }
+    t.fmap[0] = all_map(N[0]); t.fmap[1] = all_map(N[1]);
+    t.K1n = N[1]; t.col_nlo = N[1]; t.col_gap = 0; t.K2n = p->Nh;
+    Space& d = p->sp[SDNS_SPACE_TP];
+    d = t;
+    if (p->cfg.dealias == SDNS_DEALIAS_23) {
+        // truncation of the backward input, |k_i| <= kcut_i (solvers/NS.py:29-31 dealias_direct;
+        // cutoff spectralDNS3D_short.py:44-46).  Truncated lines/columns are never transformed.
+        for (int i = 0; i < 2; ++i) {
+            int kc = p->cfg.kcut[i] >= 0 ? p->cfg.kcut[i] : default_kcut(N[i]);
+            if (2 * kc + 1 < N[i]) { d.bmap[i].nlo = kc + 1; d.bmap[i].nhi = kc; d.bmap[i].shift = 0; }
+        }
+        int kc2 = p->cfg.kcut[2] >= 0 ? p->cfg.kcut[2] : default_kcut(N[2]);
+        if (kc2 + 1 < p->Nh) d.K2n = kc2 + 1;
+        d.K1n = d.bmap[1].nlo + d.bmap[1].nhi;
+        d.col_nlo = d.bmap[1].nlo; d.col_gap = N[1] - d.K1n;
+        d.bmap[1].shift = N[1] - d.K1n;            // B1 reads the compact axis-1 layout
+    } else if (p->cfg.dealias == SDNS_DEALIAS_32) {
+        // zero padding N -> 3N/2 per axis on backward, corner truncation on forward
+        for (int i = 0; i < 3; ++i) d.M[i] = (3 * N[i]) / 2;
+        for (int i = 0; i < 2; ++i) {
+            d.bmap[i].nlo = N[i] / 2; d.bmap[i].nhi = N[i] - N[i] / 2; d.bmap[i].shift = d.M[i] - N[i];
+            d.fmap[i] = d.bmap[i];
+        }
+    }
+    for (int s = 0; s < 2; ++s) {
+        Space& q = p->sp[s];
+        q.K2p = (q.K2n + 1) & ~1;
+        q.scale = 1.0 / ((double)q.M[0] * q.M[1] * q.M[2]);
+    }
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename T>
+static void fill_tables(sdns_plan* p) {
+    typedef typename C2<T>::type V;
+    std::vector<char>& h = p->host_tables;
+    auto add_tw = [&](int n) {
+        if (p->tw_off.count(n)) return;
+        size_t off = align_up(h.size(), 256);
+        h.resize(off + sizeof(V) * n);
+        V* tw = reinterpret_cast<V*>(h.data() + off);
+        for (int j = 0; j < n; ++j) {
+            long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
+            tw[j].x = (T)cosl(ang); tw[j].y = (T)sinl(ang);
+        }
+        p->tw_off[n] = off;
+    };
+    for (int s = 0; s < 2; ++s) for (int i = 0; i < 3; ++i) add_tw(p->sp[s].M[i]);
+    auto add_k = [&](int n, int len, double L, bool real_axis) {
+        size_t off = align_up(h.size(), 256);
+        h.resize(off + sizeof(T) * len);
+        T* k = reinterpret_cast<T*>(h.data() + off);
+        for (int i = 0; i < len; ++i) {
+            int kk = real_axis ? i : (i < (n + 1) / 2 ? i : i - n);
+            // same evaluation order as the oracle: k*2*pi/L in double, then cast (NS.py:38-41)
+            k[i] = (T)(((double)kk * 2.0 * M_PI) / L);
+        }
+        return off;
+    };
+    p->kx_off = add_k(p->N[0], p->N[0], p->cfg.L[0], false);
+    p->ky_off = add_k(p->N[1], p->N[1], p->cfg.L[1], false);
+    p->kz_off = add_k(p->N[2], p->Nh, p->cfg.L[2], true);
+}
+
+extern "C" int sdns_abi_version(void) { return SDNS_ABI_VERSION; }
+extern "C" const char* sdns_last_error(void) { return g_err.c_str(); }
+extern "C" int sdns_size_supported(int n, int precision) {
+    (void)precision;
+    return size_ok(n) ? SDNS_OK : SDNS_ERR_SIZE;
+}
+
+extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
+    if (!out || !cfg) return fail(SDNS_ERR_ARG, "null argument");
+    if (cfg->abi_version != SDNS_ABI_VERSION) return fail(SDNS_ERR_ARG, "ABI version mismatch");
+    if (cfg->precision != SDNS_SINGLE && cfg->precision != SDNS_DOUBLE) return fail(SDNS_ERR_ARG, "precision");
+    if (cfg->nranks != 1 || cfg->rank != 0)
+        return fail(SDNS_ERR_ARG, "this build drives one GPU per plan (nranks must be 1)");
+    if (cfg->solver < SDNS_NS || cfg->solver > SDNS_MHD) return fail(SDNS_ERR_ARG, "solver");
+    if (cfg->solver == SDNS_NS && cfg->convection != SDNS_CONV_VORTEX)
+        return fail(SDNS_ERR_ARG, "NS: only convection='Vortex' is compiled in");
+    if (cfg->solver == SDNS_VV && cfg->convection != SDNS_CONV_VORTEX)
+        return fail(SDNS_ERR_ARG, "VV supports only convection='Vortex' (solvers/VV.py:87-88)");
+    if (cfg->solver == SDNS_MHD && cfg->convection != SDNS_CONV_DIVERGENCE)
+        return fail(SDNS_ERR_ARG, "MHD supports only convection='Divergence' (solvers/MHD.py:114-115)");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(SDNS_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce) +
+                    " (libsdns_b200 has no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    sdns_plan* p = new sdns_plan();
+    p->cfg = *cfg;
+    for (int i = 0; i < 3; ++i) {
+        p->N[i] = cfg->N[i];
+        if (p->N[i] < 2 || p->N[i] % 2) { delete p; return fail(SDNS_ERR_SIZE, "N must be even"); }
+        if (!(cfg->L[i] > 0)) { delete p; return fail(SDNS_ERR_ARG, "L must be positive"); }
+    }
+    p->Nh = p->N[2] / 2 + 1;
+    p->Nhp = (p->Nh + 1) & ~1;
+    p->prec = cfg->precision;
+    p->rs = p->prec ? 8 : 4; p->cs = 2 * p->rs;
+    p->stream = 0; p->ws = nullptr; p->ws_bytes = 0; p->launches = 0;
+    p->prof = false; p->ev_used = 0;
+    for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_n[i] = 0; }
+    build_spaces(p);
+    for (int s = 0; s < 2; ++s) for (int i = 0; i < 3; ++i)
+        if (!size_ok(p->sp[s].M[i])) {
+            char b[128]; snprintf(b, sizeof b, "no compiled transform of length %d (have 2^k, 3*2^k for 16..3072)", p->sp[s].M[i]);
+            delete p; return fail(SDNS_ERR_SIZE, b);
+        }
+    if (p->prec) fill_tables<double>(p); else fill_tables<float>(p);
+    // scratch: A holds W0 (B0 out) and W2 (Z out); B holds W1 (B1 out) and W3 (F1 out)
+    const int nz = cfg->solver == SDNS_MHD ? 9 : 6;    // widest field count through the pipeline
+    size_t a = 0, b = 0;
+    for (int s = 0; s < 2; ++s) {
+        const Space& q = p->sp[s];
+        size_t w0 = (size_t)6 * q.M[0] * q.K1n * q.K2p;
+        size_t w1 = (size_t)6 * q.M[0] * q.M[1] * q.K2p;
+        size_t w2 = (size_t)nz * q.M[0] * q.M[1] * p->Nhp;
+        size_t w3 = (size_t)nz * q.M[0] * p->N[1] * p->Nhp;
+        a = std::max(a, std::max(w0, w2)); b = std::max(b, std::max(w1, w3));
+    }
+    p->bytes_A = align_up(a * p->cs, 256); p->bytes_B = align_up(b * p->cs, 256);
+    p->red_blocks = 1024;
+    p->off_tab = 0;
+    p->off_A = align_up(p->host_tables.size(), 256);
+    p->off_B = p->off_A + p->bytes_A;
+    p->off_red = p->off_B + p->bytes_B;
+    p->ws_need = p->off_red + align_up(sizeof(double) * p->red_blocks, 256);
+    *out = p;
+    return SDNS_OK;
+}
+
+extern "C" int sdns_plan_destroy(sdns_plan* p) {
+    if (p) for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+    delete p; return SDNS_OK;
+}
+
+extern "C" int sdns_workspace_bytes(const sdns_plan* p, size_t* bytes) {
+    if (!p || !bytes) return fail(SDNS_ERR_ARG, "null argument");
+    *bytes = p->ws_need; return SDNS_OK;
+}
+
+extern "C" int sdns_plan_set_workspace(sdns_plan* p, void* dptr, size_t bytes) {
+    if (!p || !dptr) return fail(SDNS_ERR_ARG, "null argument");
+    if (bytes < p->ws_need) return fail(SDNS_ERR_WORKSPACE, "workspace too small");
+    if ((uintptr_t)dptr % 256) return fail(SDNS_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    p->ws = (char*)dptr; p->ws_bytes = bytes;
+    CUDA_TRY(cudaMemcpyAsync(p->ws + p->off_tab, p->host_tables.data(), p->host_tables.size(),
+                             cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SDNS_OK;
+}
+
+extern "C" int sdns_plan_set_stream(sdns_plan* p, void* s) {
+    if (!p) return fail(SDNS_ERR_ARG, "null plan");
+    p->stream = (cudaStream_t)s; return SDNS_OK;
+}
+extern "C" int sdns_sync(sdns_plan* p) {
+    if (!p) return fail(SDNS_ERR_ARG, "null plan");
+    CUDA_TRY(cudaStreamSynchronize(p->stream)); return SDNS_OK;
+}
+extern "C" int sdns_local_shapes(const sdns_plan* p, int32_t sp[3], int32_t ph[3], int32_t pd[3]) {
+    if (!p) return fail(SDNS_ERR_ARG, "null plan");
+    sp[0] = p->N[0]; sp[1] = p->N[1]; sp[2] = p->Nh;
+    for (int i = 0; i < 3; ++i) { ph[i] = p->sp[0].M[i]; pd[i] = p->sp[1].M[i]; }
+    return SDNS_OK;
+}
+extern "C" int sdns_launch_count(const sdns_plan* p, long long* c) {
+    if (!p || !c) return fail(SDNS_ERR_ARG, "null argument");
+    *c = p->launches; return SDNS_OK;
+}
+
+static int need_ws(sdns_plan* p) {
+    if (!p) return fail(SDNS_ERR_ARG, "null plan");
+    if (!p->ws) return fail(SDNS_ERR_WORKSPACE, "call sdns_plan_set_workspace first");
+    return SDNS_OK;
+}
+
+static cudaEvent_t get_event(sdns_plan* p) {
+    if (p->ev_used == p->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); p->ev_pool.push_back(e); }
+    return p->ev_pool[p->ev_used++];
+}
+
+// bytes = algorithmic HBM bytes of this launch: every input element read once + every output
+// element written once at the pass's actual (pruned / padded) sizes
+static int do_launch(sdns_plan* p, int fam, int n, const void* args, double bytes = 0) {
+    sdns_plan::Rec r; r.fam = fam; r.bytes = bytes;
+    if (p->prof) { r.a = get_event(p); cudaEventRecord(r.a, p->stream); }
+    int e = g_launch[fam][p->prec](n, args, p->stream);
+    if (p->prof) { r.b = get_event(p); cudaEventRecord(r.b, p->stream); p->recs.push_back(r); }
+    p->launches++;
+    if (e == -1000) { char b[96]; snprintf(b, sizeof b, "no kernel for length %d (family %d)", n, fam); return fail(SDNS_ERR_SIZE, b); }
+    if (e != 0) { char b[160]; snprintf(b, sizeof b, "kernel launch (family %d, n=%d): %s", fam, n, cudaGetErrorString((cudaError_t)e)); return fail(SDNS_ERR_CUDA, b); }
+    return SDNS_OK;
+}
+
+// ---- typed pipeline --------------------------------------------------------------------
+template <typename T>
+struct Pipe {
+    typedef typename C2<T>::type V;
+    sdns_plan* p;
+    const Space& q;
+    V* A; V* B;
+    Pipe(sdns_plan* p_, int space) : p(p_), q(p_->sp[space]) {
+        A = reinterpret_cast<V*>(p->ws + p->off_A); B = reinterpret_cast<V*>(p->ws + p->off_B);
+    }
+    const V* tw(int n) const { return reinterpret_cast<const V*>(p->ws + p->off_tab + p->tw_off.at(n)); }
+    void base(StridedArgs<T>& a) const {
+        memset(&a, 0, sizeof a);
+        a.kx = reinterpret_cast<const T*>(p->ws + p->kx_off);
+        a.ky = reinterpret_cast<const T*>(p->ws + p->ky_off);
+        a.kz = reinterpret_cast<const T*>(p->ws + p->kz_off);
+        a.N0 = p->N[0]; a.N1 = p->N[1]; a.N2 = p->N[2];
+        a.mask_nyquist = p->cfg.mask_nyquist;
+        a.scale = (T)1;
+        a.st_fs = (long long)p->N[0] * p->N[1] * p->Nh;
+    }
+    long long dense_fs() const { return (long long)p->N[0] * p->N[1] * p->Nh; }
+
+    // B0: dense spectral (nf,N0,N1,Nh) -> A as W0 (nfo, M0, K1n, K2p)
+    int b0(int fam, const V* in, int nf) {
+        StridedArgs<T> a; base(a);
+        a.in = in; a.out = A;
+        a.in_fs = dense_fs(); a.in_ls = (long long)p->N[1] * p->Nh; a.in_os = p->Nh;
+        a.cw = q.K2n; a.ncols = (long long)q.K1n * q.K2n;
+        a.col_nlo = q.col_nlo; a.col_gap = q.col_gap;
+        a.imap = q.bmap[0]; a.omap = all_map(q.M[0]);
+        a.out_fs = (long long)q.M[0] * q.K1n * q.K2p; a.out_ls = (long long)q.K1n * q.K2p; a.out_os = q.K2p;
+        a.tw = tw(q.M[0]); a.nfields = nf;
+        const int nfo = (fam == FAM_PLAIN_BWD) ? nf : 6;
+        const double cols = (double)q.K1n * q.K2n;
+        const double bytes = (nf * cols * (q.bmap[0].nlo + q.bmap[0].nhi) + nfo * cols * q.M[0]) * p->cs;
+        return do_launch(p, fam, q.M[0], &a, bytes);
+    }
+    // B1: A (W0) -> B as W1 (nf, M0, M1, K2p)
+    int b1(int nf) {
+        StridedArgs<T> a; base(a);
+        a.in = A; a.out = B;
+        a.in_fs = (long long)q.M[0] * q.K1n * q.K2p; a.in_ls = q.K2p; a.in_os = (long long)q.K1n * q.K2p;
+        a.cw = q.K2n; a.ncols = (long long)q.M[0] * q.K2n;
+        a.col_nlo = q.M[0]; a.col_gap = 0;
+        a.imap = q.bmap[1];
+        if (q.K1n == p->N[1] && q.M[1] == p->N[1]) a.imap = all_map(q.M[1]);
+        a.omap = all_map(q.M[1]);
+        a.out_fs = (long long)q.M[0] * q.M[1] * q.K2p; a.out_ls = q.K2p; a.out_os = (long long)q.M[1] * q.K2p;
+        a.tw = tw(q.M[1]); a.nfields = nf;
+        const double bytes = (double)nf * q.M[0] * q.K2n * ((double)q.K1n + q.M[1]) * p->cs;
+        return do_launch(p, FAM_PLAIN_BWD, q.M[1], &a, bytes);
+    }
+    // Z: B (W1) -> A as W2 (nfo, M0, M1, Nhp)   [fused], or to/from user real arrays [plain]
+    int z(int fam, const void* in, void* out, int nf, bool in_is_W1, bool out_is_W2) {
+        ZArgs<T> a; memset(&a, 0, sizeof a);
+        a.in = in; a.out = out;
+        const long long plane = (long long)q.M[0] * q.M[1];
+        a.in_ls = in_is_W1 ? q.K2p : q.M[2]; a.in_fs = plane * a.in_ls;
+        a.out_ls = out_is_W2 ? p->Nhp : q.M[2]; a.out_fs = plane * a.out_ls;
+        a.nlines = plane; a.nin_keep = q.K2n; a.nout_keep = p->Nh; a.nf = nf;
+        a.tw = tw(q.M[2]);
+        a.scale = (fam == FAM_Z_C2R) ? (T)1 : (T)q.scale;
+        const int nin = (fam == FAM_Z_CROSS || fam == FAM_Z_MHD) ? 6 : nf;
+        const int nout = fam == FAM_Z_CROSS ? 3 : (fam == FAM_Z_MHD ? 9 : nf);
+        const double bin = in_is_W1 ? (double)q.K2n * p->cs : (double)q.M[2] * p->rs;
+        const double bout = out_is_W2 ? (double)p->Nh * p->cs : (double)q.M[2] * p->rs;
+        return do_launch(p, fam, q.M[2], &a, (double)plane * (nin * bin + nout * bout));
+    }
+    // F1: A (W2) -> B as W3 (nf, M0, N1, Nhp)
+    int f1(int nf) {
+        StridedArgs<T> a; base(a);
+        a.in = A; a.out = B;
+        a.in_fs = (long long)q.M[0] * q.M[1] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[1] * p->Nhp;
+        a.cw = p->Nh; a.ncols = (long long)q.M[0] * p->Nh;
+        a.col_nlo = q.M[0]; a.col_gap = 0;
+        a.imap = all_map(q.M[1]); a.omap = q.fmap[1];
+        a.out_fs = (long long)q.M[0] * p->N[1] * p->Nhp; a.out_ls = p->Nhp; a.out_os = (long long)p->N[1] * p->Nhp;
+        a.tw = tw(q.M[1]); a.nfields = nf;
+        const double bytes = (double)nf * q.M[0] * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
+        return do_launch(p, FAM_PLAIN_FWD, q.M[1], &a, bytes);
+    }
+    // F0 geometry: B (W3) -> dense spectral
+    void f0_geom(StridedArgs<T>& a, int nf) {
+        base(a);
+        a.in = B;
+        a.in_fs = (long long)q.M[0] * p->N[1] * p->Nhp; a.in_ls = (long long)p->N[1] * p->Nhp; a.in_os = p->Nhp;
+        a.cw = p->Nh; a.ncols = (long long)p->N[1] * p->Nh;
+        a.col_nlo = p->N[1]; a.col_gap = 0;
+        a.imap = all_map(q.M[0]); a.omap = q.fmap[0];
+        a.out_fs = dense_fs(); a.out_ls = (long long)p->N[1] * p->Nh; a.out_os = p->Nh;
+        a.tw = tw(q.M[0]); a.nfields = nf;
+    }
+};
+
+template <typename T>
+static int backward_t(sdns_plan* p, int space, int nc, const void* in, void* out) {
+    typedef typename C2<T>::type V;
+    Pipe<T> P(p, space);
+    for (int c0 = 0; c0 < nc; c0 += 6) {
+        int nf = std::min(6, nc - c0);
+        const V* src = reinterpret_cast<const V*>(in) + (long long)c0 * P.dense_fs();
+        T* dst = reinterpret_cast<T*>(out) + (long long)c0 * P.q.M[0] * P.q.M[1] * P.q.M[2];
+        int e;
+        if ((e = P.b0(FAM_PLAIN_BWD, src, nf))) return e;
+        if ((e = P.b1(nf))) return e;
+        if ((e = P.z(FAM_Z_C2R, P.B, dst, nf, true, false))) return e;
+    }
+    return SDNS_OK;
+}
+
+template <typename T>
+static int forward_t(sdns_plan* p, int space, int nc, const void* in, void* out) {
+    typedef typename C2<T>::type V;
+    Pipe<T> P(p, space);
+    const int chunk = p->cfg.solver == SDNS_MHD ? 9 : 6;
+    for (int c0 = 0; c0 < nc; c0 += chunk) {
+        int nf = std::min(chunk, nc - c0);
+        const T* src = reinterpret_cast<const T*>(in) + (long long)c0 * P.q.M[0] * P.q.M[1] * P.q.M[2];
+        V* dst = reinterpret_cast<V*>(out) + (long long)c0 * P.dense_fs();
+        int e;
+        if ((e = P.z(FAM_Z_R2C, src, P.A, nf, false, true))) return e;
+        if ((e = P.f1(nf))) return e;
+        StridedArgs<T> a; P.f0_geom(a, nf);
+        a.out = dst;
+        const double bytes = (double)nf * p->N[1] * p->Nh * ((double)P.q.M[0] + p->N[0]) * p->cs;
+        if ((e = do_launch(p, FAM_PLAIN_FWD, P.q.M[0], &a, bytes))) return e;
+    }
+    return SDNS_OK;
+}
+
+struct StageOut {
+    int out_mode; void* rhs; void* u0; void* u1; void* u2; void* p_hat; const void* source;
+    double adt, bdt; int rk;
+};
+
+template <typename T>
+static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const StageOut& so) {
+    typedef typename C2<T>::type V;
+    Pipe<T> P(p, SDNS_SPACE_TP);
+    const V* u = reinterpret_cast<const V*>(u_hat);
+    int e;
+    const int solver = p->cfg.solver;
+    if (solver == SDNS_NS) { if ((e = P.b0(FAM_NS_B0, u, 3))) return e; }
+    else if (solver == SDNS_VV) { if ((e = P.b0(FAM_VV_B0, u, 3))) return e; }
+    else { if ((e = P.b0(FAM_PLAIN_BWD, u, 6))) return e; }
+    if ((e = P.b1(6))) return e;
+    const int nprod = solver == SDNS_MHD ? 9 : 3;
+    if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true))) return e;
+    if ((e = P.f1(nprod))) return e;
+    StridedArgs<T> a; P.f0_geom(a, nprod);
+    a.out_mode = so.out_mode;
+    a.u_hat = u;
+    a.rhs = reinterpret_cast<V*>(so.rhs);
+    a.u0 = reinterpret_cast<V*>(so.u0); a.u1 = reinterpret_cast<V*>(so.u1); a.u2 = reinterpret_cast<V*>(so.u2);
+    a.source = reinterpret_cast<const V*>(so.source);
+    a.p_hat = reinterpret_cast<V*>(so.p_hat);
+    a.nu = (T)nu; a.eta = (T)eta; a.adt = (T)so.adt; a.bdt = (T)so.bdt; a.rk = so.rk;
+    const int fam = solver == SDNS_NS ? FAM_NS_F0 : (solver == SDNS_VV ? FAM_VV_F0 : FAM_MHD_F0);
+    // epilogue traffic: read the product fields; state reads/writes of the stage update
+    const int ns = solver == SDNS_MHD ? 6 : 3;
+    double st;   // state arrays touched, in units of one ns-component spectral vector
+    if (so.out_mode == OUT_RHS) st = 2;                               // read u_hat, write rhs
+    else st = so.rk == 0 ? 1 + 3 : (so.rk < 3 ? 3 + 2 : 2 + 1);       // see passes.cuh RK4 stage
+    const double dense = (double)p->N[0] * p->N[1] * p->Nh * p->cs;
+    const double bytes = (double)nprod * p->N[1] * p->Nh * P.q.M[0] * p->cs + st * ns * dense
+                         + (so.source ? ns * dense : 0) + (so.p_hat ? dense : 0);
+    return do_launch(p, fam, P.q.M[0], &a, bytes);
+}
+
+extern "C" int sdns_forward(sdns_plan* p, int space, int nc, const void* in, void* out) {
+    int e = need_ws(p); if (e) return e;
+    if (space < 0 || space > 1 || nc < 1 || !in || !out) return fail(SDNS_ERR_ARG, "sdns_forward: bad argument");
+    return p->prec ? forward_t<double>(p, space, nc, in, out) : forward_t<float>(p, space, nc, in, out);
+}
+extern "C" int sdns_backward(sdns_plan* p, int space, int nc, const void* in, void* out) {
+    int e = need_ws(p); if (e) return e;
+    if (space < 0 || space > 1 || nc < 1 || !in || !out) return fail(SDNS_ERR_ARG, "sdns_backward: bad argument");
+    return p->prec ? backward_t<double>(p, space, nc, in, out) : backward_t<float>(p, space, nc, in, out);
+}
+
+extern "C" int sdns_compute_rhs(sdns_plan* p, void* rhs, const void* u_hat, double nu, double eta,
+                                const void* source, void* p_hat) {
+    int e = need_ws(p); if (e) return e;
+    if (!rhs || !u_hat) return fail(SDNS_ERR_ARG, "sdns_compute_rhs: null array");
+    StageOut so; memset(&so, 0, sizeof so);
+    so.out_mode = OUT_RHS; so.rhs = rhs; so.source = source; so.p_hat = p_hat;
+    return p->prec ? rhs_t<double>(p, u_hat, nu, eta, so) : rhs_t<float>(p, u_hat, nu, eta, so);
+}
+
+// a, b of maths/integrators.py:185-186 in context.float, products a[rk]*dt, b[rk]*dt in that type
+template <typename T>
+static void rk_coeffs(int rk, double dt, double* adt, double* bdt) {
+    const T a[4] = {(T)(1. / 6.), (T)(1. / 3.), (T)(1. / 3.), (T)(1. / 6.)};
+    const T b[3] = {(T)0.5, (T)0.5, (T)1.};
+    const T d = (T)dt;
+    *adt = (double)(T)(a[rk] * d);
+    *bdt = rk < 3 ? (double)(T)(b[rk] * d) : 0.0;
+}
+
+extern "C" int sdns_rk4_step(sdns_plan* p, void* u_hat, void* u1, void* u2, double dt, double nu,
+                             double eta, const void* source) {
+    int e = need_ws(p); if (e) return e;
+    if (!u_hat || !u1 || !u2) return fail(SDNS_ERR_ARG, "sdns_rk4_step: null array");
+    for (int rk = 0; rk < 4; ++rk) {
+        StageOut so; memset(&so, 0, sizeof so);
+        so.out_mode = OUT_STAGE; so.u0 = u_hat; so.u1 = u1; so.u2 = u2; so.source = source; so.rk = rk;
+        if (p->prec) rk_coeffs<double>(rk, dt, &so.adt, &so.bdt); else rk_coeffs<float>(rk, dt, &so.adt, &so.bdt);
+        e = p->prec ? rhs_t<double>(p, u_hat, nu, eta, so) : rhs_t<float>(p, u_hat, nu, eta, so);
+        if (e) return e;
+    }
+    return SDNS_OK;
+}
+
+// ---- small elementwise kernels (integrators other than RK4, cross2) ---------------------
+template <typename T>
+__global__ void euler_kernel(typename C2<T>::type* u, const typename C2<T>::type* r, T dt, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        typename C2<T>::type a = u[i], b = r[i];
+        a.x += b.x * dt; a.y += b.y * dt; u[i] = a;
+    }
+}
+// AB2 (integrators.py:167-175): u0 += rhs*dt (tstep 0) or 1.5*rhs*dt - 0.5*u1 ; u1 = rhs*dt
+template <typename T>
+__global__ void ab2_kernel(typename C2<T>::type* u, typename C2<T>::type* u1, const typename C2<T>::type* r,
+                           T dt, int first, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        typename C2<T>::type a = u[i], b = r[i], o = u1[i];
+        const T rx = b.x * dt, ry = b.y * dt;
+        if (first) { a.x += rx; a.y += ry; }
+        else { a.x += ((T)1.5 * rx - (T)0.5 * o.x); a.y += ((T)1.5 * ry - (T)0.5 * o.y); }
+        u[i] = a; o.x = rx; o.y = ry; u1[i] = o;
+    }
+}
+template <typename T>
+__global__ void cross2_kernel(typename C2<T>::type* c, const typename C2<T>::type* b, const T* kx, const T* ky,
+                              const T* kz, int N0, int N1, int Nh, int over_k2) {
+    typedef typename C2<T>::type V;
+    const long long n = (long long)N0 * N1 * Nh;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int i2 = (int)(i % Nh); const long long r = i / Nh;
+        const int i1 = (int)(r % N1); const int i0 = (int)(r / N1);
+        T k0 = kx[i0], k1 = ky[i1], k2 = kz[i2];
+        if (over_k2) {
+            T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;
+            if (ksq == (T)0) ksq = (T)1;
+            k0 /= ksq; k1 /= ksq; k2 /= ksq;
+        }
+        const V b0 = b[i], b1 = b[n + i], b2 = b[2 * n + i];
+        c[i] = icross<T, V>(k1, b2, k2, b1);
+        c[n + i] = icross<T, V>(k2, b0, k0, b2);
+        c[2 * n + i] = icross<T, V>(k0, b1, k1, b0);
+    }
+}
+
+static int ncomp_state(const sdns_plan* p) { return p->cfg.solver == SDNS_MHD ? 6 : 3; }
+
+extern "C" int sdns_euler_step(sdns_plan* p, void* u_hat, void* rhs, double dt, double nu, double eta,
+                               const void* source) {
+    int e = sdns_compute_rhs(p, rhs, u_hat, nu, eta, source, nullptr); if (e) return e;
+    const long long n = (long long)ncomp_state(p) * p->N[0] * p->N[1] * p->Nh;
+    if (p->prec) euler_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)u_hat, (const double2*)rhs, dt, n);
+    else euler_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)u_hat, (const float2*)rhs, (float)dt, n);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+
+extern "C" int sdns_ab2_step(sdns_plan* p, void* u_hat, void* u1, void* rhs, double dt, int tstep,
+                             double nu, double eta, const void* source) {
+    int e = sdns_compute_rhs(p, rhs, u_hat, nu, eta, source, nullptr); if (e) return e;
+    const long long n = (long long)ncomp_state(p) * p->N[0] * p->N[1] * p->Nh;
+    if (p->prec) ab2_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)u_hat, (double2*)u1, (const double2*)rhs, dt, tstep == 0, n);
+    else ab2_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)u_hat, (float2*)u1, (const float2*)rhs, (float)dt, tstep == 0, n);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+
+extern "C" int sdns_cross2(sdns_plan* p, void* c, const void* b, int over_k2) {
+    int e = need_ws(p); if (e) return e;
+    if (!c || !b || c == b) return fail(SDNS_ERR_ARG, "sdns_cross2: c and b must be distinct arrays");
+    if (p->prec)
+        cross2_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)c, (const double2*)b,
+            (const double*)(p->ws + p->kx_off), (const double*)(p->ws + p->ky_off), (const double*)(p->ws + p->kz_off),
+            p->N[0], p->N[1], p->Nh, over_k2);
+    else
+        cross2_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)c, (const float2*)b,
+            (const float*)(p->ws + p->kx_off), (const float*)(p->ws + p->ky_off), (const float*)(p->ws + p->kz_off),
+            p->N[0], p->N[1], p->Nh, over_k2);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+
+extern "C" int sdns_energy(sdns_plan* p, const void* u_hat, int nc, double* out) {
+    int e = need_ws(p); if (e) return e;
+    if (!u_hat || !out || nc < 1) return fail(SDNS_ERR_ARG, "sdns_energy: bad argument");
+    const long long n = (long long)nc * p->N[0] * p->N[1] * p->Nh;
+    double* red = reinterpret_cast<double*>(p->ws + p->off_red);
+    const int nb = p->red_blocks;
+    if (p->prec) energy_kernel<double><<<nb, 256, 0, p->stream>>>((const double2*)u_hat, n, p->Nh, p->N[2], red);
+    else energy_kernel<float><<<nb, 256, 0, p->stream>>>((const float2*)u_hat, n, p->Nh, p->N[2], red);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> h(nb);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), red, sizeof(double) * nb, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    double s = 0; for (int i = 0; i < nb; ++i) s += h[i];
+    *out = s;
+    return SDNS_OK;
+}
+
+extern "C" int sdns_rk4_steps_host(sdns_plan* p, void* host_u, void* du, void* d1, void* d2, int nsteps,
+                                   double dt, double nu, double eta) {
+    int e = need_ws(p); if (e) return e;
+    if (!host_u || !du || !d1 || !d2 || nsteps < 0) return fail(SDNS_ERR_ARG, "sdns_rk4_steps_host: bad argument");
+    const size_t bytes = (size_t)ncomp_state(p) * p->N[0] * p->N[1] * p->Nh * p->cs;
+    CUDA_TRY(cudaMemcpyAsync(du, host_u, bytes, cudaMemcpyHostToDevice, p->stream));
+    for (int s = 0; s < nsteps; ++s) { e = sdns_rk4_step(p, du, d1, d2, dt, nu, eta, nullptr); if (e) return e; }
+    CUDA_TRY(cudaMemcpyAsync(host_u, du, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SDNS_OK;
+}
+
+// ---- profiling ----------------------------------------------------------------------------
+extern "C" int sdns_profile_enable(sdns_plan* p, int on) {
+    if (!p) return fail(SDNS_ERR_ARG, "null plan");
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    p->prof = on != 0; p->recs.clear(); p->ev_used = 0;
+    for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_n[i] = 0; }
+    return SDNS_OK;
+}
+extern "C" int sdns_profile_read(sdns_plan* p, int family, double* total_ms, long long* launches, double* bytes) {
+    if (!p || family < 0 || family >= FAM_COUNT) return fail(SDNS_ERR_ARG, "sdns_profile_read: bad argument");
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    for (const sdns_plan::Rec& r : p->recs) {
+        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        p->prof_ms[r.fam] += ms; p->prof_bytes[r.fam] += r.bytes; p->prof_n[r.fam]++;
+    }
+    p->recs.clear(); p->ev_used = 0;
+    if (total_ms) *total_ms = p->prof_ms[family];
+    if (launches) *launches = p->prof_n[family];
+    if (bytes) *bytes = p->prof_bytes[family];
+    return SDNS_OK;
+}

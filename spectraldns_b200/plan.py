@@ -1,0 +1,212 @@
+"""Plan: the Python face of one sdns_plan (include/sdns_b200.h).
+
+PyTorch is used only to allocate device buffers and to name the CUDA stream; every arithmetic
+operation goes through the C ABI into the hand-written sm_100a kernels.  There is no CPU path.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Plan(object):
+    """One grid / precision / solver configuration bound to one GPU.
+
+    Mirrors what the reference's get_context() builds (solvers/NS.py:12-48): the spaces T and
+    Tp, wavenumbers, masks -- all of which live inside the C plan -- plus scratch memory.
+    """
+
+    def __init__(self, N, L=(2*np.pi,)*3, precision='double', dealias='2/3-rule', solver='NS',
+                 convection=None, mask_nyquist=True, decomposition='slab', kcut=None, device=0):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.SdnsError('no CUDA device: spectraldns_b200 has no CPU fallback')
+        self.lib = _lib.lib()
+        self.N = tuple(int(n) for n in N)
+        self.L = tuple(float(l) for l in L)
+        self.precision = precision
+        self.dealias = dealias
+        self.solver = solver
+        if convection is None:
+            convection = 'Divergence' if solver == 'MHD' else 'Vortex'
+        self.convection = convection
+        self.float = np.dtype(np.float32 if precision == 'single' else np.float64)
+        self.complex = np.dtype(np.complex64 if precision == 'single' else np.complex128)
+        self.tfloat = torch.float32 if precision == 'single' else torch.float64
+        self.tcomplex = torch.complex64 if precision == 'single' else torch.complex128
+        self.device = torch.device('cuda', device)
+        cfg = _lib.SdnsConfig()
+        cfg.abi_version = _lib.SDNS_ABI_VERSION
+        for i in range(3):
+            cfg.N[i] = self.N[i]
+            cfg.L[i] = self.L[i]
+            cfg.kcut[i] = -1 if kcut is None else int(kcut[i])
+        cfg.precision = _lib.SINGLE if precision == 'single' else _lib.DOUBLE
+        cfg.dealias = _lib.DEALIAS[dealias]
+        cfg.solver = _lib.SOLVER[solver]
+        cfg.convection = _lib.CONVECTION[convection]
+        cfg.mask_nyquist = 1 if mask_nyquist else 0
+        cfg.decomposition = _lib.DECOMP[decomposition]
+        cfg.prune = 1
+        cfg.rank, cfg.nranks, cfg.device = 0, 1, device
+        self._p = C.c_void_p()
+        _lib.check(self.lib.sdns_plan_create(C.byref(self._p), C.byref(cfg)))
+        sp, ph, pd = (C.c_int32*3)(), (C.c_int32*3)(), (C.c_int32*3)()
+        _lib.check(self.lib.sdns_local_shapes(self._p, C.byref(sp), C.byref(ph), C.byref(pd)))
+        self.spectral_shape = tuple(sp)
+        self.physical_shape = tuple(ph)
+        self.padded_shape = tuple(pd)
+        self.ncomp = 6 if solver == 'MHD' else 3
+        nb = C.c_size_t()
+        _lib.check(self.lib.sdns_workspace_bytes(self._p, C.byref(nb)))
+        self.workspace_bytes = nb.value
+        with torch.cuda.device(self.device):
+            self._ws = torch.empty(nb.value + 256, dtype=torch.uint8, device=self.device)
+            off = (-self._ws.data_ptr()) % 256
+            self.use_current_stream()
+            _lib.check(self.lib.sdns_plan_set_workspace(self._p, self._ws.data_ptr() + off, nb.value))
+
+    def __del__(self):
+        try:
+            if getattr(self, '_p', None):
+                self.lib.sdns_plan_destroy(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+    # -- plumbing ---------------------------------------------------------
+    def use_current_stream(self):
+        """Enqueue on torch's current stream (so torch.cuda.Event brackets the kernels)."""
+        torch = _torch()
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.sdns_plan_set_stream(self._p, C.c_void_p(s)))
+
+    def sync(self):
+        _lib.check(self.lib.sdns_sync(self._p))
+
+    def launch_count(self):
+        c = C.c_longlong()
+        _lib.check(self.lib.sdns_launch_count(self._p, C.byref(c)))
+        return c.value
+
+    def empty_spectral(self, ncomp=None):
+        torch = _torch()
+        shape = self.spectral_shape if ncomp == 0 else ((ncomp or self.ncomp),) + self.spectral_shape
+        return torch.zeros(shape, dtype=self.tcomplex, device=self.device)
+
+    def empty_physical(self, ncomp=None, padded=False):
+        torch = _torch()
+        s = self.padded_shape if padded else self.physical_shape
+        shape = s if ncomp == 0 else ((ncomp or self.ncomp),) + s
+        return torch.zeros(shape, dtype=self.tfloat, device=self.device)
+
+    def to_device(self, a, complex_=None):
+        torch = _torch()
+        a = np.ascontiguousarray(a)
+        if np.iscomplexobj(a):
+            a = a.astype(self.complex, copy=False)
+        else:
+            a = a.astype(self.float, copy=False)
+        return torch.from_numpy(a).to(self.device)
+
+    @staticmethod
+    def to_host(t):
+        return t.detach().cpu().numpy()
+
+    def _chk(self, t, dtype, shape_tail, name):
+        if t.dtype != dtype or not t.is_contiguous() or not t.is_cuda:
+            raise ValueError('%s: need a contiguous CUDA tensor of dtype %s' % (name, dtype))
+        if tuple(t.shape[-3:]) != tuple(shape_tail):
+            raise ValueError('%s: trailing shape %s != %s' % (name, tuple(t.shape[-3:]), tuple(shape_tail)))
+        return t.numel() // int(np.prod(shape_tail))
+
+    # -- transforms (T/VT and Tp/VTp forward/backward) ---------------------
+    def forward(self, u, out=None, padded=False):
+        s = self.padded_shape if padded else self.physical_shape
+        nc = self._chk(u, self.tfloat, s, 'forward input')
+        if out is None:
+            out = _torch().empty(tuple(u.shape[:-3]) + self.spectral_shape, dtype=self.tcomplex, device=self.device)
+        assert self._chk(out, self.tcomplex, self.spectral_shape, 'forward output') == nc
+        _lib.check(self.lib.sdns_forward(self._p, _lib.SPACE_TP if padded else _lib.SPACE_T, nc,
+                                         u.data_ptr(), out.data_ptr()))
+        return out
+
+    def backward(self, u_hat, out=None, padded=False, dealias=False):
+        """padded/dealias select the reference's Tp space (solvers/NS.py:29-32)."""
+        use_tp = padded or dealias
+        s = self.padded_shape if use_tp else self.physical_shape
+        nc = self._chk(u_hat, self.tcomplex, self.spectral_shape, 'backward input')
+        if out is None:
+            out = _torch().empty(tuple(u_hat.shape[:-3]) + s, dtype=self.tfloat, device=self.device)
+        assert self._chk(out, self.tfloat, s, 'backward output') == nc
+        _lib.check(self.lib.sdns_backward(self._p, _lib.SPACE_TP if use_tp else _lib.SPACE_T, nc,
+                                          u_hat.data_ptr(), out.data_ptr()))
+        return out
+
+    # -- the hot path --------------------------------------------------------
+    def compute_rhs(self, rhs, u_hat, nu, eta=0.0, source=None, p_hat=None):
+        assert self._chk(rhs, self.tcomplex, self.spectral_shape, 'rhs') == self.ncomp
+        assert self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat') == self.ncomp
+        _lib.check(self.lib.sdns_compute_rhs(self._p, rhs.data_ptr(), u_hat.data_ptr(), float(nu), float(eta),
+                                             source.data_ptr() if source is not None else None,
+                                             p_hat.data_ptr() if p_hat is not None else None))
+        return rhs
+
+    def rk4_step(self, u_hat, u1, u2, dt, nu, eta=0.0, source=None):
+        for t, n in ((u_hat, 'u_hat'), (u1, 'u1'), (u2, 'u2')):
+            assert self._chk(t, self.tcomplex, self.spectral_shape, n) == self.ncomp
+        _lib.check(self.lib.sdns_rk4_step(self._p, u_hat.data_ptr(), u1.data_ptr(), u2.data_ptr(), float(dt),
+                                          float(nu), float(eta),
+                                          source.data_ptr() if source is not None else None))
+        return u_hat
+
+    def euler_step(self, u_hat, rhs, dt, nu, eta=0.0, source=None):
+        _lib.check(self.lib.sdns_euler_step(self._p, u_hat.data_ptr(), rhs.data_ptr(), float(dt), float(nu),
+                                            float(eta), source.data_ptr() if source is not None else None))
+        return u_hat
+
+    def ab2_step(self, u_hat, u1, rhs, dt, tstep, nu, eta=0.0, source=None):
+        _lib.check(self.lib.sdns_ab2_step(self._p, u_hat.data_ptr(), u1.data_ptr(), rhs.data_ptr(), float(dt),
+                                          int(tstep), float(nu), float(eta),
+                                          source.data_ptr() if source is not None else None))
+        return u_hat
+
+    def rk4_steps_host(self, host_u_hat, u_hat, u1, u2, nsteps, dt, nu, eta=0.0):
+        """integrate() for a caller that keeps the state in (pinned) host memory: H2D, nsteps RK4
+        steps, D2H.  host_u_hat is a torch CPU tensor (ideally pinned) or a numpy array."""
+        ptr = host_u_hat.data_ptr() if hasattr(host_u_hat, 'data_ptr') else host_u_hat.ctypes.data
+        _lib.check(self.lib.sdns_rk4_steps_host(self._p, ptr, u_hat.data_ptr(), u1.data_ptr(), u2.data_ptr(),
+                                                int(nsteps), float(dt), float(nu), float(eta)))
+        return host_u_hat
+
+    def cross2(self, c, b, over_k2=False):
+        _lib.check(self.lib.sdns_cross2(self._p, c.data_ptr(), b.data_ptr(), 1 if over_k2 else 0))
+        return c
+
+    def energy(self, u_hat):
+        nc = self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat')
+        out = C.c_double()
+        _lib.check(self.lib.sdns_energy(self._p, u_hat.data_ptr(), nc, C.byref(out)))
+        return out.value
+
+    # -- measurement ---------------------------------------------------------
+    FAMILIES = ['plain_fwd_c2c', 'plain_bwd_c2c', 'ns_b0', 'vv_b0', 'ns_f0', 'vv_f0', 'mhd_f0',
+                'c2r', 'r2c', 'z_cross', 'z_mhd']
+
+    def profile(self, on=True):
+        _lib.check(self.lib.sdns_profile_enable(self._p, 1 if on else 0))
+
+    def profile_read(self):
+        """{family: (total_ms, launches, algorithmic_bytes)} since profile(True)."""
+        out = {}
+        for i, name in enumerate(self.FAMILIES):
+            ms, n, b = C.c_double(), C.c_longlong(), C.c_double()
+            _lib.check(self.lib.sdns_profile_read(self._p, i, C.byref(ms), C.byref(n), C.byref(b)))
+            if n.value:
+                out[name] = (ms.value, n.value, b.value)
+        return out

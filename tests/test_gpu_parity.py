@@ -1,0 +1,203 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI against the
+CPU oracle and the golden fixtures generated from the unmodified reference.
+
+Tolerances (BASELINE.json north_star): relative L2 <= 1e-11 in double, <= 1e-4 in single."""
+import glob
+import os
+import numpy as np
+import pytest
+from conftest import golden, rel_l2, GOLDEN
+import sdns_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'double': 1e-11, 'single': 1e-4}
+ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, '*.npz')))
+
+
+def make_plan(N, L=(2*np.pi,)*3, precision='double', dealias='2/3-rule', solver='NS', mask_nyquist=True):
+    from spectraldns_b200.plan import Plan
+    return Plan(N, L, precision, dealias, solver, mask_nyquist=mask_nyquist)
+
+
+def test_library_loaded_and_native():
+    from spectraldns_b200 import _lib
+    L = _lib.lib()
+    assert L.sdns_abi_version() == 1
+    assert L.sdns_size_supported(256, 1) == 0
+    assert L.sdns_size_supported(100, 1) != 0
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('N', [(16, 16, 16), (32, 32, 32), (64, 32, 16), (16, 32, 64), (128, 128, 128),
+                               (24, 48, 96), (192, 16, 32)])
+def test_plain_transforms(N, precision):
+    """T.forward / T.backward (solvers/NS.py:93,103): rfftn/prod(N) and its inverse."""
+    o = so.Oracle(N, precision=precision, dealias='None')
+    p = make_plan(N, precision=precision, dealias='None')
+    rng = np.random.RandomState(1)
+    u = rng.standard_normal((3,)+tuple(N)).astype(o.float)
+    u_hat = p.to_host(p.forward(p.to_device(u)))
+    ref = o.forward(u.astype(np.float64)) if precision == 'double' else o.forward(u)
+    assert rel_l2(u_hat, ref) < TOL[precision]
+    back = p.to_host(p.backward(p.to_device(ref.astype(o.complex))))
+    assert rel_l2(back, u) < TOL[precision]
+    # odd component counts and a single scalar field
+    for nc in (1, 2, 5):
+        v = rng.standard_normal((nc,)+tuple(N)).astype(o.float)
+        vh = p.to_host(p.forward(p.to_device(v)))
+        assert rel_l2(vh, o.forward(v)) < TOL[precision]
+        vb = p.to_host(p.backward(p.to_device(vh)))
+        assert rel_l2(vb, v) < 10*TOL[precision]
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('dealias', ['2/3-rule', '3/2-rule'])
+@pytest.mark.parametrize('N', [(16, 16, 16), (32, 16, 64), (64, 64, 64)])
+def test_dealiased_space_transforms(N, dealias, precision):
+    """Tp.backward / Tp.forward (solvers/NS.py:29-32): truncated input or 3/2 padding."""
+    o = so.Oracle(N, precision=precision, dealias=dealias)
+    p = make_plan(N, precision=precision, dealias=dealias)
+    rng = np.random.RandomState(2)
+    u_hat = o.forward(rng.standard_normal((3,)+tuple(N)).astype(o.float))
+    ref = o._bwd_p(u_hat)
+    got = p.to_host(p.backward(p.to_device(u_hat), padded=True))
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < TOL[precision]
+    w = rng.standard_normal(ref.shape).astype(o.float)
+    got_f = p.to_host(p.forward(p.to_device(w), padded=True))
+    assert rel_l2(got_f, o._fwd_p(w)) < TOL[precision]
+
+
+def _state0(o, g):
+    if 'u0_hat' in g:
+        return g['u0_hat']
+    if str(g['solver']) == 'MHD':
+        return o.forward(so.taylor_green_mhd(o))
+    u = o.forward(so.taylor_green(o))
+    if str(g['solver']) == 'VV':
+        u = o.cross2(o.K, u)
+    return u
+
+
+@pytest.mark.parametrize('name', ALL)
+def test_golden_rhs_and_rk4(name):
+    """ComputeRHS and N RK4 steps against fixtures produced by the unmodified reference
+    (oracle/make_golden.py): velocity (state) field, relative L2."""
+    g = golden(name)
+    prec, solver = str(g['precision']), str(g['solver'])
+    mask = 'nodealias' not in name
+    o = so.Oracle(g['N'], g['L'], prec, str(g['dealias']), mask_nyquist=mask)
+    p = make_plan(g['N'], g['L'], prec, str(g['dealias']), solver, mask_nyquist=mask)
+    u0 = _state0(o, g).astype(o.complex)
+    eta = float(g['eta']) if 'eta' in g else 0.0
+    conv = 'Divergence' if solver == 'MHD' else 'Vortex'
+    if 'rhs_'+conv in g.files:
+        d_u = p.to_device(u0)
+        rhs = p.compute_rhs(p.empty_spectral(), d_u, float(g['nu']), eta)
+        assert rel_l2(p.to_host(rhs), g['rhs_'+conv]) < TOL[prec], 'rhs'
+        assert rel_l2(p.to_host(d_u), u0) == 0.0          # input untouched
+    d_u = p.to_device(u0)
+    u1, u2 = p.empty_spectral(), p.empty_spectral()
+    for _ in range(int(g['nsteps'])):
+        p.rk4_step(d_u, u1, u2, float(g['dt']), float(g['nu']), eta)
+    err = rel_l2(p.to_host(d_u), g['u_hat'])
+    assert err < TOL[prec], err
+
+
+def test_pressure_and_source():
+    g = golden('iso_ns_16_double')
+    o = so.Oracle(g['N'], g['L'], 'double', '2/3-rule')
+    p = make_plan(g['N'], g['L'], 'double', '2/3-rule', 'NS')
+    rng = np.random.RandomState(5)
+    src = (rng.standard_normal(g['u0_hat'].shape) + 1j*rng.standard_normal(g['u0_hat'].shape))*1e-2
+    ref, P = o.ns_rhs(g['u0_hat'], float(g['nu']), source=src, return_p=True)
+    p_hat = p.empty_spectral(0)
+    rhs = p.compute_rhs(p.empty_spectral(), p.to_device(g['u0_hat']), float(g['nu']),
+                        source=p.to_device(src), p_hat=p_hat)
+    assert rel_l2(p.to_host(rhs), ref) < 1e-11
+    assert rel_l2(p.to_host(p_hat), P) < 1e-11
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_tg_known_answers_on_gpu(precision):
+    """tests/TG.py:116-126 of the reference at 32^3 (BASELINE.json configs[0]) through the GPU path:
+    k and w after 10 RK4 steps."""
+    N = (32, 32, 32)
+    o = so.Oracle(N, precision=precision)
+    p = make_plan(N, precision=precision)
+    U = p.to_device(so.taylor_green(o))
+    u = p.forward(U)
+    u1, u2 = p.empty_spectral(), p.empty_spectral()
+    for _ in range(10):
+        p.rk4_step(u, u1, u2, 0.01, 0.000625)
+    Uf = p.to_host(p.backward(u)).astype(np.float64)
+    curl_hat = p.cross2(p.empty_spectral(), u)
+    W = p.to_host(p.backward(curl_hat)).astype(np.float64)
+    k = np.sum(Uf*Uf)/np.prod(N)/2
+    w = np.sum(W*W)/np.prod(N)/2
+    nt = 7 if precision == 'double' else 5
+    assert round(float(w) - 0.375249930801, nt) == 0
+    assert round(float(k) - 0.124953117517, nt) == 0
+    # Parseval (tests/TG.py:101-109)
+    assert abs(p.energy(u)/2 - k) < (1e-12 if precision == 'double' else 1e-6)
+
+
+def test_integrators_euler_ab2():
+    """maths/integrators.py:161-175 through sdns_euler_step / sdns_ab2_step."""
+    g = golden('iso_ns_16_double')
+    o = so.Oracle(g['N'], g['L'], 'double', '2/3-rule')
+    p = make_plan(g['N'], g['L'], 'double', '2/3-rule', 'NS')
+    nu, dt = float(g['nu']), float(g['dt'])
+    fn = lambda u: o.ns_rhs(u, nu)
+    ref = g['u0_hat'].copy()
+    d_u, rhs = p.to_device(g['u0_hat']), p.empty_spectral()
+    for _ in range(3):
+        ref = o.forward_euler_step(ref, fn, dt)
+        p.euler_step(d_u, rhs, dt, nu)
+    assert rel_l2(p.to_host(d_u), ref) < 1e-11
+    ref, r1 = g['u0_hat'].copy(), np.zeros_like(g['u0_hat'])
+    d_u, u1 = p.to_device(g['u0_hat']), p.empty_spectral()
+    for ts in range(3):
+        ref, r1 = o.ab2_step(ref, r1, fn, dt, ts)
+        p.ab2_step(d_u, u1, rhs, dt, ts, nu)
+    assert rel_l2(p.to_host(d_u), ref) < 1e-11
+
+
+@pytest.mark.parametrize('cfg', [((256, 256, 256), 'double', '2/3-rule'),
+                                 ((128, 128, 128), 'single', '3/2-rule'),
+                                 ((512, 64, 128), 'double', '2/3-rule')])
+def test_full_size_properties(cfg):
+    """Size-independent properties at sizes the oracle does not finish in seconds:
+    forward(backward(x)) == x, Parseval, RK4 keeps the field solenoidal, energy decays."""
+    N, prec, dealias = cfg
+    import torch
+    p = make_plan(N, precision=prec, dealias=dealias)
+    tol = TOL[prec]
+    g = torch.Generator(device='cuda').manual_seed(0)
+    u = torch.randn((3,)+tuple(N), dtype=p.tfloat, device='cuda', generator=g)
+    u_hat = p.forward(u)
+    back = p.backward(u_hat)
+    assert float((back-u).norm()/u.norm()) < tol
+    e_phys = float((u.double()**2).sum())/np.prod(N)
+    assert abs(p.energy(u_hat) - e_phys)/e_phys < 10*tol
+    # TG step: analytic field, energy must decay and stay divergence free
+    o = so.Oracle((16, 16, 16))        # only for the mesh formula
+    X = [torch.arange(n, dtype=torch.float64, device='cuda')*2*np.pi/n for n in N]
+    U = torch.zeros((3,)+tuple(N), dtype=p.tfloat, device='cuda')
+    U[0] = (torch.sin(X[0])[:, None, None]*torch.cos(X[1])[None, :, None]*torch.cos(X[2])[None, None, :]).to(p.tfloat)
+    U[1] = (-torch.cos(X[0])[:, None, None]*torch.sin(X[1])[None, :, None]*torch.cos(X[2])[None, None, :]).to(p.tfloat)
+    uh = p.forward(U)
+    e0 = p.energy(uh)
+    assert abs(e0/2 - 0.125) < 1e-6
+    u1, u2 = p.empty_spectral(), p.empty_spectral()
+    for _ in range(2):
+        p.rk4_step(uh, u1, u2, 0.01, 0.000625)
+    e1 = p.energy(uh)
+    assert 0 < e1 < e0
+    # analytic TG decay rate at t=0: dk/dt = -2 nu w = -2*nu*0.375 -> k(0.02) ~ 0.125 - 9.4e-6
+    assert abs(e1/2 - (0.125 - 2*0.000625*0.375*0.02)) < 1e-6
+    k = [torch.fft.fftfreq(N[0], 1./N[0], device='cuda'), torch.fft.fftfreq(N[1], 1./N[1], device='cuda'),
+         torch.fft.rfftfreq(N[2], 1./N[2], device='cuda')]
+    div = (k[0][:, None, None]*uh[0] + k[1][None, :, None]*uh[1] + k[2][None, None, :]*uh[2])
+    assert float(div.abs().max()) < (1e-12 if prec == 'double' else 1e-5)
