@@ -103,6 +103,11 @@ int sdns_backward(sdns_plan* plan, int space, int ncomp, const void* cplx_in, vo
 int sdns_compute_rhs(sdns_plan* plan, void* rhs, const void* u_hat, double nu, double eta,
                      const void* source, void* p_hat);
 
+/* solver.conv(rhs, u_hat, ...) alone, i.e. the function returned by getConvection()
+ * (NS.py:164-201, VV.py:85-103, MHD.py:112-130): the dealiased nonlinear term without the Nyquist
+ * mask, pressure and diffusion. */
+int sdns_compute_conv(sdns_plan* plan, void* rhs, const void* u_hat);
+
 /* integrate() for params.integrator == 'RK4'  (maths/integrators.py:150-159,177-191;
  * cython_integrators.in:8-52): four ComputeRHS evaluations with the stage updates fused into the
  * last transform pass.  u_hat is updated in place; u1, u2 are the integrator's work arrays

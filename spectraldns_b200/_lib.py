@@ -21,7 +21,7 @@ SPACE_T, SPACE_TP = 0, 1
 SYMBOLS = ['sdns_abi_version', 'sdns_last_error', 'sdns_size_supported', 'sdns_plan_create',
            'sdns_plan_destroy', 'sdns_workspace_bytes', 'sdns_plan_set_workspace',
            'sdns_plan_set_stream', 'sdns_sync', 'sdns_local_shapes', 'sdns_forward', 'sdns_backward',
-           'sdns_compute_rhs', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2',
+           'sdns_compute_rhs', 'sdns_compute_conv', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2',
            'sdns_energy', 'sdns_rk4_steps_host', 'sdns_launch_count',
            'sdns_profile_enable', 'sdns_profile_read']
 
@@ -74,6 +74,7 @@ def lib():
     L.sdns_forward.argtypes = [vp, i32, i32, vp, vp]
     L.sdns_backward.argtypes = [vp, i32, i32, vp, vp]
     L.sdns_compute_rhs.argtypes = [vp, vp, vp, dbl, dbl, vp, vp]
+    L.sdns_compute_conv.argtypes = [vp, vp, vp]
     L.sdns_rk4_step.argtypes = [vp, vp, vp, vp, dbl, dbl, dbl, vp]
     L.sdns_euler_step.argtypes = [vp, vp, vp, dbl, dbl, dbl, vp]
     L.sdns_ab2_step.argtypes = [vp, vp, vp, vp, dbl, i32, dbl, dbl, vp]

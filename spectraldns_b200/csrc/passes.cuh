@@ -27,7 +27,7 @@ __device__ __forceinline__ int axis_mem(const AxisMap& a, int M, int j) {
 
 enum StridedMode { S_PLAIN = 0, S_NS_B0 = 1, S_VV_B0 = 2, S_NS_F0 = 3, S_VV_F0 = 4, S_MHD_F0 = 5 };
 enum ZMode { Z_C2R = 0, Z_R2C = 1, Z_CROSS = 2, Z_MHD = 3 };
-enum OutMode { OUT_RHS = 0, OUT_STAGE = 1 };
+enum OutMode { OUT_RHS = 0, OUT_STAGE = 1, OUT_CONV = 2 };   // OUT_CONV: convection term only (solver.conv)
 
 template <typename T>
 struct StridedArgs {
@@ -179,6 +179,10 @@ strided_kernel(const StridedArgs<T> a) {
                 V e2 = icross<T, V>(k0, d1, k1, d0);
                 d0 = e0; d1 = e1; d2 = e2;
             }
+            if (a.out_mode == OUT_CONV) {
+                a.rhs[off] = d0; a.rhs[a.st_fs + off] = d1; a.rhs[2 * a.st_fs + off] = d2;
+                continue;
+            }
             if (nyq12 || (a.mask_nyquist && 2 * i0 == a.N0)) { d0 = czero<V>(); d1 = czero<V>(); d2 = czero<V>(); }
             const V w0 = a.u_hat[off], w1 = a.u_hat[a.st_fs + off], w2 = a.u_hat[2 * a.st_fs + off];
             const T z = a.nu * ksq;
@@ -301,6 +305,11 @@ mhd_f0_kernel(const StridedArgs<T> a) {
             // rhs[:3] = -i/2 * S ; rhs[3:] = +i/2 * D
             d[f].x = hs * acc[f][q].y;      d[f].y = -hs * acc[f][q].x;
             d[3 + f].x = -hs * acc[3 + f][q].y; d[3 + f].y = hs * acc[3 + f][q].x;
+        }
+        if (a.out_mode == OUT_CONV) {
+#pragma unroll
+            for (int f = 0; f < 6; ++f) a.rhs[f * a.st_fs + off] = d[f];
+            continue;
         }
         if (nyq12 || (a.mask_nyquist && 2 * i0 == a.N0)) {
 #pragma unroll

@@ -440,6 +440,7 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
     const int ns = solver == SDNS_MHD ? 6 : 3;
     double st;   // state arrays touched, in units of one ns-component spectral vector
     if (so.out_mode == OUT_RHS) st = 2;                               // read u_hat, write rhs
+    else if (so.out_mode == OUT_CONV) st = 1;
     else st = so.rk == 0 ? 1 + 3 : (so.rk < 3 ? 3 + 2 : 2 + 1);       // see passes.cuh RK4 stage
     const double dense = (double)p->N[0] * p->N[1] * p->Nh * p->cs;
     const double bytes = (double)nprod * p->N[1] * p->Nh * P.q.M[0] * p->cs + st * ns * dense
@@ -465,6 +466,14 @@ extern "C" int sdns_compute_rhs(sdns_plan* p, void* rhs, const void* u_hat, doub
     StageOut so; memset(&so, 0, sizeof so);
     so.out_mode = OUT_RHS; so.rhs = rhs; so.source = source; so.p_hat = p_hat;
     return p->prec ? rhs_t<double>(p, u_hat, nu, eta, so) : rhs_t<float>(p, u_hat, nu, eta, so);
+}
+
+extern "C" int sdns_compute_conv(sdns_plan* p, void* rhs, const void* u_hat) {
+    int e = need_ws(p); if (e) return e;
+    if (!rhs || !u_hat) return fail(SDNS_ERR_ARG, "sdns_compute_conv: null array");
+    StageOut so; memset(&so, 0, sizeof so);
+    so.out_mode = OUT_CONV; so.rhs = rhs;
+    return p->prec ? rhs_t<double>(p, u_hat, 0, 0, so) : rhs_t<float>(p, u_hat, 0, 0, so);
 }
 
 // a, b of maths/integrators.py:185-186 in context.float, products a[rk]*dt, b[rk]*dt in that type

@@ -157,6 +157,11 @@ class Plan(object):
                                              p_hat.data_ptr() if p_hat is not None else None))
         return rhs
 
+    def compute_conv(self, rhs, u_hat):
+        """solver.conv: the dealiased nonlinear term only."""
+        _lib.check(self.lib.sdns_compute_conv(self._p, rhs.data_ptr(), u_hat.data_ptr()))
+        return rhs
+
     def rk4_step(self, u_hat, u1, u2, dt, nu, eta=0.0, source=None):
         for t, n in ((u_hat, 'u_hat'), (u1, 'u1'), (u2, 'u2')):
             assert self._chk(t, self.tcomplex, self.spectral_shape, n) == self.ncomp
