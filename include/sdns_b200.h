@@ -125,6 +125,13 @@ int sdns_ab2_step(sdns_plan* plan, void* u_hat, void* u1, void* rhs, double dt, 
  * cython_maths.in:32-86).  over_k2 != 0 selects K_over_K2 (VV.py:64). */
 int sdns_cross2(sdns_plan* plan, void* c, const void* b, int over_k2);
 
+/* cross1(c, a, b): real c = a x b over n points per component (maths/cross.py:16-28,
+ * cython_maths.in:13-30); cross2 with a dense real a (cython_maths.in:39-60); project(u, K, K_over_K2)
+ * (maths/maths.py:8-11).  Stand-alone versions of operators that the RHS kernels fuse. */
+int sdns_cross1(sdns_plan* plan, void* c, const void* a, const void* b, long long n);
+int sdns_cross2_dense(sdns_plan* plan, void* c, const void* a_real, const void* b);
+int sdns_project(sdns_plan* plan, void* u_hat);
+
 /* shenfun.fourier.energy_fourier(u_hat, T) of ncomp components (tests/TG.py:101,
  * demo/Isotropic.py:67,167-182): Hermitian-weighted sum |u_hat|^2 of the LOCAL block.
  * Synchronous (returns the value). */

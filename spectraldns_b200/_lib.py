@@ -21,7 +21,7 @@ SPACE_T, SPACE_TP = 0, 1
 SYMBOLS = ['sdns_abi_version', 'sdns_last_error', 'sdns_size_supported', 'sdns_plan_create',
            'sdns_plan_destroy', 'sdns_workspace_bytes', 'sdns_plan_set_workspace',
            'sdns_plan_set_stream', 'sdns_sync', 'sdns_local_shapes', 'sdns_forward', 'sdns_backward',
-           'sdns_compute_rhs', 'sdns_compute_conv', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2',
+           'sdns_compute_rhs', 'sdns_compute_conv', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2', 'sdns_cross1', 'sdns_cross2_dense', 'sdns_project',
            'sdns_energy', 'sdns_rk4_steps_host', 'sdns_launch_count',
            'sdns_profile_enable', 'sdns_profile_read']
 
@@ -79,6 +79,9 @@ def lib():
     L.sdns_euler_step.argtypes = [vp, vp, vp, dbl, dbl, dbl, vp]
     L.sdns_ab2_step.argtypes = [vp, vp, vp, vp, dbl, i32, dbl, dbl, vp]
     L.sdns_cross2.argtypes = [vp, vp, vp, i32]
+    L.sdns_cross1.argtypes = [vp, vp, vp, vp, C.c_longlong]
+    L.sdns_cross2_dense.argtypes = [vp, vp, vp, vp]
+    L.sdns_project.argtypes = [vp, vp]
     L.sdns_energy.argtypes = [vp, vp, i32, C.POINTER(dbl)]
     L.sdns_rk4_steps_host.argtypes = [vp, vp, vp, vp, vp, i32, dbl, dbl, dbl]
     L.sdns_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]

@@ -1,0 +1,115 @@
+"""Classical Navier-Stokes solver module on the B200 path.
+
+Same module-level interface as the reference's solvers/NS.py (get_context :12-72, get_curl /
+get_velocity / get_pressure / set_velocity / get_divergence :86-110, end_of_tstep :112-122,
+getConvection :164-201, add_pressure_diffusion :203-217, ComputeRHS :219-261).  The arithmetic of
+ComputeRHS -- u x curl(u) on the dealiased space, Nyquist mask, pressure projection, viscous term,
+Source -- is five CUDA launches behind sdns_compute_rhs; the context's numpy arrays are host
+mirrors of device-resident state."""
+from shenfun import VectorSpace, Array, Function
+from .spectralinit import *          # noqa: F401,F403
+from . import _common
+from ._common import device_state    # noqa: F401  (solve() and getintegrator() use solver.device_state)
+
+_last_context = None
+
+
+def get_context():
+    """Spaces, wavenumbers and solution arrays of the NS solver, as an attribute dict."""
+    global _last_context
+    float, complex, mpitype = datatypes(params.precision)
+    collapse_fourier = params.dealias != '3/2-rule'
+    dim = len(params.N)
+    V, T, Tp, _engine = _common.build_spaces(comm, params, float, 'NS')
+    VT = VectorSpace(T)
+    VTp = VectorSpace(Tp)
+    mask = T.get_mask_nyquist() if params.mask_nyquist else None
+    X, K, K2, K_over_K2 = _common.wavenumber_arrays(T, VT, float)
+
+    U = Array(VT)
+    U_hat = Function(VT, buffer=_common.pinned_like(VT.shape(True), complex)[0])
+    P = Array(T)
+    P_hat = Function(T)
+    u_dealias = Array(VTp)
+    u = U_hat                         # primary variable
+    dU = Function(VT)                 # right hand side
+    curl = Array(VT)
+    Source = Function(VT)
+    work = work_arrays()
+    hdf5file = NSFile(config.params.solver,
+                      checkpoint={'space': VT, 'data': {'0': {'U': [U_hat]}}},
+                      results={'space': VT, 'data': {'U': [U], 'P': [P]}})
+    context = config.AttributeDict(locals())
+    context.pop('context', None)
+    _last_context = context
+    device_state(context)
+    return context
+
+
+class NSFile(HDF5File):
+    """Transforms the stored components to physical space before a results write."""
+    def update_components(self, **context):
+        get_velocity(**context)
+        get_pressure(**context)
+
+
+def get_curl(curl, U_hat, work, VT, K, **context):
+    return compute_curl(curl, U_hat, work, VT, K)
+
+
+def get_velocity(U, U_hat, VT, **context):
+    return VT.backward(U_hat, U)
+
+
+def get_pressure(P, P_hat, T, **context):
+    return T.backward(-1j*P_hat, P)
+
+
+def set_velocity(U, U_hat, VT, **context):
+    return VT.forward(U, U_hat)
+
+
+def get_divergence(T, K, U_hat, mask, **context):
+    div_u = Array(T)
+    return T.backward(1j*(K[0]*U_hat[0]+K[1]*U_hat[1]+K[2]*U_hat[2]), div_u)
+
+
+def end_of_tstep(context):
+    """Shorten the last step so that the run ends on params.T (used by adaptive runs)."""
+    if abs(params.t - params.T) < 1e-12:
+        return True
+    if (abs(params.t + params.dt - params.T) < 1e-12 or params.t + params.dt >= params.T + 1e-12):
+        params.dt = params.T - params.t
+    return False
+
+
+def compute_curl(c, a, work, T, K):
+    """c = F^-1(1j*K x a)"""
+    curl_hat = work[(a, 0, False)]
+    curl_hat = cross2(curl_hat, K, a)
+    return T.backward(curl_hat, c)
+
+
+def getConvection(convection):
+    """Nonlinear term selector.  'Vortex' (u x curl u, the default) is compiled into the CUDA
+    pipeline; the other three forms of the reference are not on the B200 path yet."""
+    if convection != 'Vortex':
+        raise NotImplementedError("NS convection %r is not on the B200 path (use 'Vortex')" % convection)
+    return _common.Convection(convection)
+
+
+def add_pressure_diffusion(rhs, u_hat, nu, K2, K, P_hat, K_over_K2):
+    """Fused into the last transform pass of ComputeRHS (kernel family ns_f0); not callable alone."""
+    raise NotImplementedError('add_pressure_diffusion is fused into ComputeRHS on the B200 path')
+
+
+add_pressure_diffusion._sdns_builtin = True
+
+
+def ComputeRHS(rhs, u_hat, solver, work, Tp, VTp, P_hat, K, K2, u_dealias,
+               K_over_K2, Source, mask, **context):
+    """rhs = F(u x curl u) masked, minus pressure gradient and nu k^2 u_hat, plus Source."""
+    if not getattr(getattr(solver, 'conv', None), '_sdns_builtin', True) or \
+            not getattr(solver.add_pressure_diffusion, '_sdns_builtin', False):
+        raise NotImplementedError('overriding conv/add_pressure_diffusion is not supported by the fused CUDA RHS')
+    return _common.run_rhs(_common.dev_of(context), rhs, u_hat, Source, P_hat)

@@ -611,6 +611,75 @@ extern "C" int sdns_rk4_steps_host(sdns_plan* p, void* host_u, void* du, void* d
     return SDNS_OK;
 }
 
+// ---- standalone pointwise operators of the fine-grained plug-in surface (optimization/__init__.py:12-55)
+template <typename T>
+__global__ void cross1_kernel(T* c, const T* a, const T* b, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const T a0 = a[i], a1 = a[n + i], a2 = a[2 * n + i];
+        const T b0 = b[i], b1 = b[n + i], b2 = b[2 * n + i];
+        c[i] = a1 * b2 - a2 * b1; c[n + i] = a2 * b0 - a0 * b2; c[2 * n + i] = a0 * b1 - a1 * b0;
+    }
+}
+template <typename T>
+__global__ void cross2_dense_kernel(typename C2<T>::type* c, const T* a, const typename C2<T>::type* b, long long n) {
+    typedef typename C2<T>::type V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const T a0 = a[i], a1 = a[n + i], a2 = a[2 * n + i];
+        const V b0 = b[i], b1 = b[n + i], b2 = b[2 * n + i];
+        c[i] = icross<T, V>(a1, b2, a2, b1);
+        c[n + i] = icross<T, V>(a2, b0, a0, b2);
+        c[2 * n + i] = icross<T, V>(a0, b1, a1, b0);
+    }
+}
+// project(u, K, K_over_K2): u -= sum(K_over_K2*u, 0)*K   (maths/maths.py:8-11)
+template <typename T>
+__global__ void project_kernel(typename C2<T>::type* u, const T* kx, const T* ky, const T* kz, int N0, int N1, int Nh) {
+    typedef typename C2<T>::type V;
+    const long long n = (long long)N0 * N1 * Nh;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int i2 = (int)(i % Nh); const long long r = i / Nh;
+        const int i1 = (int)(r % N1); const int i0 = (int)(r / N1);
+        const T k0 = kx[i0], k1 = ky[i1], k2 = kz[i2];
+        T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;
+        const T ks = ksq == (T)0 ? (T)1 : ksq;
+        V u0 = u[i], u1 = u[n + i], u2 = u[2 * n + i];
+        V p;
+        p.x = u0.x * (k0 / ks) + u1.x * (k1 / ks); p.x += u2.x * (k2 / ks);
+        p.y = u0.y * (k0 / ks) + u1.y * (k1 / ks); p.y += u2.y * (k2 / ks);
+        u0.x -= p.x * k0; u0.y -= p.y * k0; u1.x -= p.x * k1; u1.y -= p.y * k1; u2.x -= p.x * k2; u2.y -= p.y * k2;
+        u[i] = u0; u[n + i] = u1; u[2 * n + i] = u2;
+    }
+}
+
+extern "C" int sdns_cross1(sdns_plan* p, void* c, const void* a, const void* b, long long n) {
+    if (!p || !c || !a || !b || n < 1) return fail(SDNS_ERR_ARG, "sdns_cross1: bad argument");
+    if (p->prec) cross1_kernel<double><<<1184, 256, 0, p->stream>>>((double*)c, (const double*)a, (const double*)b, n);
+    else cross1_kernel<float><<<1184, 256, 0, p->stream>>>((float*)c, (const float*)a, (const float*)b, n);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+extern "C" int sdns_cross2_dense(sdns_plan* p, void* c, const void* a, const void* b) {
+    if (!p || !c || !a || !b || c == b) return fail(SDNS_ERR_ARG, "sdns_cross2_dense: bad argument");
+    const long long n = (long long)p->N[0] * p->N[1] * p->Nh;
+    if (p->prec) cross2_dense_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)c, (const double*)a, (const double2*)b, n);
+    else cross2_dense_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)c, (const float*)a, (const float2*)b, n);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+extern "C" int sdns_project(sdns_plan* p, void* u) {
+    int e = need_ws(p); if (e) return e;
+    if (!u) return fail(SDNS_ERR_ARG, "sdns_project: null array");
+    if (p->prec) project_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)u,
+        (const double*)(p->ws + p->kx_off), (const double*)(p->ws + p->ky_off), (const double*)(p->ws + p->kz_off), p->N[0], p->N[1], p->Nh);
+    else project_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)u,
+        (const float*)(p->ws + p->kx_off), (const float*)(p->ws + p->ky_off), (const float*)(p->ws + p->kz_off), p->N[0], p->N[1], p->Nh);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+
 // ---- profiling ----------------------------------------------------------------------------
 extern "C" int sdns_profile_enable(sdns_plan* p, int on) {
     if (!p) return fail(SDNS_ERR_ARG, "null plan");

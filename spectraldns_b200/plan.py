@@ -193,6 +193,18 @@ class Plan(object):
         _lib.check(self.lib.sdns_cross2(self._p, c.data_ptr(), b.data_ptr(), 1 if over_k2 else 0))
         return c
 
+    def cross1(self, c, a, b):
+        _lib.check(self.lib.sdns_cross1(self._p, c.data_ptr(), a.data_ptr(), b.data_ptr(), a.numel()//3))
+        return c
+
+    def cross2_dense(self, c, a, b):
+        _lib.check(self.lib.sdns_cross2_dense(self._p, c.data_ptr(), a.data_ptr(), b.data_ptr()))
+        return c
+
+    def project(self, u_hat):
+        _lib.check(self.lib.sdns_project(self._p, u_hat.data_ptr()))
+        return u_hat
+
     def energy(self, u_hat):
         nc = self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat')
         out = C.c_double()

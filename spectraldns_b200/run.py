@@ -1,0 +1,31 @@
+"""Run a spectralDNS demo/test script unchanged on the B200 path:
+
+    python -m spectraldns_b200.run /path/to/demo/TG.py [script arguments ...]
+
+Puts spectraldns_b200/compat first on sys.path so that `spectralDNS`, `shenfun`, `mpi4py`,
+`mpi4py_fft` (and `h5py` when it is not installed) resolve to the B200 implementations."""
+import os
+import runpy
+import sys
+
+COMPAT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'compat')
+
+
+def activate():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (COMPAT, root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    for mod in ('spectralDNS', 'shenfun', 'mpi4py', 'mpi4py_fft'):
+        if mod in sys.modules and COMPAT not in (getattr(sys.modules[mod], '__file__', '') or ''):
+            raise RuntimeError('%s was already imported from elsewhere' % mod)
+
+
+if __name__ == '__main__':
+    if len(sys.argv) < 2:
+        raise SystemExit(__doc__)
+    activate()
+    script = sys.argv[1]
+    sys.argv = sys.argv[1:]
+    sys.path.insert(0, os.path.dirname(os.path.abspath(script)))
+    runpy.run_path(script, run_name='__main__')

@@ -1,0 +1,141 @@
+"""CPU tests of the reference-facing host layer (no GPU): config semantics, module surface,
+library symbols.  Compute calls are covered by the -m gpu tests."""
+import ctypes
+import os
+import re
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def compat():
+    sys.path.insert(0, ROOT)
+    from spectraldns_b200 import run
+    run.activate()
+    import spectralDNS
+    return spectralDNS
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every function include/sdns_b200.h declares."""
+    hdr = open(os.path.join(ROOT, 'include', 'sdns_b200.h')).read()
+    declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(sdns_\w+)\s*\(', hdr, flags=re.M))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(os.path.join(ROOT, 'spectraldns_b200', 'libsdns_b200.so'))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    from spectraldns_b200 import _lib
+    assert set(_lib.SYMBOLS) == declared
+    assert lib.sdns_abi_version() == 1
+    for n in (8, 12, 16, 24, 256, 384, 768, 1024, 2048, 3072):
+        assert lib.sdns_size_supported(n, 1) == 0
+    assert lib.sdns_size_supported(60, 1) != 0
+
+
+def test_plan_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from spectraldns_b200 import _lib
+    from spectraldns_b200.plan import Plan
+    with pytest.raises(_lib.SdnsError):
+        Plan((32, 32, 32))
+    # and straight through the C ABI
+    L = _lib.lib()
+    cfg = _lib.SdnsConfig()
+    cfg.abi_version = 1
+    for i in range(3):
+        cfg.N[i], cfg.L[i], cfg.kcut[i] = 32, 2*np.pi, -1
+    cfg.precision, cfg.dealias, cfg.nranks = 1, 1, 1
+    p = ctypes.c_void_p()
+    rc = L.sdns_plan_create(ctypes.byref(p), ctypes.byref(cfg))
+    assert rc == -3 and b'no CPU fallback' in L.sdns_last_error()
+
+
+def test_config_matches_reference_semantics(compat):
+    """Same option names/defaults/derived values as the reference's config.py (:96-239)."""
+    config = compat.config
+    config.update({'nu': 0.000625, 'dt': 0.01, 'T': 0.1, 'L': [2*np.pi, '4*pi', 6*np.pi], 'M': [4, 5, 6]})
+    ns = config.triplyperiodic.parse_args(['--precision', 'single', 'MHD', '--eta', '0.02'])
+    config.params.update(vars(ns))
+    P = config.params
+    assert list(P.N) == [16, 32, 64] and P.M.flags.writeable is False
+    assert np.allclose(P.L, [2*np.pi, 4*np.pi, 6*np.pi])
+    assert np.allclose(P.dx, P.L/P.N)
+    assert isinstance(P.nu, np.float32) and isinstance(P.dt, np.float32) and isinstance(P.eta, np.float32)
+    assert P.solver == 'MHD' and P.dealias == '2/3-rule' and P.integrator == 'RK4'
+    assert P.convection == 'Vortex' and P.decomposition == 'slab' and P.mask_nyquist is True
+    assert P.write_result == 1e8 and P.checkpoint == 1e8 and P.ntol == 7 and P.optimization == ''
+    ns = config.triplyperiodic.parse_args(['--no-mask_nyquist', '--dealias', '3/2-rule', '--optimization',
+                                           'cython', '--N', ] if False else ['--no-mask_nyquist', 'NS'])
+    assert ns.mask_nyquist is False and ns.solver == 'NS'
+    # demos add their own arguments and N trumps M (tests/TG.py:139-142)
+    config.triplyperiodic.add_argument('--N', default=[32, 32, 32], nargs=3)
+    ns = config.triplyperiodic.parse_args(['NS'])
+    config.params.update(vars(ns))
+    assert list(config.params.N) == [32, 32, 32]
+    with pytest.raises(SystemExit):
+        config.triplyperiodic.parse_args(['--dealias', 'bogus', 'NS'])
+    config.update({'L': [2*np.pi]*3, 'M': [6, 6, 6]})
+
+
+def test_solver_module_surface(compat):
+    """The names solve(), the demos and the tests read from a solver module."""
+    import importlib
+    for name in ('NS', 'VV', 'MHD'):
+        m = importlib.import_module('spectralDNS.solvers.' + name)
+        for attr in ('get_context', 'getConvection', 'ComputeRHS', 'getintegrator', 'comm', 'rank',
+                     'num_processes', 'params', 'profiler', 'Timer', 'MemoryUsage', 'create_profile',
+                     'cross1', 'cross2', 'project', 'update', 'regression_test', 'additional_callback',
+                     'end_of_tstep', 'set_source', 'solve_linear', 'datatypes', 'get_divergence',
+                     'work_arrays', 'HDF5File', 'optimizer', 'device_state'):
+            assert hasattr(m, attr), (name, attr)
+    from spectralDNS.solvers import NS, VV
+    for attr in ('get_velocity', 'get_curl', 'get_pressure', 'set_velocity', 'add_pressure_diffusion'):
+        assert hasattr(NS, attr)
+    for attr in ('get_velocity', 'get_curl', 'compute_velocity', 'add_linear'):
+        assert hasattr(VV, attr)
+    assert NS.datatypes('single')[:2] == (np.float32, np.complex64)
+    import shenfun
+    for attr in ('FunctionSpace', 'TensorProductSpace', 'VectorSpace', 'CompositeSpace', 'Array',
+                 'Function', 'CachedArrayDict', 'ShenfunFile'):
+        assert hasattr(shenfun, attr)
+    from shenfun.fourier import energy_fourier  # noqa: F401
+    from mpi4py_fft import generate_xdmf        # noqa: F401
+
+
+def test_hdf5file_cadence_and_killfile(compat, tmp_path, monkeypatch):
+    """h5io/HDF5File.py:64-120: results every write_result steps, checkpoint every `checkpoint`."""
+    from spectraldns_b200.io import HDF5File
+    monkeypatch.chdir(tmp_path)
+    u_hat, u = np.ones((3, 4, 4, 3), dtype=complex), np.ones((3, 4, 4, 4))
+    f = HDF5File('run', checkpoint={'space': None, 'data': {'0': {'U': [u_hat]}}},
+                 results={'space': None, 'data': {'U': [u]}})
+    P = compat.config.AttributeDict(tstep=1, t=0.01, write_result=2, checkpoint=4, filemode='w')
+    f.update(P)
+    assert f.cfile is None and f.wfile is None
+    P.tstep = 2
+    f.update(P)
+    assert os.path.exists('run_w.npz') and not os.path.exists('run_c.npz')
+    P.tstep, P.t = 4, 0.04
+    f.update(P)
+    z = np.load('run_c.npz')
+    assert int(z['attr__tstep']) == 4 and abs(float(z['attr__t']) - 0.04) < 1e-15 and 'U/3D/0' in z.files
+    open('killspectraldns', 'w').close()
+    P.tstep = 5
+    with pytest.raises(SystemExit):
+        f.update(P)
+    assert not os.path.exists('killspectraldns')
+    f.close()
+
+
+def test_timer_interface(compat, capsys):
+    from spectralDNS.utilities import Timer
+    t = Timer()
+    t(); t()
+    t.final(True)
+    out = capsys.readouterr().out
+    assert 'Fastest = (' in out and 'Slowest = (' in out and 'Time = ' in out
