@@ -5,7 +5,7 @@ from shenfun import VectorSpace, Array, Function
 from .spectralinit import *          # noqa: F401,F403
 from . import _common
 from ._common import device_state    # noqa: F401
-from .NS import end_of_tstep         # noqa: F401
+from .NS import end_of_tstep, set_velocity, compute_curl, NSFile   # noqa: F401  (VV builds on NS, reference VV.py:19)
 
 _last_context = None
 

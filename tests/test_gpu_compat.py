@@ -200,7 +200,7 @@ def test_forced_isotropic_callback_parity(sdns, precision, dealias):
         assert abs(e - target) < (1e-7 if precision == 'double' else 1e-4)     # demo/Isotropic.py:184
 
     args = ['--M', '5', '5', '5', '--precision', precision, '--dealias', dealias, 'NS']
-    solver = get_solver(update=update, parse_args=args)
+    solver = get_solver(update=update, regression_test=lambda c: None, parse_args=args)
     nu = float(config.params.nu)
     c = solver.get_context()
     c.U_hat[:] = u0
