@@ -87,6 +87,19 @@ int sdns_plan_set_workspace(sdns_plan* plan, void* device_ptr, size_t bytes);
 int sdns_plan_set_stream(sdns_plan* plan, void* cuda_stream);
 int sdns_sync(sdns_plan* plan);                          /* cudaStreamSynchronize on the plan stream */
 
+/* Slab decomposition, one process per GPU of one node (replaces mpi4py-fft's Pencil/Transfer =
+ * MPI_Alltoallw inside every shenfun transform; in-tree analogue spectralDNS3D_short.py:50-62).
+ * For nranks > 1 the library owns the workspace (cudaMalloc) so that it can be mapped into the
+ * peers with CUDA IPC: every rank calls sdns_comm_alloc, publishes the 64-byte handle from
+ * sdns_comm_handle to all ranks (the host layer uses torch.distributed.all_gather), then calls
+ * sdns_comm_open with the nranks handles in rank order.  The transposes have no kernel of their
+ * own: the pass in front of each one stores directly into the owning GPU's buffer over NVLink and a
+ * device-side flag barrier orders the passes.  sdns_comm_status reports a barrier timeout. */
+int sdns_comm_alloc(sdns_plan* plan);
+int sdns_comm_handle(sdns_plan* plan, void* handle64);
+int sdns_comm_open(sdns_plan* plan, const void* handles, int nranks);
+int sdns_comm_status(sdns_plan* plan, int* timed_out);
+
 /* local array extents of this rank (T.shape(True), T.shape(False), Tp.shape(False)) */
 int sdns_local_shapes(const sdns_plan* plan, int32_t spectral[3], int32_t physical[3], int32_t padded[3]);
 

@@ -20,7 +20,8 @@ SPACE_T, SPACE_TP = 0, 1
 # every symbol include/sdns_b200.h declares (tests check that the library exports them all)
 SYMBOLS = ['sdns_abi_version', 'sdns_last_error', 'sdns_size_supported', 'sdns_plan_create',
            'sdns_plan_destroy', 'sdns_workspace_bytes', 'sdns_plan_set_workspace',
-           'sdns_plan_set_stream', 'sdns_sync', 'sdns_local_shapes', 'sdns_forward', 'sdns_backward',
+           'sdns_plan_set_stream', 'sdns_sync', 'sdns_local_shapes', 'sdns_comm_alloc', 'sdns_comm_handle',
+           'sdns_comm_open', 'sdns_comm_status', 'sdns_forward', 'sdns_backward',
            'sdns_compute_rhs', 'sdns_compute_conv', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2', 'sdns_cross1', 'sdns_cross2_dense', 'sdns_project',
            'sdns_energy', 'sdns_rk4_steps_host', 'sdns_launch_count',
            'sdns_profile_enable', 'sdns_profile_read']
@@ -70,6 +71,10 @@ def lib():
     L.sdns_plan_set_workspace.argtypes = [vp, vp, C.c_size_t]
     L.sdns_plan_set_stream.argtypes = [vp, vp]
     L.sdns_sync.argtypes = [vp]
+    L.sdns_comm_alloc.argtypes = [vp]
+    L.sdns_comm_handle.argtypes = [vp, vp]
+    L.sdns_comm_open.argtypes = [vp, vp, i32]
+    L.sdns_comm_status.argtypes = [vp, C.POINTER(i32)]
     L.sdns_local_shapes.argtypes = [vp, C.POINTER(C.c_int32*3), C.POINTER(C.c_int32*3), C.POINTER(C.c_int32*3)]
     L.sdns_forward.argtypes = [vp, i32, i32, vp, vp]
     L.sdns_backward.argtypes = [vp, i32, i32, vp, vp]

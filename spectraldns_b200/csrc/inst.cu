@@ -22,7 +22,7 @@ template <typename T, int N, int MODE, int DIR>
 static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
     typedef SCfg<T, N, MODE> C;
     static_assert(plan_ok(N, C::E), "no radix plan");
-    auto kern = strided_kernel<T, N, C::E, C::TC, DIR, MODE, C::NBUF>;
+    auto kern = strided_kernel<T, N, C::E, C::TC, DIR, MODE, C::NBUF, C::minBlocks>;
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC), MODE == S_PLAIN ? a.nfields : 1);
@@ -46,7 +46,7 @@ template <typename T, int M, int MODE>
 static int run_z(const ZArgs<T>& a, cudaStream_t st) {
     typedef ZCfg<T, M, MODE> C;
     static_assert(plan_ok(M, C::E), "no radix plan");
-    auto kern = z_kernel<T, M, C::E, C::LPC, MODE, C::SYNC, C::NBUF>;
+    auto kern = z_kernel<T, M, C::E, C::LPC, MODE, C::SYNC, C::NBUF, (C::minBlocks < 1 ? 1 : C::minBlocks)>;
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     dim3 grid((unsigned)((a.nlines + C::LPC - 1) / C::LPC));

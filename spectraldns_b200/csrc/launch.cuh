@@ -21,18 +21,40 @@ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 // launch geometry of the strided kernels
+// elements per thread: keep a line inside one warp (P = N/E <= 32) while the register budget
+// allows it (fp32: E <= 32, fp64: E <= 16 for single-field kernels), else 64 or 128 threads per line
+constexpr int pick_E(int N, int emax) {
+    const int b = (N % 3 == 0) ? 12 : 8;
+    int e = b;
+    while (N / e > 32 && 2 * e <= emax && plan_ok(N, 2 * e)) e *= 2;
+    while (N / e > 128 && plan_ok(N, 2 * e)) e *= 2;
+    return e;
+}
+
 template <typename T, int N, int MODE>
 struct SCfg {
-    static constexpr bool heavy = (MODE == S_NS_F0 || MODE == S_VV_F0);
-    static constexpr int E0 = (N % 3 == 0) ? 12 : 8;
-    static constexpr int E = (N / E0 > 64) ? 2 * E0 : E0;
+    static constexpr bool heavy = (MODE == S_NS_F0 || MODE == S_VV_F0);   // park two fields in smem
+    static constexpr int E = pick_E(N, sizeof(T) == 8 ? 8 : (heavy ? 16 : 24));
     static constexpr int P = N / E;
     static constexpr int maxThreads = sizeof(T) == 8 ? (heavy ? 256 : 512) : (heavy ? 512 : 1024);
     static constexpr int TCfull = 128 / (2 * (int)sizeof(T));
     static constexpr int TC = cmin(TCfull, cmax(1, maxThreads / P));
     static constexpr size_t bytes1 = (size_t)N * TC * 2 * sizeof(T);
-    static constexpr int NBUF = (2 * bytes1 <= 100 * 1024) ? 2 : 1;
-    static constexpr size_t smem = bytes1 * NBUF;
+#ifdef SDNS_STRIDED_NBUF
+    static constexpr int NBUF = SDNS_STRIDED_NBUF;
+#else
+    static constexpr int NBUF = heavy ? 1 : ((2 * bytes1 <= 100 * 1024) ? 2 : 1);
+#endif
+    static constexpr size_t smem = bytes1 * (NBUF + (heavy ? 2 : 0));
+    // resident CTAs per SM the register allocator must allow: what shared memory and the thread
+    // count permit, at most 4 (2 for the epilogue kernels)
+    static constexpr int bySmem = (int)((224 * 1024) / (smem + 1024));
+    static constexpr int byThreads = 2048 / (P * TC);
+    static constexpr bool b0 = (MODE == S_NS_B0 || MODE == S_VV_B0);
+    static constexpr int needRegs = sizeof(T) == 8 ? (heavy ? 128 : (b0 ? 96 : 80) * (E > 12 ? 2 : 1))
+                                                   : (heavy ? (E > 12 ? 128 : 100) : (E > 16 ? 80 : (b0 ? 72 : 64)));
+    static constexpr int byRegs = 65536 / (P * TC * needRegs);
+    static constexpr int minBlocks = cmax(1, cmin(cmin(cmin(bySmem, byThreads), byRegs), heavy ? 2 : 4));
 };
 
 // MHD epilogue: six accumulators per thread -> fewer elements per thread
@@ -50,15 +72,18 @@ struct MCfg {
 
 template <typename T, int M, int MODE>
 struct ZCfg {
-    static constexpr int E0 = (M % 3 == 0) ? 12 : 8;
-    static constexpr int E = (M / E0 > 128) ? 2 * E0 : E0;
+    static constexpr bool park = (MODE == Z_CROSS);     // two real-space pairs parked in smem
+    static constexpr int E = pick_E(M, sizeof(T) == 8 ? ((MODE == Z_C2R || MODE == Z_R2C) ? 16 : 12) : (MODE == Z_MHD ? 16 : 32));
     static constexpr int P = M / E;
     static constexpr int LPC = cmax(1, 128 / P);
     static constexpr int SYNC = (P <= 32) ? 1 : 0;
-    static constexpr int NBUF = 2;
+    static constexpr int NBUF = park ? 1 : 2;
     static constexpr int PADW = 128 / (2 * (int)sizeof(T));
     static constexpr int LP = M + M / PADW + 1;
-    static constexpr size_t smem = (size_t)LP * LPC * NBUF * 2 * sizeof(T);
+    static constexpr size_t smem = ((size_t)LP * LPC * NBUF + (park ? (size_t)2 * E * P * LPC : 0)) * 2 * sizeof(T);
+    static constexpr int needRegs = (sizeof(T) == 8 ? (E > 12 ? 200 : 128) : (E > 16 ? 128 : 96)) * (MODE == Z_MHD ? 2 : 1);
+    static constexpr int minBlocks = cmax(1, cmin(cmin(cmin((int)((224 * 1024) / (smem + 1024)), 2048 / (P * LPC)),
+                                                       65536 / (P * LPC * needRegs)), 4));
 };
 
 template <typename K>

@@ -57,9 +57,27 @@ struct StridedArgs {
     long long st_fs;              // field stride of the dense state arrays (= N0*N1*Nh)
     T nu, eta, adt, bdt;
     int rk;
+    // slab decomposition (one process per GPU): the pass that precedes a global transpose stores
+    // straight into the destination rank's buffer (NVLink peer memory), element (f, i, column) of
+    // the output going to rank i / xchunk at line index i % xchunk.  xchunk == 0: single GPU.
+    int xchunk;
+    long long c1_out_off;         // added to the run index of the output base (global x0 / compact k1)
+    int k1_off;                   // global index of local k1 = 0 (Nyquist test in the epilogues)
+    V* peer_out[8];
 };
 
 template <typename V> __device__ __forceinline__ V czero() { V z; z.x = 0; z.y = 0; return z; }
+
+// address of output element (field f, line index i) of the column whose base offset is obase
+template <typename T>
+__device__ __forceinline__ typename C2<T>::type* out_addr(const StridedArgs<T>& a, int f, int i, long long obase) {
+    if (a.xchunk > 0) {
+        const int dest = i / a.xchunk;
+        const int il = i - dest * a.xchunk;
+        return a.peer_out[dest] + (f * a.out_fs + (long long)il * a.out_ls + obase);
+    }
+    return a.out + (f * a.out_fs + (long long)i * a.out_ls + obase);
+}
 template <typename T, typename V> __device__ __forceinline__ V cscale(V a, T s) { a.x *= s; a.y *= s; return a; }
 
 // i*(ka*b - kb*a) for real ka,kb, complex a,b   (one component of cross2)
@@ -73,8 +91,8 @@ __device__ __forceinline__ V icross(T ka, V b, T kb, V a) {
 // Strided c2c pass over a tile of TC adjacent columns (TC*sizeof(V) = 128 bytes -> every
 // global access of a warp covers whole 128-byte lines; thread index = column + TC*t).
 // ---------------------------------------------------------------------------------------
-template <typename T, int N, int E, int TC, int DIR, int MODE, int NBUF>
-__global__ void __launch_bounds__((N / E) * TC)
+template <typename T, int N, int E, int TC, int DIR, int MODE, int NBUF, int MINB>
+__global__ void __launch_bounds__((N / E) * TC, MINB)
 strided_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -88,7 +106,7 @@ strided_kernel(const StridedArgs<T> a) {
     const int c2 = valid ? (int)(col % a.cw) : 0;
     const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
     const long long ibase = (long long)c1m * a.in_os + c2;
-    const long long obase = (long long)c1 * a.out_os + c2;
+    const long long obase = ((long long)c1 + a.c1_out_off) * a.out_os + c2;
     SmemLine<TC, 0> map; map.base = c;
     int phase = 0;
     constexpr int BUFSTRIDE = N * TC;
@@ -105,7 +123,7 @@ strided_kernel(const StridedArgs<T> a) {
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int i = axis_mem(a.omap, N, t + q * P);
-            if (valid && i >= 0) a.out[f * a.out_fs + (long long)i * a.out_ls + obase] = cscale<T>(x[q], a.scale);
+            if (valid && i >= 0) *out_addr<T>(a, f, i, obase) = cscale<T>(x[q], a.scale);
         }
     } else if (MODE == S_NS_B0 || MODE == S_VV_B0) {
         // in: 3 dense spectral fields.  out: 6 fields (NS: u_hat, i k x u_hat ; VV: i k x w_hat / k^2, w_hat)
@@ -146,24 +164,34 @@ strided_kernel(const StridedArgs<T> a) {
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 const int i = axis_mem(a.omap, N, t + q * P);
-                if (valid && i >= 0) a.out[f * a.out_fs + (long long)i * a.out_ls + obase] = x[q];
+                if (valid && i >= 0) *out_addr<T>(a, f, i, obase) = x[q];
             }
         }
     } else if (MODE == S_NS_F0 || MODE == S_VV_F0) {
-        V r[3][E];
-#pragma unroll
+        // Three forward transforms; the results of the first two are parked in thread-private
+        // shared-memory slots ([field][q][thread], conflict free) so that only one field lives in
+        // registers: ~100 instead of 172 registers -> two resident CTAs per SM whose load /
+        // transform / epilogue phases overlap.
+        constexpr int NT = P * TC;
+        V* park = sm + NBUF * BUFSTRIDE;
+        V x[E];
+#pragma unroll 1
         for (int f = 0; f < 3; ++f) {
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 const int i = axis_mem(a.imap, N, t + q * P);
-                r[f][q] = (valid && i >= 0) ? a.in[f * a.in_fs + (long long)i * a.in_ls + ibase] : czero<V>();
+                x[q] = (valid && i >= 0) ? a.in[f * a.in_fs + (long long)i * a.in_ls + ibase] : czero<V>();
             }
-            fft_line<T, N, E, DIR, 0, NBUF>(r[f], t, a.tw, sm, map, BUFSTRIDE, phase);
+            fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+            if (f < 2) {
+#pragma unroll
+                for (int q = 0; q < E; ++q) park[(f * E + q) * NT + threadIdx.x] = x[q];
+            }
         }
         if (!valid) return;
         const int i1 = c1, i2 = c2;
         const T k1 = a.ky[i1], k2 = a.kz[i2];
-        const bool nyq12 = a.mask_nyquist && ((2 * i1 == a.N1) || (2 * i2 == a.N2));
+        const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int i0 = axis_mem(a.omap, N, t + q * P);
@@ -171,7 +199,8 @@ strided_kernel(const StridedArgs<T> a) {
             const long long off = (long long)i0 * a.out_ls + obase;
             const T k0 = a.kx[i0];
             T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;
-            V d0 = cscale<T>(r[0][q], a.scale), d1 = cscale<T>(r[1][q], a.scale), d2 = cscale<T>(r[2][q], a.scale);
+            V d0 = cscale<T>(park[q * NT + threadIdx.x], a.scale), d1 = cscale<T>(park[(E + q) * NT + threadIdx.x], a.scale),
+              d2 = cscale<T>(x[q], a.scale);
             if (MODE == S_VV_F0) {
                 // rhs = i*(K x v_hat)   (VV.py:99)
                 V e0 = icross<T, V>(k1, d2, k2, d1);
@@ -290,7 +319,7 @@ mhd_f0_kernel(const StridedArgs<T> a) {
     }
     if (!valid) return;
     const int i1 = c1, i2 = c2;
-    const bool nyq12 = a.mask_nyquist && ((2 * i1 == a.N1) || (2 * i2 == a.N2));
+    const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
     const T hs = (T)0.5 * a.scale;
 #pragma unroll
     for (int q = 0; q < E; ++q) {
@@ -415,8 +444,8 @@ __device__ __forceinline__ void unpack_store_pair(const V (&x)[E], V* __restrict
     }
 }
 
-template <typename T, int M, int E, int LPC, int MODE, int SYNC, int NBUF>
-__global__ void __launch_bounds__((M / E) * LPC)
+template <typename T, int M, int E, int LPC, int MODE, int SYNC, int NBUF, int MINB>
+__global__ void __launch_bounds__((M / E) * LPC, MINB)
 z_kernel(const ZArgs<T> a) {
     typedef typename C2<T>::type V;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -471,41 +500,57 @@ z_kernel(const ZArgs<T> a) {
         // fused: 6 spectral lines -> real space -> products -> spectral lines
         const V* in = reinterpret_cast<const V*>(a.in);
         V* out = reinterpret_cast<V*>(a.out);
-        V p01[E], p23[E], p45[E];
-        load_pair<T, M, E>(p01, in + 0 * a.in_fs + line * a.in_ls, in + 1 * a.in_fs + line * a.in_ls, t, a.nin_keep);
-        fft_line<T, M, E, +1, SYNC, NBUF>(p01, t, a.tw, sm, map, BUFSTRIDE, phase);
-        load_pair<T, M, E>(p23, in + 2 * a.in_fs + line * a.in_ls, in + 3 * a.in_fs + line * a.in_ls, t, a.nin_keep);
-        fft_line<T, M, E, +1, SYNC, NBUF>(p23, t, a.tw, sm, map, BUFSTRIDE, phase);
-        load_pair<T, M, E>(p45, in + 4 * a.in_fs + line * a.in_ls, in + 5 * a.in_fs + line * a.in_ls, t, a.nin_keep);
-        fft_line<T, M, E, +1, SYNC, NBUF>(p45, t, a.tw, sm, map, BUFSTRIDE, phase);
         const int nk = valid ? a.nout_keep : 0;
         if (MODE == Z_CROSS) {
-            // fields: a = (p01.x, p01.y, p23.x), b = (p23.y, p45.x, p45.y); c = a x b (cross1)
+            // Pairs (a0,a1), (a2,b0), (b1,b2): the first two go to thread-private shared-memory
+            // slots after their inverse transform, so one work array lives in registers.
+            constexpr int NT = P * LPC;
+            V* park = sm + NBUF * BUFSTRIDE;
             V x[E];
+#pragma unroll 1
+            for (int pr = 0; pr < 3; ++pr) {
+                load_pair<T, M, E>(x, in + (2 * pr) * a.in_fs + line * a.in_ls,
+                                   in + (2 * pr + 1) * a.in_fs + line * a.in_ls, t, a.nin_keep);
+                fft_line<T, M, E, +1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+                if (pr < 2) {
+#pragma unroll
+                    for (int q = 0; q < E; ++q) park[(pr * E + q) * NT + threadIdx.x] = x[q];
+                }
+            }
+            T* park_r = reinterpret_cast<T*>(park);
 #pragma unroll
             for (int q = 0; q < E; ++q) {
-                const T a0 = p01[q].x, a1 = p01[q].y, a2 = p23[q].x;
-                const T b0 = p23[q].y, b1 = p45[q].x, b2 = p45[q].y;
-                x[q].x = a1 * b2 - a2 * b1;
+                const V p01 = park[q * NT + threadIdx.x], p23 = park[(E + q) * NT + threadIdx.x];
+                const T a0 = p01.x, a1 = p01.y, a2 = p23.x;
+                const T b0 = p23.y, b1 = x[q].x, b2 = x[q].y;
+                x[q].x = a1 * b2 - a2 * b1;                  // c = a x b (cross1)
                 x[q].y = a2 * b0 - a0 * b2;
-                p01[q].x = a0 * b1 - a1 * b0;      // third component kept for the second transform
-                p01[q].y = (T)0;
+                park_r[2 * (q * NT + threadIdx.x)] = a0 * b1 - a1 * b0;   // third component, own slot
             }
             fft_line<T, M, E, -1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
             unpack_store_pair<T, M, E, SYNC, NBUF>(x, out + 0 * a.out_fs + line * a.out_ls,
                                                    out + 1 * a.out_fs + line * a.out_ls, t, nk, a.scale, sm, map,
                                                    BUFSTRIDE, phase);
-            fft_line<T, M, E, -1, SYNC, NBUF>(p01, t, a.tw, sm, map, BUFSTRIDE, phase);
+#pragma unroll
+            for (int q = 0; q < E; ++q) { x[q].x = park_r[2 * (q * NT + threadIdx.x)]; x[q].y = (T)0; }
+            fft_line<T, M, E, -1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
             if (valid) {
                 V* C = out + 2 * a.out_fs + line * a.out_ls;
 #pragma unroll
                 for (int q = 0; q < E; ++q) {
                     const int k = t + q * P;
-                    if (k < nk) C[k] = cscale<T>(p01[q], a.scale);
+                    if (k < nk) C[k] = cscale<T>(x[q], a.scale);
                 }
             }
         } else {
             // MHD (MHD.py:119-127, 99-110): u = (p01.x,p01.y,p23.x), b = (p23.y,p45.x,p45.y)
+            V p01[E], p23[E], p45[E];
+            load_pair<T, M, E>(p01, in + 0 * a.in_fs + line * a.in_ls, in + 1 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p01, t, a.tw, sm, map, BUFSTRIDE, phase);
+            load_pair<T, M, E>(p23, in + 2 * a.in_fs + line * a.in_ls, in + 3 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p23, t, a.tw, sm, map, BUFSTRIDE, phase);
+            load_pair<T, M, E>(p45, in + 4 * a.in_fs + line * a.in_ls, in + 5 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p45, t, a.tw, sm, map, BUFSTRIDE, phase);
             // z0 = u + b, z1 = u - b ; ZZ[i][j] = F(z0_i * z1_j)
             T z0[3][E], z1[3][E];
 #pragma unroll

@@ -45,11 +45,22 @@ struct Space {
     int col_nlo, col_gap;  // compact axis-1 index -> memory index
     int K2n, K2p;          // axis-2 modes entering the backward transform, padded pitch
     double scale;          // 1/prod(M)
+    // slab decomposition: this rank owns spectral k1 in [rank*N1l, (rank+1)*N1l) and physical x0 in
+    // [rank*M0l, (rank+1)*M0l)  (spectralDNS3D_short.py:28-29)
+    int M0l;               // local physical planes
+    int K1l;               // kept axis-1 modes owned by this rank
+    int lcol_nlo, lcol_gap;// local compact axis-1 index -> local memory index
+    int c1off;             // global compact index of this rank's first kept axis-1 mode
 };
 
 struct sdns_plan {
     sdns_config cfg;
     int N[3], Nh, Nhp;
+    int P, rank, N1l;       // ranks, this rank, local spectral extent of axis 1
+    size_t off_C, bytes_C, off_flags;
+    bool own_ws;            // workspace cudaMalloc'ed by the library (multi-GPU: IPC-shared)
+    char* peer_ws[8];       // base of every rank's workspace (peer_ws[rank] == ws)
+    unsigned int epoch;
     int prec;               // 0 f32, 1 f64
     size_t rs, cs;          // sizeof real / complex
     Space sp[2];            // SDNS_SPACE_T, SDNS_SPACE_TP
@@ -107,6 +118,17 @@ static void build_spaces(sdns_plan* p) {
         Space& q = p->sp[s];
         q.K2p = (q.K2n + 1) & ~1;
         q.scale = 1.0 / ((double)q.M[0] * q.M[1] * q.M[2]);
+        q.M0l = q.M[0] / p->P;
+        // kept axis-1 modes (global memory indices [0,col_nlo) and [N1-(K1n-col_nlo), N1)) owned here
+        const int lo = p->rank * p->N1l, hi = lo + p->N1l;
+        const int nlo = q.col_nlo, nhi = q.K1n - q.col_nlo, hstart = N[1] - nhi;
+        const int a1 = std::max(0, std::min(hi, nlo) - lo);                  // low run: local [0, a1)
+        const int b0 = std::max(lo, hstart), b1 = hi;                         // high run: global [b0, b1)
+        const int nb = (nhi > 0 && b1 > b0) ? b1 - b0 : 0;
+        q.K1l = a1 + nb;
+        q.lcol_nlo = a1;
+        q.lcol_gap = nb > 0 ? (b0 - lo) - a1 : 0;
+        q.c1off = a1 > 0 ? lo : (nb > 0 ? b0 - (N[1] - q.K1n) : 0);
     }
 }
 
@@ -128,19 +150,20 @@ static void fill_tables(sdns_plan* p) {
         p->tw_off[n] = off;
     };
     for (int s = 0; s < 2; ++s) for (int i = 0; i < 3; ++i) add_tw(p->sp[s].M[i]);
-    auto add_k = [&](int n, int len, double L, bool real_axis) {
+    auto add_k = [&](int n, int len, double L, bool real_axis, int first = 0) {
         size_t off = align_up(h.size(), 256);
         h.resize(off + sizeof(T) * len);
         T* k = reinterpret_cast<T*>(h.data() + off);
-        for (int i = 0; i < len; ++i) {
+        for (int j = 0; j < len; ++j) {
+            const int i = j + first;
             int kk = real_axis ? i : (i < (n + 1) / 2 ? i : i - n);
             // same evaluation order as the oracle: k*2*pi/L in double, then cast (NS.py:38-41)
-            k[i] = (T)(((double)kk * 2.0 * M_PI) / L);
+            k[j] = (T)(((double)kk * 2.0 * M_PI) / L);
         }
         return off;
     };
     p->kx_off = add_k(p->N[0], p->N[0], p->cfg.L[0], false);
-    p->ky_off = add_k(p->N[1], p->N[1], p->cfg.L[1], false);
+    p->ky_off = add_k(p->N[1], p->N1l, p->cfg.L[1], false, p->rank * p->N1l);
     p->kz_off = add_k(p->N[2], p->Nh, p->cfg.L[2], true);
 }
 
@@ -155,8 +178,10 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     if (!out || !cfg) return fail(SDNS_ERR_ARG, "null argument");
     if (cfg->abi_version != SDNS_ABI_VERSION) return fail(SDNS_ERR_ARG, "ABI version mismatch");
     if (cfg->precision != SDNS_SINGLE && cfg->precision != SDNS_DOUBLE) return fail(SDNS_ERR_ARG, "precision");
-    if (cfg->nranks != 1 || cfg->rank != 0)
-        return fail(SDNS_ERR_ARG, "this build drives one GPU per plan (nranks must be 1)");
+    if (cfg->nranks < 1 || cfg->nranks > 8 || cfg->rank < 0 || cfg->rank >= cfg->nranks)
+        return fail(SDNS_ERR_ARG, "rank/nranks: 1..8 ranks (one process per GPU of one node)");
+    if (cfg->nranks > 1 && cfg->decomposition != SDNS_SLAB)
+        return fail(SDNS_ERR_ARG, "multi-GPU runs use the slab decomposition (pencil is not on the B200 path yet)");
     if (cfg->solver < SDNS_NS || cfg->solver > SDNS_MHD) return fail(SDNS_ERR_ARG, "solver");
     if (cfg->solver == SDNS_NS && cfg->convection != SDNS_CONV_VORTEX)
         return fail(SDNS_ERR_ARG, "NS: only convection='Vortex' is compiled in");
@@ -179,12 +204,19 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     }
     p->Nh = p->N[2] / 2 + 1;
     p->Nhp = (p->Nh + 1) & ~1;
+    p->P = cfg->nranks; p->rank = cfg->rank;
+    p->own_ws = false; p->epoch = 0;
+    for (int r = 0; r < 8; ++r) p->peer_ws[r] = nullptr;
+    if (p->N[1] % p->P) { delete p; return fail(SDNS_ERR_SIZE, "N[1] must be divisible by the number of ranks"); }
+    p->N1l = p->N[1] / p->P;
     p->prec = cfg->precision;
     p->rs = p->prec ? 8 : 4; p->cs = 2 * p->rs;
     p->stream = 0; p->ws = nullptr; p->ws_bytes = 0; p->launches = 0;
     p->prof = false; p->ev_used = 0;
     for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_n[i] = 0; }
     build_spaces(p);
+    for (int s = 0; s < 2; ++s)
+        if (p->sp[s].M[0] % p->P) { delete p; return fail(SDNS_ERR_SIZE, "N[0] (and 3N[0]/2) must be divisible by the number of ranks"); }
     for (int s = 0; s < 2; ++s) for (int i = 0; i < 3; ++i)
         if (!size_ok(p->sp[s].M[i])) {
             char b[128]; snprintf(b, sizeof b, "no compiled transform of length %d (have 2^k, 3*2^k for 16..3072)", p->sp[s].M[i]);
@@ -193,28 +225,37 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     if (p->prec) fill_tables<double>(p); else fill_tables<float>(p);
     // scratch: A holds W0 (B0 out) and W2 (Z out); B holds W1 (B1 out) and W3 (F1 out)
     const int nz = cfg->solver == SDNS_MHD ? 9 : 6;    // widest field count through the pipeline
-    size_t a = 0, b = 0;
+    size_t a = 0, b = 0, c = 0;
     for (int s = 0; s < 2; ++s) {
         const Space& q = p->sp[s];
-        size_t w0 = (size_t)6 * q.M[0] * q.K1n * q.K2p;
-        size_t w1 = (size_t)6 * q.M[0] * q.M[1] * q.K2p;
-        size_t w2 = (size_t)nz * q.M[0] * q.M[1] * p->Nhp;
-        size_t w3 = (size_t)nz * q.M[0] * p->N[1] * p->Nhp;
-        a = std::max(a, std::max(w0, w2)); b = std::max(b, std::max(w1, w3));
+        size_t w0 = (size_t)6 * q.M0l * q.K1n * q.K2p;
+        size_t w1 = (size_t)6 * q.M0l * q.M[1] * q.K2p;
+        size_t w2 = (size_t)nz * q.M0l * q.M[1] * p->Nhp;
+        size_t w3 = (size_t)nz * q.M[0] * p->N1l * p->Nhp;
+        a = std::max(a, std::max(w0, w2));
+        if (p->P == 1) b = std::max(b, std::max(w1, w3));      // single GPU: W3 reuses W1's buffer
+        else { b = std::max(b, w1); c = std::max(c, w3); }      // multi GPU: peers write W3 while W1 is live
     }
     p->bytes_A = align_up(a * p->cs, 256); p->bytes_B = align_up(b * p->cs, 256);
+    p->bytes_C = align_up(c * p->cs, 256);
     p->red_blocks = 1024;
     p->off_tab = 0;
     p->off_A = align_up(p->host_tables.size(), 256);
     p->off_B = p->off_A + p->bytes_A;
-    p->off_red = p->off_B + p->bytes_B;
-    p->ws_need = p->off_red + align_up(sizeof(double) * p->red_blocks, 256);
+    p->off_C = p->P == 1 ? p->off_B : p->off_B + p->bytes_B;
+    p->off_red = p->off_B + p->bytes_B + p->bytes_C;
+    p->off_flags = p->off_red + align_up(sizeof(double) * p->red_blocks, 256);
+    p->ws_need = p->off_flags + 256;
     *out = p;
     return SDNS_OK;
 }
 
 extern "C" int sdns_plan_destroy(sdns_plan* p) {
-    if (p) for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+    if (p) {
+        for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+        for (int r = 0; r < 8; ++r) if (p->peer_ws[r] && r != p->rank) cudaIpcCloseMemHandle(p->peer_ws[r]);
+        if (p->own_ws && p->ws) cudaFree(p->ws);
+    }
     delete p; return SDNS_OK;
 }
 
@@ -227,10 +268,109 @@ extern "C" int sdns_plan_set_workspace(sdns_plan* p, void* dptr, size_t bytes) {
     if (!p || !dptr) return fail(SDNS_ERR_ARG, "null argument");
     if (bytes < p->ws_need) return fail(SDNS_ERR_WORKSPACE, "workspace too small");
     if ((uintptr_t)dptr % 256) return fail(SDNS_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    if (p->P > 1 && !p->own_ws)
+        return fail(SDNS_ERR_STATE, "multi-GPU plans allocate their IPC-shared workspace with sdns_comm_alloc");
     p->ws = (char*)dptr; p->ws_bytes = bytes;
+    p->peer_ws[p->rank] = p->ws;
     CUDA_TRY(cudaMemcpyAsync(p->ws + p->off_tab, p->host_tables.data(), p->host_tables.size(),
                              cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemsetAsync(p->ws + p->off_flags, 0, 256, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SDNS_OK;
+}
+
+// ---- slab decomposition over NVLink peer memory (one process per GPU) -----------------------
+// The all-to-all of mpi4py-fft's Transfer (MPI_Alltoallw; in-tree analogue spectralDNS3D_short.py:53,59)
+// has no kernel of its own here: B0 and F1 store each output element directly into the owning rank's
+// buffer.  That needs every rank's workspace mapped in every process: cudaMalloc + CUDA IPC.
+extern "C" int sdns_comm_alloc(sdns_plan* p) {
+    if (!p) return fail(SDNS_ERR_ARG, "null plan");
+    if (p->ws) return fail(SDNS_ERR_STATE, "workspace already set");
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, p->ws_need));
+    p->own_ws = true;
+    int e = sdns_plan_set_workspace(p, d, p->ws_need);
+    if (e) { cudaFree(d); p->own_ws = false; p->ws = nullptr; }
+    return e;
+}
+extern "C" int sdns_comm_handle(sdns_plan* p, void* handle64) {
+    if (!p || !handle64 || !p->own_ws) return fail(SDNS_ERR_STATE, "sdns_comm_handle: call sdns_comm_alloc first");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, p->ws));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return SDNS_OK;
+}
+extern "C" int sdns_comm_open(sdns_plan* p, const void* handles, int nranks) {
+    if (!p || !handles || nranks != p->P) return fail(SDNS_ERR_ARG, "sdns_comm_open: bad argument");
+    if (!p->own_ws) return fail(SDNS_ERR_STATE, "sdns_comm_open: call sdns_comm_alloc first");
+    for (int r = 0; r < nranks; ++r) {
+        if (r == p->rank) { p->peer_ws[r] = p->ws; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * r, 64);
+        void* d = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess));
+        p->peer_ws[r] = (char*)d;
+    }
+    return SDNS_OK;
+}
+
+namespace sdns {
+// ---------------------------------------------------------------------------------------
+// Cross-GPU barrier over peer memory (one process per GPU, flags exchanged through CUDA IPC):
+// thread r publishes this rank's epoch in rank r's flag array with a system-scope release, then
+// waits for rank r's epoch in the local array.  Launched as <<<1, 32>>> between the pass that
+// stores into the peers and the pass that reads what the peers stored.
+// ---------------------------------------------------------------------------------------
+struct BarrierArgs {
+    unsigned int* peer_flags[8];     // peer_flags[r] = flag array living on rank r
+    unsigned int* status;            // local: set to 1 on timeout
+    int rank, nranks;
+    unsigned int epoch;
+    long long timeout_cycles;
+};
+
+__global__ void xbarrier_kernel(const BarrierArgs b) {
+    const int r = threadIdx.x;
+    if (r >= b.nranks) return;
+    __threadfence_system();
+    unsigned int* remote = b.peer_flags[r] + b.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(b.epoch) : "memory");
+    const unsigned int* local = b.peer_flags[b.rank] + r;
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
+        if ((int)(v - b.epoch) >= 0) break;
+        if (clock64() - t0 > b.timeout_cycles) { *b.status = 1u; break; }
+    } while (true);
+    __threadfence_system();
+}
+
+}  // namespace sdns
+
+static int xbarrier(sdns_plan* p) {
+    if (p->P == 1) return SDNS_OK;
+    for (int r = 0; r < p->P; ++r) if (!p->peer_ws[r]) return fail(SDNS_ERR_STATE, "peers not opened (sdns_comm_open)");
+    BarrierArgs b;
+    for (int r = 0; r < 8; ++r) b.peer_flags[r] = r < p->P ? reinterpret_cast<unsigned int*>(p->peer_ws[r] + p->off_flags) : nullptr;
+    b.status = reinterpret_cast<unsigned int*>(p->ws + p->off_flags) + 32;
+    b.rank = p->rank; b.nranks = p->P; b.epoch = ++p->epoch;
+    b.timeout_cycles = 20000000000LL;      // ~10 s: a missing peer must not hang the GPU
+    xbarrier_kernel<<<1, 32, 0, p->stream>>>(b);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+
+extern "C" int sdns_comm_status(sdns_plan* p, int* timed_out) {
+    if (!p || !timed_out) return fail(SDNS_ERR_ARG, "null argument");
+    unsigned int v = 0;
+    if (p->ws) {
+        CUDA_TRY(cudaMemcpyAsync(&v, p->ws + p->off_flags + 32 * sizeof(unsigned int), sizeof v, cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+    }
+    *timed_out = (int)v;
     return SDNS_OK;
 }
 
@@ -244,8 +384,9 @@ extern "C" int sdns_sync(sdns_plan* p) {
 }
 extern "C" int sdns_local_shapes(const sdns_plan* p, int32_t sp[3], int32_t ph[3], int32_t pd[3]) {
     if (!p) return fail(SDNS_ERR_ARG, "null plan");
-    sp[0] = p->N[0]; sp[1] = p->N[1]; sp[2] = p->Nh;
+    sp[0] = p->N[0]; sp[1] = p->N1l; sp[2] = p->Nh;
     for (int i = 0; i < 3; ++i) { ph[i] = p->sp[0].M[i]; pd[i] = p->sp[1].M[i]; }
+    ph[0] = p->sp[0].M0l; pd[0] = p->sp[1].M0l;
     return SDNS_OK;
 }
 extern "C" int sdns_launch_count(const sdns_plan* p, long long* c) {
@@ -283,9 +424,10 @@ struct Pipe {
     typedef typename C2<T>::type V;
     sdns_plan* p;
     const Space& q;
-    V* A; V* B;
+    V* A; V* B; V* C;
     Pipe(sdns_plan* p_, int space) : p(p_), q(p_->sp[space]) {
         A = reinterpret_cast<V*>(p->ws + p->off_A); B = reinterpret_cast<V*>(p->ws + p->off_B);
+        C = reinterpret_cast<V*>(p->ws + p->off_C);
     }
     const V* tw(int n) const { return reinterpret_cast<const V*>(p->ws + p->off_tab + p->tw_off.at(n)); }
     void base(StridedArgs<T>& a) const {
@@ -296,45 +438,53 @@ struct Pipe {
         a.N0 = p->N[0]; a.N1 = p->N[1]; a.N2 = p->N[2];
         a.mask_nyquist = p->cfg.mask_nyquist;
         a.scale = (T)1;
-        a.st_fs = (long long)p->N[0] * p->N[1] * p->Nh;
+        a.st_fs = dense_fs();
+        a.k1_off = p->rank * p->N1l;
     }
-    long long dense_fs() const { return (long long)p->N[0] * p->N[1] * p->Nh; }
+    long long dense_fs() const { return (long long)p->N[0] * p->N1l * p->Nh; }
+    void peers(StridedArgs<T>& a, size_t off, int chunk) const {
+        if (p->P == 1) return;
+        a.xchunk = chunk;
+        for (int r = 0; r < p->P; ++r) a.peer_out[r] = reinterpret_cast<V*>(p->peer_ws[r] + off);
+    }
 
-    // B0: dense spectral (nf,N0,N1,Nh) -> A as W0 (nfo, M0, K1n, K2p)
+    // B0: local dense spectral (nf, N0, N1l, Nh) -> W0 (nfo, M0l, K1n, K2p) of the rank owning each x0
     int b0(int fam, const V* in, int nf) {
         StridedArgs<T> a; base(a);
         a.in = in; a.out = A;
-        a.in_fs = dense_fs(); a.in_ls = (long long)p->N[1] * p->Nh; a.in_os = p->Nh;
-        a.cw = q.K2n; a.ncols = (long long)q.K1n * q.K2n;
-        a.col_nlo = q.col_nlo; a.col_gap = q.col_gap;
+        a.in_fs = dense_fs(); a.in_ls = (long long)p->N1l * p->Nh; a.in_os = p->Nh;
+        a.cw = q.K2n; a.ncols = (long long)q.K1l * q.K2n;
+        a.col_nlo = q.lcol_nlo; a.col_gap = q.lcol_gap;
         a.imap = q.bmap[0]; a.omap = all_map(q.M[0]);
-        a.out_fs = (long long)q.M[0] * q.K1n * q.K2p; a.out_ls = (long long)q.K1n * q.K2p; a.out_os = q.K2p;
+        a.out_fs = (long long)q.M0l * q.K1n * q.K2p; a.out_ls = (long long)q.K1n * q.K2p; a.out_os = q.K2p;
+        a.c1_out_off = q.c1off;
+        peers(a, p->off_A, q.M0l);
         a.tw = tw(q.M[0]); a.nfields = nf;
         const int nfo = (fam == FAM_PLAIN_BWD) ? nf : 6;
-        const double cols = (double)q.K1n * q.K2n;
+        const double cols = (double)q.K1l * q.K2n;
         const double bytes = (nf * cols * (q.bmap[0].nlo + q.bmap[0].nhi) + nfo * cols * q.M[0]) * p->cs;
+        if (a.ncols == 0) return SDNS_OK;              // this rank owns no mode that survives the truncation
         return do_launch(p, fam, q.M[0], &a, bytes);
     }
-    // B1: A (W0) -> B as W1 (nf, M0, M1, K2p)
+    // B1: A (W0) -> B as W1 (nf, M0l, M1, K2p)
     int b1(int nf) {
         StridedArgs<T> a; base(a);
         a.in = A; a.out = B;
-        a.in_fs = (long long)q.M[0] * q.K1n * q.K2p; a.in_ls = q.K2p; a.in_os = (long long)q.K1n * q.K2p;
-        a.cw = q.K2n; a.ncols = (long long)q.M[0] * q.K2n;
-        a.col_nlo = q.M[0]; a.col_gap = 0;
+        a.in_fs = (long long)q.M0l * q.K1n * q.K2p; a.in_ls = q.K2p; a.in_os = (long long)q.K1n * q.K2p;
+        a.cw = q.K2n; a.ncols = (long long)q.M0l * q.K2n;
+        a.col_nlo = q.M0l; a.col_gap = 0;
         a.imap = q.bmap[1];
-        if (q.K1n == p->N[1] && q.M[1] == p->N[1]) a.imap = all_map(q.M[1]);
         a.omap = all_map(q.M[1]);
-        a.out_fs = (long long)q.M[0] * q.M[1] * q.K2p; a.out_ls = q.K2p; a.out_os = (long long)q.M[1] * q.K2p;
+        a.out_fs = (long long)q.M0l * q.M[1] * q.K2p; a.out_ls = q.K2p; a.out_os = (long long)q.M[1] * q.K2p;
         a.tw = tw(q.M[1]); a.nfields = nf;
-        const double bytes = (double)nf * q.M[0] * q.K2n * ((double)q.K1n + q.M[1]) * p->cs;
+        const double bytes = (double)nf * q.M0l * q.K2n * ((double)q.K1n + q.M[1]) * p->cs;
         return do_launch(p, FAM_PLAIN_BWD, q.M[1], &a, bytes);
     }
-    // Z: B (W1) -> A as W2 (nfo, M0, M1, Nhp)   [fused], or to/from user real arrays [plain]
+    // Z: B (W1) -> A as W2 (nfo, M0l, M1, Nhp)   [fused], or to/from user real arrays [plain]
     int z(int fam, const void* in, void* out, int nf, bool in_is_W1, bool out_is_W2) {
         ZArgs<T> a; memset(&a, 0, sizeof a);
         a.in = in; a.out = out;
-        const long long plane = (long long)q.M[0] * q.M[1];
+        const long long plane = (long long)q.M0l * q.M[1];
         a.in_ls = in_is_W1 ? q.K2p : q.M[2]; a.in_fs = plane * a.in_ls;
         a.out_ls = out_is_W2 ? p->Nhp : q.M[2]; a.out_fs = plane * a.out_ls;
         a.nlines = plane; a.nin_keep = q.K2n; a.nout_keep = p->Nh; a.nf = nf;
@@ -346,28 +496,30 @@ struct Pipe {
         const double bout = out_is_W2 ? (double)p->Nh * p->cs : (double)q.M[2] * p->rs;
         return do_launch(p, fam, q.M[2], &a, (double)plane * (nin * bin + nout * bout));
     }
-    // F1: A (W2) -> B as W3 (nf, M0, N1, Nhp)
+    // F1: A (W2) -> W3 (nf, M0, N1l, Nhp) of the rank owning each k1
     int f1(int nf) {
         StridedArgs<T> a; base(a);
-        a.in = A; a.out = B;
-        a.in_fs = (long long)q.M[0] * q.M[1] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[1] * p->Nhp;
-        a.cw = p->Nh; a.ncols = (long long)q.M[0] * p->Nh;
-        a.col_nlo = q.M[0]; a.col_gap = 0;
+        a.in = A; a.out = C;
+        a.in_fs = (long long)q.M0l * q.M[1] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[1] * p->Nhp;
+        a.cw = p->Nh; a.ncols = (long long)q.M0l * p->Nh;
+        a.col_nlo = q.M0l; a.col_gap = 0;
         a.imap = all_map(q.M[1]); a.omap = q.fmap[1];
-        a.out_fs = (long long)q.M[0] * p->N[1] * p->Nhp; a.out_ls = p->Nhp; a.out_os = (long long)p->N[1] * p->Nhp;
+        a.out_fs = (long long)q.M[0] * p->N1l * p->Nhp; a.out_ls = p->Nhp; a.out_os = (long long)p->N1l * p->Nhp;
+        a.c1_out_off = (long long)p->rank * q.M0l;
+        peers(a, p->off_C, p->N1l);
         a.tw = tw(q.M[1]); a.nfields = nf;
-        const double bytes = (double)nf * q.M[0] * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
+        const double bytes = (double)nf * q.M0l * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
         return do_launch(p, FAM_PLAIN_FWD, q.M[1], &a, bytes);
     }
-    // F0 geometry: B (W3) -> dense spectral
+    // F0 geometry: W3 -> local dense spectral
     void f0_geom(StridedArgs<T>& a, int nf) {
         base(a);
-        a.in = B;
-        a.in_fs = (long long)q.M[0] * p->N[1] * p->Nhp; a.in_ls = (long long)p->N[1] * p->Nhp; a.in_os = p->Nhp;
-        a.cw = p->Nh; a.ncols = (long long)p->N[1] * p->Nh;
-        a.col_nlo = p->N[1]; a.col_gap = 0;
+        a.in = C;
+        a.in_fs = (long long)q.M[0] * p->N1l * p->Nhp; a.in_ls = (long long)p->N1l * p->Nhp; a.in_os = p->Nhp;
+        a.cw = p->Nh; a.ncols = (long long)p->N1l * p->Nh;
+        a.col_nlo = p->N1l; a.col_gap = 0;
         a.imap = all_map(q.M[0]); a.omap = q.fmap[0];
-        a.out_fs = dense_fs(); a.out_ls = (long long)p->N[1] * p->Nh; a.out_os = p->Nh;
+        a.out_fs = dense_fs(); a.out_ls = (long long)p->N1l * p->Nh; a.out_os = p->Nh;
         a.tw = tw(q.M[0]); a.nfields = nf;
     }
 };
@@ -379,9 +531,10 @@ static int backward_t(sdns_plan* p, int space, int nc, const void* in, void* out
     for (int c0 = 0; c0 < nc; c0 += 6) {
         int nf = std::min(6, nc - c0);
         const V* src = reinterpret_cast<const V*>(in) + (long long)c0 * P.dense_fs();
-        T* dst = reinterpret_cast<T*>(out) + (long long)c0 * P.q.M[0] * P.q.M[1] * P.q.M[2];
+        T* dst = reinterpret_cast<T*>(out) + (long long)c0 * P.q.M0l * P.q.M[1] * P.q.M[2];
         int e;
         if ((e = P.b0(FAM_PLAIN_BWD, src, nf))) return e;
+        if ((e = xbarrier(p))) return e;
         if ((e = P.b1(nf))) return e;
         if ((e = P.z(FAM_Z_C2R, P.B, dst, nf, true, false))) return e;
     }
@@ -395,14 +548,15 @@ static int forward_t(sdns_plan* p, int space, int nc, const void* in, void* out)
     const int chunk = p->cfg.solver == SDNS_MHD ? 9 : 6;
     for (int c0 = 0; c0 < nc; c0 += chunk) {
         int nf = std::min(chunk, nc - c0);
-        const T* src = reinterpret_cast<const T*>(in) + (long long)c0 * P.q.M[0] * P.q.M[1] * P.q.M[2];
+        const T* src = reinterpret_cast<const T*>(in) + (long long)c0 * P.q.M0l * P.q.M[1] * P.q.M[2];
         V* dst = reinterpret_cast<V*>(out) + (long long)c0 * P.dense_fs();
         int e;
         if ((e = P.z(FAM_Z_R2C, src, P.A, nf, false, true))) return e;
         if ((e = P.f1(nf))) return e;
+        if ((e = xbarrier(p))) return e;
         StridedArgs<T> a; P.f0_geom(a, nf);
         a.out = dst;
-        const double bytes = (double)nf * p->N[1] * p->Nh * ((double)P.q.M[0] + p->N[0]) * p->cs;
+        const double bytes = (double)nf * p->N1l * p->Nh * ((double)P.q.M[0] + p->N[0]) * p->cs;
         if ((e = do_launch(p, FAM_PLAIN_FWD, P.q.M[0], &a, bytes))) return e;
     }
     return SDNS_OK;
@@ -423,10 +577,12 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
     if (solver == SDNS_NS) { if ((e = P.b0(FAM_NS_B0, u, 3))) return e; }
     else if (solver == SDNS_VV) { if ((e = P.b0(FAM_VV_B0, u, 3))) return e; }
     else { if ((e = P.b0(FAM_PLAIN_BWD, u, 6))) return e; }
+    if ((e = xbarrier(p))) return e;
     if ((e = P.b1(6))) return e;
     const int nprod = solver == SDNS_MHD ? 9 : 3;
     if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true))) return e;
     if ((e = P.f1(nprod))) return e;
+    if ((e = xbarrier(p))) return e;
     StridedArgs<T> a; P.f0_geom(a, nprod);
     a.out_mode = so.out_mode;
     a.u_hat = u;
@@ -442,8 +598,8 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
     if (so.out_mode == OUT_RHS) st = 2;                               // read u_hat, write rhs
     else if (so.out_mode == OUT_CONV) st = 1;
     else st = so.rk == 0 ? 1 + 3 : (so.rk < 3 ? 3 + 2 : 2 + 1);       // see passes.cuh RK4 stage
-    const double dense = (double)p->N[0] * p->N[1] * p->Nh * p->cs;
-    const double bytes = (double)nprod * p->N[1] * p->Nh * P.q.M[0] * p->cs + st * ns * dense
+    const double dense = (double)p->N[0] * p->N1l * p->Nh * p->cs;
+    const double bytes = (double)nprod * p->N1l * p->Nh * P.q.M[0] * p->cs + st * ns * dense
                          + (so.source ? ns * dense : 0) + (so.p_hat ? dense : 0);
     return do_launch(p, fam, P.q.M[0], &a, bytes);
 }
@@ -546,7 +702,7 @@ static int ncomp_state(const sdns_plan* p) { return p->cfg.solver == SDNS_MHD ? 
 extern "C" int sdns_euler_step(sdns_plan* p, void* u_hat, void* rhs, double dt, double nu, double eta,
                                const void* source) {
     int e = sdns_compute_rhs(p, rhs, u_hat, nu, eta, source, nullptr); if (e) return e;
-    const long long n = (long long)ncomp_state(p) * p->N[0] * p->N[1] * p->Nh;
+    const long long n = (long long)ncomp_state(p) * p->N[0] * p->N1l * p->Nh;
     if (p->prec) euler_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)u_hat, (const double2*)rhs, dt, n);
     else euler_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)u_hat, (const float2*)rhs, (float)dt, n);
     p->launches++;
@@ -557,7 +713,7 @@ extern "C" int sdns_euler_step(sdns_plan* p, void* u_hat, void* rhs, double dt, 
 extern "C" int sdns_ab2_step(sdns_plan* p, void* u_hat, void* u1, void* rhs, double dt, int tstep,
                              double nu, double eta, const void* source) {
     int e = sdns_compute_rhs(p, rhs, u_hat, nu, eta, source, nullptr); if (e) return e;
-    const long long n = (long long)ncomp_state(p) * p->N[0] * p->N[1] * p->Nh;
+    const long long n = (long long)ncomp_state(p) * p->N[0] * p->N1l * p->Nh;
     if (p->prec) ab2_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)u_hat, (double2*)u1, (const double2*)rhs, dt, tstep == 0, n);
     else ab2_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)u_hat, (float2*)u1, (const float2*)rhs, (float)dt, tstep == 0, n);
     p->launches++;
@@ -571,11 +727,11 @@ extern "C" int sdns_cross2(sdns_plan* p, void* c, const void* b, int over_k2) {
     if (p->prec)
         cross2_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)c, (const double2*)b,
             (const double*)(p->ws + p->kx_off), (const double*)(p->ws + p->ky_off), (const double*)(p->ws + p->kz_off),
-            p->N[0], p->N[1], p->Nh, over_k2);
+            p->N[0], p->N1l, p->Nh, over_k2);
     else
         cross2_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)c, (const float2*)b,
             (const float*)(p->ws + p->kx_off), (const float*)(p->ws + p->ky_off), (const float*)(p->ws + p->kz_off),
-            p->N[0], p->N[1], p->Nh, over_k2);
+            p->N[0], p->N1l, p->Nh, over_k2);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return SDNS_OK;
@@ -584,7 +740,7 @@ extern "C" int sdns_cross2(sdns_plan* p, void* c, const void* b, int over_k2) {
 extern "C" int sdns_energy(sdns_plan* p, const void* u_hat, int nc, double* out) {
     int e = need_ws(p); if (e) return e;
     if (!u_hat || !out || nc < 1) return fail(SDNS_ERR_ARG, "sdns_energy: bad argument");
-    const long long n = (long long)nc * p->N[0] * p->N[1] * p->Nh;
+    const long long n = (long long)nc * p->N[0] * p->N1l * p->Nh;
     double* red = reinterpret_cast<double*>(p->ws + p->off_red);
     const int nb = p->red_blocks;
     if (p->prec) energy_kernel<double><<<nb, 256, 0, p->stream>>>((const double2*)u_hat, n, p->Nh, p->N[2], red);
@@ -603,7 +759,7 @@ extern "C" int sdns_rk4_steps_host(sdns_plan* p, void* host_u, void* du, void* d
                                    double dt, double nu, double eta) {
     int e = need_ws(p); if (e) return e;
     if (!host_u || !du || !d1 || !d2 || nsteps < 0) return fail(SDNS_ERR_ARG, "sdns_rk4_steps_host: bad argument");
-    const size_t bytes = (size_t)ncomp_state(p) * p->N[0] * p->N[1] * p->Nh * p->cs;
+    const size_t bytes = (size_t)ncomp_state(p) * p->N[0] * p->N1l * p->Nh * p->cs;
     CUDA_TRY(cudaMemcpyAsync(du, host_u, bytes, cudaMemcpyHostToDevice, p->stream));
     for (int s = 0; s < nsteps; ++s) { e = sdns_rk4_step(p, du, d1, d2, dt, nu, eta, nullptr); if (e) return e; }
     CUDA_TRY(cudaMemcpyAsync(host_u, du, bytes, cudaMemcpyDeviceToHost, p->stream));
@@ -661,7 +817,7 @@ extern "C" int sdns_cross1(sdns_plan* p, void* c, const void* a, const void* b, 
 }
 extern "C" int sdns_cross2_dense(sdns_plan* p, void* c, const void* a, const void* b) {
     if (!p || !c || !a || !b || c == b) return fail(SDNS_ERR_ARG, "sdns_cross2_dense: bad argument");
-    const long long n = (long long)p->N[0] * p->N[1] * p->Nh;
+    const long long n = (long long)p->N[0] * p->N1l * p->Nh;
     if (p->prec) cross2_dense_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)c, (const double*)a, (const double2*)b, n);
     else cross2_dense_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)c, (const float*)a, (const float2*)b, n);
     p->launches++;
@@ -672,9 +828,9 @@ extern "C" int sdns_project(sdns_plan* p, void* u) {
     int e = need_ws(p); if (e) return e;
     if (!u) return fail(SDNS_ERR_ARG, "sdns_project: null array");
     if (p->prec) project_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)u,
-        (const double*)(p->ws + p->kx_off), (const double*)(p->ws + p->ky_off), (const double*)(p->ws + p->kz_off), p->N[0], p->N[1], p->Nh);
+        (const double*)(p->ws + p->kx_off), (const double*)(p->ws + p->ky_off), (const double*)(p->ws + p->kz_off), p->N[0], p->N1l, p->Nh);
     else project_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)u,
-        (const float*)(p->ws + p->kx_off), (const float*)(p->ws + p->ky_off), (const float*)(p->ws + p->kz_off), p->N[0], p->N[1], p->Nh);
+        (const float*)(p->ws + p->kx_off), (const float*)(p->ws + p->ky_off), (const float*)(p->ws + p->kz_off), p->N[0], p->N1l, p->Nh);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return SDNS_OK;

@@ -22,7 +22,8 @@ class Plan(object):
     """
 
     def __init__(self, N, L=(2*np.pi,)*3, precision='double', dealias='2/3-rule', solver='NS',
-                 convection=None, mask_nyquist=True, decomposition='slab', kcut=None, device=0):
+                 convection=None, mask_nyquist=True, decomposition='slab', kcut=None, device=0,
+                 rank=0, nranks=1):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.SdnsError('no CUDA device: spectraldns_b200 has no CPU fallback')
@@ -53,7 +54,8 @@ class Plan(object):
         cfg.mask_nyquist = 1 if mask_nyquist else 0
         cfg.decomposition = _lib.DECOMP[decomposition]
         cfg.prune = 1
-        cfg.rank, cfg.nranks, cfg.device = 0, 1, device
+        cfg.rank, cfg.nranks, cfg.device = int(rank), int(nranks), device
+        self.rank, self.nranks = int(rank), int(nranks)
         self._p = C.c_void_p()
         _lib.check(self.lib.sdns_plan_create(C.byref(self._p), C.byref(cfg)))
         sp, ph, pd = (C.c_int32*3)(), (C.c_int32*3)(), (C.c_int32*3)()
@@ -66,10 +68,37 @@ class Plan(object):
         _lib.check(self.lib.sdns_workspace_bytes(self._p, C.byref(nb)))
         self.workspace_bytes = nb.value
         with torch.cuda.device(self.device):
-            self._ws = torch.empty(nb.value + 256, dtype=torch.uint8, device=self.device)
-            off = (-self._ws.data_ptr()) % 256
             self.use_current_stream()
-            _lib.check(self.lib.sdns_plan_set_workspace(self._p, self._ws.data_ptr() + off, nb.value))
+            if self.nranks == 1:
+                # PyTorch is the device-memory allocator
+                self._ws = torch.empty(nb.value + 256, dtype=torch.uint8, device=self.device)
+                off = (-self._ws.data_ptr()) % 256
+                _lib.check(self.lib.sdns_plan_set_workspace(self._p, self._ws.data_ptr() + off, nb.value))
+            else:
+                self._open_peers()
+
+    def _open_peers(self):
+        """Slab decomposition: the library cudaMallocs the workspace so that it can be shared with
+        the other ranks through CUDA IPC; handles travel over torch.distributed."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise _lib.SdnsError('nranks > 1 needs an initialised torch.distributed process group')
+        if dist.get_world_size() != self.nranks or dist.get_rank() != self.rank:
+            raise _lib.SdnsError('rank/nranks do not match the torch.distributed process group')
+        _lib.check(self.lib.sdns_comm_alloc(self._p))
+        buf = (C.c_char*64)()
+        _lib.check(self.lib.sdns_comm_handle(self._p, buf))
+        mine = bytes(buf.raw)
+        handles = [None]*self.nranks
+        dist.all_gather_object(handles, mine)
+        blob = b''.join(handles)
+        _lib.check(self.lib.sdns_comm_open(self._p, C.c_char_p(blob), self.nranks))
+        dist.barrier()
+
+    def comm_timed_out(self):
+        v = C.c_int()
+        _lib.check(self.lib.sdns_comm_status(self._p, C.byref(v)))
+        return bool(v.value)
 
     def __del__(self):
         try:
