@@ -27,20 +27,36 @@ NU, DT = 0.000625, 0.01       # tests/TG.py:131-133 of the reference
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=('ours', 'reference'))
     ap.add_argument('--grid', type=int, default=256)
     ap.add_argument('--precision', default='double', choices=('single', 'double'))
     ap.add_argument('--dealias', default='2/3-rule', choices=('2/3-rule', '3/2-rule', 'None'))
     ap.add_argument('--solver', default='NS', choices=('NS', 'VV', 'MHD'))
+    ap.add_argument('--scaling', default='weak', choices=('weak', 'strong'),
+                    help='N>1: weak = grid grows with the GPU count (per-GPU work fixed), strong = fixed grid')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
     return ap.parse_args()
 
 
-def workload_name(a):
-    return 'Taylor-Green %s %d^3 %s RK4 %s slab' % (a.solver, a.grid, a.precision, a.dealias)
+def grid_for(a, world):
+    """N=1: grid^3.  N>1 weak scaling: double N0, N1, N2 in turn (256^3 -> 512x256x256 -> 512x512x256
+    -> 512^3 on 8 GPUs) so that every GPU keeps grid^3 points; strong scaling keeps grid^3."""
+    N = [a.grid]*3
+    if world > 1 and a.scaling == 'weak':
+        w, i = world, 0
+        while w > 1:
+            N[i % 3] *= 2
+            w //= 2
+            i += 1
+    return tuple(N)
+
+
+def workload_name(a, N=None):
+    N = N or (a.grid,)*3
+    return 'Taylor-Green %s %dx%dx%d %s RK4 %s slab' % (a.solver, N[0], N[1], N[2], a.precision, a.dealias)
 
 
 def peaks():
@@ -56,11 +72,10 @@ def peaks():
 # ---------------------------------------------------------------------------------------------
 # CPU oracle port (also the --impl reference arm)
 # ---------------------------------------------------------------------------------------------
-def cpu_oracle_steps(a, max_steps, max_seconds, warm=0):
+def cpu_oracle_steps(a, N, max_steps, max_seconds, warm=0):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import numpy as np
     import sdns_oracle as so
-    N = (a.grid,)*3
     o = so.Oracle(N, precision=a.precision, dealias=a.dealias)
     if a.solver == 'MHD':
         u = o.forward(so.taylor_green_mhd(o))
@@ -89,19 +104,20 @@ def run_reference(a):
         return
     # bounded: stop after ~150 s of timed work whatever K is
     warm = 1 if a.warmup > 0 else 0
-    spt, n, cores = cpu_oracle_steps(a, a.steps, 150.0, warm=warm)
-    pts = float(a.grid)**3
+    N = grid_for(a, max(1, a.gpus))
+    spt, n, cores = cpu_oracle_steps(a, N, a.steps, 150.0, warm=warm)
+    pts = float(N[0])*N[1]*N[2]
     val = pts/spt
     line = {
         'impl': 'reference', 'metric': 'grid_points_steps_per_s', 'value': val, 'unit': 'points*steps/s',
         'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': spt*1e3,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'higher_is_better': True, 'scaling': a.scaling if a.gpus > 1 else 'weak', 'vs_baseline': None,
         'dtype': 'f64' if a.precision == 'double' else 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(a), 'grid': [a.grid]*3, 'integrator': 'RK4',
+        'config': {'workload': workload_name(a, N), 'grid': list(N), 'integrator': 'RK4',
                    'note': 'CPU oracle port of the reference path (numpy + scipy.fft pocketfft, workers=all cores, '
                            'single rank); the reference stack shenfun/mpi4py-fft/pyfftw/mpirun is absent from the image'},
         'cpu_baseline': {'value': val, 'unit': 'points*steps/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d full RK4 steps of the %d^3 workload (%d warm-up)' % (n, a.grid, warm)},
+                         'sample': '%d full RK4 steps of the %dx%dx%d workload (%d warm-up)' % (n, N[0], N[1], N[2], warm)},
         'e2e': {'value': val, 'unit': 'points*steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
@@ -117,7 +133,7 @@ class ClockSampler(object):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '50'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -173,10 +189,13 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    N = (a.grid,)*3
-    p = Plan(N, precision=a.precision, dealias=a.dealias, solver=a.solver, device=local)
+    N = grid_for(a, world)
+    p = Plan(N, precision=a.precision, dealias=a.dealias, solver=a.solver, device=local,
+             rank=rank, nranks=world)
     # synthetic Taylor-Green field generated on the device (tests/TG.py:23-28 / tests/TGMHD.py:4-12)
     X = [torch.arange(n, dtype=torch.float64, device='cuda')*2*np.pi/n for n in N]
+    M0l = N[0]//world
+    X[0] = X[0][rank*M0l:(rank+1)*M0l]          # this rank's slab of physical space
     s0, c0 = torch.sin(X[0])[:, None, None], torch.cos(X[0])[:, None, None]
     s1, c1 = torch.sin(X[1])[None, :, None], torch.cos(X[1])[None, :, None]
     c2 = torch.cos(X[2])[None, None, :]
@@ -215,8 +234,12 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    energy = p.energy(u)/2
+    et = torch.tensor([p.energy(u)/2], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(et)
+    energy = float(et.item())
     assert np.isfinite(energy) and 0 < energy < 1, energy
+    assert not p.comm_timed_out()
 
     # ---- end to end through the host-buffer call (H2D + step + D2H every step) ------------
     host = torch.empty(u.shape, dtype=u.dtype, pin_memory=True)
@@ -248,12 +271,12 @@ def run_ours(a):
             dist.destroy_process_group()
         return
 
-    pts = float(a.grid)**3
-    value = world*pts/(ms*1e-3)
+    pts = float(N[0])*N[1]*N[2]
+    value = pts/(ms*1e-3)
     peak, peak_src = peaks()
     tot = sum(v[0] for v in prof.values())
     kern = max(prof, key=lambda k: prof[k][0])
-    kms, kn, kb = prof[kern]
+    kms, kn, kb = prof[kern][:3]
     achieved = kb/kms*1e-6 if kms > 0 else 0.0       # bytes/ms -> GB/s
     traffic = None
     tf = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -266,17 +289,18 @@ def run_ours(a):
     line = {
         'metric': 'grid_points_steps_per_s', 'value': value, 'unit': 'points*steps/s',
         'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'higher_is_better': True, 'scaling': a.scaling if world > 1 else 'weak', 'vs_baseline': None,
         'dtype': 'f64' if a.precision == 'double' else 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(a), 'grid': [a.grid]*3, 'integrator': 'RK4',
+        'config': {'workload': workload_name(a, N), 'grid': list(N), 'integrator': 'RK4',
                    'transforms_per_step': 60 if a.solver == 'MHD' else 36,
-                   'multi_gpu': 'replicas only (one full grid per GPU)' if world > 1 else 'single GPU',
+                   'multi_gpu': ('slab decomposition over %d GPUs: transposes are peer-memory stores fused into the '
+                                 'FFT passes (no NCCL on the data path); %s scaling' % (world, a.scaling)) if world > 1 else 'single GPU',
                    'l2': 'inputs larger than L2 (state %.0f MB, scratch %.0f MB)' % (state_bytes/1e6, p.workspace_bytes/1e6),
                    'timing': 'CUDA events on the launch stream, max over ranks',
                    'kinetic_energy_after_run': energy},
         'clocks': clocks,
-        'e2e': {'value': world*pts/te, 'unit': 'points*steps/s', 'ms_per_step': te*1e3,
-                'h2d_bytes_per_step': state_bytes, 'd2h_bytes_per_step': state_bytes,
+        'e2e': {'value': pts/te, 'unit': 'points*steps/s', 'ms_per_step': te*1e3,
+                'h2d_bytes_per_step': state_bytes*world, 'd2h_bytes_per_step': state_bytes*world,
                 'call': 'sdns_rk4_steps_host: pinned host state -> device, one RK4 step, device -> host'},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'kernel': kern, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
@@ -289,8 +313,20 @@ def run_ours(a):
                      'all_kernels': {k: {'ms_per_launch': v[0]/v[1], 'launches_per_step': v[1]/npf,
                                          'GBps': v[2]/v[0]*1e-6, 'share': v[0]/tot} for k, v in prof.items()}},
     }
+    if world > 1:
+        # NVLink side of the roofline (rank 0's view): bytes the exchange passes store into peers
+        xk = {k: v for k, v in prof.items() if v[3] > 0}
+        xbytes = sum(v[3] for v in xk.values())/npf
+        xms = sum(v[0] for v in xk.values())/npf
+        line['nvlink'] = {'bytes_per_step_per_gpu': xbytes, 'exchange_kernels': sorted(xk),
+                          'exchange_kernel_ms_per_step': xms,
+                          'achieved_GBps_per_direction': xbytes*1e-9/(xms*1e-3) if xms else None,
+                          'peak_measured_GBps': 770.0, 'peak_nominal_GBps': 900.0,
+                          'frac_of_measured': (xbytes*1e-9/(xms*1e-3))/770.0 if xms else None,
+                          'note': 'transposes are peer stores issued by the FFT pass in front of them, so the '
+                                  'kernel time also covers that pass\'s local HBM traffic'}
     if world == 1 and not a.no_cpu_baseline:
-        spt, n, cores = cpu_oracle_steps(a, 50, a.cpu_seconds)
+        spt, n, cores = cpu_oracle_steps(a, N, 50, a.cpu_seconds)
         line['cpu_baseline'] = {'value': pts/spt, 'unit': 'points*steps/s', 'cores': cores, 'kind': 'port',
                                 'ms_per_step': spt*1e3,
                                 'sample': '%d full RK4 steps of the same %d^3 workload with the numpy/scipy.fft '

@@ -166,6 +166,8 @@ int sdns_launch_count(const sdns_plan* plan, long long* count);
  * time, the launch count and the summed algorithmic HBM bytes since sdns_profile_enable. */
 int sdns_profile_enable(sdns_plan* plan, int on);
 int sdns_profile_read(sdns_plan* plan, int family, double* total_ms, long long* launches, double* bytes);
+/* bytes the family's launches stored into peer GPUs over NVLink (slab transposes) */
+int sdns_profile_read_nvlink(sdns_plan* plan, int family, double* bytes);
 
 #ifdef __cplusplus
 }

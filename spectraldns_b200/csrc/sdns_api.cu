@@ -76,9 +76,9 @@ struct sdns_plan {
     // optional per-family profiling (bench.py roofline): CUDA events around every launch
     bool prof;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used;
-    struct Rec { int fam; cudaEvent_t a, b; double bytes; };
+    struct Rec { int fam; cudaEvent_t a, b; double bytes, remote; };
     std::vector<Rec> recs;
-    double prof_ms[FAM_COUNT]; double prof_bytes[FAM_COUNT]; long long prof_n[FAM_COUNT];
+    double prof_ms[FAM_COUNT]; double prof_bytes[FAM_COUNT]; double prof_remote[FAM_COUNT]; long long prof_n[FAM_COUNT];
 };
 
 static AxisMap all_map(int n) { AxisMap m; m.nlo = n; m.nhi = 0; m.shift = 0; return m; }
@@ -213,7 +213,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->rs = p->prec ? 8 : 4; p->cs = 2 * p->rs;
     p->stream = 0; p->ws = nullptr; p->ws_bytes = 0; p->launches = 0;
     p->prof = false; p->ev_used = 0;
-    for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_n[i] = 0; }
+    for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_remote[i] = 0; p->prof_n[i] = 0; }
     build_spaces(p);
     for (int s = 0; s < 2; ++s)
         if (p->sp[s].M[0] % p->P) { delete p; return fail(SDNS_ERR_SIZE, "N[0] (and 3N[0]/2) must be divisible by the number of ranks"); }
@@ -407,8 +407,8 @@ static cudaEvent_t get_event(sdns_plan* p) {
 
 // bytes = algorithmic HBM bytes of this launch: every input element read once + every output
 // element written once at the pass's actual (pruned / padded) sizes
-static int do_launch(sdns_plan* p, int fam, int n, const void* args, double bytes = 0) {
-    sdns_plan::Rec r; r.fam = fam; r.bytes = bytes;
+static int do_launch(sdns_plan* p, int fam, int n, const void* args, double bytes = 0, double remote = 0) {
+    sdns_plan::Rec r; r.fam = fam; r.bytes = bytes; r.remote = remote;
     if (p->prof) { r.a = get_event(p); cudaEventRecord(r.a, p->stream); }
     int e = g_launch[fam][p->prec](n, args, p->stream);
     if (p->prof) { r.b = get_event(p); cudaEventRecord(r.b, p->stream); p->recs.push_back(r); }
@@ -464,7 +464,8 @@ struct Pipe {
         const double cols = (double)q.K1l * q.K2n;
         const double bytes = (nf * cols * (q.bmap[0].nlo + q.bmap[0].nhi) + nfo * cols * q.M[0]) * p->cs;
         if (a.ncols == 0) return SDNS_OK;              // this rank owns no mode that survives the truncation
-        return do_launch(p, fam, q.M[0], &a, bytes);
+        const double remote = nfo * cols * q.M[0] * p->cs * (p->P - 1) / p->P;   // stored into peers over NVLink
+        return do_launch(p, fam, q.M[0], &a, bytes, remote);
     }
     // B1: A (W0) -> B as W1 (nf, M0l, M1, K2p)
     int b1(int nf) {
@@ -509,7 +510,8 @@ struct Pipe {
         peers(a, p->off_C, p->N1l);
         a.tw = tw(q.M[1]); a.nfields = nf;
         const double bytes = (double)nf * q.M0l * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
-        return do_launch(p, FAM_PLAIN_FWD, q.M[1], &a, bytes);
+        const double remote = (double)nf * q.M0l * p->Nh * p->N[1] * p->cs * (p->P - 1) / p->P;
+        return do_launch(p, FAM_PLAIN_FWD, q.M[1], &a, bytes, remote);
     }
     // F0 geometry: W3 -> local dense spectral
     void f0_geom(StridedArgs<T>& a, int nf) {
@@ -841,7 +843,7 @@ extern "C" int sdns_profile_enable(sdns_plan* p, int on) {
     if (!p) return fail(SDNS_ERR_ARG, "null plan");
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     p->prof = on != 0; p->recs.clear(); p->ev_used = 0;
-    for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_n[i] = 0; }
+    for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_remote[i] = 0; p->prof_n[i] = 0; }
     return SDNS_OK;
 }
 extern "C" int sdns_profile_read(sdns_plan* p, int family, double* total_ms, long long* launches, double* bytes) {
@@ -849,11 +851,18 @@ extern "C" int sdns_profile_read(sdns_plan* p, int family, double* total_ms, lon
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     for (const sdns_plan::Rec& r : p->recs) {
         float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
-        p->prof_ms[r.fam] += ms; p->prof_bytes[r.fam] += r.bytes; p->prof_n[r.fam]++;
+        p->prof_ms[r.fam] += ms; p->prof_bytes[r.fam] += r.bytes; p->prof_remote[r.fam] += r.remote; p->prof_n[r.fam]++;
     }
     p->recs.clear(); p->ev_used = 0;
     if (total_ms) *total_ms = p->prof_ms[family];
     if (launches) *launches = p->prof_n[family];
     if (bytes) *bytes = p->prof_bytes[family];
+    return SDNS_OK;
+}
+
+extern "C" int sdns_profile_read_nvlink(sdns_plan* p, int family, double* bytes) {
+    if (!p || !bytes || family < 0 || family >= FAM_COUNT) return fail(SDNS_ERR_ARG, "sdns_profile_read_nvlink: bad argument");
+    int e = sdns_profile_read(p, family, nullptr, nullptr, nullptr); if (e) return e;
+    *bytes = p->prof_remote[family];
     return SDNS_OK;
 }

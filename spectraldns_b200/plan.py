@@ -248,11 +248,13 @@ class Plan(object):
         _lib.check(self.lib.sdns_profile_enable(self._p, 1 if on else 0))
 
     def profile_read(self):
-        """{family: (total_ms, launches, algorithmic_bytes)} since profile(True)."""
+        """{family: (total_ms, launches, algorithmic_hbm_bytes, nvlink_bytes_stored)} since profile(True)."""
         out = {}
         for i, name in enumerate(self.FAMILIES):
             ms, n, b = C.c_double(), C.c_longlong(), C.c_double()
             _lib.check(self.lib.sdns_profile_read(self._p, i, C.byref(ms), C.byref(n), C.byref(b)))
             if n.value:
-                out[name] = (ms.value, n.value, b.value)
+                r = C.c_double()
+                _lib.check(self.lib.sdns_profile_read_nvlink(self._p, i, C.byref(r)))
+                out[name] = (ms.value, n.value, b.value, r.value)
         return out

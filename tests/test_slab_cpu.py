@@ -1,0 +1,144 @@
+"""CPU test of the N>1 path's host logic: two gloo processes replay the slab pipeline (axis-0 pass,
+peer 'stores' = all_to_all, axis-1 pass, axis-2 pass) in numpy using spectraldns_b200.slab and must
+reproduce the single-process oracle transform on their slabs, for the 2/3-rule (pruned, compact
+axis-1 set), the 3/2-rule and no dealiasing."""
+import os
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle')]
+
+
+def _axis_pad(a, axis, M, N):
+    """scatter N spectral entries (fftfreq order) into a length-M axis (corner copy)."""
+    if M == N:
+        return a
+    sh = list(a.shape)
+    sh[axis] = M
+    out = np.zeros(sh, dtype=a.dtype)
+    lo = [slice(None)]*a.ndim
+    hi_s = [slice(None)]*a.ndim
+    hi_d = [slice(None)]*a.ndim
+    lo[axis] = slice(0, N//2)
+    hi_s[axis] = slice(N//2, N)
+    hi_d[axis] = slice(M-(N-N//2), M)
+    out[tuple(lo)] = a[tuple(lo)]
+    out[tuple(hi_d)] = a[tuple(hi_s)]
+    return out
+
+
+def _a2a(dist, recv, send, rank, world):
+    """all_to_all from point-to-point messages (gloo has no alltoall): what the GPU path does with
+    direct peer stores."""
+    reqs = []
+    for r in range(world):
+        if r == rank:
+            recv[r].copy_(send[r])
+        else:
+            reqs.append(dist.isend(send[r], r))
+            reqs.append(dist.irecv(recv[r], r))
+    for q in reqs:
+        q.wait()
+
+
+def _worker(rank, world, port, dealias, N, ret):
+    import torch
+    import torch.distributed as dist
+    import sdns_oracle as so
+    from spectraldns_b200.slab import SlabLayout
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        o = so.Oracle(N, dealias=dealias)
+        L = SlabLayout(N, world, rank, dealias)
+        rng = np.random.RandomState(4)
+        u_hat = o.forward(rng.standard_normal(tuple(N)))               # global spectrum (same on all ranks)
+        mine = u_hat[:, L.k1_slice, :]                                  # this rank's slab
+        M = L.M
+        # ---- B0: axis-0 inverse on owned kept columns, truncation/padding at load
+        cols = mine[:, L.local_kept, :L.K2n]
+        if dealias == '2/3-rule':
+            kc0 = so.dealias_cutoff(N[0])
+            m0 = np.abs(np.fft.fftfreq(N[0], 1./N[0])) <= kc0
+            cols = cols*m0[:, None, None]
+        w = np.fft.ifft(_axis_pad(cols, 0, M[0], N[0]), axis=0)*M[0]    # (M0, K1l, K2n)
+        # ---- peer stores: x0 chunk d goes to rank d at compact k1 offset c1off
+        dest = L.backward_destinations()
+        send = [torch.from_numpy(np.ascontiguousarray(w[dest == d])) for d in range(world)]
+        all_layouts = [SlabLayout(N, world, r, dealias) for r in range(world)]
+        recv = [torch.zeros((L.M0l, all_layouts[r].K1l, L.K2n), dtype=torch.complex128) for r in range(world)]
+        _a2a(dist, recv, send, rank, world)
+        W0 = np.zeros((L.M0l, L.K1n, L.K2n), dtype=complex)
+        for r in range(world):
+            c = all_layouts[r].c1off
+            W0[:, c:c+all_layouts[r].K1l] = recv[r].numpy()
+        # ---- B1: compact axis 1 -> full, inverse; Z: c2r
+        full1 = np.zeros((L.M0l, M[1], L.K2n), dtype=complex)
+        if dealias == '3/2-rule':
+            full1 = _axis_pad(W0, 1, M[1], N[1])
+        else:
+            full1[:, L.kept1] = W0
+        w1 = np.fft.ifft(full1, axis=1)*M[1]
+        zin = np.zeros((L.M0l, M[1], M[2]//2+1), dtype=complex)
+        zin[..., :L.K2n] = w1
+        phys = np.fft.irfft(zin, n=M[2], axis=2)*M[2]
+        ref = o._bwd_p(u_hat)[L.x0_slice]
+        e_b = np.linalg.norm(phys-ref)/np.linalg.norm(ref)
+        # ---- forward: Z r2c, F1 axis 1 (+truncation), stores to the k1 owner, F0 axis 0
+        v = rng.standard_normal(o.M)                                    # global physical field
+        z = np.fft.rfft(v[L.x0_slice], axis=2)[..., :L.Nh]/np.prod(M)
+        f1 = np.fft.fft(z, axis=1)
+        if dealias == '3/2-rule':
+            f1 = np.concatenate([f1[:, :N[1]//2], f1[:, M[1]-(N[1]-N[1]//2):]], axis=1)
+        owner = L.forward_destinations()
+        send = [torch.from_numpy(np.ascontiguousarray(f1[:, owner == d])) for d in range(world)]
+        recv = [torch.zeros((L.M0l, L.N1l, L.Nh), dtype=torch.complex128) for _ in range(world)]
+        _a2a(dist, recv, send, rank, world)
+        W3 = np.concatenate([t.numpy() for t in recv], axis=0)         # (M0, N1l, Nh): x0 chunks in rank order
+        f0 = np.fft.fft(W3, axis=0)
+        if dealias == '3/2-rule':
+            f0 = np.concatenate([f0[:N[0]//2], f0[M[0]-(N[0]-N[0]//2):]], axis=0)
+        ref_f = o._fwd_p(v)[:, L.k1_slice]
+        e_f = np.linalg.norm(f0-ref_f)/np.linalg.norm(ref_f)
+        ret[rank] = (float(e_b), float(e_f), L.spectral_shape(), L.physical_shape())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('dealias', ['2/3-rule', '3/2-rule', 'None'])
+def test_slab_pipeline_two_ranks_gloo(dealias):
+    import torch.multiprocessing as mp
+    N = (16, 32, 16)
+    port = 29610 + ['2/3-rule', '3/2-rule', 'None'].index(dealias)
+    ctx = mp.get_context('spawn')
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, dealias, N, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for r in range(2):
+        e_b, e_f, ss, ps = ret[r]
+        assert e_b < 1e-13 and e_f < 1e-13, (r, e_b, e_f)
+        assert ss == (16, 16, 9)
+        assert ps == ((12, 48, 24) if dealias == '3/2-rule' else (8, 32, 16))
+
+
+def test_slab_layout_matches_c_plan_rules():
+    from spectraldns_b200.slab import SlabLayout
+    # 2/3-rule at N1=1024 on 8 ranks: middle ranks own no surviving mode (B0 has nothing to do there)
+    K1l = [SlabLayout((1024, 1024, 1024), 8, r).K1l for r in range(8)]
+    L0 = SlabLayout((1024, 1024, 1024), 8, 0)
+    assert sum(K1l) == L0.K1n == 2*so_cut(1024)+1
+    assert K1l[0] == 128 and K1l[3] == 0 and K1l[4] == 0 and K1l[7] == 128
+    offs = [SlabLayout((1024, 1024, 1024), 8, r).c1off for r in range(8)]
+    assert offs[0] == 0 and offs[1] == 128 and offs[7] == L0.K1n - 128
+    with pytest.raises(ValueError):
+        SlabLayout((32, 30, 32), 4, 0)
+
+
+def so_cut(n):
+    return int(np.ceil(2./3.*(n//2+1))) - 1
