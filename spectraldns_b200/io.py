@@ -24,7 +24,9 @@ class _Handle(object):
 class ShenfunFile(object):
     """ShenfunFile(name, space, mode=) with .open()/.close()/.f.attrs/.write(tstep, data, as_scalar=)."""
     def __init__(self, name, space=None, mode='w', **kw):
-        self.filename = name + '.npz'
+        from .spaces import world
+        rank, nranks, _ = world()
+        self.filename = name + ('_rank%d' % rank if nranks > 1 else '') + '.npz'
         self.space = space
         self.mode = mode
         self._attrs = _Attrs()

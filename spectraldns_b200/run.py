@@ -11,7 +11,22 @@ import sys
 COMPAT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'compat')
 
 
+def init_distributed():
+    """Under torchrun (one process per GPU): bind the GPU and create the NCCL process group that
+    stands in for MPI.COMM_WORLD (reductions, rendezvous of the CUDA-IPC handles)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get('LOCAL_RANK', os.environ.get('RANK', '0')))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+
 def activate():
+    init_distributed()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (COMPAT, root):
         if p not in sys.path:

@@ -15,6 +15,19 @@ from .plan import Plan
 from . import _lib
 
 
+def world():
+    """(rank, nranks, cuda device) of this process: torch.distributed when a process group exists
+    (one process per GPU, launched by torchrun), else a single rank on the current device."""
+    import torch
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0, 1, torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+
 class FunctionSpace(object):
     """FunctionSpace(N, 'F', domain=(0, L), dtype=...) (solvers/NS.py:17-19)."""
     def __init__(self, N, family='F', domain=(0, 2*np.pi), dtype=float, **kw):
@@ -35,8 +48,11 @@ class Engine(object):
     def __init__(self, N, L, precision, dealias, solver='NS', mask_nyquist=True, decomposition='slab'):
         self.key = (tuple(int(n) for n in N), tuple(float(l) for l in L), precision, dealias, solver,
                     bool(mask_nyquist), decomposition)
+        rank, nranks, device = world()
+        self.rank, self.nranks = rank, nranks
         self.plan = Plan(self.key[0], self.key[1], precision, dealias, solver,
-                         mask_nyquist=mask_nyquist, decomposition=decomposition)
+                         mask_nyquist=mask_nyquist, decomposition='slab' if nranks > 1 else decomposition,
+                         device=device, rank=rank, nranks=nranks)
         self._stage = {}
 
     @classmethod
@@ -104,15 +120,34 @@ class TensorProductSpace(object):
         return self._engine
 
     # -- shapes / meshes (NS.py:37-48) ---------------------------------------
-    def shape(self, forward_output=False):
+    def _ranks(self):
+        if self._engine is not None:
+            return self._engine.rank, self._engine.nranks
+        r, n, _ = world()
+        return r, n
+
+    def global_shape(self, forward_output=False):
         if forward_output:
             return (self.N[0], self.N[1], self.N[2]//2+1)
         return tuple(self.M)
 
-    global_shape = shape
+    def shape(self, forward_output=False):
+        """Local shape: slab decomposition, spectral space split on axis 1, physical on axis 0
+        (spectralDNS3D_short.py:28-29)."""
+        r, n = self._ranks()
+        g = self.global_shape(forward_output)
+        if n == 1:
+            return g
+        return (g[0], g[1]//n, g[2]) if forward_output else (g[0]//n, g[1], g[2])
 
     def local_slice(self, forward_output=False):
-        return tuple(slice(0, n) for n in self.shape(forward_output))
+        r, n = self._ranks()
+        g = self.global_shape(forward_output)
+        ax = 1 if forward_output else 0
+        out = [slice(0, m) for m in g]
+        c = g[ax]//n
+        out[ax] = slice(r*c, (r+1)*c)
+        return tuple(out)
 
     def dims(self):
         return 3
@@ -125,8 +160,11 @@ class TensorProductSpace(object):
         for i in range(3):
             s = [1, 1, 1]
             s[i] = self.M[i]
-            x = (np.arange(self.M[i], dtype=float)*self.L[i]/self.M[i]).reshape(s)
-            X.append(np.broadcast_to(x, self.M) if broadcast else x)
+            x = (np.arange(self.M[i], dtype=float)*self.L[i]/self.M[i])
+            x = x[self.local_slice(False)[i]]
+            s[i] = len(x)
+            x = x.reshape(s)
+            X.append(np.broadcast_to(x, self.shape(False)) if broadcast else x)
         return X
 
     def local_wavenumbers(self, broadcast=False, scaled=False, eliminate_highest_freq=False):
@@ -136,6 +174,7 @@ class TensorProductSpace(object):
             k = np.fft.fftfreq(n, 1./n) if i < 2 else np.fft.rfftfreq(n, 1./n)
             if scaled:
                 k = k*2*np.pi/self.L[i]
+            k = k[self.local_slice(True)[i]]
             s = [1, 1, 1]
             s[i] = len(k)
             k = k.reshape(s)
@@ -143,13 +182,13 @@ class TensorProductSpace(object):
         return K
 
     def get_mask_nyquist(self):
-        mask = np.ones(self.shape(True), dtype=int)
+        mask = np.ones(self.global_shape(True), dtype=int)
         for i, n in enumerate(self.N):
             if n % 2 == 0:
                 s = [slice(None)]*3
                 s[i] = n//2
                 mask[tuple(s)] = 0
-        return mask
+        return np.ascontiguousarray(mask[self.local_slice(True)])
 
     def mask_nyquist(self, u_hat, mask=None):
         u_hat *= (self.get_mask_nyquist() if mask is None else mask)
@@ -172,13 +211,13 @@ class TensorProductSpace(object):
         p = eng.plan
         tp = self._which == _lib.SPACE_TP
         if forward:
-            d_in = eng.upload('fi', np.asarray(src).reshape((ncomp,)+tuple(self.M)), p.float, p.tfloat)
+            d_in = eng.upload('fi', np.asarray(src).reshape((ncomp,)+self.shape(False)), p.float, p.tfloat)
             d_out = eng.stage('fo', (ncomp,)+self.shape(True), p.tcomplex)
             p.use_current_stream()
             p.forward(d_in, out=d_out, padded=tp)
         else:
             d_in = eng.upload('bi', np.asarray(src).reshape((ncomp,)+self.shape(True)), p.complex, p.tcomplex)
-            d_out = eng.stage('bo', (ncomp,)+tuple(self.M), p.tfloat)
+            d_out = eng.stage('bo', (ncomp,)+self.shape(False), p.tfloat)
             p.use_current_stream()
             p.backward(d_in, out=d_out, padded=tp)
         res = d_out.cpu().numpy().reshape(np.shape(dst))
