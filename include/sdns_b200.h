@@ -145,6 +145,15 @@ int sdns_cross1(sdns_plan* plan, void* c, const void* a, const void* b, long lon
 int sdns_cross2_dense(sdns_plan* plan, void* c, const void* a_real, const void* b);
 int sdns_project(sdns_plan* plan, void* u_hat);
 
+/* Building blocks of adaptiveRK (BS5_adaptive / BS5_fixed, maths/integrators.py:15-147,193-225):
+ * out = base + sum_t coeffs[t]*arrays[t] over ncomp spectral components (base may be NULL), and the
+ * per-component error sums sum |err/(atol + max(|u0|,|u1|)*rtol)|^2 of integrators.py:86-92
+ * (synchronous; out[ncomp], local block -- the caller reduces over ranks). */
+int sdns_lincomb(sdns_plan* plan, void* out, const void* base, int nterms, const double* coeffs,
+                 const void* const* arrays, int ncomp);
+int sdns_errnorm(sdns_plan* plan, const void* u0, const void* u1, const void* err, double atol, double rtol,
+                 int ncomp, double* out);
+
 /* shenfun.fourier.energy_fourier(u_hat, T) of ncomp components (tests/TG.py:101,
  * demo/Isotropic.py:67,167-182): Hermitian-weighted sum |u_hat|^2 of the LOCAL block.
  * Synchronous (returns the value). */

@@ -83,6 +83,24 @@ def case_tg(name, margs, fname, nsteps=10):
                         u_hat=u_hat, k=k, w=w)    # u0_hat = forward(taylor_green), regenerated in tests
 
 
+def case_integrator(integrator, fname, margs):
+    """tests/test_NSVV.py:73-92: the same TG problem under every explicit integrator (run to T=0.1;
+    the adaptive one chooses its own steps)."""
+    solver, c = ref_solver('NS', margs + ['--integrator', integrator])
+    p = config.params
+    o = oracle_for(c, p)
+    f0 = so.isotropic_field(o, seed=5)
+    c.u[:] = f0
+    p.t, p.tstep, p.T, p.dt = 0.0, 0, 0.05, 0.005
+    with contextlib.redirect_stdout(io.StringIO()):
+        solve(solver, c)
+    print('%-28s integrator %-13s steps=%d t=%.6f' % (fname, integrator, p.tstep, p.t))
+    np.savez_compressed(os.path.join(OUT, fname), solver='NS', N=p.N, L=p.L, precision=p.precision,
+                        dealias=p.dealias, nu=float(p.nu), dt=0.005, T=0.05, integrator=integrator,
+                        nsteps=int(p.tstep), t_end=float(p.t), u0_hat=f0, u_hat=np.array(c.u))
+    p.dt, p.T, p.integrator = 0.01, 0.1, 'RK4'
+
+
 def case_mhd(margs, fname, nsteps=10):
     """tests/test_MHD.py:32-50 / tests/TGMHD.py:4-26."""
     solver, c = ref_solver('MHD', margs)
@@ -178,3 +196,5 @@ if __name__ == '__main__':
     case_broadband('MHD', m4, 'iso_mhd_16_double', convections=('Divergence',))
     case_broadband('MHD', m4+['--dealias', '3/2-rule'], 'iso_mhd_16_double_pad', convections=('Divergence',))
     case_broadband('MHD', m4+['--precision', 'single'], 'iso_mhd_16_single', convections=('Divergence',))
+    for integ in ('ForwardEuler', 'AB2', 'BS5_fixed', 'BS5_adaptive'):
+        case_integrator(integ, 'integ_ns_16_%s' % integ.lower(), m4)

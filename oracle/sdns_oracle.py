@@ -276,6 +276,63 @@ class Oracle(object):
             un = u0 + (1.5*rhs*dt - 0.5*u1)
         return un.astype(self.complex), (rhs*dt).astype(self.complex)
 
+    def bs5_solve(self, u0, rhs_fn, dt, T, adaptive, TOL=1e-6):
+        """maths/integrators.py:15-147 (adaptiveRK) with the BS5 tableau of :199-208 driven by the
+        time loop of spectralDNS/__init__.py:94-111 and NS.end_of_tstep (solvers/NS.py:112-122).
+        Returns (u, number of steps, t)."""
+        A = np.array([[0, 0, 0, 0, 0, 0, 0, 0],
+                      [1/6, 0, 0, 0, 0, 0, 0, 0],
+                      [2/27, 4/27, 0, 0, 0, 0, 0, 0],
+                      [183/1372, -162/343, 1053/1372, 0, 0, 0, 0, 0],
+                      [68/297, -4/11, 42/143, 1960/3861, 0, 0, 0, 0],
+                      [597/22528, 81/352, 63099/585728, 58653/366080, 4617/20480, 0, 0, 0],
+                      [174197/959244, -30942/79937, 8152137/19744439, 666106/1039181, -29421/29068, 482048/414219, 0, 0],
+                      [587/8064, 0, 4440339/15491840, 24353/124800, 387/44800, 2152/5985, 7267/94080, 0]],
+                     dtype=self.float)
+        b = np.array([587/8064, 0, 4440339/15491840, 24353/124800, 387/44800, 2152/5985, 7267/94080, 0], dtype=self.float)
+        bhat = np.array([2479/34992, 0, 123/416, 612941/3411720, 43/1440, 2272/6561, 79937/1113912, 3293/556956],
+                        dtype=self.float)
+        s = 8
+        u0 = np.array(u0, dtype=self.complex)
+        fY = np.zeros((s,)+u0.shape, dtype=u0.dtype)
+        offset, t, tstep = 0, 0.0, 0
+        dt = self.float(dt)
+        while t + dt <= T + 1e-12:
+            facmax, fac, facmin = 2, 0.8, 0.01
+            while True:
+                dt_prev = dt
+                offset = (offset - 1) % s
+                for i in range(s):
+                    if tstep == 0 or i != 0:
+                        fY[(i+offset) % s] = u0
+                        for j in range(i):
+                            fY[(i+offset) % s] += dt*A[i, j]*fY[(j+offset) % s]
+                        fY[(i+offset) % s] = rhs_fn(fY[(i+offset) % s])
+                u_new = u0.copy()
+                err = np.zeros_like(u0)
+                for j in range(s):
+                    u_new += dt*b[j]*fY[(j+offset) % s]
+                    err += dt*(b[j]-bhat[j])*fY[(j+offset) % s]
+                sc = TOL + np.maximum(np.abs(u0), np.abs(u_new))*TOL
+                nsq = np.array([np.sum(np.power(np.abs(err[k]/sc[k]), 2)) for k in range(u0.shape[0])])
+                est = np.max(np.sqrt(nsq))/np.sqrt(np.prod(self.sshape))
+                factor = min(facmax, max(facmin, fac*pow((1/est), 1.0/5)))
+                if adaptive:
+                    dt = dt*factor
+                    if est > 1.0:
+                        facmax = 1
+                        offset += 1
+                        continue
+                break
+            u0 = u_new
+            t += dt_prev
+            tstep += 1
+            if abs(t - T) < 1e-12:                      # NS.end_of_tstep
+                break
+            if abs(t + dt - T) < 1e-12 or t + dt >= T + 1e-12:
+                dt = self.float(T - t)
+        return u0, tstep, t
+
     def solve(self, u_hat, solver, nsteps, dt, nu, eta=None, convection='Vortex', source=None):
         """nsteps of the while-loop body of spectralDNS/__init__.py:94-98 with RK4."""
         if solver == 'NS':

@@ -103,7 +103,93 @@ def getintegrator(rhs, u0, solver, context):
                           float(params.nu), eta(), src)
             after()
             return u0, params.dt, params.dt
+    elif name in ('BS5_adaptive', 'BS5_fixed'):
+        integrate = _bs5(name == 'BS5_adaptive', rhs, u0, solver, context, dev, before, after, eta)
     else:
-        raise NotImplementedError("integrator %r is not on the B200 path yet (RK4, ForwardEuler, AB2 are)" % name)
+        raise NotImplementedError("unknown integrator %r" % name)
     integrate.__name__ = name
     return integrate
+
+
+# Bogacki-Shampine 5(4) pair, first-same-as-last (the tableau the reference hard-codes at
+# maths/integrators.py:199-208)
+_BS5_A = [[0, 0, 0, 0, 0, 0, 0, 0],
+          [1/6, 0, 0, 0, 0, 0, 0, 0],
+          [2/27, 4/27, 0, 0, 0, 0, 0, 0],
+          [183/1372, -162/343, 1053/1372, 0, 0, 0, 0, 0],
+          [68/297, -4/11, 42/143, 1960/3861, 0, 0, 0, 0],
+          [597/22528, 81/352, 63099/585728, 58653/366080, 4617/20480, 0, 0, 0],
+          [174197/959244, -30942/79937, 8152137/19744439, 666106/1039181, -29421/29068, 482048/414219, 0, 0],
+          [587/8064, 0, 4440339/15491840, 24353/124800, 387/44800, 2152/5985, 7267/94080, 0]]
+_BS5_B = [587/8064, 0, 4440339/15491840, 24353/124800, 387/44800, 2152/5985, 7267/94080, 0]
+_BS5_BHAT = [2479/34992, 0, 123/416, 612941/3411720, 43/1440, 2272/6561, 79937/1113912, 3293/556956]
+
+
+def _bs5(adaptive, rhs, u0, solver, context, dev, before, after, eta):
+    """adaptiveRK of the reference (maths/integrators.py:15-147) with every stage vector resident on
+    the GPU: stage values through sdns_lincomb, right-hand sides through sdns_compute_rhs, the
+    error estimate through sdns_errnorm.  Step-size controller, FSAL rotation (`offset`) and the
+    rejected-step callback protocol are the reference's."""
+    params = solver.params
+    plan = dev.plan
+    fl = context.float
+    A = np.array(_BS5_A, dtype=fl)
+    b = np.array(_BS5_B, dtype=fl)
+    bhat = np.array(_BS5_BHAT, dtype=fl)
+    s = A.shape[0]
+    err_order = 4
+    offset = [0]
+    fY = [plan.empty_spectral(dev.ncomp) for _ in range(s)]
+    ytmp = plan.empty_spectral(dev.ncomp)
+    unew = plan.empty_spectral(dev.ncomp)
+    err = plan.empty_spectral(dev.ncomp)
+    default_cb = getattr(solver.additional_callback, '_sdns_default', False)
+    ntot = float(np.prod(context.T.shape(True)))
+
+    def callback():
+        if not default_cb:
+            dev.device_newer = True
+            dev.sync_to_host()
+            solver.additional_callback(context)
+
+    def integrate():
+        src = before()
+        dt = float(params.dt)
+        tstep = int(params.tstep)
+        aTOL = rTOL = float(params.TOL)
+        facmax, fac, facmin = 2, 0.8, 0.01
+        nu = float(params.nu)
+        while True:
+            dt_prev = dt
+            offset[0] = (offset[0] - 1) % s                       # first-same-as-last rotation
+            for i in range(s):
+                slot = fY[(i + offset[0]) % s]
+                if tstep == 0 or i != 0:
+                    terms = [(dt*float(A[i, j]), fY[(j + offset[0]) % s]) for j in range(i) if A[i, j] != 0]
+                    plan.lincomb(ytmp, dev.u, [c for c, _ in terms], [x for _, x in terms])
+                    plan.compute_rhs(slot, ytmp, nu, eta(), source=src)
+                if i == 0:
+                    if not default_cb:
+                        context.fu0 = slot.cpu().numpy()
+                    callback()
+            plan.lincomb(unew, dev.u, [dt*float(b[j]) for j in range(s)], [fY[(j + offset[0]) % s] for j in range(s)])
+            plan.lincomb(err, None, [dt*float(b[j] - bhat[j]) for j in range(s)],
+                         [fY[(j + offset[0]) % s] for j in range(s)])
+            nsq = plan.errnorm(dev.u, unew, err, aTOL, rTOL)
+            nsq = np.array([solver.comm.allreduce(float(v)) for v in nsq])
+            est = float(np.max(np.sqrt(nsq)))/np.sqrt(ntot)
+            exponent = 1.0/(err_order + 1)
+            factor = min(facmax, max(facmin, fac*pow((1/est), exponent))) if est > 0 else facmax
+            if adaptive:
+                dt = dt*factor
+                if est > 1.0:
+                    facmax = 1
+                    context.is_step_rejected_callback = True
+                    context.dt_rejected = dt_prev
+                    callback()
+                    offset[0] += 1
+                    continue
+            break
+        dev.u.copy_(unew)
+        after()
+        return u0, fl(dt), fl(dt_prev)

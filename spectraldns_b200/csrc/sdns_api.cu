@@ -838,6 +838,86 @@ extern "C" int sdns_project(sdns_plan* p, void* u) {
     return SDNS_OK;
 }
 
+// ---- building blocks of the embedded Runge-Kutta integrator (maths/integrators.py:15-147) ---------
+struct LinArgs { const void* x[9]; double c[9]; int n; };
+
+// out = (base ? base : 0) + sum_t c_t * x_t     (complex arrays of n elements)
+template <typename T>
+__global__ void lincomb_kernel(typename C2<T>::type* out, const typename C2<T>::type* base, LinArgs la, long long n) {
+    typedef typename C2<T>::type V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        V s; s.x = 0; s.y = 0;
+        if (base) s = base[i];
+        for (int t = 0; t < la.n; ++t) {
+            const V v = reinterpret_cast<const V*>(la.x[t])[i];
+            const T c = (T)la.c[t];
+            s.x += c * v.x; s.y += c * v.y;
+        }
+        out[i] = s;
+    }
+}
+
+// per component: sum |err / (atol + max(|u0|,|u1|)*rtol)|^2   (integrators.py:86-92)
+template <typename T>
+__global__ void errnorm_kernel(const typename C2<T>::type* u0, const typename C2<T>::type* u1,
+                               const typename C2<T>::type* err, T atol, T rtol, long long n, double* out) {
+    typedef typename C2<T>::type V;
+    double s = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const V a = u0[i], b = u1[i], e = err[i];
+        const T ma = sqrt(a.x * a.x + a.y * a.y), mb = sqrt(b.x * b.x + b.y * b.y);
+        const T sc = atol + (ma > mb ? ma : mb) * rtol;
+        const T r = sqrt(e.x * e.x + e.y * e.y) / sc;
+        s += (double)r * (double)r;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double ws[32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[blockIdx.x] = s;
+    }
+}
+
+extern "C" int sdns_lincomb(sdns_plan* p, void* out, const void* base, int nterms, const double* coeffs,
+                            const void* const* arrays, int ncomp) {
+    if (!p || !out || nterms < 0 || nterms > 9 || (nterms && (!coeffs || !arrays)) || ncomp < 1)
+        return fail(SDNS_ERR_ARG, "sdns_lincomb: bad argument");
+    LinArgs la; la.n = nterms;
+    for (int t = 0; t < nterms; ++t) { la.x[t] = arrays[t]; la.c[t] = coeffs[t]; }
+    const long long n = (long long)ncomp * p->N[0] * p->N1l * p->Nh;
+    if (p->prec) lincomb_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)out, (const double2*)base, la, n);
+    else lincomb_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)out, (const float2*)base, la, n);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+
+extern "C" int sdns_errnorm(sdns_plan* p, const void* u0, const void* u1, const void* err, double atol, double rtol,
+                            int ncomp, double* out) {
+    int e = need_ws(p); if (e) return e;
+    if (!u0 || !u1 || !err || !out || ncomp < 1) return fail(SDNS_ERR_ARG, "sdns_errnorm: bad argument");
+    const long long n = (long long)p->N[0] * p->N1l * p->Nh;
+    double* red = reinterpret_cast<double*>(p->ws + p->off_red);
+    const int nb = p->red_blocks;
+    std::vector<double> h(nb);
+    for (int k = 0; k < ncomp; ++k) {
+        if (p->prec) errnorm_kernel<double><<<nb, 256, 0, p->stream>>>((const double2*)u0 + k * n, (const double2*)u1 + k * n,
+                                                                       (const double2*)err + k * n, atol, rtol, n, red);
+        else errnorm_kernel<float><<<nb, 256, 0, p->stream>>>((const float2*)u0 + k * n, (const float2*)u1 + k * n,
+                                                              (const float2*)err + k * n, (float)atol, (float)rtol, n, red);
+        p->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(h.data(), red, sizeof(double) * nb, cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        double s = 0; for (int i = 0; i < nb; ++i) s += h[i];
+        out[k] = s;
+    }
+    return SDNS_OK;
+}
+
 // ---- profiling ----------------------------------------------------------------------------
 extern "C" int sdns_profile_enable(sdns_plan* p, int on) {
     if (!p) return fail(SDNS_ERR_ARG, "null plan");

@@ -234,6 +234,23 @@ class Plan(object):
         _lib.check(self.lib.sdns_project(self._p, u_hat.data_ptr()))
         return u_hat
 
+    def lincomb(self, out, base, coeffs, arrays):
+        """out = base + sum_t coeffs[t]*arrays[t] (base may be None); <= 9 terms."""
+        n = len(coeffs)
+        cs = (C.c_double*max(n, 1))(*[float(c) for c in coeffs])
+        ps = (C.c_void_p*max(n, 1))(*[a.data_ptr() for a in arrays])
+        nc = out.numel() // int(np.prod(self.spectral_shape))
+        _lib.check(self.lib.sdns_lincomb(self._p, out.data_ptr(), base.data_ptr() if base is not None else None,
+                                         n, cs, ps, nc))
+        return out
+
+    def errnorm(self, u0, u1, err, atol, rtol):
+        nc = u0.numel() // int(np.prod(self.spectral_shape))
+        out = (C.c_double*nc)()
+        _lib.check(self.lib.sdns_errnorm(self._p, u0.data_ptr(), u1.data_ptr(), err.data_ptr(), float(atol),
+                                         float(rtol), nc, out))
+        return np.array(out[:])
+
     def energy(self, u_hat):
         nc = self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat')
         out = C.c_double()

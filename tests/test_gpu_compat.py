@@ -87,7 +87,7 @@ def test_tg_solvers(sdns, name, mesh, tmp_path, monkeypatch):
     config.params.T = 0.1
 
 
-@pytest.mark.parametrize('integrator,ntol', [('RK4', 7), ('ForwardEuler', 4), ('AB2', 4)])
+@pytest.mark.parametrize('integrator,ntol', [('RK4', 7), ('ForwardEuler', 4), ('AB2', 4), ('BS5_adaptive', 7), ('BS5_fixed', 7)])
 def test_integrators(sdns, integrator, ntol):
     """tests/test_NSVV.py:73-92 of the reference (the explicit fixed-step integrators)."""
     config, get_solver, solve = sdns.config, sdns.get_solver, sdns.solve
@@ -100,6 +100,25 @@ def test_integrators(sdns, integrator, ntol):
     tg_initialize(solver, context, config)
     solve(solver, context)
     config.params.ntol, config.params.integrator = 7, 'RK4'
+
+
+@pytest.mark.parametrize('integrator', ['ForwardEuler', 'AB2', 'BS5_fixed', 'BS5_adaptive'])
+def test_integrator_fields_match_reference(sdns, integrator):
+    """Field-level parity of every explicit integrator with the reference's own
+    (maths/integrators.py:15-175) on a broadband field, fixtures integ_ns_16_*."""
+    config, get_solver, solve = sdns.config, sdns.get_solver, sdns.solve
+    g = golden('integ_ns_16_' + integrator.lower())
+    config.update({'nu': float(g['nu']), 'dt': float(g['dt']), 'T': float(g['T']), 'convection': 'Vortex'})
+    solver = get_solver(regression_test=lambda c: None, parse_args=MESH['uniform'] + ['--integrator', integrator, 'NS'])
+    c = solver.get_context()
+    c.U_hat[:] = g['u0_hat']
+    config.params.t, config.params.tstep = 0.0, 0
+    solve(solver, c)
+    assert config.params.tstep == int(g['nsteps'])
+    assert abs(config.params.t - float(g['t_end'])) < 1e-12
+    assert rel_l2(np.array(c.U_hat), g['u_hat']) < 1e-10
+    config.update({'nu': 0.000625, 'dt': 0.01, 'T': 0.1})
+    config.params.integrator = 'RK4'
 
 
 def test_update_callback_sees_current_fields(sdns):
@@ -244,6 +263,6 @@ def test_reference_scripts_run_unchanged(tmp_path):
     rc, out = _run([py, os.path.join(ref, 'demo', 'Isotropic.py'), '--N', '32', '32', '32', '--T', '0.02',
                     '--compute_energy', '5', 'NS'], str(tmp_path))
     assert rc == 0, out[-3000:]
-    rc, out = _run([py, '-m', 'pytest', '-x', '-q', os.path.join(ref, 'tests', 'test_NSVV.py'), '-k', 'test_solvers',
+    rc, out = _run([py, '-m', 'pytest', '-x', '-q', os.path.join(ref, 'tests', 'test_NSVV.py'),
                     os.path.join(ref, 'tests', 'test_MHD.py'), '-p', 'no:cacheprovider'], str(tmp_path))
     assert rc == 0, out[-4000:]

@@ -12,7 +12,8 @@ import sdns_oracle as so
 pytestmark = pytest.mark.gpu
 
 TOL = {'double': 1e-11, 'single': 1e-4}
-ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, '*.npz')))
+ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, '*.npz'))
+             if not os.path.basename(f).startswith('integ_'))
 
 
 def make_plan(N, L=(2*np.pi,)*3, precision='double', dealias='2/3-rule', solver='NS', mask_nyquist=True):
