@@ -193,3 +193,5 @@ def _bs5(adaptive, rhs, u0, solver, context, dev, before, after, eta):
         dev.u.copy_(unew)
         after()
         return u0, fl(dt), fl(dt_prev)
+
+    return integrate
