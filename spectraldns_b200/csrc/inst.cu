@@ -42,8 +42,44 @@ static int run_mhd_f0(const StridedArgs<T>& a, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+template <typename T, int M, int QN>
+static int run_zx_q(const ZArgs<T>& a, cudaStream_t st) {
+    typedef ZXCfg<T, M> C;
+    auto kern = zx_kernel<T, M, C::E, C::LPC, QN, C::minBlocks>;
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e;
+        int dev = 0, nsm = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * C::LPC, C::smem);
+        if (e != cudaSuccess) return (int)e;
+        blocks_per_sm = (occ > 0 ? occ : 1) * nsm;
+    }
+    const long long want = (a.nlines + C::LPC - 1) / C::LPC;
+    dim3 grid((unsigned)(want < blocks_per_sm ? want : blocks_per_sm));
+    kern<<<grid, 32 * C::LPC, C::smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int M>
+static int run_zx(const ZArgs<T>& a, cudaStream_t st) {
+    typedef ZXCfg<T, M> C;
+    if constexpr (C::ok) {
+        if (a.nin_keep <= 32 * C::QN3) return run_zx_q<T, M, C::QN3>(a, st);
+        return run_zx_q<T, M, C::QN2>(a, st);
+    } else {
+        return -1;
+    }
+}
+
 template <typename T, int M, int MODE>
 static int run_z(const ZArgs<T>& a, cudaStream_t st) {
+    if constexpr (MODE == Z_CROSS && ZXCfg<T, M>::ok) {
+#ifndef SDNS_NO_ZX
+        return run_zx<T, M>(a, st);
+#endif
+    }
     typedef ZCfg<T, M, MODE> C;
     static_assert(plan_ok(M, C::E), "no radix plan");
     auto kern = z_kernel<T, M, C::E, C::LPC, MODE, C::SYNC, C::NBUF, (C::minBlocks < 1 ? 1 : C::minBlocks)>;

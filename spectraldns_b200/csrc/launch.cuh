@@ -86,6 +86,22 @@ struct ZCfg {
                                                        65536 / (P * LPC * needRegs)), 4));
 };
 
+// warp-per-line fused z kernel (zx_kernel): available when M/E == 32
+template <typename T, int M>
+struct ZXCfg {
+    static constexpr int E = M / 32;
+    static constexpr bool ok = (M % 32 == 0) && (E == 8 || E == 12 || E == 16 || E == 24 || E == 32) && plan_ok(M, E)
+                               && (sizeof(T) == 4 || E <= 12);
+    static constexpr int LPC = 4;
+    static constexpr int PADW = 128 / (2 * (int)sizeof(T));
+    static constexpr int LP = M + M / PADW + 1;
+    static constexpr size_t smem = ((size_t)LP * LPC + (size_t)2 * E * 32 * LPC) * 2 * sizeof(T);
+    static constexpr int QN3 = (M / 3 + 2 + 31) / 32;        // covers the 2/3-rule and 3/2-rule mode counts
+    static constexpr int QN2 = E / 2 + 1;                    // all M/2+1 modes
+    static constexpr int needRegs = sizeof(T) == 8 ? (E > 8 ? 255 : 168) : (E > 16 ? 255 : (E > 8 ? 168 : 128));
+    static constexpr int minBlocks = cmax(1, cmin(cmin((int)((216 * 1024) / (smem + 1024)), 16), 65536 / (128 * needRegs)));
+};
+
 template <typename K>
 inline cudaError_t set_smem(K kern, size_t smem) {
     if (smem > 48 * 1024)

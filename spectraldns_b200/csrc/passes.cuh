@@ -578,6 +578,156 @@ z_kernel(const ZArgs<T> a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fused z-pass for lines that live in ONE warp (P = M/E = 32), NS / VV cross product.
+//   * every spectral element is read from HBM exactly once: thread t keeps the raw modes
+//     kk = t + 32 q' (q' < QN); the Hermitian mirror A[M-k] needed by the two-lines-per-FFT
+//     packing sits in lane (32-t)%32 and comes over with a warp shuffle, as does the mirror of
+//     the r2c unpack -- no second global read, no shared-memory round trip;
+//   * persistent warps, software pipelined: the loads of the next pair (or of the next line's
+//     first pair) are in flight while the current pair is transformed;
+//   * two of the three real-space pairs are parked in thread-private shared-memory slots.
+// ---------------------------------------------------------------------------------------
+template <typename V> __device__ __forceinline__ V shfl_c(V v, int src) {
+    V r; r.x = __shfl_sync(0xffffffffu, v.x, src); r.y = __shfl_sync(0xffffffffu, v.y, src); return r;
+}
+
+template <typename T, int QN, typename V>
+__device__ __forceinline__ void zx_load_raw(V (&raw)[2 * QN], const V* __restrict__ A, const V* __restrict__ B,
+                                            int t, int nkeep) {
+#pragma unroll
+    for (int q = 0; q < QN; ++q) {
+        const int kk = t + 32 * q;
+        if (kk < nkeep) { raw[2 * q] = A[kk]; raw[2 * q + 1] = B[kk]; }
+        else { raw[2 * q] = czero<V>(); raw[2 * q + 1] = czero<V>(); }
+    }
+}
+
+// x[q] = Za[k] + i Zb[k], k = t + 32 q, from the raw half spectra (see load_pair for the algebra)
+template <typename T, int E, int QN, typename V>
+__device__ __forceinline__ void zx_build(V (&x)[E], const V (&raw)[2 * QN], int t) {
+    const int src = (32 - t) & 31;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        V va = czero<V>(), vb = czero<V>();
+        if (q < E / 2) {
+            if (q < QN) { va = raw[2 * q]; vb = raw[2 * q + 1]; }
+        } else {
+            // mirror: k > M/2 -> element M-k = (32-t) + 32 (E-1-q), held by lane (32-t)%32 in slot E-1-q;
+            // lane 0 holds its own mirror 32 (E-q) in slot E-q
+            constexpr int dummy = 0; (void)dummy;
+            const int sq = E - 1 - q;
+            V ma = czero<V>(), mb = czero<V>();
+            if (sq < QN) { ma = shfl_c(raw[2 * (sq < QN ? sq : 0)], src); mb = shfl_c(raw[2 * (sq < QN ? sq : 0) + 1], src); }
+            V oa = czero<V>(), ob = czero<V>();
+            if (E - q < QN) { oa = raw[2 * (E - q < QN ? E - q : 0)]; ob = raw[2 * (E - q < QN ? E - q : 0) + 1]; }
+            if (q == E / 2) {
+                if (t == 0) { va = oa; vb = ob; }               // k = M/2: direct, slot E/2
+                else { va = cconj(ma); vb = cconj(mb); }
+            } else {
+                va = cconj(t == 0 ? oa : ma); vb = cconj(t == 0 ? ob : mb);
+            }
+        }
+        if (t == 0 && (q == 0 || q == E / 2)) { va.y = 0; vb.y = 0; }   // c2r ignores Im of DC / Nyquist
+        x[q].x = va.x - vb.y; x[q].y = va.y + vb.x;
+    }
+}
+
+// r2c unpack with the mirror from shuffles: x = FFT(c + i d); stores C[k], D[k] for k <= M/2, k < nk
+template <typename T, int E, typename V>
+__device__ __forceinline__ void zx_unpack_store(const V (&x)[E], V* __restrict__ C, V* __restrict__ D,
+                                                int t, int nk, T s) {
+    const int src = (32 - t) & 31;
+    const T h = (T)0.5 * s;
+#pragma unroll
+    for (int q = 0; q <= E / 2; ++q) {
+        V zm;
+        if (q < E / 2) {
+            const V sh = shfl_c(x[E - 1 - q], src);
+            zm = (t == 0) ? x[(E - q) % E] : sh;
+        } else {
+            zm = x[E / 2];                                   // only lane 0 stores k = M/2
+        }
+        const int k = t + 32 * q;
+        if ((q < E / 2 || t == 0) && k < nk) {
+            V c, d;
+            c.x = h * (x[q].x + zm.x); c.y = h * (x[q].y - zm.y);
+            d.x = h * (x[q].y + zm.y); d.y = -h * (x[q].x - zm.x);
+            C[k] = c;
+            D[k] = d;
+        }
+    }
+}
+
+template <typename T, int M, int E, int LPC, int QN, int MINB>
+__global__ void __launch_bounds__(32 * LPC, MINB)
+zx_kernel(const ZArgs<T> a) {
+    typedef typename C2<T>::type V;
+    static_assert(M / E == 32, "one warp per line");
+    extern __shared__ __align__(16) unsigned char smraw[];
+    V* sm = reinterpret_cast<V*>(smraw);
+    constexpr int PADW = 128 / (int)sizeof(V);
+    constexpr int LP = M + M / PADW + 1;
+    const int t = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    V* ex = sm + w * LP;                                   // this warp's exchange line
+    V* park = sm + LPC * LP + w * (2 * E * 32);            // this warp's parking slots [2E][32]
+    T* park_r = reinterpret_cast<T*>(park);
+    SmemLine<1, PADW> map; map.base = 0;
+    int phase = 0;
+    const V* in = reinterpret_cast<const V*>(a.in);
+    V* out = reinterpret_cast<V*>(a.out);
+    const long long stride = (long long)gridDim.x * LPC;
+    long long line = (long long)blockIdx.x * LPC + w;
+    V nxt[2 * QN];
+    if (line < a.nlines)
+        zx_load_raw<T, QN>(nxt, in + line * a.in_ls, in + a.in_fs + line * a.in_ls, t, a.nin_keep);
+    for (; line < a.nlines; line += stride) {
+        V x[E];
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+            V raw[2 * QN];
+#pragma unroll
+            for (int i = 0; i < 2 * QN; ++i) raw[i] = nxt[i];
+            if (pr < 2) {
+                zx_load_raw<T, QN>(nxt, in + (2 * pr + 2) * a.in_fs + line * a.in_ls,
+                                   in + (2 * pr + 3) * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            } else if (line + stride < a.nlines) {
+                zx_load_raw<T, QN>(nxt, in + (line + stride) * a.in_ls, in + a.in_fs + (line + stride) * a.in_ls,
+                                   t, a.nin_keep);
+            }
+            zx_build<T, E, QN>(x, raw, t);
+            fft_line<T, M, E, +1, 1, 1>(x, t, a.tw, ex, map, 0, phase);
+            if (pr < 2) {
+#pragma unroll
+                for (int q = 0; q < E; ++q) park[(pr * E + q) * 32 + t] = x[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const V p01 = park[q * 32 + t], p23 = park[(E + q) * 32 + t];
+            const T a0 = p01.x, a1 = p01.y, a2 = p23.x;
+            const T b0 = p23.y, b1 = x[q].x, b2 = x[q].y;
+            x[q].x = a1 * b2 - a2 * b1;                      // c = a x b (cross1)
+            x[q].y = a2 * b0 - a0 * b2;
+            park_r[2 * (q * 32 + t)] = a0 * b1 - a1 * b0;
+        }
+        fft_line<T, M, E, -1, 1, 1>(x, t, a.tw, ex, map, 0, phase);
+        zx_unpack_store<T, E>(x, out + line * a.out_ls, out + a.out_fs + line * a.out_ls, t, a.nout_keep, a.scale);
+#pragma unroll
+        for (int q = 0; q < E; ++q) { x[q].x = park_r[2 * (q * 32 + t)]; x[q].y = (T)0; }
+        fft_line<T, M, E, -1, 1, 1>(x, t, a.tw, ex, map, 0, phase);
+        V* C = out + 2 * a.out_fs + line * a.out_ls;
+#pragma unroll
+        for (int q = 0; q <= E / 2; ++q) {
+            const int k = t + 32 * q;
+            if ((q < E / 2 || t == 0) && k < a.nout_keep) C[k] = cscale<T>(x[q], a.scale);
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Hermitian-weighted sum |u_hat|^2 (shenfun.fourier.energy_fourier as used by tests/TG.py:101)
 // ---------------------------------------------------------------------------------------
