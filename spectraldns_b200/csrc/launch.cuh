@@ -31,12 +31,22 @@ constexpr int pick_E(int N, int emax) {
     return e;
 }
 
+// fp64 strided kernels: P <= 64 threads per line (E up to 16) and CTAs of at most 256 threads, so that
+// three or four CTAs are resident per SM and their load / transform / store phases overlap
+constexpr int pick_E64(int N) {
+    const int b = (N % 3 == 0) ? 12 : 8;
+    int e = b;
+    while (N / e > 64 && 2 * e <= 16 + (b == 12 ? 8 : 0) && plan_ok(N, 2 * e)) e *= 2;
+    while (N / e > 128 && plan_ok(N, 2 * e)) e *= 2;
+    return e;
+}
+
 template <typename T, int N, int MODE>
 struct SCfg {
     static constexpr bool heavy = (MODE == S_NS_F0 || MODE == S_VV_F0);   // park two fields in smem
-    static constexpr int E = pick_E(N, sizeof(T) == 8 ? 8 : (heavy ? 16 : 24));
+    static constexpr int E = sizeof(T) == 8 ? (heavy ? pick_E(N, 8) : pick_E64(N)) : pick_E(N, heavy ? 16 : 24);
     static constexpr int P = N / E;
-    static constexpr int maxThreads = sizeof(T) == 8 ? (heavy ? 256 : 512) : (heavy ? 512 : 1024);
+    static constexpr int maxThreads = sizeof(T) == 8 ? 256 : (heavy ? 512 : 1024);
     static constexpr int TCfull = 128 / (2 * (int)sizeof(T));
     static constexpr int TC = cmin(TCfull, cmax(1, maxThreads / P));
     static constexpr size_t bytes1 = (size_t)N * TC * 2 * sizeof(T);

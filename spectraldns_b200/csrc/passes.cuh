@@ -24,6 +24,9 @@ struct AxisMap { int nlo, nhi, shift; };
 __device__ __forceinline__ int axis_mem(const AxisMap& a, int M, int j) {
     return j < a.nlo ? j : (j >= M - a.nhi ? j - a.shift : -1);
 }
+// branch-free form: memory index (garbage when !ok) and validity
+__device__ __forceinline__ int axis_idx(const AxisMap& a, int j) { return j < a.nlo ? j : j - a.shift; }
+__device__ __forceinline__ bool axis_ok(const AxisMap& a, int M, int j) { return j < a.nlo || j >= M - a.nhi; }
 
 enum StridedMode { S_PLAIN = 0, S_NS_B0 = 1, S_VV_B0 = 2, S_NS_F0 = 3, S_VV_F0 = 4, S_MHD_F0 = 5 };
 enum ZMode { Z_C2R = 0, Z_R2C = 1, Z_CROSS = 2, Z_MHD = 3 };
@@ -68,16 +71,6 @@ struct StridedArgs {
 
 template <typename V> __device__ __forceinline__ V czero() { V z; z.x = 0; z.y = 0; return z; }
 
-// address of output element (field f, line index i) of the column whose base offset is obase
-template <typename T>
-__device__ __forceinline__ typename C2<T>::type* out_addr(const StridedArgs<T>& a, int f, int i, long long obase) {
-    if (a.xchunk > 0) {
-        const int dest = i / a.xchunk;
-        const int il = i - dest * a.xchunk;
-        return a.peer_out[dest] + (f * a.out_fs + (long long)il * a.out_ls + obase);
-    }
-    return a.out + (f * a.out_fs + (long long)i * a.out_ls + obase);
-}
 template <typename T, typename V> __device__ __forceinline__ V cscale(V a, T s) { a.x *= s; a.y *= s; return a; }
 
 // i*(ka*b - kb*a) for real ka,kb, complex a,b   (one component of cross2)
@@ -85,6 +78,64 @@ template <typename T, typename V>
 __device__ __forceinline__ V icross(T ka, V b, T kb, V a) {
     // (ka*b - kb*a) * i = ( -(ka*b.y - kb*a.y), ka*b.x - kb*a.x )
     V r; r.x = -(ka * b.y - kb * a.y); r.y = ka * b.x - kb * a.x; return r;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// L2 prefetch of one transform line (costs issue slots but no registers): used where a kernel reads
+// several fields one after the other, so that only the first one pays DRAM latency.
+template <typename T, int N, int E, typename V>
+__device__ __forceinline__ void prefetch_line(const V* __restrict__ pin, long long ls, const AxisMap& m, int t, bool valid) {
+    constexpr int P = N / E;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int j = t + q * P;
+        if (valid && axis_ok(m, N, j)) prefetch_l2(pin + (long long)axis_idx(m, j) * ls);
+    }
+}
+
+// Loads of one transform line: base pointer hoisted, predicated LDG, no branches.
+template <typename T, int N, int E, typename V>
+__device__ __forceinline__ void load_line(V (&x)[E], const V* __restrict__ pin, long long ls, const AxisMap& m,
+                                          int t, bool valid) {
+    constexpr int P = N / E;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int j = t + q * P;
+        const long long off = (long long)axis_idx(m, j) * ls;
+        V v = czero<V>();
+        if (valid && axis_ok(m, N, j)) v = pin[off];
+        x[q] = v;
+    }
+}
+
+// Stores of one transform line.  Single GPU: pout + i*ls.  Slab decomposition: element i goes to
+// rank i / xchunk (reciprocal multiply, exact for i < 2^22) at line index i % xchunk.
+template <typename T, int N, int E, bool SCALE, typename V>
+__device__ __forceinline__ void store_line(const V (&x)[E], const StridedArgs<T>& a, int f, long long obase,
+                                           int t, bool valid, T scale) {
+    constexpr int P = N / E;
+    const long long fo = f * a.out_fs + obase;
+    if (a.xchunk == 0) {
+        V* pout = a.out + fo;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int j = t + q * P;
+            const long long off = (long long)axis_idx(a.omap, j) * a.out_ls;
+            if (valid && axis_ok(a.omap, N, j)) pout[off] = SCALE ? cscale<T>(x[q], scale) : x[q];
+        }
+    } else {
+        const float inv = 1.0f / (float)a.xchunk;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int j = t + q * P;
+            const int i = axis_idx(a.omap, j);
+            const int dest = __float2int_rz(((float)i + 0.5f) * inv);
+            const int il = i - dest * a.xchunk;
+            if (valid && axis_ok(a.omap, N, j))
+                a.peer_out[dest][fo + (long long)il * a.out_ls] = SCALE ? cscale<T>(x[q], scale) : x[q];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -114,58 +165,51 @@ strided_kernel(const StridedArgs<T> a) {
     if (MODE == S_PLAIN) {
         const int f = blockIdx.y;
         V x[E];
-#pragma unroll
-        for (int q = 0; q < E; ++q) {
-            const int i = axis_mem(a.imap, N, t + q * P);
-            x[q] = (valid && i >= 0) ? a.in[f * a.in_fs + (long long)i * a.in_ls + ibase] : czero<V>();
-        }
+        load_line<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
         fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-#pragma unroll
-        for (int q = 0; q < E; ++q) {
-            const int i = axis_mem(a.omap, N, t + q * P);
-            if (valid && i >= 0) *out_addr<T>(a, f, i, obase) = cscale<T>(x[q], a.scale);
-        }
+        store_line<T, N, E, true>(x, a, f, obase, t, valid, a.scale);
     } else if (MODE == S_NS_B0 || MODE == S_VV_B0) {
         // in: 3 dense spectral fields.  out: 6 fields (NS: u_hat, i k x u_hat ; VV: i k x w_hat / k^2, w_hat)
         const T k1 = valid ? a.ky[c1m] : (T)0;
         const T k2 = valid ? a.kz[c2] : (T)0;
+        const V* pin = a.in + ibase;
+#ifndef SDNS_NO_PREFETCH
+        prefetch_line<T, N, E>(pin + a.in_fs, a.in_ls, a.imap, t, valid);
+        prefetch_line<T, N, E>(pin + 2 * a.in_fs, a.in_ls, a.imap, t, valid);
+#endif
 #pragma unroll 1
         for (int f = 0; f < 6; ++f) {
             V x[E];
             const bool direct = (MODE == S_NS_B0) ? (f < 3) : (f >= 3);
             const int g = f % 3;               // component
             const int ga = (g + 1) % 3, gb = (g + 2) % 3;
+            if (direct) {
+                load_line<T, N, E>(x, pin + g * a.in_fs, a.in_ls, a.imap, t, valid);
+            } else {
+                // component g of i*(K x b) = i*(K[ga]*b[gb] - K[gb]*b[ga])
+                const V* pa = pin + ga * a.in_fs;
+                const V* pb = pin + gb * a.in_fs;
 #pragma unroll
-            for (int q = 0; q < E; ++q) {
-                const int i = axis_mem(a.imap, N, t + q * P);
-                V v = czero<V>();
-                if (valid && i >= 0) {
-                    const long long off = (long long)i * a.in_ls + ibase;
-                    if (direct) {
-                        v = a.in[g * a.in_fs + off];
-                    } else {
-                        // component g of i*(K x b) = i*(K[ga]*b[gb] - K[gb]*b[ga])
-                        const T k0 = a.kx[i];
-                        T ka = ga == 0 ? k0 : (ga == 1 ? k1 : k2);
-                        T kb = gb == 0 ? k0 : (gb == 1 ? k1 : k2);
-                        if (MODE == S_VV_B0) {
-                            T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;   // NS.py:42-44
-                            if (ksq == (T)0) ksq = (T)1;                        // NS.py:46-48
-                            ka = ka / ksq; kb = kb / ksq;                       // K_over_K2
-                        }
-                        const V bb = a.in[gb * a.in_fs + off];
-                        const V ba = a.in[ga * a.in_fs + off];
-                        v = icross<T, V>(ka, bb, kb, ba);
+                for (int q = 0; q < E; ++q) {
+                    const int j = t + q * P;
+                    const int i = axis_idx(a.imap, j);
+                    const bool ok = valid && axis_ok(a.imap, N, j);
+                    const long long off = (long long)i * a.in_ls;
+                    V bb = czero<V>(), ba = czero<V>();
+                    T k0 = (T)0;
+                    if (ok) { bb = pb[off]; ba = pa[off]; k0 = a.kx[i]; }
+                    T ka = ga == 0 ? k0 : (ga == 1 ? k1 : k2);
+                    T kb = gb == 0 ? k0 : (gb == 1 ? k1 : k2);
+                    if (MODE == S_VV_B0) {
+                        T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;   // NS.py:42-44
+                        if (ksq == (T)0) ksq = (T)1;                        // NS.py:46-48
+                        ka = ka / ksq; kb = kb / ksq;                       // K_over_K2
                     }
+                    x[q] = icross<T, V>(ka, bb, kb, ba);
                 }
-                x[q] = v;
             }
             fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                const int i = axis_mem(a.omap, N, t + q * P);
-                if (valid && i >= 0) *out_addr<T>(a, f, i, obase) = x[q];
-            }
+            store_line<T, N, E, false>(x, a, f, obase, t, valid, (T)1);
         }
     } else if (MODE == S_NS_F0 || MODE == S_VV_F0) {
         // Three forward transforms; the results of the first two are parked in thread-private
@@ -177,11 +221,7 @@ strided_kernel(const StridedArgs<T> a) {
         V x[E];
 #pragma unroll 1
         for (int f = 0; f < 3; ++f) {
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                const int i = axis_mem(a.imap, N, t + q * P);
-                x[q] = (valid && i >= 0) ? a.in[f * a.in_fs + (long long)i * a.in_ls + ibase] : czero<V>();
-            }
+            load_line<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
             fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
             if (f < 2) {
 #pragma unroll
@@ -299,11 +339,7 @@ mhd_f0_kernel(const StridedArgs<T> a) {
     for (int ij = 0; ij < 9; ++ij) {
         const int i = ij / 3, j = ij % 3;
         V x[E];
-#pragma unroll
-        for (int q = 0; q < E; ++q) {
-            const int m = axis_mem(a.imap, N, t + q * P);
-            x[q] = (valid && m >= 0) ? a.in[ij * a.in_fs + (long long)m * a.in_ls + ibase] : czero<V>();
-        }
+        load_line<T, N, E>(x, a.in + (ij * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
         fft_line<T, N, E, -1, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
 #pragma unroll
         for (int q = 0; q < E; ++q) {
