@@ -46,7 +46,9 @@ struct SCfg {
     static constexpr bool heavy = (MODE == S_NS_F0 || MODE == S_VV_F0);   // park two fields in smem
     static constexpr int E = sizeof(T) == 8 ? (heavy ? pick_E(N, 8) : pick_E64(N)) : pick_E(N, heavy ? 16 : 24);
     static constexpr int P = N / E;
-    static constexpr int maxThreads = sizeof(T) == 8 ? 256 : (heavy ? 512 : 1024);
+    // the passes that store into peer GPUs (B0 family) keep 128-byte rows: NVLink likes the larger packets
+    static constexpr bool b0m = (MODE == S_NS_B0 || MODE == S_VV_B0);
+    static constexpr int maxThreads = sizeof(T) == 8 ? (b0m ? 512 : 256) : (heavy ? 512 : 1024);
     static constexpr int TCfull = 128 / (2 * (int)sizeof(T));
     static constexpr int TC = cmin(TCfull, cmax(1, maxThreads / P));
     static constexpr size_t bytes1 = (size_t)N * TC * 2 * sizeof(T);
