@@ -171,7 +171,8 @@ int sdns_launch_count(const sdns_plan* plan, long long* count);
 /* Measurement aid (no reference counterpart; the reference's own metric is Timer, utilities/__init__.py:18-68):
  * with profiling on, every kernel launch is bracketed by CUDA events on the plan stream.
  * sdns_profile_read returns, per kernel family (0 plain fwd c2c, 1 plain bwd c2c, 2 NS B0, 3 VV B0,
- * 4 NS F0, 5 VV F0, 6 MHD F0, 7 c2r, 8 r2c, 9 fused z cross, 10 fused z MHD), the summed device
+ * 4 NS F0, 5 VV F0, 6 MHD F0, 7 c2r, 8 r2c, 9 fused z cross, 10 fused z MHD, 11 NS gradient B0,
+ * 12 z dot product, 13 z symmetric products, 14 NS divergence-form F0), the summed device
  * time, the launch count and the summed algorithmic HBM bytes since sdns_profile_enable. */
 int sdns_profile_enable(sdns_plan* plan, int on);
 int sdns_profile_read(sdns_plan* plan, int family, double* total_ms, long long* launches, double* bytes);

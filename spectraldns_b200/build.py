@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libsdns_b200.so')
-NFAM = 11
+NFAM = 15
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

@@ -91,10 +91,11 @@ def compute_curl(c, a, work, T, K):
 
 
 def getConvection(convection):
-    """Nonlinear term selector.  'Vortex' (u x curl u, the default) is compiled into the CUDA
-    pipeline; the other three forms of the reference are not on the B200 path yet."""
-    if convection != 'Vortex':
-        raise NotImplementedError("NS convection %r is not on the B200 path (use 'Vortex')" % convection)
+    """Nonlinear term selector: 'Vortex' u x curl(u) (default), 'Standard' u_j du_i/dx_j,
+    'Divergence' d(u_i u_j)/dx_j, 'Skewed' their mean -- all compiled into the CUDA pipeline
+    (kernel families ns_b0/z_cross, ns_grad_b0/z_dot, z_uu/nsdiv_f0)."""
+    if convection not in ('Vortex', 'Standard', 'Divergence', 'Skewed'):
+        raise NotImplementedError(convection)
     return _common.Convection(convection)
 
 

@@ -14,8 +14,9 @@ def build_spaces(comm, params, float_, solver_name):
     V = [FunctionSpace(params.N[i], 'F', domain=(0, params.L[i]),
                        dtype=(float_ if i == dim-1 else (np.complex64 if float_ == np.float32 else np.complex128)))
          for i in range(dim)]
+    conv = params.convection if solver_name == 'NS' else None      # VV: Vortex, MHD: Divergence only
     eng = Engine.get(params.N, params.L, params.precision, params.dealias, solver_name,
-                     params.mask_nyquist, params.decomposition)
+                     params.mask_nyquist, params.decomposition, conv)
     T = TensorProductSpace(comm, V, dtype=float_, slab=(params.decomposition == 'slab'),
                            engine=eng, which=0, solver=solver_name, mask_nyquist=params.mask_nyquist)
     Tp = T.get_dealiased(padding_factor=1.5 if params.dealias == '3/2-rule' else 1,
@@ -68,6 +69,8 @@ def run_rhs(dev, rhs, u_hat, source, want_p):
     """ComputeRHS on host arrays: stage in, five kernel launches, stage out."""
     params = config.params
     plan = dev.plan
+    if plan.solver == 'NS' and params.convection != plan.convection:
+        raise RuntimeError('params.convection changed after get_context(): the CUDA plan was built for %r' % plan.convection)
     plan.use_current_stream()
     d_u = dev.device_input(u_hat)
     src = dev.refresh_source(source)

@@ -42,6 +42,18 @@ static int run_mhd_f0(const StridedArgs<T>& a, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+template <typename T, int N>
+static int run_nsdiv_f0(const StridedArgs<T>& a, cudaStream_t st) {
+    typedef MCfg<T, N> C;
+    static_assert(plan_ok(N, C::E), "no radix plan");
+    auto kern = nsdiv_f0_kernel<T, N, C::E, C::TC, C::NBUF>;
+    static bool once = false;
+    if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
+    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC));
+    kern<<<grid, C::P * C::TC, C::smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
 template <typename T, int M, int QN>
 static int run_zx_q(const ZArgs<T>& a, cudaStream_t st) {
     typedef ZXCfg<T, M> C;
@@ -115,6 +127,14 @@ int SDNS_FN(int n, const void* args, cudaStream_t st) {
 #define X(N) case N: return run_z<T, N, Z_CROSS>(*(const ZArgs<T>*)args, st);
 #elif SDNS_FAMILY == 10
 #define X(N) case N: return run_z<T, N, Z_MHD>(*(const ZArgs<T>*)args, st);
+#elif SDNS_FAMILY == 11
+#define X(N) case N: return run_strided<T, N, S_NS_GRAD_B0, +1>(*(const StridedArgs<T>*)args, st);
+#elif SDNS_FAMILY == 12
+#define X(N) case N: return run_z<T, N, Z_DOT>(*(const ZArgs<T>*)args, st);
+#elif SDNS_FAMILY == 13
+#define X(N) case N: return run_z<T, N, Z_UU>(*(const ZArgs<T>*)args, st);
+#elif SDNS_FAMILY == 14
+#define X(N) case N: return run_nsdiv_f0<T, N>(*(const StridedArgs<T>*)args, st);
 #endif
         SDNS_SIZES(X)
 #undef X

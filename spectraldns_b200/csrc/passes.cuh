@@ -28,8 +28,8 @@ __device__ __forceinline__ int axis_mem(const AxisMap& a, int M, int j) {
 __device__ __forceinline__ int axis_idx(const AxisMap& a, int j) { return j < a.nlo ? j : j - a.shift; }
 __device__ __forceinline__ bool axis_ok(const AxisMap& a, int M, int j) { return j < a.nlo || j >= M - a.nhi; }
 
-enum StridedMode { S_PLAIN = 0, S_NS_B0 = 1, S_VV_B0 = 2, S_NS_F0 = 3, S_VV_F0 = 4, S_MHD_F0 = 5 };
-enum ZMode { Z_C2R = 0, Z_R2C = 1, Z_CROSS = 2, Z_MHD = 3 };
+enum StridedMode { S_PLAIN = 0, S_NS_B0 = 1, S_VV_B0 = 2, S_NS_F0 = 3, S_VV_F0 = 4, S_MHD_F0 = 5, S_NS_GRAD_B0 = 6 };
+enum ZMode { Z_C2R = 0, Z_R2C = 1, Z_CROSS = 2, Z_MHD = 3, Z_DOT = 4, Z_UU = 5 };
 enum OutMode { OUT_RHS = 0, OUT_STAGE = 1, OUT_CONV = 2 };   // OUT_CONV: convection term only (solver.conv)
 
 template <typename T>
@@ -63,6 +63,9 @@ struct StridedArgs {
     // slab decomposition (one process per GPU): the pass that precedes a global transpose stores
     // straight into the destination rank's buffer (NVLink peer memory), element (f, i, column) of
     // the output going to rank i / xchunk at line index i % xchunk.  xchunk == 0: single GPU.
+    int comp;                     // S_NS_GRAD_B0: component whose gradient is formed (NS.py:138-145)
+    const V* addin;               // divergence-form epilogue: spectral term added to the convection (Skewed)
+    T cfac;                       // divergence-form epilogue: factor on the convection (-1 or -0.5)
     int xchunk;
     long long c1_out_off;         // added to the run index of the output base (global x0 / compact k1)
     int k1_off;                   // global index of local k1 = 0 (Nyquist test in the epilogues)
@@ -168,7 +171,7 @@ strided_kernel(const StridedArgs<T> a) {
         load_line<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
         fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
         store_line<T, N, E, true>(x, a, f, obase, t, valid, a.scale);
-    } else if (MODE == S_NS_B0 || MODE == S_VV_B0) {
+    } else if (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0) {
         // in: 3 dense spectral fields.  out: 6 fields (NS: u_hat, i k x u_hat ; VV: i k x w_hat / k^2, w_hat)
         const T k1 = valid ? a.ky[c1m] : (T)0;
         const T k2 = valid ? a.kz[c2] : (T)0;
@@ -180,11 +183,25 @@ strided_kernel(const StridedArgs<T> a) {
 #pragma unroll 1
         for (int f = 0; f < 6; ++f) {
             V x[E];
-            const bool direct = (MODE == S_NS_B0) ? (f < 3) : (f >= 3);
+            const bool direct = (MODE == S_VV_B0) ? (f >= 3) : (f < 3);
             const int g = f % 3;               // component
             const int ga = (g + 1) % 3, gb = (g + 2) % 3;
             if (direct) {
                 load_line<T, N, E>(x, pin + g * a.in_fs, a.in_ls, a.imap, t, valid);
+            } else if (MODE == S_NS_GRAD_B0) {
+                // field 3+g = 1j*K[g]*u_hat[comp]   (standard_convection, NS.py:138-145)
+                const V* pc = pin + a.comp * a.in_fs;
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    const int j = t + q * P;
+                    const int i = axis_idx(a.imap, j);
+                    const bool ok = valid && axis_ok(a.imap, N, j);
+                    V b = czero<V>();
+                    T k0 = (T)0;
+                    if (ok) { b = pc[(long long)i * a.in_ls]; k0 = a.kx[i]; }
+                    const T kg = g == 0 ? k0 : (g == 1 ? k1 : k2);
+                    x[q].x = -kg * b.y; x[q].y = kg * b.x;
+                }
             } else {
                 // component g of i*(K x b) = i*(K[ga]*b[gb] - K[gb]*b[ga])
                 const V* pa = pin + ga * a.in_fs;
@@ -418,6 +435,110 @@ mhd_f0_kernel(const StridedArgs<T> a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// NS divergence-form F0 (NS.py:147-162,176-189): six product fields UU_ij (i<=j, order 00 01 02 11 12 22)
+// -> conv_i = 1j * sum_j K_j UU_ij (+ addin_i), rhs_i = cfac * conv_i, then the usual Nyquist mask,
+// pressure projection, viscous term, Source and stage update.
+// ---------------------------------------------------------------------------------------
+template <typename T, int N, int E, int TC, int NBUF>
+__global__ void __launch_bounds__((N / E) * TC)
+nsdiv_f0_kernel(const StridedArgs<T> a) {
+    typedef typename C2<T>::type V;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    V* sm = reinterpret_cast<V*>(smraw);
+    constexpr int P = N / E;
+    const int c = threadIdx.x % TC;
+    const int t = threadIdx.x / TC;
+    const long long col = (long long)blockIdx.x * TC + c;
+    const bool valid = col < a.ncols;
+    const int c1 = valid ? (int)(col / a.cw) : 0;
+    const int c2 = valid ? (int)(col % a.cw) : 0;
+    const long long ibase = (long long)c1 * a.in_os + c2;
+    const long long obase = (long long)c1 * a.out_os + c2;
+    SmemLine<TC, 0> map; map.base = c;
+    int phase = 0;
+    constexpr int BUFSTRIDE = N * TC;
+    const T k1 = valid ? a.ky[c1] : (T)0, k2 = valid ? a.kz[c2] : (T)0;
+    V acc[3][E];
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+#pragma unroll
+        for (int q = 0; q < E; ++q) acc[f][q] = czero<V>();
+#pragma unroll
+    for (int ij = 0; ij < 6; ++ij) {
+        const int i = ij < 3 ? 0 : (ij < 5 ? 1 : 2);
+        const int j = ij < 3 ? ij : (ij < 5 ? ij - 2 : 2);
+        V x[E];
+        load_line<T, N, E>(x, a.in + (ij * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
+        fft_line<T, N, E, -1, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int j0 = t + q * P;
+            const T k0 = axis_ok(a.omap, N, j0) ? a.kx[axis_idx(a.omap, j0)] : (T)0;
+            const T ki = i == 0 ? k0 : (i == 1 ? k1 : k2);
+            const T kj = j == 0 ? k0 : (j == 1 ? k1 : k2);
+            acc[i][q].x += kj * x[q].x; acc[i][q].y += kj * x[q].y;
+            if (i != j) { acc[j][q].x += ki * x[q].x; acc[j][q].y += ki * x[q].y; }
+        }
+    }
+    if (!valid) return;
+    const int i1 = c1, i2 = c2;
+    const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int j0 = t + q * P;
+        if (!axis_ok(a.omap, N, j0)) continue;
+        const int i0 = axis_idx(a.omap, j0);
+        const long long off = (long long)i0 * a.out_ls + obase;
+        const T k0 = a.kx[i0];
+        T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;
+        V d[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            V cv; cv.x = -a.scale * acc[f][q].y; cv.y = a.scale * acc[f][q].x;       // 1j * acc
+            if (a.addin) cv = cadd(cv, a.addin[f * a.st_fs + off]);
+            d[f].x = a.cfac * cv.x; d[f].y = a.cfac * cv.y;
+        }
+        if (a.out_mode == OUT_CONV) {
+#pragma unroll
+            for (int f = 0; f < 3; ++f) a.rhs[f * a.st_fs + off] = d[f];
+            continue;
+        }
+        if (nyq12 || (a.mask_nyquist && 2 * i0 == a.N0)) { d[0] = czero<V>(); d[1] = czero<V>(); d[2] = czero<V>(); }
+        const T ks = ksq == (T)0 ? (T)1 : ksq;
+        const T q0 = k0 / ks, q1 = k1 / ks, q2 = k2 / ks;
+        V p;
+        p.x = d[0].x * q0 + d[1].x * q1; p.x += d[2].x * q2;
+        p.y = d[0].y * q0 + d[1].y * q1; p.y += d[2].y * q2;
+        if (a.p_hat) a.p_hat[off] = p;
+        const T kk[3] = {k0, k1, k2};
+        const T z = a.nu * ksq;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const long long o = f * a.st_fs + off;
+            const V w = a.u_hat[o];
+            V dd = d[f];
+            dd.x -= p.x * kk[f] + z * w.x; dd.y -= p.y * kk[f] + z * w.y;
+            if (a.source) dd = cadd(dd, a.source[o]);
+            if (a.out_mode == OUT_RHS) {
+                a.rhs[o] = dd;
+            } else {
+                V b1, b2;
+                if (a.rk == 0) { b1 = w; b2 = w; a.u1[o] = b1; }
+                else { b2 = a.u2[o]; if (a.rk < 3) b1 = a.u1[o]; }
+                b2.x += a.adt * dd.x; b2.y += a.adt * dd.y;
+                if (a.rk < 3) {
+                    a.u2[o] = b2;
+                    V n; n.x = b1.x + a.bdt * dd.x; n.y = b1.y + a.bdt * dd.y;
+                    a.u0[o] = n;
+                } else {
+                    a.u0[o] = b2;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Contiguous-axis pass.  Lines of one CTA: LPC; thread index = t + P*line.
 // Two real lines ride on one complex transform of length M (a + i b).
 // ---------------------------------------------------------------------------------------
@@ -577,6 +698,51 @@ z_kernel(const ZArgs<T> a) {
                     const int k = t + q * P;
                     if (k < nk) C[k] = cscale<T>(x[q], a.scale);
                 }
+            }
+        } else if (MODE == Z_DOT) {
+            // sum_j a_j b_j with a = (f0,f1,f2), b = (f3,f4,f5): u_j du_i/dx_j (NS.py:138-145) -> one field
+            V p01[E], p23[E], p45[E];
+            load_pair<T, M, E>(p01, in + 0 * a.in_fs + line * a.in_ls, in + 1 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p01, t, a.tw, sm, map, BUFSTRIDE, phase);
+            load_pair<T, M, E>(p23, in + 2 * a.in_fs + line * a.in_ls, in + 3 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p23, t, a.tw, sm, map, BUFSTRIDE, phase);
+            load_pair<T, M, E>(p45, in + 4 * a.in_fs + line * a.in_ls, in + 5 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p45, t, a.tw, sm, map, BUFSTRIDE, phase);
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                p01[q].x = p01[q].x * p23[q].y + p01[q].y * p45[q].x + p23[q].x * p45[q].y;
+                p01[q].y = (T)0;
+            }
+            fft_line<T, M, E, -1, SYNC, NBUF>(p01, t, a.tw, sm, map, BUFSTRIDE, phase);
+            if (valid) {
+                V* C = out + line * a.out_ls;
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    const int k = t + q * P;
+                    if (k < nk) C[k] = cscale<T>(p01[q], a.scale);
+                }
+            }
+        } else if (MODE == Z_UU) {
+            // three fields u -> six products u_i u_j, i <= j (divergence_convection, NS.py:147-162)
+            V p01[E], p2[E];
+            load_pair<T, M, E>(p01, in + 0 * a.in_fs + line * a.in_ls, in + 1 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p01, t, a.tw, sm, map, BUFSTRIDE, phase);
+            load_pair<T, M, E>(p2, in + 2 * a.in_fs + line * a.in_ls, (const V*)nullptr, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p2, t, a.tw, sm, map, BUFSTRIDE, phase);
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr) {
+                V x[E];
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    const T u0 = p01[q].x, u1 = p01[q].y, u2 = p2[q].x;
+                    // output order: 00 01 | 02 11 | 12 22
+                    x[q].x = pr == 0 ? u0 * u0 : (pr == 1 ? u0 * u2 : u1 * u2);
+                    x[q].y = pr == 0 ? u0 * u1 : (pr == 1 ? u1 * u1 : u2 * u2);
+                }
+                fft_line<T, M, E, -1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+                unpack_store_pair<T, M, E, SYNC, NBUF>(x, out + (2 * pr) * a.out_fs + line * a.out_ls,
+                                                       out + (2 * pr + 1) * a.out_fs + line * a.out_ls,
+                                                       t, nk, a.scale, sm, map, BUFSTRIDE, phase);
             }
         } else {
             // MHD (MHD.py:119-127, 99-110): u = (p01.x,p01.y,p23.x), b = (p23.y,p45.x,p45.y)

@@ -24,6 +24,7 @@ typedef int (*launch_fn)(int, const void*, cudaStream_t);
 static launch_fn g_launch[FAM_COUNT][2] = {
 #define ROW(f) { sdns_launch_##f##_f32, sdns_launch_##f##_f64 },
     ROW(0) ROW(1) ROW(2) ROW(3) ROW(4) ROW(5) ROW(6) ROW(7) ROW(8) ROW(9) ROW(10)
+    ROW(11) ROW(12) ROW(13) ROW(14)
 #undef ROW
 };
 
@@ -57,7 +58,7 @@ struct sdns_plan {
     sdns_config cfg;
     int N[3], Nh, Nhp;
     int P, rank, N1l;       // ranks, this rank, local spectral extent of axis 1
-    size_t off_C, bytes_C, off_flags;
+    size_t off_C, bytes_C, off_flags, off_D, bytes_D, off_S, bytes_S;
     bool own_ws;            // workspace cudaMalloc'ed by the library (multi-GPU: IPC-shared)
     char* peer_ws[8];       // base of every rank's workspace (peer_ws[rank] == ws)
     unsigned int epoch;
@@ -183,8 +184,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     if (cfg->nranks > 1 && cfg->decomposition != SDNS_SLAB)
         return fail(SDNS_ERR_ARG, "multi-GPU runs use the slab decomposition (pencil is not on the B200 path yet)");
     if (cfg->solver < SDNS_NS || cfg->solver > SDNS_MHD) return fail(SDNS_ERR_ARG, "solver");
-    if (cfg->solver == SDNS_NS && cfg->convection != SDNS_CONV_VORTEX)
-        return fail(SDNS_ERR_ARG, "NS: only convection='Vortex' is compiled in");
+    if (cfg->convection < SDNS_CONV_VORTEX || cfg->convection > SDNS_CONV_SKEWED) return fail(SDNS_ERR_ARG, "convection");
     if (cfg->solver == SDNS_VV && cfg->convection != SDNS_CONV_VORTEX)
         return fail(SDNS_ERR_ARG, "VV supports only convection='Vortex' (solvers/VV.py:87-88)");
     if (cfg->solver == SDNS_MHD && cfg->convection != SDNS_CONV_DIVERGENCE)
@@ -243,7 +243,13 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->off_A = align_up(p->host_tables.size(), 256);
     p->off_B = p->off_A + p->bytes_A;
     p->off_C = p->P == 1 ? p->off_B : p->off_B + p->bytes_B;
-    p->off_red = p->off_B + p->bytes_B + p->bytes_C;
+    const bool needD = cfg->solver == SDNS_NS && (cfg->convection == SDNS_CONV_STANDARD || cfg->convection == SDNS_CONV_SKEWED);
+    const bool needS = cfg->solver == SDNS_NS && cfg->convection == SDNS_CONV_SKEWED;
+    p->bytes_D = needD ? align_up((size_t)3 * p->sp[1].M0l * p->sp[1].M[1] * p->Nhp * p->cs, 256) : 0;
+    p->bytes_S = needS ? align_up((size_t)3 * p->N[0] * p->N1l * p->Nh * p->cs, 256) : 0;
+    p->off_D = p->off_B + p->bytes_B + p->bytes_C;
+    p->off_S = p->off_D + p->bytes_D;
+    p->off_red = p->off_S + p->bytes_S;
     p->off_flags = p->off_red + align_up(sizeof(double) * p->red_blocks, 256);
     p->ws_need = p->off_flags + 256;
     *out = p;
@@ -449,9 +455,9 @@ struct Pipe {
     }
 
     // B0: local dense spectral (nf, N0, N1l, Nh) -> W0 (nfo, M0l, K1n, K2p) of the rank owning each x0
-    int b0(int fam, const V* in, int nf) {
+    int b0(int fam, const V* in, int nf, int comp = 0) {
         StridedArgs<T> a; base(a);
-        a.in = in; a.out = A;
+        a.in = in; a.out = A; a.comp = comp;
         a.in_fs = dense_fs(); a.in_ls = (long long)p->N1l * p->Nh; a.in_os = p->Nh;
         a.cw = q.K2n; a.ncols = (long long)q.K1l * q.K2n;
         a.col_nlo = q.lcol_nlo; a.col_gap = q.lcol_gap;
@@ -491,16 +497,16 @@ struct Pipe {
         a.nlines = plane; a.nin_keep = q.K2n; a.nout_keep = p->Nh; a.nf = nf;
         a.tw = tw(q.M[2]);
         a.scale = (fam == FAM_Z_C2R) ? (T)1 : (T)q.scale;
-        const int nin = (fam == FAM_Z_CROSS || fam == FAM_Z_MHD) ? 6 : nf;
-        const int nout = fam == FAM_Z_CROSS ? 3 : (fam == FAM_Z_MHD ? 9 : nf);
+        const int nin = (fam == FAM_Z_CROSS || fam == FAM_Z_MHD || fam == FAM_Z_DOT) ? 6 : (fam == FAM_Z_UU ? 3 : nf);
+        const int nout = fam == FAM_Z_CROSS ? 3 : (fam == FAM_Z_MHD ? 9 : (fam == FAM_Z_DOT ? 1 : (fam == FAM_Z_UU ? 6 : nf)));
         const double bin = in_is_W1 ? (double)q.K2n * p->cs : (double)q.M[2] * p->rs;
         const double bout = out_is_W2 ? (double)p->Nh * p->cs : (double)q.M[2] * p->rs;
         return do_launch(p, fam, q.M[2], &a, (double)plane * (nin * bin + nout * bout));
     }
     // F1: A (W2) -> W3 (nf, M0, N1l, Nhp) of the rank owning each k1
-    int f1(int nf) {
+    int f1(int nf, const V* src = nullptr) {
         StridedArgs<T> a; base(a);
-        a.in = A; a.out = C;
+        a.in = src ? src : A; a.out = C;
         a.in_fs = (long long)q.M0l * q.M[1] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[1] * p->Nhp;
         a.cw = p->Nh; a.ncols = (long long)q.M0l * p->Nh;
         a.col_nlo = q.M0l; a.col_gap = 0;
@@ -576,15 +582,53 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
     const V* u = reinterpret_cast<const V*>(u_hat);
     int e;
     const int solver = p->cfg.solver;
+    const int conv = p->cfg.convection;
+    int nprod = solver == SDNS_MHD ? 9 : 3;
+    bool divform = false;
+    T f0scale = (T)1;
+    if (solver == SDNS_NS && conv != SDNS_CONV_VORTEX) {
+        V* D = reinterpret_cast<V*>(p->ws + p->off_D);
+        V* S = reinterpret_cast<V*>(p->ws + p->off_S);
+        if (conv == SDNS_CONV_STANDARD || conv == SDNS_CONV_SKEWED) {
+            // u_j du_i/dx_j (NS.py:138-145): per component i six backward transforms (u, grad u_i) and one product
+            const long long dfs = (long long)P.q.M0l * P.q.M[1] * p->Nhp;
+            for (int i = 0; i < 3; ++i) {
+                if ((e = P.b0(FAM_NS_GRAD_B0, u, 3, i))) return e;
+                if ((e = xbarrier(p))) return e;
+                if ((e = P.b1(6))) return e;
+                if ((e = P.z(FAM_Z_DOT, P.B, D + i * dfs, 6, true, true))) return e;
+            }
+            if ((e = P.f1(3, D))) return e;
+            if ((e = xbarrier(p))) return e;
+            if (conv == SDNS_CONV_STANDARD) {
+                f0scale = (T)-1;                                   // rhs = -conv (NS.py:170)
+            } else {
+                // Skewed (NS.py:184-189): keep the standard term in spectral space, add it in the divergence epilogue
+                StridedArgs<T> a0; P.f0_geom(a0, 3);
+                a0.out_mode = OUT_CONV; a0.rhs = S; a0.u_hat = u;
+                if ((e = do_launch(p, FAM_NS_F0, P.q.M[0], &a0))) return e;
+            }
+        }
+        if (conv == SDNS_CONV_DIVERGENCE || conv == SDNS_CONV_SKEWED) {
+            // d/dx_j (u_i u_j) (NS.py:147-162): three backward, six forward transforms
+            if ((e = P.b0(FAM_PLAIN_BWD, u, 3))) return e;
+            if ((e = xbarrier(p))) return e;
+            if ((e = P.b1(3))) return e;
+            if ((e = P.z(FAM_Z_UU, P.B, P.A, 3, true, true))) return e;
+            if ((e = P.f1(6))) return e;
+            if ((e = xbarrier(p))) return e;
+            nprod = 6; divform = true;
+        }
+    } else {
     if (solver == SDNS_NS) { if ((e = P.b0(FAM_NS_B0, u, 3))) return e; }
     else if (solver == SDNS_VV) { if ((e = P.b0(FAM_VV_B0, u, 3))) return e; }
     else { if ((e = P.b0(FAM_PLAIN_BWD, u, 6))) return e; }
     if ((e = xbarrier(p))) return e;
     if ((e = P.b1(6))) return e;
-    const int nprod = solver == SDNS_MHD ? 9 : 3;
     if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true))) return e;
     if ((e = P.f1(nprod))) return e;
     if ((e = xbarrier(p))) return e;
+    }
     StridedArgs<T> a; P.f0_geom(a, nprod);
     a.out_mode = so.out_mode;
     a.u_hat = u;
@@ -593,7 +637,12 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
     a.source = reinterpret_cast<const V*>(so.source);
     a.p_hat = reinterpret_cast<V*>(so.p_hat);
     a.nu = (T)nu; a.eta = (T)eta; a.adt = (T)so.adt; a.bdt = (T)so.bdt; a.rk = so.rk;
-    const int fam = solver == SDNS_NS ? FAM_NS_F0 : (solver == SDNS_VV ? FAM_VV_F0 : FAM_MHD_F0);
+    a.scale = f0scale;
+    if (divform) {
+        a.cfac = conv == SDNS_CONV_SKEWED ? (T)-0.5 : (T)-1;
+        a.addin = conv == SDNS_CONV_SKEWED ? reinterpret_cast<const V*>(p->ws + p->off_S) : nullptr;
+    }
+    const int fam = divform ? FAM_NSDIV_F0 : (solver == SDNS_NS ? FAM_NS_F0 : (solver == SDNS_VV ? FAM_VV_F0 : FAM_MHD_F0));
     // epilogue traffic: read the product fields; state reads/writes of the stage update
     const int ns = solver == SDNS_MHD ? 6 : 3;
     double st;   // state arrays touched, in units of one ns-component spectral vector

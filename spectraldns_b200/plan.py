@@ -259,7 +259,7 @@ class Plan(object):
 
     # -- measurement ---------------------------------------------------------
     FAMILIES = ['plain_fwd_c2c', 'plain_bwd_c2c', 'ns_b0', 'vv_b0', 'ns_f0', 'vv_f0', 'mhd_f0',
-                'c2r', 'r2c', 'z_cross', 'z_mhd']
+                'c2r', 'r2c', 'z_cross', 'z_mhd', 'ns_grad_b0', 'z_dot', 'z_uu', 'nsdiv_f0']
 
     def profile(self, on=True):
         _lib.check(self.lib.sdns_profile_enable(self._p, 1 if on else 0))

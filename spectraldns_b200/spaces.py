@@ -45,23 +45,25 @@ class Engine(object):
     """One C plan (spaces T and Tp of one grid) plus reusable device staging buffers."""
     _cache = {}
 
-    def __init__(self, N, L, precision, dealias, solver='NS', mask_nyquist=True, decomposition='slab'):
+    def __init__(self, N, L, precision, dealias, solver='NS', mask_nyquist=True, decomposition='slab',
+                 convection=None):
         self.key = (tuple(int(n) for n in N), tuple(float(l) for l in L), precision, dealias, solver,
-                    bool(mask_nyquist), decomposition)
+                    bool(mask_nyquist), decomposition, convection)
         rank, nranks, device = world()
         self.rank, self.nranks = rank, nranks
         self.plan = Plan(self.key[0], self.key[1], precision, dealias, solver,
-                         mask_nyquist=mask_nyquist, decomposition='slab' if nranks > 1 else decomposition,
+                         convection=convection, mask_nyquist=mask_nyquist,
+                         decomposition='slab' if nranks > 1 else decomposition,
                          device=device, rank=rank, nranks=nranks)
         self._stage = {}
 
     @classmethod
-    def get(cls, N, L, precision, dealias, solver='NS', mask_nyquist=True, decomposition='slab'):
+    def get(cls, N, L, precision, dealias, solver='NS', mask_nyquist=True, decomposition='slab', convection=None):
         key = (tuple(int(n) for n in N), tuple(float(l) for l in L), precision, dealias, solver,
-               bool(mask_nyquist), decomposition)
+               bool(mask_nyquist), decomposition, convection)
         e = cls._cache.get(key)
         if e is None:
-            e = cls(N, L, precision, dealias, solver, mask_nyquist, decomposition)
+            e = cls(N, L, precision, dealias, solver, mask_nyquist, decomposition, convection)
             cls._cache[key] = e
         return e
 

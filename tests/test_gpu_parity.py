@@ -16,9 +16,10 @@ ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, '*
              if not os.path.basename(f).startswith('integ_'))
 
 
-def make_plan(N, L=(2*np.pi,)*3, precision='double', dealias='2/3-rule', solver='NS', mask_nyquist=True):
+def make_plan(N, L=(2*np.pi,)*3, precision='double', dealias='2/3-rule', solver='NS', mask_nyquist=True,
+              convection=None):
     from spectraldns_b200.plan import Plan
-    return Plan(N, L, precision, dealias, solver, mask_nyquist=mask_nyquist)
+    return Plan(N, L, precision, dealias, solver, convection=convection, mask_nyquist=mask_nyquist)
 
 
 def test_library_loaded_and_native():
@@ -104,6 +105,31 @@ def test_golden_rhs_and_rk4(name):
         p.rk4_step(d_u, u1, u2, float(g['dt']), float(g['nu']), eta)
     err = rel_l2(p.to_host(d_u), g['u_hat'])
     assert err < TOL[prec], err
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('dealias', ['2/3-rule', '3/2-rule'])
+@pytest.mark.parametrize('conv', ['Standard', 'Divergence', 'Skewed'])
+def test_ns_convection_forms(conv, dealias, precision):
+    """NS.getConvection 'Standard' / 'Divergence' / 'Skewed' (solvers/NS.py:138-189): ComputeRHS against the
+    reference fixture (2/3-rule, double) and the oracle, plus two RK4 steps."""
+    g = golden('iso_ns_16_double')
+    N = tuple(int(n) for n in g['N'])
+    o = so.Oracle(N, g['L'], precision, dealias)
+    p = make_plan(N, g['L'], precision, dealias, 'NS', convection=conv)
+    u0 = g['u0_hat'].astype(o.complex)
+    nu = float(g['nu'])
+    rhs = p.to_host(p.compute_rhs(p.empty_spectral(), p.to_device(u0), nu))
+    assert rel_l2(rhs, o.ns_rhs(u0, nu, conv)) < TOL[precision]
+    if dealias == '2/3-rule' and precision == 'double':
+        assert rel_l2(rhs, g['rhs_' + conv]) < 1e-11            # the unmodified reference
+    cv = p.to_host(p.compute_conv(p.empty_spectral(), p.to_device(u0)))
+    assert rel_l2(cv, o.ns_conv(u0, conv)) < TOL[precision]
+    d_u, u1, u2 = p.to_device(u0), p.empty_spectral(), p.empty_spectral()
+    for _ in range(2):
+        p.rk4_step(d_u, u1, u2, 0.005, nu)
+    ref = o.solve(u0, 'NS', 2, 0.005, nu, convection=conv)
+    assert rel_l2(p.to_host(d_u), ref) < TOL[precision]
 
 
 def test_pressure_and_source():
