@@ -18,7 +18,8 @@ OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libsdns_b200.so')
 NFAM = 15
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
-FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',
+         '-Xfatbin=-compress-all']      # compressed cubins: the .so travels to the GPU box with the tree
 
 
 def _nvcc():
