@@ -150,12 +150,38 @@ __device__ __forceinline__ void fft_stage(V (&x)[E], int t, const V* __restrict_
     for (int m = 0; m < NB; ++m) {
         if (Ns > 1) {
             const int jm = (t + m * P) % Ns;
+#ifdef SDNS_TW_TABLE_ALL
 #pragma unroll
             for (int k = 1; k < R; ++k) {
                 V w = __ldg(&tw[(jm * k) * TS]);
                 if (DIR > 0) w.y = -w.y;
                 x[m + k * NB] = cmul(x[m + k * NB], w);
             }
+#else
+            // one table load per butterfly; the powers w^2..w^(R-1) by multiplication (the L1/LSU path,
+            // not the FP pipe, is the busy unit of these kernels)
+            V w1 = __ldg(&tw[jm * TS]);
+            if (DIR > 0) w1.y = -w1.y;
+            x[m + NB] = cmul(x[m + NB], w1);
+            if (R > 2) {
+                const V w2 = cmul(w1, w1);
+                x[m + 2 * NB] = cmul(x[m + 2 * NB], w2);
+                if (R > 3) {
+                    const V w3 = cmul(w2, w1);
+                    x[m + 3 * NB] = cmul(x[m + 3 * NB], w3);
+                    if (R > 4) {
+                        const V w4 = cmul(w2, w2);
+                        x[m + 4 * NB] = cmul(x[m + 4 * NB], w4);
+                        if (R > 5) {
+                            const V w5 = cmul(w4, w1), w6 = cmul(w3, w3), w7 = cmul(w4, w3);
+                            x[m + 5 * NB] = cmul(x[m + 5 * NB], w5);
+                            x[m + 6 * NB] = cmul(x[m + 6 * NB], w6);
+                            x[m + 7 * NB] = cmul(x[m + 7 * NB], w7);
+                        }
+                    }
+                }
+            }
+#endif
         }
         if (R == 2) dft2<DIR>(x[m], x[m + NB]);
         else if (R == 4) dft4<DIR>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB]);

@@ -30,6 +30,26 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+template <typename T, int N, int MODE>
+static int run_f0x(const StridedArgs<T>& a, cudaStream_t st) {
+    typedef FXCfg<T, N> C;
+    auto kern = f0x_kernel<T, N, C::E, C::TC, MODE, C::minBlocks>;
+    static bool once = false;
+    if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
+    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC));
+    kern<<<grid, C::threads, C::smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int N, int MODE>
+static int run_f0(const StridedArgs<T>& a, cudaStream_t st) {
+#ifndef SDNS_NO_F0X
+    if constexpr (FXCfg<T, N>::ok) return run_f0x<T, N, MODE>(a, st);
+    else
+#endif
+    return run_strided<T, N, MODE, -1>(a, st);
+}
+
 template <typename T, int N>
 static int run_mhd_f0(const StridedArgs<T>& a, cudaStream_t st) {
     typedef MCfg<T, N> C;
@@ -114,9 +134,9 @@ int SDNS_FN(int n, const void* args, cudaStream_t st) {
 #elif SDNS_FAMILY == 3
 #define X(N) case N: return run_strided<T, N, S_VV_B0, +1>(*(const StridedArgs<T>*)args, st);
 #elif SDNS_FAMILY == 4
-#define X(N) case N: return run_strided<T, N, S_NS_F0, -1>(*(const StridedArgs<T>*)args, st);
+#define X(N) case N: return run_f0<T, N, S_NS_F0>(*(const StridedArgs<T>*)args, st);
 #elif SDNS_FAMILY == 5
-#define X(N) case N: return run_strided<T, N, S_VV_F0, -1>(*(const StridedArgs<T>*)args, st);
+#define X(N) case N: return run_f0<T, N, S_VV_F0>(*(const StridedArgs<T>*)args, st);
 #elif SDNS_FAMILY == 6
 #define X(N) case N: return run_mhd_f0<T, N>(*(const StridedArgs<T>*)args, st);
 #elif SDNS_FAMILY == 7

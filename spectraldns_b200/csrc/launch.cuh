@@ -70,6 +70,36 @@ struct SCfg {
     static constexpr int minBlocks = cmax(1, cmin(cmin(cmin(bySmem, byThreads), byRegs), heavy ? 2 : 4));
 };
 
+// field-parallel F0 (f0x_kernel): 3 thread groups; shared memory = 3 exchange buffers that double as parking
+constexpr int fx_blocks(int P, int tc, int csize, int N, int regs) {
+    const int threads = 3 * P * tc;
+    if (threads > 1024) return 0;
+    const long long smem = 3LL * N * tc * csize;
+    if (smem > 200 * 1024) return 0;
+    const int bs = (int)((216 * 1024) / (smem + 1024)), br = 65536 / (threads * regs), bt = 2048 / threads;
+    return cmin(cmin(bs, br), cmin(bt, 3));
+}
+// tile width: the widest one (rows of >= 64 bytes) that still lets two CTAs share an SM, else the widest that fits
+constexpr int fx_tc(int P, int tcfull, int csize, int N, int regs) {
+    const int tmin = 64 / csize;
+    for (int tc = tcfull; tc >= tmin; tc /= 2) if (fx_blocks(P, tc, csize, N, regs) >= 2) return tc;
+    for (int tc = tcfull; tc >= 1; tc /= 2) if (fx_blocks(P, tc, csize, N, regs) >= 1) return tc;
+    return 0;
+}
+
+template <typename T, int N>
+struct FXCfg {
+    static constexpr int E = sizeof(T) == 8 ? pick_E(N, 8) : pick_E(N, 16);
+    static constexpr int P = N / E;
+    static constexpr int csize = 2 * (int)sizeof(T);
+    static constexpr int needRegs = sizeof(T) == 8 ? 84 : (E > 12 ? 84 : 64);
+    static constexpr int TC = fx_tc(P, 128 / csize, csize, N, needRegs);
+    static constexpr bool ok = TC > 0 && plan_ok(N, E);
+    static constexpr size_t smem = (size_t)3 * N * (TC > 0 ? TC : 1) * csize;
+    static constexpr int threads = 3 * P * (TC > 0 ? TC : 1);
+    static constexpr int minBlocks = cmax(1, fx_blocks(P, TC > 0 ? TC : 1, csize, N, needRegs));
+};
+
 // MHD epilogue: six accumulators per thread -> fewer elements per thread
 template <typename T, int N>
 struct MCfg {

@@ -319,6 +319,116 @@ strided_kernel(const StridedArgs<T> a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// F0 for NS / VV, field-parallel: the CTA has three thread groups, group g transforms field g, so a
+// tile has ONE load phase and ONE transform phase (the strided_kernel F0 branch runs three of each
+// back to back and is latency-bound).  After its last exchange a group parks its result in its own
+// exchange buffer ([q][thread]); the epilogue points are then split across the groups.
+// ---------------------------------------------------------------------------------------
+template <typename T, int N, int E, int TC, int MODE, int MINB>
+__global__ void __launch_bounds__(3 * (N / E) * TC, MINB)
+f0x_kernel(const StridedArgs<T> a) {
+    typedef typename C2<T>::type V;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    V* sm = reinterpret_cast<V*>(smraw);
+    constexpr int P = N / E;
+    constexpr int NT = P * TC;
+    const int g = threadIdx.x / NT;                 // field handled by this thread group
+    const int tid = threadIdx.x - g * NT;
+    const int c = tid % TC;
+    const int t = tid / TC;
+    const long long col = (long long)blockIdx.x * TC + c;
+    const bool valid = col < a.ncols;
+    const int c1 = valid ? (int)(col / a.cw) : 0;
+    const int c2 = valid ? (int)(col % a.cw) : 0;
+    const long long ibase = (long long)c1 * a.in_os + c2;
+    const long long obase = (long long)c1 * a.out_os + c2;
+    SmemLine<TC, 0> map; map.base = c;
+    int phase = 0;
+    V* ex = sm + g * (N * TC);
+    {
+        V x[E];
+        load_line<T, N, E>(x, a.in + (g * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
+        fft_line<T, N, E, -1, 0, 1>(x, t, a.tw, ex, map, 0, phase);
+        __syncthreads();                              // every gather from the exchange buffers is done
+#pragma unroll
+        for (int q = 0; q < E; ++q) ex[q * NT + tid] = x[q];
+    }
+    __syncthreads();
+    if (!valid) return;
+    const V* pk0 = sm;
+    const V* pk1 = sm + N * TC;
+    const V* pk2 = sm + 2 * N * TC;
+    const int i1 = c1, i2 = c2;
+    const T k1 = a.ky[i1], k2 = a.kz[i2];
+    const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
+#pragma unroll 1
+    for (int q = g; q < E; q += 3) {
+        const int j0 = t + q * P;
+        if (!axis_ok(a.omap, N, j0)) continue;
+        const int i0 = axis_idx(a.omap, j0);
+        const long long off = (long long)i0 * a.out_ls + obase;
+        const T k0 = a.kx[i0];
+        T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;
+        V d0 = cscale<T>(pk0[q * NT + tid], a.scale), d1 = cscale<T>(pk1[q * NT + tid], a.scale),
+          d2 = cscale<T>(pk2[q * NT + tid], a.scale);
+        if (MODE == S_VV_F0) {
+            // rhs = i*(K x v_hat)   (VV.py:99)
+            V e0 = icross<T, V>(k1, d2, k2, d1);
+            V e1 = icross<T, V>(k2, d0, k0, d2);
+            V e2 = icross<T, V>(k0, d1, k1, d0);
+            d0 = e0; d1 = e1; d2 = e2;
+        }
+        if (a.out_mode == OUT_CONV) {
+            a.rhs[off] = d0; a.rhs[a.st_fs + off] = d1; a.rhs[2 * a.st_fs + off] = d2;
+            continue;
+        }
+        if (nyq12 || (a.mask_nyquist && 2 * i0 == a.N0)) { d0 = czero<V>(); d1 = czero<V>(); d2 = czero<V>(); }
+        const V w0 = a.u_hat[off], w1 = a.u_hat[a.st_fs + off], w2 = a.u_hat[2 * a.st_fs + off];
+        const T z = a.nu * ksq;
+        if (MODE == S_NS_F0) {
+            const T ks = ksq == (T)0 ? (T)1 : ksq;
+            const T q0 = k0 / ks, q1 = k1 / ks, q2 = k2 / ks;       // K_over_K2 (NS.py:46-48)
+            V p;
+            p.x = d0.x * q0 + d1.x * q1; p.x += d2.x * q2;
+            p.y = d0.y * q0 + d1.y * q1; p.y += d2.y * q2;
+            if (a.p_hat) a.p_hat[off] = p;
+            d0.x -= p.x * k0; d0.y -= p.y * k0;
+            d1.x -= p.x * k1; d1.y -= p.y * k1;
+            d2.x -= p.x * k2; d2.y -= p.y * k2;
+        }
+        d0.x -= z * w0.x; d0.y -= z * w0.y;
+        d1.x -= z * w1.x; d1.y -= z * w1.y;
+        d2.x -= z * w2.x; d2.y -= z * w2.y;
+        if (a.source) {
+            d0 = cadd(d0, a.source[off]); d1 = cadd(d1, a.source[a.st_fs + off]);
+            d2 = cadd(d2, a.source[2 * a.st_fs + off]);
+        }
+        V dd[3] = {d0, d1, d2};
+        V ww[3] = {w0, w1, w2};
+        if (a.out_mode == OUT_RHS) {
+#pragma unroll
+            for (int f = 0; f < 3; ++f) a.rhs[f * a.st_fs + off] = dd[f];
+        } else {
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                const long long o = f * a.st_fs + off;
+                V b1, b2;
+                if (a.rk == 0) { b1 = ww[f]; b2 = ww[f]; a.u1[o] = b1; }
+                else { b2 = a.u2[o]; if (a.rk < 3) b1 = a.u1[o]; }
+                b2.x += a.adt * dd[f].x; b2.y += a.adt * dd[f].y;
+                if (a.rk < 3) {
+                    a.u2[o] = b2;
+                    V n; n.x = b1.x + a.bdt * dd[f].x; n.y = b1.y + a.bdt * dd[f].y;
+                    a.u0[o] = n;
+                } else {
+                    a.u0[o] = b2;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // MHD F0: 9 Elsasser product fields ZZ[i][j] -> 6 rhs components (MHD.py:89-97), Nyquist mask,
 // pressure projection on the first three, -nu k^2 u, -eta k^2 b (MHD.py:132-149), RK4 stage.
 // Register budget: six accumulators of EH = E elements; the transforms stream through one
