@@ -102,11 +102,55 @@ __device__ __forceinline__ void dft5(V& a0, V& a1, V& a2, V& a3, V& a4) {
     a2 = cadd(b2, r2); a3 = csub(b2, r2);
 }
 
+// multiply by W16^m (sign DIR), m a compile-time constant in 0..15
+template <int DIR, int m, typename T, typename V>
+__device__ __forceinline__ V mulw16(V a) {
+    const T c = (T)0.92387953251128675612818318939679L;   // cos(pi/8)
+    const T s = (T)0.38268343236508977172845998403040L;   // sin(pi/8)
+    const T h = (T)0.70710678118654752440084436210485L;
+    constexpr int mm = m & 15;
+    if (mm == 0) return a;
+    if (mm == 4) return rot90<DIR>(a);
+    if (mm == 8) { V r; r.x = -a.x; r.y = -a.y; return r; }
+    if (mm == 12) return rot90<-DIR>(a);
+    // W = cos(th) + i*DIR*sin(th), th = 2*pi*mm/16
+    T wr, wi;
+    if (mm == 1) { wr = c; wi = s; } else if (mm == 2) { wr = h; wi = h; } else if (mm == 3) { wr = s; wi = c; }
+    else if (mm == 5) { wr = -s; wi = c; } else if (mm == 6) { wr = -h; wi = h; } else if (mm == 7) { wr = -c; wi = s; }
+    else if (mm == 9) { wr = -c; wi = -s; } else if (mm == 10) { wr = -h; wi = -h; } else if (mm == 11) { wr = -s; wi = -c; }
+    else if (mm == 13) { wr = s; wi = -c; } else if (mm == 14) { wr = h; wi = -h; } else { wr = c; wi = -s; }
+    if (DIR < 0) wi = -wi;
+    V r; r.x = a.x * wr - a.y * wi; r.y = a.x * wi + a.y * wr; return r;
+}
+
+// 16-point DFT as 4 x 4: radix-4 over n2 (stride 4), twiddle W16^(n1*k2), radix-4 over n1, transpose
+template <int DIR, typename T, typename V>
+__device__ __forceinline__ void dft16(V& a0, V& a1, V& a2, V& a3, V& a4, V& a5, V& a6, V& a7,
+                                      V& a8, V& a9, V& a10, V& a11, V& a12, V& a13, V& a14, V& a15) {
+    dft4<DIR>(a0, a4, a8, a12);      // n1 = 0: slots (0,4,8,12) <- k2 = 0..3
+    dft4<DIR>(a1, a5, a9, a13);      // n1 = 1
+    dft4<DIR>(a2, a6, a10, a14);     // n1 = 2
+    dft4<DIR>(a3, a7, a11, a15);     // n1 = 3
+    // slot n1 + 4*k2 holds B[n1][k2]; multiply by W16^(n1*k2)
+    a5 = mulw16<DIR, 1, T>(a5);  a9 = mulw16<DIR, 2, T>(a9);   a13 = mulw16<DIR, 3, T>(a13);
+    a6 = mulw16<DIR, 2, T>(a6);  a10 = mulw16<DIR, 4, T>(a10); a14 = mulw16<DIR, 6, T>(a14);
+    a7 = mulw16<DIR, 3, T>(a7);  a11 = mulw16<DIR, 6, T>(a11); a15 = mulw16<DIR, 9, T>(a15);
+    dft4<DIR>(a0, a1, a2, a3);       // k2 = 0: slots (0,1,2,3) <- k1 = 0..3  => X[4*k1 + 0]
+    dft4<DIR>(a4, a5, a6, a7);       // k2 = 1                                 => X[4*k1 + 1]
+    dft4<DIR>(a8, a9, a10, a11);     // k2 = 2
+    dft4<DIR>(a12, a13, a14, a15);   // k2 = 3
+    // slot k1 + 4*k2 holds X[4*k1 + k2]: transpose to natural order
+    V t;
+    t = a1; a1 = a4; a4 = t;      t = a2; a2 = a8; a8 = t;      t = a3; a3 = a12; a12 = t;
+    t = a6; a6 = a9; a9 = t;      t = a7; a7 = a13; a13 = t;    t = a11; a11 = a14; a14 = t;
+}
+
 // ---------------------------------------------------------------------------------------
-// radix plan: largest radix in {8,4,2,3,5} dividing both what is left of N and E
+// radix plan: largest radix in {16,8,4,2,3,5} dividing both what is left of N and E
 // ---------------------------------------------------------------------------------------
 __host__ __device__ constexpr int pick_radix(int rem, int E) {
-    return (rem % 8 == 0 && E % 8 == 0) ? 8 :
+    return (rem % 16 == 0 && E % 16 == 0) ? 16 :
+           (rem % 8 == 0 && E % 8 == 0) ? 8 :
            (rem % 4 == 0 && E % 4 == 0) ? 4 :
            (rem % 2 == 0 && E % 2 == 0) ? 2 :
            (rem % 3 == 0 && E % 3 == 0) ? 3 :
@@ -177,6 +221,17 @@ __device__ __forceinline__ void fft_stage(V (&x)[E], int t, const V* __restrict_
                             x[m + 5 * NB] = cmul(x[m + 5 * NB], w5);
                             x[m + 6 * NB] = cmul(x[m + 6 * NB], w6);
                             x[m + 7 * NB] = cmul(x[m + 7 * NB], w7);
+                            if (R > 8) {
+                                const V w8 = cmul(w4, w4);
+                                x[m + 8 * NB] = cmul(x[m + 8 * NB], w8);
+                                x[m + 9 * NB] = cmul(x[m + 9 * NB], cmul(w8, w1));
+                                x[m + 10 * NB] = cmul(x[m + 10 * NB], cmul(w5, w5));
+                                x[m + 11 * NB] = cmul(x[m + 11 * NB], cmul(w8, w3));
+                                x[m + 12 * NB] = cmul(x[m + 12 * NB], cmul(w6, w6));
+                                x[m + 13 * NB] = cmul(x[m + 13 * NB], cmul(w8, w5));
+                                x[m + 14 * NB] = cmul(x[m + 14 * NB], cmul(w7, w7));
+                                x[m + 15 * NB] = cmul(x[m + 15 * NB], cmul(w8, w7));
+                            }
                         }
                     }
                 }
@@ -187,6 +242,9 @@ __device__ __forceinline__ void fft_stage(V (&x)[E], int t, const V* __restrict_
         else if (R == 4) dft4<DIR>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB]);
         else if (R == 8) dft8<DIR, T>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB],
                                       x[m + 4 * NB], x[m + 5 * NB], x[m + 6 * NB], x[m + 7 * NB]);
+        else if (R == 16) dft16<DIR, T>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB], x[m + 4 * NB], x[m + 5 * NB],
+                                        x[m + 6 * NB], x[m + 7 * NB], x[m + 8 * NB], x[m + 9 * NB], x[m + 10 * NB],
+                                        x[m + 11 * NB], x[m + 12 * NB], x[m + 13 * NB], x[m + 14 * NB], x[m + 15 * NB]);
         else if (R == 3) dft3<DIR, T>(x[m], x[m + NB], x[m + 2 * NB]);
         else if (R == 5) dft5<DIR, T>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB], x[m + 4 * NB]);
     }

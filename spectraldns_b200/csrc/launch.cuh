@@ -36,6 +36,13 @@ constexpr int pick_E(int N, int emax) {
 // three or four CTAs are resident per SM and their load / transform / store phases overlap
 constexpr int pick_E64(int N) {
     const int b = (N % 3 == 0) ? 12 : 8;
+#ifndef SDNS_NO_RADIX16
+    if (b == 8 && N >= 256 && N % 256 == 0) {           // 16 x 16 (x 2,4,8): one exchange fewer than 8 x 8 x 4
+        int e = 16;
+        while (N / e > 64 && plan_ok(N, 2 * e) && 2 * e <= 32) e *= 2;
+        return e;
+    }
+#endif
     int e = b;
     while (N / e > 64 && 2 * e <= 16 + (b == 12 ? 8 : 0) && plan_ok(N, 2 * e)) e *= 2;
     while (N / e > 128 && plan_ok(N, 2 * e)) e *= 2;
@@ -56,7 +63,7 @@ struct SCfg {
 #ifdef SDNS_STRIDED_NBUF
     static constexpr int NBUF = SDNS_STRIDED_NBUF;
 #else
-    static constexpr int NBUF = heavy ? 1 : ((2 * bytes1 <= 100 * 1024) ? 2 : 1);
+    static constexpr int NBUF = (heavy || num_stages(N, E) <= 2) ? 1 : ((2 * bytes1 <= 100 * 1024) ? 2 : 1);
 #endif
     static constexpr size_t smem = bytes1 * (NBUF + (heavy ? 2 : 0));
     // resident CTAs per SM the register allocator must allow: what shared memory and the thread
@@ -64,7 +71,7 @@ struct SCfg {
     static constexpr int bySmem = (int)((224 * 1024) / (smem + 1024));
     static constexpr int byThreads = 2048 / (P * TC);
     static constexpr bool b0 = (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0);
-    static constexpr int needRegs = sizeof(T) == 8 ? (heavy ? 128 : (b0 ? 96 : 80) * (E > 12 ? 2 : 1))
+    static constexpr int needRegs = sizeof(T) == 8 ? (heavy ? 128 : (E > 12 ? (b0 ? 168 : 128) : (b0 ? 96 : 80)))
                                                    : (heavy ? (E > 12 ? 128 : 100) : (E > 16 ? 80 : (b0 ? 72 : 64)));
     static constexpr int byRegs = 65536 / (P * TC * needRegs);
     static constexpr int minBlocks = cmax(1, cmin(cmin(cmin(bySmem, byThreads), byRegs), heavy ? 2 : 4));
