@@ -48,9 +48,9 @@ def _run(cmd):
 def build(force=False, jobs=None, verbose=False, sizes=None):
     """Compile every CUDA translation unit for sm_100a and link libsdns_b200.so."""
     os.makedirs(OBJ, exist_ok=True)
-    extra = []
+    extra = os.environ.get('SDNS_EXTRA_FLAGS', '').split()      # experiment switches, e.g. -DSDNS_NO_F0X
     if sizes:
-        extra = ['-DSDNS_SIZES(X)=' + ' '.join('X(%d)' % s for s in sizes)]
+        extra = extra + ['-DSDNS_SIZES(X)=' + ' '.join('X(%d)' % s for s in sizes)]
     digest = _sources_digest(' '.join(extra))
     stamp = os.path.join(OBJ, 'stamp')
     if (not force and os.path.exists(LIB) and os.path.exists(stamp)

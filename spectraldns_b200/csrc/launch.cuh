@@ -52,7 +52,12 @@ constexpr int pick_E64(int N) {
 template <typename T, int N, int MODE>
 struct SCfg {
     static constexpr bool heavy = (MODE == S_NS_F0 || MODE == S_VV_F0);   // park two fields in smem
-    static constexpr int E = sizeof(T) == 8 ? (heavy ? pick_E(N, 8) : pick_E64(N)) : pick_E(N, heavy ? 16 : 24);
+    static constexpr bool b0e = (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0);
+#ifdef SDNS_F0_E16
+    static constexpr int E = sizeof(T) == 8 ? (b0e ? pick_E(N, 8) : pick_E64(N)) : pick_E(N, heavy ? 16 : 24);
+#else
+    static constexpr int E = sizeof(T) == 8 ? ((heavy || b0e) ? pick_E(N, 8) : pick_E64(N)) : pick_E(N, heavy ? 16 : 24);
+#endif
     static constexpr int P = N / E;
     // the passes that store into peer GPUs (B0 family) keep 128-byte rows: NVLink likes the larger packets
     static constexpr bool b0m = (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0);
@@ -96,12 +101,16 @@ constexpr int fx_tc(int P, int tcfull, int csize, int N, int regs) {
 
 template <typename T, int N>
 struct FXCfg {
+#ifdef SDNS_F0_E16
+    static constexpr int E = sizeof(T) == 8 ? pick_E64(N) : pick_E(N, 16);
+#else
     static constexpr int E = sizeof(T) == 8 ? pick_E(N, 8) : pick_E(N, 16);
+#endif
     static constexpr int P = N / E;
     static constexpr int csize = 2 * (int)sizeof(T);
-    static constexpr int needRegs = sizeof(T) == 8 ? 84 : (E > 12 ? 84 : 64);
+    static constexpr int needRegs = sizeof(T) == 8 ? (E > 12 ? 128 : 84) : (E > 12 ? 84 : 64);
     static constexpr int TC = fx_tc(P, 128 / csize, csize, N, needRegs);
-    static constexpr bool ok = TC > 0 && plan_ok(N, E);
+    static constexpr bool ok = TC > 0 && plan_ok(N, E) && sizeof(T) == 8;   // fp32: the register version is faster
     static constexpr size_t smem = (size_t)3 * N * (TC > 0 ? TC : 1) * csize;
     static constexpr int threads = 3 * P * (TC > 0 ? TC : 1);
     static constexpr int minBlocks = cmax(1, fx_blocks(P, TC > 0 ? TC : 1, csize, N, needRegs));

@@ -503,7 +503,9 @@ struct Pipe {
         const double bout = out_is_W2 ? (double)p->Nh * p->cs : (double)q.M[2] * p->rs;
         return do_launch(p, fam, q.M[2], &a, (double)plane * (nin * bin + nout * bout));
     }
-    // F1: A (W2) -> W3 (nf, M0, N1l, Nhp) of the rank owning each k1
+    // F1: A (W2) -> W3 (nf, N1l, M0, Nhp) of the rank owning each k1.  x0 is the second-fastest axis of
+    // W3 on purpose: F1 *stores* with the large stride (M0*Nhp), F0 *loads* its axis-0 lines with a
+    // stride of one k2 row -- loads stall warps on TLB/DRAM-page misses, stores do not.
     int f1(int nf, const V* src = nullptr) {
         StridedArgs<T> a; base(a);
         a.in = src ? src : A; a.out = C;
@@ -511,7 +513,7 @@ struct Pipe {
         a.cw = p->Nh; a.ncols = (long long)q.M0l * p->Nh;
         a.col_nlo = q.M0l; a.col_gap = 0;
         a.imap = all_map(q.M[1]); a.omap = q.fmap[1];
-        a.out_fs = (long long)q.M[0] * p->N1l * p->Nhp; a.out_ls = p->Nhp; a.out_os = (long long)p->N1l * p->Nhp;
+        a.out_fs = (long long)p->N1l * q.M[0] * p->Nhp; a.out_ls = (long long)q.M[0] * p->Nhp; a.out_os = p->Nhp;
         a.c1_out_off = (long long)p->rank * q.M0l;
         peers(a, p->off_C, p->N1l);
         a.tw = tw(q.M[1]); a.nfields = nf;
@@ -523,7 +525,7 @@ struct Pipe {
     void f0_geom(StridedArgs<T>& a, int nf) {
         base(a);
         a.in = C;
-        a.in_fs = (long long)q.M[0] * p->N1l * p->Nhp; a.in_ls = (long long)p->N1l * p->Nhp; a.in_os = p->Nhp;
+        a.in_fs = (long long)p->N1l * q.M[0] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[0] * p->Nhp;
         a.cw = p->Nh; a.ncols = (long long)p->N1l * p->Nh;
         a.col_nlo = p->N1l; a.col_gap = 0;
         a.imap = all_map(q.M[0]); a.omap = q.fmap[0];
