@@ -124,7 +124,8 @@ int sdns_compute_conv(sdns_plan* plan, void* rhs, const void* u_hat);
 /* integrate() for params.integrator == 'RK4'  (maths/integrators.py:150-159,177-191;
  * cython_integrators.in:8-52): four ComputeRHS evaluations with the stage updates fused into the
  * last transform pass.  u_hat is updated in place; u1, u2 are the integrator's work arrays
- * (u0.copy() at integrators.py:181,187). */
+ * (u0.copy() at integrators.py:181,187): same size as u_hat, contents unspecified on return (the
+ * library keeps them in a k1-major layout internally). */
 int sdns_rk4_step(sdns_plan* plan, void* u_hat, void* u1, void* u2, double dt, double nu, double eta,
                   const void* source);
 

@@ -58,6 +58,10 @@ struct StridedArgs {
     const V* source;              // optional
     V* p_hat;                     // optional (NS OUT_RHS)
     long long st_fs;              // field stride of the dense state arrays (= N0*N1*Nh)
+    // element (i0, c1, c2) of u_hat sits at i0*uh_ls + c1*uh_os + c2, of the integrator's work arrays
+    // (u1, u2, and u0 between stages) at i0*t_ls + c1*t_os + c2: the library keeps those k1-major so
+    // that the axis-0 passes touch them with small strides; rhs / source / p_hat / final u0 use out_ls/out_os
+    long long uh_ls, uh_os, t_ls, t_os;
     T nu, eta, adt, bdt;
     int rk;
     // slab decomposition (one process per GPU): the pass that precedes a global transpose stores
@@ -270,7 +274,9 @@ strided_kernel(const StridedArgs<T> a) {
                 continue;
             }
             if (nyq12 || (a.mask_nyquist && 2 * i0 == a.N0)) { d0 = czero<V>(); d1 = czero<V>(); d2 = czero<V>(); }
-            const V w0 = a.u_hat[off], w1 = a.u_hat[a.st_fs + off], w2 = a.u_hat[2 * a.st_fs + off];
+            const long long offu = (long long)i0 * a.uh_ls + (long long)c1 * a.uh_os + c2;
+            const long long offt = (long long)i0 * a.t_ls + (long long)c1 * a.t_os + c2;
+            const V w0 = a.u_hat[offu], w1 = a.u_hat[a.st_fs + offu], w2 = a.u_hat[2 * a.st_fs + offu];
             const T z = a.nu * ksq;
             if (MODE == S_NS_F0) {
                 const T ks = ksq == (T)0 ? (T)1 : ksq;
@@ -300,7 +306,7 @@ strided_kernel(const StridedArgs<T> a) {
                 // u0 = u1 + b*dt*rhs (rk<3); u2 += a*dt*rhs; u0 = u2 after rk 3.
 #pragma unroll
                 for (int f = 0; f < 3; ++f) {
-                    const long long o = f * a.st_fs + off;
+                    const long long o = f * a.st_fs + offt;
                     V b1, b2;
                     if (a.rk == 0) { b1 = ww[f]; b2 = ww[f]; a.u1[o] = b1; }
                     else { b2 = a.u2[o]; if (a.rk < 3) b1 = a.u1[o]; }
@@ -310,7 +316,7 @@ strided_kernel(const StridedArgs<T> a) {
                         V n; n.x = b1.x + a.bdt * dd[f].x; n.y = b1.y + a.bdt * dd[f].y;
                         a.u0[o] = n;
                     } else {
-                        a.u0[o] = b2;
+                        a.u0[f * a.st_fs + off] = b2;                  // final u0: reference layout
                     }
                 }
             }
@@ -383,7 +389,9 @@ f0x_kernel(const StridedArgs<T> a) {
             continue;
         }
         if (nyq12 || (a.mask_nyquist && 2 * i0 == a.N0)) { d0 = czero<V>(); d1 = czero<V>(); d2 = czero<V>(); }
-        const V w0 = a.u_hat[off], w1 = a.u_hat[a.st_fs + off], w2 = a.u_hat[2 * a.st_fs + off];
+        const long long offu = (long long)i0 * a.uh_ls + (long long)c1 * a.uh_os + c2;
+        const long long offt = (long long)i0 * a.t_ls + (long long)c1 * a.t_os + c2;
+        const V w0 = a.u_hat[offu], w1 = a.u_hat[a.st_fs + offu], w2 = a.u_hat[2 * a.st_fs + offu];
         const T z = a.nu * ksq;
         if (MODE == S_NS_F0) {
             const T ks = ksq == (T)0 ? (T)1 : ksq;
@@ -411,7 +419,7 @@ f0x_kernel(const StridedArgs<T> a) {
         } else {
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
-                const long long o = f * a.st_fs + off;
+                const long long o = f * a.st_fs + offt;
                 V b1, b2;
                 if (a.rk == 0) { b1 = ww[f]; b2 = ww[f]; a.u1[o] = b1; }
                 else { b2 = a.u2[o]; if (a.rk < 3) b1 = a.u1[o]; }
@@ -421,7 +429,7 @@ f0x_kernel(const StridedArgs<T> a) {
                     V n; n.x = b1.x + a.bdt * dd[f].x; n.y = b1.y + a.bdt * dd[f].y;
                     a.u0[o] = n;
                 } else {
-                    a.u0[o] = b2;
+                    a.u0[f * a.st_fs + off] = b2;                  // final u0: reference layout
                 }
             }
         }
@@ -520,7 +528,8 @@ mhd_f0_kernel(const StridedArgs<T> a) {
 #pragma unroll
         for (int f = 0; f < 6; ++f) {
             const long long o = f * a.st_fs + off;
-            const V w = a.u_hat[o];
+            const long long ot = f * a.st_fs + (long long)i0 * a.t_ls + (long long)c1 * a.t_os + c2;
+            const V w = a.u_hat[f * a.st_fs + (long long)i0 * a.uh_ls + (long long)c1 * a.uh_os + c2];
             const T z = f < 3 ? zu : zb;
             V dd = d[f];
             dd.x -= z * w.x; dd.y -= z * w.y;
@@ -529,13 +538,13 @@ mhd_f0_kernel(const StridedArgs<T> a) {
                 a.rhs[o] = dd;
             } else {
                 V b1, b2;
-                if (a.rk == 0) { b1 = w; b2 = w; a.u1[o] = b1; }
-                else { b2 = a.u2[o]; if (a.rk < 3) b1 = a.u1[o]; }
+                if (a.rk == 0) { b1 = w; b2 = w; a.u1[ot] = b1; }
+                else { b2 = a.u2[ot]; if (a.rk < 3) b1 = a.u1[ot]; }
                 b2.x += a.adt * dd.x; b2.y += a.adt * dd.y;
                 if (a.rk < 3) {
-                    a.u2[o] = b2;
+                    a.u2[ot] = b2;
                     V n; n.x = b1.x + a.bdt * dd.x; n.y = b1.y + a.bdt * dd.y;
-                    a.u0[o] = n;
+                    a.u0[ot] = n;
                 } else {
                     a.u0[o] = b2;
                 }
@@ -625,7 +634,8 @@ nsdiv_f0_kernel(const StridedArgs<T> a) {
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
             const long long o = f * a.st_fs + off;
-            const V w = a.u_hat[o];
+            const long long ot = f * a.st_fs + (long long)i0 * a.t_ls + (long long)c1 * a.t_os + c2;
+            const V w = a.u_hat[f * a.st_fs + (long long)i0 * a.uh_ls + (long long)c1 * a.uh_os + c2];
             V dd = d[f];
             dd.x -= p.x * kk[f] + z * w.x; dd.y -= p.y * kk[f] + z * w.y;
             if (a.source) dd = cadd(dd, a.source[o]);
@@ -633,13 +643,13 @@ nsdiv_f0_kernel(const StridedArgs<T> a) {
                 a.rhs[o] = dd;
             } else {
                 V b1, b2;
-                if (a.rk == 0) { b1 = w; b2 = w; a.u1[o] = b1; }
-                else { b2 = a.u2[o]; if (a.rk < 3) b1 = a.u1[o]; }
+                if (a.rk == 0) { b1 = w; b2 = w; a.u1[ot] = b1; }
+                else { b2 = a.u2[ot]; if (a.rk < 3) b1 = a.u1[ot]; }
                 b2.x += a.adt * dd.x; b2.y += a.adt * dd.y;
                 if (a.rk < 3) {
-                    a.u2[o] = b2;
+                    a.u2[ot] = b2;
                     V n; n.x = b1.x + a.bdt * dd.x; n.y = b1.y + a.bdt * dd.y;
-                    a.u0[o] = n;
+                    a.u0[ot] = n;
                 } else {
                     a.u0[o] = b2;
                 }

@@ -58,7 +58,7 @@ struct sdns_plan {
     sdns_config cfg;
     int N[3], Nh, Nhp;
     int P, rank, N1l;       // ranks, this rank, local spectral extent of axis 1
-    size_t off_C, bytes_C, off_flags, off_D, bytes_D, off_S, bytes_S;
+    size_t off_C, bytes_C, off_flags, off_D, bytes_D, off_S, bytes_S, off_U, bytes_U;
     bool own_ws;            // workspace cudaMalloc'ed by the library (multi-GPU: IPC-shared)
     char* peer_ws[8];       // base of every rank's workspace (peer_ws[rank] == ws)
     unsigned int epoch;
@@ -249,7 +249,10 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->bytes_S = needS ? align_up((size_t)3 * p->N[0] * p->N1l * p->Nh * p->cs, 256) : 0;
     p->off_D = p->off_B + p->bytes_B + p->bytes_C;
     p->off_S = p->off_D + p->bytes_D;
-    p->off_red = p->off_S + p->bytes_S;
+    // inter-stage copy of the RK4 state in the k1-major work layout
+    p->bytes_U = align_up((size_t)(cfg->solver == SDNS_MHD ? 6 : 3) * p->N[0] * p->N1l * p->Nh * p->cs, 256);
+    p->off_U = p->off_S + p->bytes_S;
+    p->off_red = p->off_U + p->bytes_U;
     p->off_flags = p->off_red + align_up(sizeof(double) * p->red_blocks, 256);
     p->ws_need = p->off_flags + 256;
     *out = p;
@@ -446,6 +449,8 @@ struct Pipe {
         a.scale = (T)1;
         a.st_fs = dense_fs();
         a.k1_off = p->rank * p->N1l;
+        a.uh_ls = (long long)p->N1l * p->Nh; a.uh_os = p->Nh;          // reference layout (N0, N1l, Nh)
+        a.t_ls = p->Nh; a.t_os = (long long)p->N[0] * p->Nh;           // work layout (N1l, N0, Nh)
     }
     long long dense_fs() const { return (long long)p->N[0] * p->N1l * p->Nh; }
     void peers(StridedArgs<T>& a, size_t off, int chunk) const {
@@ -455,10 +460,12 @@ struct Pipe {
     }
 
     // B0: local dense spectral (nf, N0, N1l, Nh) -> W0 (nfo, M0l, K1n, K2p) of the rank owning each x0
-    int b0(int fam, const V* in, int nf, int comp = 0) {
+    int b0(int fam, const V* in, int nf, int comp = 0, bool work_layout = false) {
         StridedArgs<T> a; base(a);
         a.in = in; a.out = A; a.comp = comp;
-        a.in_fs = dense_fs(); a.in_ls = (long long)p->N1l * p->Nh; a.in_os = p->Nh;
+        a.in_fs = dense_fs();
+        if (work_layout) { a.in_ls = p->Nh; a.in_os = (long long)p->N[0] * p->Nh; }
+        else { a.in_ls = (long long)p->N1l * p->Nh; a.in_os = p->Nh; }
         a.cw = q.K2n; a.ncols = (long long)q.K1l * q.K2n;
         a.col_nlo = q.lcol_nlo; a.col_gap = q.lcol_gap;
         a.imap = q.bmap[0]; a.omap = all_map(q.M[0]);
@@ -575,6 +582,7 @@ static int forward_t(sdns_plan* p, int space, int nc, const void* in, void* out)
 struct StageOut {
     int out_mode; void* rhs; void* u0; void* u1; void* u2; void* p_hat; const void* source;
     double adt, bdt; int rk;
+    bool in_work_layout;      // u_hat is the library's k1-major inter-stage copy
 };
 
 template <typename T>
@@ -595,7 +603,7 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
             // u_j du_i/dx_j (NS.py:138-145): per component i six backward transforms (u, grad u_i) and one product
             const long long dfs = (long long)P.q.M0l * P.q.M[1] * p->Nhp;
             for (int i = 0; i < 3; ++i) {
-                if ((e = P.b0(FAM_NS_GRAD_B0, u, 3, i))) return e;
+                if ((e = P.b0(FAM_NS_GRAD_B0, u, 3, i, so.in_work_layout))) return e;
                 if ((e = xbarrier(p))) return e;
                 if ((e = P.b1(6))) return e;
                 if ((e = P.z(FAM_Z_DOT, P.B, D + i * dfs, 6, true, true))) return e;
@@ -613,7 +621,7 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
         }
         if (conv == SDNS_CONV_DIVERGENCE || conv == SDNS_CONV_SKEWED) {
             // d/dx_j (u_i u_j) (NS.py:147-162): three backward, six forward transforms
-            if ((e = P.b0(FAM_PLAIN_BWD, u, 3))) return e;
+            if ((e = P.b0(FAM_PLAIN_BWD, u, 3, 0, so.in_work_layout))) return e;
             if ((e = xbarrier(p))) return e;
             if ((e = P.b1(3))) return e;
             if ((e = P.z(FAM_Z_UU, P.B, P.A, 3, true, true))) return e;
@@ -622,9 +630,9 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
             nprod = 6; divform = true;
         }
     } else {
-    if (solver == SDNS_NS) { if ((e = P.b0(FAM_NS_B0, u, 3))) return e; }
-    else if (solver == SDNS_VV) { if ((e = P.b0(FAM_VV_B0, u, 3))) return e; }
-    else { if ((e = P.b0(FAM_PLAIN_BWD, u, 6))) return e; }
+    if (solver == SDNS_NS) { if ((e = P.b0(FAM_NS_B0, u, 3, 0, so.in_work_layout))) return e; }
+    else if (solver == SDNS_VV) { if ((e = P.b0(FAM_VV_B0, u, 3, 0, so.in_work_layout))) return e; }
+    else { if ((e = P.b0(FAM_PLAIN_BWD, u, 6, 0, so.in_work_layout))) return e; }
     if ((e = xbarrier(p))) return e;
     if ((e = P.b1(6))) return e;
     if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true))) return e;
@@ -640,6 +648,7 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
     a.p_hat = reinterpret_cast<V*>(so.p_hat);
     a.nu = (T)nu; a.eta = (T)eta; a.adt = (T)so.adt; a.bdt = (T)so.bdt; a.rk = so.rk;
     a.scale = f0scale;
+    if (so.in_work_layout) { a.uh_ls = a.t_ls; a.uh_os = a.t_os; }
     if (divform) {
         a.cfac = conv == SDNS_CONV_SKEWED ? (T)-0.5 : (T)-1;
         a.addin = conv == SDNS_CONV_SKEWED ? reinterpret_cast<const V*>(p->ws + p->off_S) : nullptr;
@@ -699,11 +708,18 @@ extern "C" int sdns_rk4_step(sdns_plan* p, void* u_hat, void* u1, void* u2, doub
                              double eta, const void* source) {
     int e = need_ws(p); if (e) return e;
     if (!u_hat || !u1 || !u2) return fail(SDNS_ERR_ARG, "sdns_rk4_step: null array");
+    // Between stages the state lives in the workspace in the k1-major work layout (u1, u2 too): the
+    // axis-0 passes then read and write it with a stride of one k2 row instead of N1*Nh elements.
+    // Stage 0 reads the caller's u_hat (reference layout), stage 3 writes it back in that layout.
+    void* u0w = p->ws + p->off_U;
     for (int rk = 0; rk < 4; ++rk) {
         StageOut so; memset(&so, 0, sizeof so);
-        so.out_mode = OUT_STAGE; so.u0 = u_hat; so.u1 = u1; so.u2 = u2; so.source = source; so.rk = rk;
+        so.out_mode = OUT_STAGE; so.u1 = u1; so.u2 = u2; so.source = source; so.rk = rk;
+        so.u0 = rk < 3 ? u0w : u_hat;
+        so.in_work_layout = rk > 0;
         if (p->prec) rk_coeffs<double>(rk, dt, &so.adt, &so.bdt); else rk_coeffs<float>(rk, dt, &so.adt, &so.bdt);
-        e = p->prec ? rhs_t<double>(p, u_hat, nu, eta, so) : rhs_t<float>(p, u_hat, nu, eta, so);
+        const void* uin = rk == 0 ? u_hat : u0w;
+        e = p->prec ? rhs_t<double>(p, uin, nu, eta, so) : rhs_t<float>(p, uin, nu, eta, so);
         if (e) return e;
     }
     return SDNS_OK;
