@@ -139,3 +139,50 @@ def test_timer_interface(compat, capsys):
     t.final(True)
     out = capsys.readouterr().out
     assert 'Fastest = (' in out and 'Slowest = (' in out and 'Time = ' in out
+
+
+def test_c_abi_error_behaviour():
+    """Argument validation happens before any CUDA call, so it is testable without a GPU: every entry
+    returns a negative sdns_status and sdns_last_error() names the problem."""
+    from spectraldns_b200 import _lib
+    L = _lib.lib()
+
+    def cfg(**kw):
+        c = _lib.SdnsConfig()
+        c.abi_version = 1
+        for i in range(3):
+            c.N[i], c.L[i], c.kcut[i] = 32, 2*np.pi, -1
+        c.precision, c.dealias, c.solver, c.convection, c.nranks = 1, 1, 0, 0, 1
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    p = ctypes.c_void_p()
+    assert L.sdns_plan_create(ctypes.byref(p), None) == -1
+    assert L.sdns_plan_create(ctypes.byref(p), ctypes.byref(cfg(abi_version=99))) == -1
+    assert b'ABI' in L.sdns_last_error()
+    assert L.sdns_plan_create(ctypes.byref(p), ctypes.byref(cfg(precision=7))) == -1
+    assert L.sdns_plan_create(ctypes.byref(p), ctypes.byref(cfg(nranks=9))) == -1
+    assert L.sdns_plan_create(ctypes.byref(p), ctypes.byref(cfg(nranks=2, rank=0, decomposition=1))) == -1
+    assert b'slab' in L.sdns_last_error()
+    assert L.sdns_plan_create(ctypes.byref(p), ctypes.byref(cfg(solver=1, convection=1))) == -1      # VV + Divergence
+    assert b'VV' in L.sdns_last_error()
+    assert L.sdns_plan_create(ctypes.byref(p), ctypes.byref(cfg(solver=2, convection=0))) == -1      # MHD + Vortex
+    assert L.sdns_plan_create(ctypes.byref(p), ctypes.byref(cfg(convection=7))) == -1
+    # null plans
+    assert L.sdns_sync(None) == -1 and L.sdns_forward(None, 0, 1, None, None) != 0
+    n = ctypes.c_size_t()
+    assert L.sdns_workspace_bytes(None, ctypes.byref(n)) == -1
+
+
+def test_slab_and_plan_size_rules_agree():
+    """spectraldns_b200.slab (host mirror) rejects exactly what sdns_plan_create rejects for sharding."""
+    from spectraldns_b200.slab import SlabLayout
+    for N, P, ok in (((64, 64, 64), 8, True), ((64, 36, 64), 8, False), ((36, 64, 64), 8, False),
+                     ((48, 48, 48), 3, True), ((32, 32, 32), 5, False)):
+        try:
+            SlabLayout(N, P, 0)
+            good = True
+        except ValueError:
+            good = False
+        assert good == ok, (N, P)
