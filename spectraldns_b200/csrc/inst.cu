@@ -25,7 +25,15 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
     auto kern = strided_kernel<T, N, C::E, C::TC, DIR, MODE, C::NBUF, C::minBlocks>;
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
-    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC), MODE == S_PLAIN ? a.nfields : 1);
+    long long tiles = (a.ncols + C::TC - 1) / C::TC;
+    const int ny = MODE == S_PLAIN ? a.nfields : 1;
+    if (a.grid_cap > 0) {
+        static int nsm = 0;
+        if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+        const long long cap = ((long long)a.grid_cap * nsm + ny - 1) / ny;
+        if (tiles > cap) tiles = cap;
+    }
+    dim3 grid((unsigned)tiles, ny);
     kern<<<grid, C::P * C::TC, C::smem, st>>>(a);
     return (int)cudaGetLastError();
 }
@@ -78,16 +86,17 @@ template <typename T, int M, int QN>
 static int run_zx_q(const ZArgs<T>& a, cudaStream_t st) {
     typedef ZXCfg<T, M> C;
     auto kern = zx_kernel<T, M, C::E, C::LPC, QN, C::minBlocks>;
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
+    static int occ_sm = 0, nsm = 0;
+    if (!occ_sm) {
         cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e;
-        int dev = 0, nsm = 0, occ = 0;
+        int dev = 0, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * C::LPC, C::smem);
         if (e != cudaSuccess) return (int)e;
-        blocks_per_sm = (occ > 0 ? occ : 1) * nsm;
+        occ_sm = occ > 0 ? occ : 1;
     }
+    const long long blocks_per_sm = (long long)((a.grid_cap > 0 && a.grid_cap < occ_sm) ? a.grid_cap : occ_sm) * nsm;
     const long long want = (a.nlines + C::LPC - 1) / C::LPC;
     dim3 grid((unsigned)(want < blocks_per_sm ? want : blocks_per_sm));
     kern<<<grid, 32 * C::LPC, C::smem, st>>>(a);

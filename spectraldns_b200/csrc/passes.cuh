@@ -73,6 +73,8 @@ struct StridedArgs {
     int xchunk;
     long long c1_out_off;         // added to the run index of the output base (global x0 / compact k1)
     int k1_off;                   // global index of local k1 = 0 (Nyquist test in the epilogues)
+    int c1_off, c2_off;           // first run / first column of this launch (the multi-GPU pipeline launches a pass in chunks)
+    int grid_cap;                 // > 0: launch at most this many CTAs per SM (grid-stride over the tiles)
     V* peer_out[8];
 };
 
@@ -158,16 +160,20 @@ strided_kernel(const StridedArgs<T> a) {
     constexpr int P = N / E;
     const int c = threadIdx.x % TC;
     const int t = threadIdx.x / TC;
-    const long long col = (long long)blockIdx.x * TC + c;
-    const bool valid = col < a.ncols;
-    const int c1 = valid ? (int)(col / a.cw) : 0;
-    const int c2 = valid ? (int)(col % a.cw) : 0;
-    const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
-    const long long ibase = (long long)c1m * a.in_os + c2;
-    const long long obase = ((long long)c1 + a.c1_out_off) * a.out_os + c2;
     SmemLine<TC, 0> map; map.base = c;
     int phase = 0;
     constexpr int BUFSTRIDE = N * TC;
+    // One tile of TC columns per CTA; launched with a capped grid (grid_cap, the multi-GPU pipeline) the CTA walks
+    // the tiles with a grid stride instead, so that an NVLink-bound pass leaves SM room for the pass beside it.
+    const long long ntiles = (a.ncols + TC - 1) / TC;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long col = tile * TC + c;
+    const bool valid = col < a.ncols;
+    const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;      // c1_off / c2_off: chunked launches
+    const int c2 = valid ? (int)(col % a.cw) + a.c2_off : 0;
+    const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
+    const long long ibase = (long long)c1m * a.in_os + c2;
+    const long long obase = ((long long)c1 + a.c1_out_off) * a.out_os + c2;
 
     if (MODE == S_PLAIN) {
         const int f = blockIdx.y;
@@ -249,7 +255,7 @@ strided_kernel(const StridedArgs<T> a) {
                 for (int q = 0; q < E; ++q) park[(f * E + q) * NT + threadIdx.x] = x[q];
             }
         }
-        if (!valid) return;
+        if (!valid) continue;
         const int i1 = c1, i2 = c2;
         const T k1 = a.ky[i1], k2 = a.kz[i2];
         const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
@@ -322,6 +328,7 @@ strided_kernel(const StridedArgs<T> a) {
             }
         }
     }
+    }   // tile loop
 }
 
 // ---------------------------------------------------------------------------------------
@@ -344,8 +351,8 @@ f0x_kernel(const StridedArgs<T> a) {
     const int t = tid / TC;
     const long long col = (long long)blockIdx.x * TC + c;
     const bool valid = col < a.ncols;
-    const int c1 = valid ? (int)(col / a.cw) : 0;
-    const int c2 = valid ? (int)(col % a.cw) : 0;
+    const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;      // c1_off / c2_off: chunked launches
+    const int c2 = valid ? (int)(col % a.cw) + a.c2_off : 0;
     const long long ibase = (long long)c1 * a.in_os + c2;
     const long long obase = (long long)c1 * a.out_os + c2;
     SmemLine<TC, 0> map; map.base = c;
@@ -453,8 +460,8 @@ mhd_f0_kernel(const StridedArgs<T> a) {
     const int t = threadIdx.x / TC;
     const long long col = (long long)blockIdx.x * TC + c;
     const bool valid = col < a.ncols;
-    const int c1 = valid ? (int)(col / a.cw) : 0;
-    const int c2 = valid ? (int)(col % a.cw) : 0;
+    const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;      // c1_off / c2_off: chunked launches
+    const int c2 = valid ? (int)(col % a.cw) + a.c2_off : 0;
     const long long ibase = (long long)c1 * a.in_os + c2;
     const long long obase = (long long)c1 * a.out_os + c2;
     SmemLine<TC, 0> map; map.base = c;
@@ -569,8 +576,8 @@ nsdiv_f0_kernel(const StridedArgs<T> a) {
     const int t = threadIdx.x / TC;
     const long long col = (long long)blockIdx.x * TC + c;
     const bool valid = col < a.ncols;
-    const int c1 = valid ? (int)(col / a.cw) : 0;
-    const int c2 = valid ? (int)(col % a.cw) : 0;
+    const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;      // c1_off / c2_off: chunked launches
+    const int c2 = valid ? (int)(col % a.cw) + a.c2_off : 0;
     const long long ibase = (long long)c1 * a.in_os + c2;
     const long long obase = (long long)c1 * a.out_os + c2;
     SmemLine<TC, 0> map; map.base = c;
@@ -674,6 +681,7 @@ struct ZArgs {
     int nf;                       // fields for Z_C2R / Z_R2C
     const V* tw;
     T scale;                      // applied on the r2c side (and Z_C2R output)
+    int grid_cap;                 // persistent kernels: resident CTAs per SM to use (0 = all), leaves room for a concurrent pass
 };
 
 template <typename T, int M, int E, typename V>

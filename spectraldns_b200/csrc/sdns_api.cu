@@ -74,6 +74,13 @@ struct sdns_plan {
     size_t kx_off, ky_off, kz_off;
     long long launches;
     int red_blocks;
+    // multi-GPU pipeline: the passes that store into the peers (B0, F1) run on their own stream in chunks, so
+    // that the NVLink exchange of one chunk overlaps the local passes (F0, B1, Z) of its neighbours
+    int nchunk;                     // chunks per pass (1: serial schedule on the plan stream)
+    int xcap, zcap;                 // CTAs per SM of the exchange passes / of the persistent z kernel while they overlap
+    cudaStream_t xstream;           // exchange stream (highest priority)
+    cudaEvent_t ev_start, ev_f1all;
+    std::vector<cudaEvent_t> ev_b0, ev_z, ev_f0;
     // optional per-family profiling (bench.py roofline): CUDA events around every launch
     bool prof;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used;
@@ -213,6 +220,29 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->rs = p->prec ? 8 : 4; p->cs = 2 * p->rs;
     p->stream = 0; p->ws = nullptr; p->ws_bytes = 0; p->launches = 0;
     p->prof = false; p->ev_used = 0;
+    p->nchunk = 1; p->xstream = nullptr; p->ev_start = nullptr; p->ev_f1all = nullptr;
+    if (p->P > 1) {
+        const char* env = getenv("SDNS_CHUNKS");
+        p->nchunk = env ? atoi(env) : 4;
+        if (p->nchunk < 1) p->nchunk = 1;
+        if (p->nchunk > 16) p->nchunk = 16;
+    }
+    { const char* e1 = getenv("SDNS_XCAP"); p->xcap = e1 ? atoi(e1) : 1;
+      const char* e2 = getenv("SDNS_ZCAP"); p->zcap = e2 ? atoi(e2) : 2; }
+    if (p->nchunk > 1) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaError_t e1 = cudaStreamCreateWithPriority(&p->xstream, cudaStreamNonBlocking, hi);
+        if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming);
+        if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_f1all, cudaEventDisableTiming);
+        for (int c = 0; c < p->nchunk && e1 == cudaSuccess; ++c) {
+            cudaEvent_t e;
+            if ((e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) == cudaSuccess) p->ev_b0.push_back(e);
+            if (e1 == cudaSuccess && (e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) == cudaSuccess) p->ev_z.push_back(e);
+            if (e1 == cudaSuccess && (e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) == cudaSuccess) p->ev_f0.push_back(e);
+        }
+        if (e1 != cudaSuccess) { std::string m = std::string("pipeline stream/events: ") + cudaGetErrorString(e1); delete p; return fail(SDNS_ERR_CUDA, m); }
+    }
     for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_remote[i] = 0; p->prof_n[i] = 0; }
     build_spaces(p);
     for (int s = 0; s < 2; ++s)
@@ -262,6 +292,12 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
 extern "C" int sdns_plan_destroy(sdns_plan* p) {
     if (p) {
         for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+        for (cudaEvent_t e : p->ev_b0) cudaEventDestroy(e);
+        for (cudaEvent_t e : p->ev_z) cudaEventDestroy(e);
+        for (cudaEvent_t e : p->ev_f0) cudaEventDestroy(e);
+        if (p->ev_start) cudaEventDestroy(p->ev_start);
+        if (p->ev_f1all) cudaEventDestroy(p->ev_f1all);
+        if (p->xstream) cudaStreamDestroy(p->xstream);
         for (int r = 0; r < 8; ++r) if (p->peer_ws[r] && r != p->rank) cudaIpcCloseMemHandle(p->peer_ws[r]);
         if (p->own_ws && p->ws) cudaFree(p->ws);
     }
@@ -416,11 +452,11 @@ static cudaEvent_t get_event(sdns_plan* p) {
 
 // bytes = algorithmic HBM bytes of this launch: every input element read once + every output
 // element written once at the pass's actual (pruned / padded) sizes
-static int do_launch(sdns_plan* p, int fam, int n, const void* args, double bytes = 0, double remote = 0) {
+static int do_launch(sdns_plan* p, cudaStream_t st, int fam, int n, const void* args, double bytes = 0, double remote = 0) {
     sdns_plan::Rec r; r.fam = fam; r.bytes = bytes; r.remote = remote;
-    if (p->prof) { r.a = get_event(p); cudaEventRecord(r.a, p->stream); }
-    int e = g_launch[fam][p->prec](n, args, p->stream);
-    if (p->prof) { r.b = get_event(p); cudaEventRecord(r.b, p->stream); p->recs.push_back(r); }
+    if (p->prof) { r.a = get_event(p); cudaEventRecord(r.a, st); }
+    int e = g_launch[fam][p->prec](n, args, st);
+    if (p->prof) { r.b = get_event(p); cudaEventRecord(r.b, st); p->recs.push_back(r); }
     p->launches++;
     if (e == -1000) { char b[96]; snprintf(b, sizeof b, "no kernel for length %d (family %d)", n, fam); return fail(SDNS_ERR_SIZE, b); }
     if (e != 0) { char b[160]; snprintf(b, sizeof b, "kernel launch (family %d, n=%d): %s", fam, n, cudaGetErrorString((cudaError_t)e)); return fail(SDNS_ERR_CUDA, b); }
@@ -428,13 +464,18 @@ static int do_launch(sdns_plan* p, int fam, int n, const void* args, double byte
 }
 
 // ---- typed pipeline --------------------------------------------------------------------
+struct Rng { int a, b; };     // half-open index range of a chunked launch; a < 0: the whole axis
+
 template <typename T>
 struct Pipe {
     typedef typename C2<T>::type V;
     sdns_plan* p;
     const Space& q;
     V* A; V* B; V* C;
-    Pipe(sdns_plan* p_, int space) : p(p_), q(p_->sp[space]) {
+    cudaStream_t st;            // stream the next pass is launched on
+    int zcap;                   // resident CTAs per SM for the persistent z kernel (0 = all)
+    int xcap;                   // CTAs per SM of the passes that store into the peers (0 = one CTA per tile)
+    Pipe(sdns_plan* p_, int space) : p(p_), q(p_->sp[space]), st(p_->stream), zcap(0), xcap(0) {
         A = reinterpret_cast<V*>(p->ws + p->off_A); B = reinterpret_cast<V*>(p->ws + p->off_B);
         C = reinterpret_cast<V*>(p->ws + p->off_C);
     }
@@ -458,82 +499,99 @@ struct Pipe {
         a.xchunk = chunk;
         for (int r = 0; r < p->P; ++r) a.peer_out[r] = reinterpret_cast<V*>(p->peer_ws[r] + off);
     }
+    static Rng whole(Rng r, int n) { if (r.a < 0) { r.a = 0; r.b = n; } return r; }
 
-    // B0: local dense spectral (nf, N0, N1l, Nh) -> W0 (nfo, M0l, K1n, K2p) of the rank owning each x0
-    int b0(int fam, const V* in, int nf, int comp = 0, bool work_layout = false) {
+    // B0: local dense spectral (nf, N0, N1l, Nh) -> W0 (nfo, M0l, K1n, K2p) of the rank owning each x0.
+    // k2: the k2 columns of this launch.
+    int b0(int fam, const V* in, int nf, int comp = 0, bool work_layout = false, Rng k2 = Rng{-1, 0}) {
+        k2 = whole(k2, q.K2n);
         StridedArgs<T> a; base(a);
         a.in = in; a.out = A; a.comp = comp;
         a.in_fs = dense_fs();
         if (work_layout) { a.in_ls = p->Nh; a.in_os = (long long)p->N[0] * p->Nh; }
         else { a.in_ls = (long long)p->N1l * p->Nh; a.in_os = p->Nh; }
-        a.cw = q.K2n; a.ncols = (long long)q.K1l * q.K2n;
+        a.cw = k2.b - k2.a; a.c2_off = k2.a; a.ncols = (long long)q.K1l * a.cw;
         a.col_nlo = q.lcol_nlo; a.col_gap = q.lcol_gap;
         a.imap = q.bmap[0]; a.omap = all_map(q.M[0]);
         a.out_fs = (long long)q.M0l * q.K1n * q.K2p; a.out_ls = (long long)q.K1n * q.K2p; a.out_os = q.K2p;
         a.c1_out_off = q.c1off;
         peers(a, p->off_A, q.M0l);
+        a.grid_cap = xcap;
         a.tw = tw(q.M[0]); a.nfields = nf;
         const int nfo = (fam == FAM_PLAIN_BWD) ? nf : 6;
-        const double cols = (double)q.K1l * q.K2n;
+        const double cols = (double)q.K1l * a.cw;
         const double bytes = (nf * cols * (q.bmap[0].nlo + q.bmap[0].nhi) + nfo * cols * q.M[0]) * p->cs;
         if (a.ncols == 0) return SDNS_OK;              // this rank owns no mode that survives the truncation
         const double remote = nfo * cols * q.M[0] * p->cs * (p->P - 1) / p->P;   // stored into peers over NVLink
-        return do_launch(p, fam, q.M[0], &a, bytes, remote);
+        return do_launch(p, st, fam, q.M[0], &a, bytes, remote);
     }
     // B1: A (W0) -> B as W1 (nf, M0l, M1, K2p)
-    int b1(int nf) {
+    int b1(int nf, Rng k2 = Rng{-1, 0}) {
+        k2 = whole(k2, q.K2n);
         StridedArgs<T> a; base(a);
         a.in = A; a.out = B;
         a.in_fs = (long long)q.M0l * q.K1n * q.K2p; a.in_ls = q.K2p; a.in_os = (long long)q.K1n * q.K2p;
-        a.cw = q.K2n; a.ncols = (long long)q.M0l * q.K2n;
+        a.cw = k2.b - k2.a; a.c2_off = k2.a; a.ncols = (long long)q.M0l * a.cw;
         a.col_nlo = q.M0l; a.col_gap = 0;
         a.imap = q.bmap[1];
         a.omap = all_map(q.M[1]);
         a.out_fs = (long long)q.M0l * q.M[1] * q.K2p; a.out_ls = q.K2p; a.out_os = (long long)q.M[1] * q.K2p;
         a.tw = tw(q.M[1]); a.nfields = nf;
-        const double bytes = (double)nf * q.M0l * q.K2n * ((double)q.K1n + q.M[1]) * p->cs;
-        return do_launch(p, FAM_PLAIN_BWD, q.M[1], &a, bytes);
+        const double bytes = (double)nf * q.M0l * a.cw * ((double)q.K1n + q.M[1]) * p->cs;
+        return do_launch(p, st, FAM_PLAIN_BWD, q.M[1], &a, bytes);
     }
-    // Z: B (W1) -> A as W2 (nfo, M0l, M1, Nhp)   [fused], or to/from user real arrays [plain]
-    int z(int fam, const void* in, void* out, int nf, bool in_is_W1, bool out_is_W2) {
+    // Z: B (W1) -> A as W2 (nfo, M0l, M1, Nhp)   [fused], or to/from user real arrays [plain].
+    // x0: the local x0 planes of this launch.
+    int z(int fam, const void* in, void* out, int nf, bool in_is_W1, bool out_is_W2, Rng x0 = Rng{-1, 0}) {
+        x0 = whole(x0, q.M0l);
         ZArgs<T> a; memset(&a, 0, sizeof a);
-        a.in = in; a.out = out;
         const long long plane = (long long)q.M0l * q.M[1];
         a.in_ls = in_is_W1 ? q.K2p : q.M[2]; a.in_fs = plane * a.in_ls;
         a.out_ls = out_is_W2 ? p->Nhp : q.M[2]; a.out_fs = plane * a.out_ls;
-        a.nlines = plane; a.nin_keep = q.K2n; a.nout_keep = p->Nh; a.nf = nf;
+        const long long l0 = (long long)x0.a * q.M[1];
+        a.in = in_is_W1 ? (const void*)(reinterpret_cast<const V*>(in) + l0 * a.in_ls)
+                        : (const void*)(reinterpret_cast<const T*>(in) + l0 * a.in_ls);
+        a.out = out_is_W2 ? (void*)(reinterpret_cast<V*>(out) + l0 * a.out_ls)
+                          : (void*)(reinterpret_cast<T*>(out) + l0 * a.out_ls);
+        a.nlines = (long long)(x0.b - x0.a) * q.M[1]; a.nin_keep = q.K2n; a.nout_keep = p->Nh; a.nf = nf;
         a.tw = tw(q.M[2]);
         a.scale = (fam == FAM_Z_C2R) ? (T)1 : (T)q.scale;
+        a.grid_cap = zcap;
         const int nin = (fam == FAM_Z_CROSS || fam == FAM_Z_MHD || fam == FAM_Z_DOT) ? 6 : (fam == FAM_Z_UU ? 3 : nf);
         const int nout = fam == FAM_Z_CROSS ? 3 : (fam == FAM_Z_MHD ? 9 : (fam == FAM_Z_DOT ? 1 : (fam == FAM_Z_UU ? 6 : nf)));
         const double bin = in_is_W1 ? (double)q.K2n * p->cs : (double)q.M[2] * p->rs;
         const double bout = out_is_W2 ? (double)p->Nh * p->cs : (double)q.M[2] * p->rs;
-        return do_launch(p, fam, q.M[2], &a, (double)plane * (nin * bin + nout * bout));
+        if (a.nlines == 0) return SDNS_OK;
+        return do_launch(p, st, fam, q.M[2], &a, (double)a.nlines * (nin * bin + nout * bout));
     }
     // F1: A (W2) -> W3 (nf, N1l, M0, Nhp) of the rank owning each k1.  x0 is the second-fastest axis of
     // W3 on purpose: F1 *stores* with the large stride (M0*Nhp), F0 *loads* its axis-0 lines with a
     // stride of one k2 row -- loads stall warps on TLB/DRAM-page misses, stores do not.
-    int f1(int nf, const V* src = nullptr) {
+    int f1(int nf, const V* src = nullptr, Rng x0 = Rng{-1, 0}) {
+        x0 = whole(x0, q.M0l);
         StridedArgs<T> a; base(a);
         a.in = src ? src : A; a.out = C;
         a.in_fs = (long long)q.M0l * q.M[1] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[1] * p->Nhp;
-        a.cw = p->Nh; a.ncols = (long long)q.M0l * p->Nh;
+        a.cw = p->Nh; a.c1_off = x0.a; a.ncols = (long long)(x0.b - x0.a) * p->Nh;
         a.col_nlo = q.M0l; a.col_gap = 0;
         a.imap = all_map(q.M[1]); a.omap = q.fmap[1];
         a.out_fs = (long long)p->N1l * q.M[0] * p->Nhp; a.out_ls = (long long)q.M[0] * p->Nhp; a.out_os = p->Nhp;
         a.c1_out_off = (long long)p->rank * q.M0l;
         peers(a, p->off_C, p->N1l);
+        a.grid_cap = xcap;
         a.tw = tw(q.M[1]); a.nfields = nf;
-        const double bytes = (double)nf * q.M0l * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
-        const double remote = (double)nf * q.M0l * p->Nh * p->N[1] * p->cs * (p->P - 1) / p->P;
-        return do_launch(p, FAM_PLAIN_FWD, q.M[1], &a, bytes, remote);
+        const double bytes = (double)nf * (x0.b - x0.a) * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
+        const double remote = (double)nf * (x0.b - x0.a) * p->Nh * p->N[1] * p->cs * (p->P - 1) / p->P;
+        if (a.ncols == 0) return SDNS_OK;
+        return do_launch(p, st, FAM_PLAIN_FWD, q.M[1], &a, bytes, remote);
     }
-    // F0 geometry: W3 -> local dense spectral
-    void f0_geom(StridedArgs<T>& a, int nf) {
+    // F0 geometry: W3 -> local dense spectral, k2 columns [k2.a, k2.b)
+    void f0_geom(StridedArgs<T>& a, int nf, Rng k2 = Rng{-1, 0}) {
+        k2 = whole(k2, p->Nh);
         base(a);
         a.in = C;
         a.in_fs = (long long)p->N1l * q.M[0] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[0] * p->Nhp;
-        a.cw = p->Nh; a.ncols = (long long)p->N1l * p->Nh;
+        a.cw = k2.b - k2.a; a.c2_off = k2.a; a.ncols = (long long)p->N1l * a.cw;
         a.col_nlo = p->N1l; a.col_gap = 0;
         a.imap = all_map(q.M[0]); a.omap = q.fmap[0];
         a.out_fs = dense_fs(); a.out_ls = (long long)p->N1l * p->Nh; a.out_os = p->Nh;
@@ -574,7 +632,7 @@ static int forward_t(sdns_plan* p, int space, int nc, const void* in, void* out)
         StridedArgs<T> a; P.f0_geom(a, nf);
         a.out = dst;
         const double bytes = (double)nf * p->N1l * p->Nh * ((double)P.q.M[0] + p->N[0]) * p->cs;
-        if ((e = do_launch(p, FAM_PLAIN_FWD, P.q.M[0], &a, bytes))) return e;
+        if ((e = do_launch(p, p->stream, FAM_PLAIN_FWD, P.q.M[0], &a, bytes))) return e;
     }
     return SDNS_OK;
 }
@@ -583,7 +641,107 @@ struct StageOut {
     int out_mode; void* rhs; void* u0; void* u1; void* u2; void* p_hat; const void* source;
     double adt, bdt; int rk;
     bool in_work_layout;      // u_hat is the library's k1-major inter-stage copy
+    bool chain;               // the previous launch sequence was stage rk-1 of the same step (pipeline: its
+                              // per-chunk F0 events order this stage's B0 chunks)
 };
+
+// the F0 launch (final forward pass + epilogue) over the k2 columns `k2` of the nprod product fields
+template <typename T>
+static int launch_f0(sdns_plan* p, Pipe<T>& P, const void* u_hat, double nu, double eta, const StageOut& so,
+                     int nprod, bool divform, T f0scale, Rng k2) {
+    typedef typename C2<T>::type V;
+    const int solver = p->cfg.solver, conv = p->cfg.convection;
+    k2 = Pipe<T>::whole(k2, p->Nh);
+    if (k2.b <= k2.a) return SDNS_OK;
+    StridedArgs<T> a; P.f0_geom(a, nprod, k2);
+    a.out_mode = so.out_mode;
+    a.u_hat = reinterpret_cast<const V*>(u_hat);
+    a.rhs = reinterpret_cast<V*>(so.rhs);
+    a.u0 = reinterpret_cast<V*>(so.u0); a.u1 = reinterpret_cast<V*>(so.u1); a.u2 = reinterpret_cast<V*>(so.u2);
+    a.source = reinterpret_cast<const V*>(so.source);
+    a.p_hat = reinterpret_cast<V*>(so.p_hat);
+    a.nu = (T)nu; a.eta = (T)eta; a.adt = (T)so.adt; a.bdt = (T)so.bdt; a.rk = so.rk;
+    a.scale = f0scale;
+    if (so.in_work_layout) { a.uh_ls = a.t_ls; a.uh_os = a.t_os; }
+    if (divform) {
+        a.cfac = conv == SDNS_CONV_SKEWED ? (T)-0.5 : (T)-1;
+        a.addin = conv == SDNS_CONV_SKEWED ? reinterpret_cast<const V*>(p->ws + p->off_S) : nullptr;
+    }
+    const int fam = divform ? FAM_NSDIV_F0 : (solver == SDNS_NS ? FAM_NS_F0 : (solver == SDNS_VV ? FAM_VV_F0 : FAM_MHD_F0));
+    // epilogue traffic: read the product fields; state reads/writes of the stage update
+    const int ns = solver == SDNS_MHD ? 6 : 3;
+    double stt;   // state arrays touched, in units of one ns-component spectral vector
+    if (so.out_mode == OUT_RHS) stt = 2;                               // read u_hat, write rhs
+    else if (so.out_mode == OUT_CONV) stt = 1;
+    else stt = so.rk == 0 ? 1 + 3 : (so.rk < 3 ? 3 + 2 : 2 + 1);      // see passes.cuh RK4 stage
+    const double w = (double)(k2.b - k2.a);
+    const double dense = (double)p->N[0] * p->N1l * w * p->cs;
+    const double bytes = (double)nprod * p->N1l * w * P.q.M[0] * p->cs + stt * ns * dense
+                         + (so.source ? ns * dense : 0) + (so.p_hat ? dense : 0);
+    return do_launch(p, P.st, fam, P.q.M[0], &a, bytes);
+}
+
+// Multi-GPU schedule of the Vortex (NS / VV) and MHD right-hand sides.  Two streams:
+//   X (exchange, high priority): B0 chunks (k2 ranges), then F1 chunks (x0 ranges) -- the passes whose stores
+//     cross NVLink;
+//   L (the plan stream): per chunk  flag barrier + B1,  then Z chunks, then barrier + F0 chunks.
+// B0(c) needs only the k2 columns F0(c) of the previous stage produced, B1(c) only what the B0(c) of all ranks
+// stored, F1(c) only the planes Z(c) produced; so the NVLink traffic of one chunk hides behind the HBM-bound
+// passes of its neighbours.  Two points stay global: Z needs every B1 chunk, F0 needs every rank's F1.
+template <typename T>
+static int rhs_pipelined(sdns_plan* p, const void* u_hat, double nu, double eta, const StageOut& so) {
+    typedef typename C2<T>::type V;
+    Pipe<T> P(p, SDNS_SPACE_TP);
+    const Space& q = P.q;
+    const V* u = reinterpret_cast<const V*>(u_hat);
+    cudaStream_t L = p->stream, X = p->xstream;
+    const int solver = p->cfg.solver;
+    const int nprod = solver == SDNS_MHD ? 9 : 3;
+    const int nc = p->nchunk;
+    int kb[17], xb[17];
+    for (int c = 0; c <= nc; ++c) {
+        long long k = (long long)q.K2n * c / nc;
+        if (q.K2n >= 16 * nc && c < nc) k = (k + 4) / 8 * 8;         // whole 128-byte rows where the axis is long enough
+        kb[c] = (int)k;
+        xb[c] = (int)((long long)q.M0l * c / nc);
+    }
+    int e;
+    P.xcap = p->xcap;                                  // NVLink-bound passes: a few CTAs per SM are enough
+    if (!so.chain) { CUDA_TRY(cudaEventRecord(p->ev_start, L)); CUDA_TRY(cudaStreamWaitEvent(X, p->ev_start, 0)); }
+    const int fam_b0 = solver == SDNS_NS ? FAM_NS_B0 : (solver == SDNS_VV ? FAM_VV_B0 : FAM_PLAIN_BWD);
+    const int nfin = solver == SDNS_MHD ? 6 : 3;
+    for (int c = 0; c < nc; ++c) {
+        if (kb[c + 1] <= kb[c]) continue;
+        if (so.chain) CUDA_TRY(cudaStreamWaitEvent(X, p->ev_f0[c], 0));
+        P.st = X;
+        if ((e = P.b0(fam_b0, u, nfin, 0, so.in_work_layout, Rng{kb[c], kb[c + 1]}))) return e;
+        CUDA_TRY(cudaEventRecord(p->ev_b0[c], X));
+        CUDA_TRY(cudaStreamWaitEvent(L, p->ev_b0[c], 0));
+        if ((e = xbarrier(p))) return e;
+        P.st = L;
+        if ((e = P.b1(6, Rng{kb[c], kb[c + 1]}))) return e;
+    }
+    P.zcap = p->zcap;                                  // leave room on every SM for the F1 chunk running beside Z
+    for (int c = 0; c < nc; ++c) {
+        if (xb[c + 1] <= xb[c]) continue;
+        P.st = L;
+        if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true, Rng{xb[c], xb[c + 1]}))) return e;
+        CUDA_TRY(cudaEventRecord(p->ev_z[c], L));
+        CUDA_TRY(cudaStreamWaitEvent(X, p->ev_z[c], 0));
+        P.st = X;
+        if ((e = P.f1(nprod, nullptr, Rng{xb[c], xb[c + 1]}))) return e;
+    }
+    CUDA_TRY(cudaEventRecord(p->ev_f1all, X));
+    CUDA_TRY(cudaStreamWaitEvent(L, p->ev_f1all, 0));
+    if ((e = xbarrier(p))) return e;
+    P.st = L;
+    for (int c = 0; c < nc; ++c) {
+        if ((e = launch_f0<T>(p, P, u_hat, nu, eta, so, nprod, false, (T)1, Rng{kb[c], kb[c + 1]}))) return e;
+        CUDA_TRY(cudaEventRecord(p->ev_f0[c], L));
+    }
+    // the k2 columns above the 2/3 cutoff feed no B0 chunk: last
+    return launch_f0<T>(p, P, u_hat, nu, eta, so, nprod, false, (T)1, Rng{kb[nc], p->Nh});
+}
 
 template <typename T>
 static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const StageOut& so) {
@@ -616,7 +774,7 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
                 // Skewed (NS.py:184-189): keep the standard term in spectral space, add it in the divergence epilogue
                 StridedArgs<T> a0; P.f0_geom(a0, 3);
                 a0.out_mode = OUT_CONV; a0.rhs = S; a0.u_hat = u;
-                if ((e = do_launch(p, FAM_NS_F0, P.q.M[0], &a0))) return e;
+                if ((e = do_launch(p, p->stream, FAM_NS_F0, P.q.M[0], &a0))) return e;
             }
         }
         if (conv == SDNS_CONV_DIVERGENCE || conv == SDNS_CONV_SKEWED) {
@@ -630,40 +788,17 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
             nprod = 6; divform = true;
         }
     } else {
-    if (solver == SDNS_NS) { if ((e = P.b0(FAM_NS_B0, u, 3, 0, so.in_work_layout))) return e; }
-    else if (solver == SDNS_VV) { if ((e = P.b0(FAM_VV_B0, u, 3, 0, so.in_work_layout))) return e; }
-    else { if ((e = P.b0(FAM_PLAIN_BWD, u, 6, 0, so.in_work_layout))) return e; }
-    if ((e = xbarrier(p))) return e;
-    if ((e = P.b1(6))) return e;
-    if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true))) return e;
-    if ((e = P.f1(nprod))) return e;
-    if ((e = xbarrier(p))) return e;
+        if (p->nchunk > 1) return rhs_pipelined<T>(p, u_hat, nu, eta, so);
+        if (solver == SDNS_NS) { if ((e = P.b0(FAM_NS_B0, u, 3, 0, so.in_work_layout))) return e; }
+        else if (solver == SDNS_VV) { if ((e = P.b0(FAM_VV_B0, u, 3, 0, so.in_work_layout))) return e; }
+        else { if ((e = P.b0(FAM_PLAIN_BWD, u, 6, 0, so.in_work_layout))) return e; }
+        if ((e = xbarrier(p))) return e;
+        if ((e = P.b1(6))) return e;
+        if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true))) return e;
+        if ((e = P.f1(nprod))) return e;
+        if ((e = xbarrier(p))) return e;
     }
-    StridedArgs<T> a; P.f0_geom(a, nprod);
-    a.out_mode = so.out_mode;
-    a.u_hat = u;
-    a.rhs = reinterpret_cast<V*>(so.rhs);
-    a.u0 = reinterpret_cast<V*>(so.u0); a.u1 = reinterpret_cast<V*>(so.u1); a.u2 = reinterpret_cast<V*>(so.u2);
-    a.source = reinterpret_cast<const V*>(so.source);
-    a.p_hat = reinterpret_cast<V*>(so.p_hat);
-    a.nu = (T)nu; a.eta = (T)eta; a.adt = (T)so.adt; a.bdt = (T)so.bdt; a.rk = so.rk;
-    a.scale = f0scale;
-    if (so.in_work_layout) { a.uh_ls = a.t_ls; a.uh_os = a.t_os; }
-    if (divform) {
-        a.cfac = conv == SDNS_CONV_SKEWED ? (T)-0.5 : (T)-1;
-        a.addin = conv == SDNS_CONV_SKEWED ? reinterpret_cast<const V*>(p->ws + p->off_S) : nullptr;
-    }
-    const int fam = divform ? FAM_NSDIV_F0 : (solver == SDNS_NS ? FAM_NS_F0 : (solver == SDNS_VV ? FAM_VV_F0 : FAM_MHD_F0));
-    // epilogue traffic: read the product fields; state reads/writes of the stage update
-    const int ns = solver == SDNS_MHD ? 6 : 3;
-    double st;   // state arrays touched, in units of one ns-component spectral vector
-    if (so.out_mode == OUT_RHS) st = 2;                               // read u_hat, write rhs
-    else if (so.out_mode == OUT_CONV) st = 1;
-    else st = so.rk == 0 ? 1 + 3 : (so.rk < 3 ? 3 + 2 : 2 + 1);       // see passes.cuh RK4 stage
-    const double dense = (double)p->N[0] * p->N1l * p->Nh * p->cs;
-    const double bytes = (double)nprod * p->N1l * p->Nh * P.q.M[0] * p->cs + st * ns * dense
-                         + (so.source ? ns * dense : 0) + (so.p_hat ? dense : 0);
-    return do_launch(p, fam, P.q.M[0], &a, bytes);
+    return launch_f0<T>(p, P, u_hat, nu, eta, so, nprod, divform, f0scale, Rng{-1, 0});
 }
 
 extern "C" int sdns_forward(sdns_plan* p, int space, int nc, const void* in, void* out) {
@@ -717,6 +852,7 @@ extern "C" int sdns_rk4_step(sdns_plan* p, void* u_hat, void* u1, void* u2, doub
         so.out_mode = OUT_STAGE; so.u1 = u1; so.u2 = u2; so.source = source; so.rk = rk;
         so.u0 = rk < 3 ? u0w : u_hat;
         so.in_work_layout = rk > 0;
+        so.chain = rk > 0;
         if (p->prec) rk_coeffs<double>(rk, dt, &so.adt, &so.bdt); else rk_coeffs<float>(rk, dt, &so.adt, &so.bdt);
         const void* uin = rk == 0 ? u_hat : u0w;
         e = p->prec ? rhs_t<double>(p, uin, nu, eta, so) : rhs_t<float>(p, uin, nu, eta, so);
