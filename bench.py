@@ -263,6 +263,7 @@ def run_ours(a):
     for _ in range(npf):
         p.rk4_step(u, u1, u2, DT, NU, eta)
     prof = p.profile_read()
+    copies = p.profile_read_copies()
     p.profile(False)
     barrier()
 
@@ -293,8 +294,11 @@ def run_ours(a):
         'dtype': 'f64' if a.precision == 'double' else 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(a, N), 'grid': list(N), 'integrator': 'RK4',
                    'transforms_per_step': 60 if a.solver == 'MHD' else 36,
-                   'multi_gpu': ('slab decomposition over %d GPUs: transposes are peer-memory stores fused into the '
-                                 'FFT passes (no NCCL on the data path); %s scaling' % (world, a.scaling)) if world > 1 else 'single GPU',
+                   'multi_gpu': ('slab decomposition over %d GPUs, %s; %s scaling' % (world, (
+                       'exchange in chunks by the copy engines over NVLink peer memory underneath the FFT passes '
+                       '(no NCCL on the data path)' if copies[2] else
+                       'transposes are peer-memory stores fused into the FFT passes (no NCCL on the data path)'),
+                       a.scaling)) if world > 1 else 'single GPU',
                    'l2': 'inputs larger than L2 (state %.0f MB, scratch %.0f MB)' % (state_bytes/1e6, p.workspace_bytes/1e6),
                    'timing': 'CUDA events on the launch stream, max over ranks',
                    'kinetic_energy_after_run': energy},
@@ -313,7 +317,19 @@ def run_ours(a):
                      'all_kernels': {k: {'ms_per_launch': v[0]/v[1], 'launches_per_step': v[1]/npf,
                                          'GBps': v[2]/v[0]*1e-6, 'share': v[0]/tot} for k, v in prof.items()}},
     }
-    if world > 1:
+    if world > 1 and copies[2]:
+        # NVLink side of the roofline (rank 0's view), copy-engine exchange: bytes sent per step; rate while the
+        # busiest per-peer copy stream is busy, and sustained over the whole step
+        xbytes, xms = copies[1]/npf, copies[0]/npf
+        line['nvlink'] = {'bytes_per_step_per_gpu': xbytes, 'copies_per_step': copies[2]/npf,
+                          'copy_stream_busy_ms_per_step': xms,
+                          'achieved_GBps_per_direction': xbytes*1e-9/(xms*1e-3) if xms else None,
+                          'sustained_over_step_GBps': xbytes*1e-9/(ms*1e-3),
+                          'peak_measured_GBps': 770.0, 'peak_nominal_GBps': 900.0,
+                          'frac_of_measured': (xbytes*1e-9/(xms*1e-3))/770.0 if xms else None,
+                          'note': 'strided cudaMemcpy2DAsync per peer and chunk on per-peer streams, concurrent with '
+                                  'the FFT passes; busy time = summed copy durations of the busiest stream'}
+    elif world > 1:
         # NVLink side of the roofline (rank 0's view): bytes the exchange passes store into peers
         xk = {k: v for k, v in prof.items() if v[3] > 0}
         xbytes = sum(v[3] for v in xk.values())/npf

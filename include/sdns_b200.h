@@ -179,6 +179,10 @@ int sdns_profile_enable(sdns_plan* plan, int on);
 int sdns_profile_read(sdns_plan* plan, int family, double* total_ms, long long* launches, double* bytes);
 /* bytes the family's launches stored into peer GPUs over NVLink (slab transposes) */
 int sdns_profile_read_nvlink(sdns_plan* plan, int family, double* bytes);
+/* copy-engine exchange (the default for nranks > 1; SDNS_EXCHANGE=store selects the fused peer stores): bytes this
+ * rank sent over NVLink since sdns_profile_enable, the number of strided copies, and the busy time of the busiest
+ * per-peer copy stream (the copies to different peers run concurrently) */
+int sdns_profile_read_copies(sdns_plan* plan, double* busy_ms, double* bytes, long long* ncopies);
 
 #ifdef __cplusplus
 }

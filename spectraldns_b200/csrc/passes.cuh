@@ -76,6 +76,8 @@ struct StridedArgs {
     int c1_off, c2_off;           // first run / first column of this launch (the multi-GPU pipeline launches a pass in chunks)
     int grid_cap;                 // > 0: launch at most this many CTAs per SM (grid-stride over the tiles)
     V* peer_out[8];
+    int self;                     // destination that uses (out_fs, out_ls, c1_out_off); all others use the second set
+    long long out_fs2, out_ls2, c1_out_off2;
 };
 
 template <typename V> __device__ __forceinline__ V czero() { V z; z.x = 0; z.y = 0; return z; }
@@ -122,7 +124,7 @@ __device__ __forceinline__ void load_line(V (&x)[E], const V* __restrict__ pin, 
 // rank i / xchunk (reciprocal multiply, exact for i < 2^22) at line index i % xchunk.
 template <typename T, int N, int E, bool SCALE, typename V>
 __device__ __forceinline__ void store_line(const V (&x)[E], const StridedArgs<T>& a, int f, long long obase,
-                                           int t, bool valid, T scale) {
+                                           long long obase2, int t, bool valid, T scale) {
     constexpr int P = N / E;
     const long long fo = f * a.out_fs + obase;
     if (a.xchunk == 0) {
@@ -134,15 +136,20 @@ __device__ __forceinline__ void store_line(const V (&x)[E], const StridedArgs<T>
             if (valid && axis_ok(a.omap, N, j)) pout[off] = SCALE ? cscale<T>(x[q], scale) : x[q];
         }
     } else {
+        // destination `self` (this rank, or -1) uses the layout of the final array; every other one the second
+        // layout (fs2, ls2, obase2): identical to the first for direct peer stores, the send-buffer layout when
+        // the copy engines carry the exchange
         const float inv = 1.0f / (float)a.xchunk;
+        const long long fo2 = f * a.out_fs2 + obase2;
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int j = t + q * P;
             const int i = axis_idx(a.omap, j);
             const int dest = __float2int_rz(((float)i + 0.5f) * inv);
             const int il = i - dest * a.xchunk;
+            const long long off = dest == a.self ? fo + (long long)il * a.out_ls : fo2 + (long long)il * a.out_ls2;
             if (valid && axis_ok(a.omap, N, j))
-                a.peer_out[dest][fo + (long long)il * a.out_ls] = SCALE ? cscale<T>(x[q], scale) : x[q];
+                a.peer_out[dest][off] = SCALE ? cscale<T>(x[q], scale) : x[q];
         }
     }
 }
@@ -174,13 +181,14 @@ strided_kernel(const StridedArgs<T> a) {
     const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
     const long long ibase = (long long)c1m * a.in_os + c2;
     const long long obase = ((long long)c1 + a.c1_out_off) * a.out_os + c2;
+    const long long obase2 = ((long long)c1 + a.c1_out_off2) * a.out_os + c2;
 
     if (MODE == S_PLAIN) {
         const int f = blockIdx.y;
         V x[E];
         load_line<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
         fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-        store_line<T, N, E, true>(x, a, f, obase, t, valid, a.scale);
+        store_line<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
     } else if (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0) {
         // in: 3 dense spectral fields.  out: 6 fields (NS: u_hat, i k x u_hat ; VV: i k x w_hat / k^2, w_hat)
         const T k1 = valid ? a.ky[c1m] : (T)0;
@@ -236,7 +244,7 @@ strided_kernel(const StridedArgs<T> a) {
                 }
             }
             fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-            store_line<T, N, E, false>(x, a, f, obase, t, valid, (T)1);
+            store_line<T, N, E, false>(x, a, f, obase, obase2, t, valid, (T)1);
         }
     } else if (MODE == S_NS_F0 || MODE == S_VV_F0) {
         // Three forward transforms; the results of the first two are parked in thread-private

@@ -74,13 +74,18 @@ struct sdns_plan {
     size_t kx_off, ky_off, kz_off;
     long long launches;
     int red_blocks;
-    // multi-GPU pipeline: the passes that store into the peers (B0, F1) run on their own stream in chunks, so
-    // that the NVLink exchange of one chunk overlaps the local passes (F0, B1, Z) of its neighbours
-    int nchunk;                     // chunks per pass (1: serial schedule on the plan stream)
-    int xcap, zcap;                 // CTAs per SM of the exchange passes / of the persistent z kernel while they overlap
-    cudaStream_t xstream;           // exchange stream (highest priority)
-    cudaEvent_t ev_start, ev_f1all;
-    std::vector<cudaEvent_t> ev_b0, ev_z, ev_f0;
+    // multi-GPU exchange.  xmode 0: B0 / F1 store straight into the peers (one launch per pass, serial schedule).
+    // xmode 1: B0 / F1 write per-destination send buffers in chunks and the copy engines move each chunk over
+    // NVLink (one stream per peer) while the SMs work on the next chunk.
+    int xmode, nchunk, nsplit;      // nsplit: streams (copy engines) per destination rank
+    std::vector<cudaStream_t> ys;   // copy streams, index = destination rank * nsplit + part (own entries unused)
+    std::vector<cudaEvent_t> ev_k;  // [nchunk] the pass of chunk c has finished
+    std::vector<cudaEvent_t> ev_y;  // [P * nsplit] copy stream drained
+    size_t off_SF, bytes_SF;        // F1 send buffers (B0's live in the W1 buffer, which is idle at that point)
+    bool b0_preissued;              // the B0 chunks (and copies) of the coming right-hand side are already enqueued
+    struct CRec { int s; cudaEvent_t a, b; double bytes; };
+    std::vector<CRec> crecs;
+    double copy_ms[32]; double copy_bytes; long long copy_n;
     // optional per-family profiling (bench.py roofline): CUDA events around every launch
     bool prof;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used;
@@ -220,28 +225,36 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->rs = p->prec ? 8 : 4; p->cs = 2 * p->rs;
     p->stream = 0; p->ws = nullptr; p->ws_bytes = 0; p->launches = 0;
     p->prof = false; p->ev_used = 0;
-    p->nchunk = 1; p->xstream = nullptr; p->ev_start = nullptr; p->ev_f1all = nullptr;
+    p->xmode = 0; p->nchunk = 1; p->nsplit = 1; p->off_SF = 0; p->bytes_SF = 0; p->b0_preissued = false;
+    p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
     if (p->P > 1) {
+        const char* xm = getenv("SDNS_EXCHANGE");           // "store": peer stores fused into the passes; default: copy engines
+        p->xmode = (xm && !strcmp(xm, "store")) ? 0 : 1;
         const char* env = getenv("SDNS_CHUNKS");
         p->nchunk = env ? atoi(env) : 4;
         if (p->nchunk < 1) p->nchunk = 1;
         if (p->nchunk > 16) p->nchunk = 16;
+        if (!p->xmode) p->nchunk = 1;
+        const char* sp = getenv("SDNS_SPLIT");
+        p->nsplit = sp ? atoi(sp) : 1;      // measured: one copy stream per peer saturates the link (profiles/tools/p2p_copy_bench.py)
+        if (p->nsplit < 1) p->nsplit = 1;
+        if (p->nsplit > 4) p->nsplit = 4;
     }
-    { const char* e1 = getenv("SDNS_XCAP"); p->xcap = e1 ? atoi(e1) : 1;
-      const char* e2 = getenv("SDNS_ZCAP"); p->zcap = e2 ? atoi(e2) : 2; }
-    if (p->nchunk > 1) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        cudaError_t e1 = cudaStreamCreateWithPriority(&p->xstream, cudaStreamNonBlocking, hi);
-        if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming);
-        if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_f1all, cudaEventDisableTiming);
-        for (int c = 0; c < p->nchunk && e1 == cudaSuccess; ++c) {
-            cudaEvent_t e;
-            if ((e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) == cudaSuccess) p->ev_b0.push_back(e);
-            if (e1 == cudaSuccess && (e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) == cudaSuccess) p->ev_z.push_back(e);
-            if (e1 == cudaSuccess && (e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) == cudaSuccess) p->ev_f0.push_back(e);
+    if (p->xmode) {
+        cudaError_t e1 = cudaSuccess;
+        for (int r = 0; r < p->P * p->nsplit && e1 == cudaSuccess; ++r) {
+            cudaStream_t y = nullptr; cudaEvent_t e = nullptr;
+            if (r / p->nsplit != p->rank) e1 = cudaStreamCreateWithFlags(&y, cudaStreamNonBlocking);
+            p->ys.push_back(y);
+            if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            p->ev_y.push_back(e);
         }
-        if (e1 != cudaSuccess) { std::string m = std::string("pipeline stream/events: ") + cudaGetErrorString(e1); delete p; return fail(SDNS_ERR_CUDA, m); }
+        for (int c = 0; c < p->nchunk && e1 == cudaSuccess; ++c) {
+            cudaEvent_t e = nullptr;
+            e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            p->ev_k.push_back(e);
+        }
+        if (e1 != cudaSuccess) { std::string m = std::string("copy streams/events: ") + cudaGetErrorString(e1); delete p; return fail(SDNS_ERR_CUDA, m); }
     }
     for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_remote[i] = 0; p->prof_n[i] = 0; }
     build_spaces(p);
@@ -255,7 +268,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     if (p->prec) fill_tables<double>(p); else fill_tables<float>(p);
     // scratch: A holds W0 (B0 out) and W2 (Z out); B holds W1 (B1 out) and W3 (F1 out)
     const int nz = cfg->solver == SDNS_MHD ? 9 : 6;    // widest field count through the pipeline
-    size_t a = 0, b = 0, c = 0;
+    size_t a = 0, b = 0, c = 0, sf = 0;
     for (int s = 0; s < 2; ++s) {
         const Space& q = p->sp[s];
         size_t w0 = (size_t)6 * q.M0l * q.K1n * q.K2p;
@@ -265,6 +278,10 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
         a = std::max(a, std::max(w0, w2));
         if (p->P == 1) b = std::max(b, std::max(w1, w3));      // single GPU: W3 reuses W1's buffer
         else { b = std::max(b, w1); c = std::max(c, w3); }      // multi GPU: peers write W3 while W1 is live
+        if (p->xmode) {
+            b = std::max(b, (size_t)6 * q.M[0] * q.K1l * q.K2p);             // B0 send buffers: P slots of (6, M0l, K1l, K2p)
+            sf = std::max(sf, (size_t)nz * p->N[1] * q.M0l * p->Nhp);        // F1 send buffers: P slots of (nz, N1l, M0l, Nhp)
+        }
     }
     p->bytes_A = align_up(a * p->cs, 256); p->bytes_B = align_up(b * p->cs, 256);
     p->bytes_C = align_up(c * p->cs, 256);
@@ -282,7 +299,9 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     // inter-stage copy of the RK4 state in the k1-major work layout
     p->bytes_U = align_up((size_t)(cfg->solver == SDNS_MHD ? 6 : 3) * p->N[0] * p->N1l * p->Nh * p->cs, 256);
     p->off_U = p->off_S + p->bytes_S;
-    p->off_red = p->off_U + p->bytes_U;
+    p->bytes_SF = align_up(sf * p->cs, 256);
+    p->off_SF = p->off_U + p->bytes_U;
+    p->off_red = p->off_SF + p->bytes_SF;
     p->off_flags = p->off_red + align_up(sizeof(double) * p->red_blocks, 256);
     p->ws_need = p->off_flags + 256;
     *out = p;
@@ -292,12 +311,9 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
 extern "C" int sdns_plan_destroy(sdns_plan* p) {
     if (p) {
         for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
-        for (cudaEvent_t e : p->ev_b0) cudaEventDestroy(e);
-        for (cudaEvent_t e : p->ev_z) cudaEventDestroy(e);
-        for (cudaEvent_t e : p->ev_f0) cudaEventDestroy(e);
-        if (p->ev_start) cudaEventDestroy(p->ev_start);
-        if (p->ev_f1all) cudaEventDestroy(p->ev_f1all);
-        if (p->xstream) cudaStreamDestroy(p->xstream);
+        for (cudaEvent_t e : p->ev_k) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : p->ev_y) if (e) cudaEventDestroy(e);
+        for (cudaStream_t y : p->ys) if (y) cudaStreamDestroy(y);
         for (int r = 0; r < 8; ++r) if (p->peer_ws[r] && r != p->rank) cudaIpcCloseMemHandle(p->peer_ws[r]);
         if (p->own_ws && p->ws) cudaFree(p->ws);
     }
@@ -494,35 +510,51 @@ struct Pipe {
         a.t_ls = p->Nh; a.t_os = (long long)p->N[0] * p->Nh;           // work layout (N1l, N0, Nh)
     }
     long long dense_fs() const { return (long long)p->N[0] * p->N1l * p->Nh; }
-    void peers(StridedArgs<T>& a, size_t off, int chunk) const {
+    // destinations of a pass that feeds a global transpose.  Direct: every rank's final array (peer memory).
+    // Staged (send != null): this rank's part goes to its final array, rank r's part to slot r of the local send
+    // buffer in the layout (fs2, ls2, c1off2) from which the copy engines move it.
+    void peers(StridedArgs<T>& a, size_t off, int chunk, V* send = nullptr, long long slot = 0,
+               long long fs2 = 0, long long ls2 = 0, long long c1off2 = 0) const {
+        a.self = -1; a.out_fs2 = a.out_fs; a.out_ls2 = a.out_ls; a.c1_out_off2 = a.c1_out_off;
         if (p->P == 1) return;
         a.xchunk = chunk;
         for (int r = 0; r < p->P; ++r) a.peer_out[r] = reinterpret_cast<V*>(p->peer_ws[r] + off);
+        if (send) {
+            for (int r = 0; r < p->P; ++r) if (r != p->rank) a.peer_out[r] = send + r * slot;
+            a.self = p->rank; a.out_fs2 = fs2; a.out_ls2 = ls2; a.c1_out_off2 = c1off2;
+        }
     }
     static Rng whole(Rng r, int n) { if (r.a < 0) { r.a = 0; r.b = n; } return r; }
 
     // B0: local dense spectral (nf, N0, N1l, Nh) -> W0 (nfo, M0l, K1n, K2p) of the rank owning each x0.
     // k2: the k2 columns of this launch.
-    int b0(int fam, const V* in, int nf, int comp = 0, bool work_layout = false, Rng k2 = Rng{-1, 0}) {
+    long long b0_slot() const { return (long long)6 * q.M0l * q.K1l * q.K2p; }
+    long long f1_slot(int nf) const { return (long long)nf * p->N1l * q.M0l * p->Nhp; }
+    V* send_f1() const { return reinterpret_cast<V*>(p->ws + p->off_SF); }
+
+    int b0(int fam, const V* in, int nf, int comp = 0, bool work_layout = false, Rng k2 = Rng{-1, 0},
+           Rng k1 = Rng{-1, 0}, bool staged = false) {
         k2 = whole(k2, q.K2n);
+        k1 = whole(k1, q.K1l);                          // compact local axis-1 modes of this launch
         StridedArgs<T> a; base(a);
         a.in = in; a.out = A; a.comp = comp;
         a.in_fs = dense_fs();
         if (work_layout) { a.in_ls = p->Nh; a.in_os = (long long)p->N[0] * p->Nh; }
         else { a.in_ls = (long long)p->N1l * p->Nh; a.in_os = p->Nh; }
-        a.cw = k2.b - k2.a; a.c2_off = k2.a; a.ncols = (long long)q.K1l * a.cw;
+        a.cw = k2.b - k2.a; a.c2_off = k2.a; a.c1_off = k1.a; a.ncols = (long long)(k1.b - k1.a) * a.cw;
         a.col_nlo = q.lcol_nlo; a.col_gap = q.lcol_gap;
         a.imap = q.bmap[0]; a.omap = all_map(q.M[0]);
         a.out_fs = (long long)q.M0l * q.K1n * q.K2p; a.out_ls = (long long)q.K1n * q.K2p; a.out_os = q.K2p;
         a.c1_out_off = q.c1off;
-        peers(a, p->off_A, q.M0l);
+        if (staged) peers(a, p->off_A, q.M0l, B, b0_slot(), (long long)q.M0l * q.K1l * q.K2p, (long long)q.K1l * q.K2p, 0);
+        else peers(a, p->off_A, q.M0l);
         a.grid_cap = xcap;
         a.tw = tw(q.M[0]); a.nfields = nf;
         const int nfo = (fam == FAM_PLAIN_BWD) ? nf : 6;
-        const double cols = (double)q.K1l * a.cw;
+        const double cols = (double)(k1.b - k1.a) * a.cw;
         const double bytes = (nf * cols * (q.bmap[0].nlo + q.bmap[0].nhi) + nfo * cols * q.M[0]) * p->cs;
         if (a.ncols == 0) return SDNS_OK;              // this rank owns no mode that survives the truncation
-        const double remote = nfo * cols * q.M[0] * p->cs * (p->P - 1) / p->P;   // stored into peers over NVLink
+        const double remote = staged ? 0 : nfo * cols * q.M[0] * p->cs * (p->P - 1) / p->P;   // stored into peers over NVLink
         return do_launch(p, st, fam, q.M[0], &a, bytes, remote);
     }
     // B1: A (W0) -> B as W1 (nf, M0l, M1, K2p)
@@ -567,7 +599,7 @@ struct Pipe {
     // F1: A (W2) -> W3 (nf, N1l, M0, Nhp) of the rank owning each k1.  x0 is the second-fastest axis of
     // W3 on purpose: F1 *stores* with the large stride (M0*Nhp), F0 *loads* its axis-0 lines with a
     // stride of one k2 row -- loads stall warps on TLB/DRAM-page misses, stores do not.
-    int f1(int nf, const V* src = nullptr, Rng x0 = Rng{-1, 0}) {
+    int f1(int nf, const V* src = nullptr, Rng x0 = Rng{-1, 0}, bool staged = false) {
         x0 = whole(x0, q.M0l);
         StridedArgs<T> a; base(a);
         a.in = src ? src : A; a.out = C;
@@ -577,21 +609,23 @@ struct Pipe {
         a.imap = all_map(q.M[1]); a.omap = q.fmap[1];
         a.out_fs = (long long)p->N1l * q.M[0] * p->Nhp; a.out_ls = (long long)q.M[0] * p->Nhp; a.out_os = p->Nhp;
         a.c1_out_off = (long long)p->rank * q.M0l;
-        peers(a, p->off_C, p->N1l);
+        if (staged) peers(a, p->off_C, p->N1l, send_f1(), f1_slot(nf), (long long)p->N1l * q.M0l * p->Nhp, (long long)q.M0l * p->Nhp, 0);
+        else peers(a, p->off_C, p->N1l);
         a.grid_cap = xcap;
         a.tw = tw(q.M[1]); a.nfields = nf;
         const double bytes = (double)nf * (x0.b - x0.a) * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
-        const double remote = (double)nf * (x0.b - x0.a) * p->Nh * p->N[1] * p->cs * (p->P - 1) / p->P;
+        const double remote = staged ? 0 : (double)nf * (x0.b - x0.a) * p->Nh * p->N[1] * p->cs * (p->P - 1) / p->P;
         if (a.ncols == 0) return SDNS_OK;
         return do_launch(p, st, FAM_PLAIN_FWD, q.M[1], &a, bytes, remote);
     }
     // F0 geometry: W3 -> local dense spectral, k2 columns [k2.a, k2.b)
-    void f0_geom(StridedArgs<T>& a, int nf, Rng k2 = Rng{-1, 0}) {
+    void f0_geom(StridedArgs<T>& a, int nf, Rng k2 = Rng{-1, 0}, Rng k1 = Rng{-1, 0}) {
         k2 = whole(k2, p->Nh);
+        k1 = whole(k1, p->N1l);
         base(a);
         a.in = C;
         a.in_fs = (long long)p->N1l * q.M[0] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[0] * p->Nhp;
-        a.cw = k2.b - k2.a; a.c2_off = k2.a; a.ncols = (long long)p->N1l * a.cw;
+        a.cw = k2.b - k2.a; a.c2_off = k2.a; a.c1_off = k1.a; a.ncols = (long long)(k1.b - k1.a) * a.cw;
         a.col_nlo = p->N1l; a.col_gap = 0;
         a.imap = all_map(q.M[0]); a.omap = q.fmap[0];
         a.out_fs = dense_fs(); a.out_ls = (long long)p->N1l * p->Nh; a.out_os = p->Nh;
@@ -641,19 +675,21 @@ struct StageOut {
     int out_mode; void* rhs; void* u0; void* u1; void* u2; void* p_hat; const void* source;
     double adt, bdt; int rk;
     bool in_work_layout;      // u_hat is the library's k1-major inter-stage copy
-    bool chain;               // the previous launch sequence was stage rk-1 of the same step (pipeline: its
-                              // per-chunk F0 events order this stage's B0 chunks)
+    const void* next_u;       // input of the right-hand side that follows immediately (RK4 stages 0-2: the
+                              // inter-stage state this stage writes), or NULL: lets the multi-GPU pipeline start
+                              // that stage's B0 chunks and their copies between this stage's F0 chunks
 };
 
 // the F0 launch (final forward pass + epilogue) over the k2 columns `k2` of the nprod product fields
 template <typename T>
 static int launch_f0(sdns_plan* p, Pipe<T>& P, const void* u_hat, double nu, double eta, const StageOut& so,
-                     int nprod, bool divform, T f0scale, Rng k2) {
+                     int nprod, bool divform, T f0scale, Rng k2, Rng k1 = Rng{-1, 0}) {
     typedef typename C2<T>::type V;
     const int solver = p->cfg.solver, conv = p->cfg.convection;
     k2 = Pipe<T>::whole(k2, p->Nh);
-    if (k2.b <= k2.a) return SDNS_OK;
-    StridedArgs<T> a; P.f0_geom(a, nprod, k2);
+    k1 = Pipe<T>::whole(k1, p->N1l);
+    if (k2.b <= k2.a || k1.b <= k1.a) return SDNS_OK;
+    StridedArgs<T> a; P.f0_geom(a, nprod, k2, k1);
     a.out_mode = so.out_mode;
     a.u_hat = reinterpret_cast<const V*>(u_hat);
     a.rhs = reinterpret_cast<V*>(so.rhs);
@@ -674,73 +710,140 @@ static int launch_f0(sdns_plan* p, Pipe<T>& P, const void* u_hat, double nu, dou
     if (so.out_mode == OUT_RHS) stt = 2;                               // read u_hat, write rhs
     else if (so.out_mode == OUT_CONV) stt = 1;
     else stt = so.rk == 0 ? 1 + 3 : (so.rk < 3 ? 3 + 2 : 2 + 1);      // see passes.cuh RK4 stage
-    const double w = (double)(k2.b - k2.a);
-    const double dense = (double)p->N[0] * p->N1l * w * p->cs;
-    const double bytes = (double)nprod * p->N1l * w * P.q.M[0] * p->cs + stt * ns * dense
+    const double w = (double)(k2.b - k2.a) * (k1.b - k1.a);       // columns of this launch
+    const double dense = (double)p->N[0] * w * p->cs;
+    const double bytes = (double)nprod * w * P.q.M[0] * p->cs + stt * ns * dense
                          + (so.source ? ns * dense : 0) + (so.p_hat ? dense : 0);
     return do_launch(p, P.st, fam, P.q.M[0], &a, bytes);
 }
 
-// Multi-GPU schedule of the Vortex (NS / VV) and MHD right-hand sides.  Two streams:
-//   X (exchange, high priority): B0 chunks (k2 ranges), then F1 chunks (x0 ranges) -- the passes whose stores
-//     cross NVLink;
-//   L (the plan stream): per chunk  flag barrier + B1,  then Z chunks, then barrier + F0 chunks.
-// B0(c) needs only the k2 columns F0(c) of the previous stage produced, B1(c) only what the B0(c) of all ranks
-// stored, F1(c) only the planes Z(c) produced; so the NVLink traffic of one chunk hides behind the HBM-bound
-// passes of its neighbours.  Two points stay global: Z needs every B1 chunk, F0 needs every rank's F1.
+// One 2-D copy per destination rank on that rank's copy stream, after `after` has fired
+static int copy_rows(sdns_plan* p, int r, cudaEvent_t after, void* dst, size_t dpitch, const void* src, size_t spitch,
+                     size_t width, size_t height) {
+    if (!width || !height) return SDNS_OK;
+    for (int i = 0; i < p->nsplit; ++i) {
+        const size_t h0 = height * i / p->nsplit, h1 = height * (i + 1) / p->nsplit;
+        if (h1 == h0) continue;
+        const int si = r * p->nsplit + i;
+        cudaStream_t y = p->ys[si];
+        CUDA_TRY(cudaStreamWaitEvent(y, after, 0));
+        sdns_plan::CRec cr; cr.s = si; cr.bytes = (double)width * (h1 - h0);
+        if (p->prof) { cr.a = get_event(p); cudaEventRecord(cr.a, y); }
+        CUDA_TRY(cudaMemcpy2DAsync((char*)dst + h0 * dpitch, dpitch, (const char*)src + h0 * spitch, spitch, width, h1 - h0,
+                                   cudaMemcpyDeviceToDevice, y));
+        if (p->prof) { cr.b = get_event(p); cudaEventRecord(cr.b, y); p->crecs.push_back(cr); }
+    }
+    return SDNS_OK;
+}
+// the plan stream waits until every copy stream has drained, then the cross-GPU barrier
+static int join_copies(sdns_plan* p) {
+    for (size_t si = 0; si < p->ys.size(); ++si) {
+        if (!p->ys[si]) continue;
+        CUDA_TRY(cudaEventRecord(p->ev_y[si], p->ys[si]));
+        CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_y[si], 0));
+    }
+    return xbarrier(p);
+}
+
+// Chunk boundary c (0..nc) of an axis of n entries.  The chunks shrink towards the end (weights 3,..,3,2,1): the
+// copy of the last chunk is the only one no later pass hides.
+static int chunk_bound(int n, int nc, int c) {
+    auto w = [&](int i) { return std::min(nc - i, 3); };
+    int tot = 0, cum = 0;
+    for (int i = 0; i < nc; ++i) { tot += w(i); if (i < c) cum += w(i); }
+    return (int)(((long long)n * cum + tot / 2) / tot);
+}
+
+// Chunk c of nc over this rank's KEPT axis-1 modes (compact local indices, what B0 transforms), and the one or two
+// memory ranges of the spectral arrays that hold them (what F0 must have written before).  The modes the 2/3 rule
+// truncates belong to no chunk: F0 handles them last (k1_truncated), underneath the last B0 copies.
+static void k1_chunk(const sdns_plan* p, const Space& q, int c, int nc, Rng* kept, Rng mem[2]) {
+    kept->a = chunk_bound(q.K1l, nc, c); kept->b = chunk_bound(q.K1l, nc, c + 1);
+    mem[0] = Rng{std::min(kept->a, q.lcol_nlo), std::min(kept->b, q.lcol_nlo)};                     // low run: memory = compact
+    mem[1] = Rng{std::max(kept->a, q.lcol_nlo) + q.lcol_gap, std::max(kept->b, q.lcol_nlo) + q.lcol_gap};   // high run
+    (void)p;
+}
+static Rng k1_truncated(const sdns_plan* p, const Space& q) {
+    return q.K1l > q.lcol_nlo ? Rng{q.lcol_nlo, q.lcol_nlo + q.lcol_gap} : Rng{q.lcol_nlo, p->N1l};
+}
+
+// B0 chunk c of the right-hand side with input u: the pass (own part straight into W0, the peers' parts into the
+// send slots in W1's buffer), then one copy per peer.
 template <typename T>
-static int rhs_pipelined(sdns_plan* p, const void* u_hat, double nu, double eta, const StageOut& so) {
+static int b0_chunk_ce(sdns_plan* p, Pipe<T>& P, const void* u_hat, bool work_layout, int c) {
+    typedef typename C2<T>::type V;
+    const Space& q = P.q;
+    const int solver = p->cfg.solver;
+    const int fam = solver == SDNS_NS ? FAM_NS_B0 : (solver == SDNS_VV ? FAM_VV_B0 : FAM_PLAIN_BWD);
+    const int nfin = solver == SDNS_MHD ? 6 : 3;
+    Rng mem[2], kept; k1_chunk(p, q, c, p->nchunk, &kept, mem);
+    int e;
+    P.st = p->stream;
+    if (kept.b > kept.a)
+        if ((e = P.b0(fam, reinterpret_cast<const V*>(u_hat), nfin, 0, work_layout, Rng{-1, 0}, kept, true))) return e;
+    CUDA_TRY(cudaEventRecord(p->ev_k[c], p->stream));
+    if (kept.b <= kept.a) return SDNS_OK;
+    const size_t cs = p->cs;
+    for (int r = 0; r < p->P; ++r) {
+        if (r == p->rank) continue;
+        const V* src = P.B + r * P.b0_slot() + (long long)kept.a * q.K2p;
+        V* dst = reinterpret_cast<V*>(p->peer_ws[r] + p->off_A) + ((long long)q.c1off + kept.a) * q.K2p;
+        if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.K1n * q.K2p * cs, src, (size_t)q.K1l * q.K2p * cs,
+                           (size_t)(kept.b - kept.a) * q.K2p * cs, (size_t)6 * q.M0l))) return e;
+    }
+    return SDNS_OK;
+}
+
+// Multi-GPU schedule of the Vortex (NS / VV) and MHD right-hand sides with the exchange on the copy engines.
+// All passes run on the plan stream; B0 and F1 are cut into chunks (axis-1 modes / x0 planes), each chunk writes
+// the peers' parts into send slots and, as soon as it has finished, one strided copy per peer moves them over
+// NVLink on that peer's copy stream -- underneath the next chunk's passes (B0 chunks alternate with the previous
+// stage's F0 chunks, F1 chunks with the Z chunks).  Before B1 and before F0 the plan stream waits for its own
+// copies and meets the other ranks at the flag barrier.
+template <typename T>
+static int rhs_ce(sdns_plan* p, const void* u_hat, double nu, double eta, const StageOut& so) {
     typedef typename C2<T>::type V;
     Pipe<T> P(p, SDNS_SPACE_TP);
     const Space& q = P.q;
-    const V* u = reinterpret_cast<const V*>(u_hat);
-    cudaStream_t L = p->stream, X = p->xstream;
     const int solver = p->cfg.solver;
     const int nprod = solver == SDNS_MHD ? 9 : 3;
     const int nc = p->nchunk;
-    int kb[17], xb[17];
-    for (int c = 0; c <= nc; ++c) {
-        long long k = (long long)q.K2n * c / nc;
-        if (q.K2n >= 16 * nc && c < nc) k = (k + 4) / 8 * 8;         // whole 128-byte rows where the axis is long enough
-        kb[c] = (int)k;
-        xb[c] = (int)((long long)q.M0l * c / nc);
-    }
+    const size_t cs = p->cs;
     int e;
-    P.xcap = p->xcap;                                  // NVLink-bound passes: a few CTAs per SM are enough
-    if (!so.chain) { CUDA_TRY(cudaEventRecord(p->ev_start, L)); CUDA_TRY(cudaStreamWaitEvent(X, p->ev_start, 0)); }
-    const int fam_b0 = solver == SDNS_NS ? FAM_NS_B0 : (solver == SDNS_VV ? FAM_VV_B0 : FAM_PLAIN_BWD);
-    const int nfin = solver == SDNS_MHD ? 6 : 3;
+    if (!p->b0_preissued)
+        for (int c = 0; c < nc; ++c) if ((e = b0_chunk_ce<T>(p, P, u_hat, so.in_work_layout, c))) return e;
+    p->b0_preissued = false;
+    if ((e = join_copies(p))) return e;
+    P.st = p->stream;
+    if ((e = P.b1(6))) return e;
     for (int c = 0; c < nc; ++c) {
-        if (kb[c + 1] <= kb[c]) continue;
-        if (so.chain) CUDA_TRY(cudaStreamWaitEvent(X, p->ev_f0[c], 0));
-        P.st = X;
-        if ((e = P.b0(fam_b0, u, nfin, 0, so.in_work_layout, Rng{kb[c], kb[c + 1]}))) return e;
-        CUDA_TRY(cudaEventRecord(p->ev_b0[c], X));
-        CUDA_TRY(cudaStreamWaitEvent(L, p->ev_b0[c], 0));
-        if ((e = xbarrier(p))) return e;
-        P.st = L;
-        if ((e = P.b1(6, Rng{kb[c], kb[c + 1]}))) return e;
+        const Rng x0{chunk_bound(q.M0l, nc, c), chunk_bound(q.M0l, nc, c + 1)};
+        if (x0.b <= x0.a) continue;
+        if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true, x0))) return e;
+        if ((e = P.f1(nprod, nullptr, x0, true))) return e;
+        CUDA_TRY(cudaEventRecord(p->ev_k[c], p->stream));
+        for (int r = 0; r < p->P; ++r) {
+            if (r == p->rank) continue;
+            const V* src = P.send_f1() + r * P.f1_slot(nprod) + (long long)x0.a * p->Nhp;
+            V* dst = reinterpret_cast<V*>(p->peer_ws[r] + p->off_C) + ((long long)p->rank * q.M0l + x0.a) * p->Nhp;
+            if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.M[0] * p->Nhp * cs, src, (size_t)q.M0l * p->Nhp * cs,
+                               (size_t)(x0.b - x0.a) * p->Nhp * cs, (size_t)nprod * p->N1l))) return e;
+        }
     }
-    P.zcap = p->zcap;                                  // leave room on every SM for the F1 chunk running beside Z
+    if ((e = join_copies(p))) return e;
     for (int c = 0; c < nc; ++c) {
-        if (xb[c + 1] <= xb[c]) continue;
-        P.st = L;
-        if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true, Rng{xb[c], xb[c + 1]}))) return e;
-        CUDA_TRY(cudaEventRecord(p->ev_z[c], L));
-        CUDA_TRY(cudaStreamWaitEvent(X, p->ev_z[c], 0));
-        P.st = X;
-        if ((e = P.f1(nprod, nullptr, Rng{xb[c], xb[c + 1]}))) return e;
+        Rng mem[2], kept; k1_chunk(p, q, c, nc, &kept, mem);
+        P.st = p->stream;
+        for (int i = 0; i < 2; ++i)
+            if (mem[i].b > mem[i].a)
+                if ((e = launch_f0<T>(p, P, u_hat, nu, eta, so, nprod, false, (T)1, Rng{-1, 0}, mem[i]))) return e;
+        if (so.next_u) if ((e = b0_chunk_ce<T>(p, P, so.next_u, true, c))) return e;
     }
-    CUDA_TRY(cudaEventRecord(p->ev_f1all, X));
-    CUDA_TRY(cudaStreamWaitEvent(L, p->ev_f1all, 0));
-    if ((e = xbarrier(p))) return e;
-    P.st = L;
-    for (int c = 0; c < nc; ++c) {
-        if ((e = launch_f0<T>(p, P, u_hat, nu, eta, so, nprod, false, (T)1, Rng{kb[c], kb[c + 1]}))) return e;
-        CUDA_TRY(cudaEventRecord(p->ev_f0[c], L));
-    }
-    // the k2 columns above the 2/3 cutoff feed no B0 chunk: last
-    return launch_f0<T>(p, P, u_hat, nu, eta, so, nprod, false, (T)1, Rng{kb[nc], p->Nh});
+    if (so.next_u) p->b0_preissued = true;
+    const Rng tr = k1_truncated(p, q);
+    P.st = p->stream;
+    if (tr.b > tr.a) return launch_f0<T>(p, P, u_hat, nu, eta, so, nprod, false, (T)1, Rng{-1, 0}, tr);
+    return SDNS_OK;
 }
 
 template <typename T>
@@ -788,7 +891,7 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
             nprod = 6; divform = true;
         }
     } else {
-        if (p->nchunk > 1) return rhs_pipelined<T>(p, u_hat, nu, eta, so);
+        if (p->xmode) return rhs_ce<T>(p, u_hat, nu, eta, so);
         if (solver == SDNS_NS) { if ((e = P.b0(FAM_NS_B0, u, 3, 0, so.in_work_layout))) return e; }
         else if (solver == SDNS_VV) { if ((e = P.b0(FAM_VV_B0, u, 3, 0, so.in_work_layout))) return e; }
         else { if ((e = P.b0(FAM_PLAIN_BWD, u, 6, 0, so.in_work_layout))) return e; }
@@ -852,7 +955,7 @@ extern "C" int sdns_rk4_step(sdns_plan* p, void* u_hat, void* u1, void* u2, doub
         so.out_mode = OUT_STAGE; so.u1 = u1; so.u2 = u2; so.source = source; so.rk = rk;
         so.u0 = rk < 3 ? u0w : u_hat;
         so.in_work_layout = rk > 0;
-        so.chain = rk > 0;
+        so.next_u = rk < 3 ? u0w : nullptr;
         if (p->prec) rk_coeffs<double>(rk, dt, &so.adt, &so.bdt); else rk_coeffs<float>(rk, dt, &so.adt, &so.bdt);
         const void* uin = rk == 0 ? u_hat : u0w;
         e = p->prec ? rhs_t<double>(p, uin, nu, eta, so) : rhs_t<float>(p, uin, nu, eta, so);
@@ -1125,8 +1228,10 @@ extern "C" int sdns_errnorm(sdns_plan* p, const void* u0, const void* u1, const 
 extern "C" int sdns_profile_enable(sdns_plan* p, int on) {
     if (!p) return fail(SDNS_ERR_ARG, "null plan");
     CUDA_TRY(cudaStreamSynchronize(p->stream));
-    p->prof = on != 0; p->recs.clear(); p->ev_used = 0;
+    for (cudaStream_t y : p->ys) if (y) CUDA_TRY(cudaStreamSynchronize(y));
+    p->prof = on != 0; p->recs.clear(); p->crecs.clear(); p->ev_used = 0;
     for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_remote[i] = 0; p->prof_n[i] = 0; }
+    p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
     return SDNS_OK;
 }
 extern "C" int sdns_profile_read(sdns_plan* p, int family, double* total_ms, long long* launches, double* bytes) {
@@ -1136,7 +1241,12 @@ extern "C" int sdns_profile_read(sdns_plan* p, int family, double* total_ms, lon
         float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
         p->prof_ms[r.fam] += ms; p->prof_bytes[r.fam] += r.bytes; p->prof_remote[r.fam] += r.remote; p->prof_n[r.fam]++;
     }
-    p->recs.clear(); p->ev_used = 0;
+    for (cudaStream_t y : p->ys) if (y) CUDA_TRY(cudaStreamSynchronize(y));
+    for (const sdns_plan::CRec& r : p->crecs) {
+        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        p->copy_ms[r.s] += ms; p->copy_bytes += r.bytes; p->copy_n++;
+    }
+    p->recs.clear(); p->crecs.clear(); p->ev_used = 0;
     if (total_ms) *total_ms = p->prof_ms[family];
     if (launches) *launches = p->prof_n[family];
     if (bytes) *bytes = p->prof_bytes[family];
@@ -1147,5 +1257,15 @@ extern "C" int sdns_profile_read_nvlink(sdns_plan* p, int family, double* bytes)
     if (!p || !bytes || family < 0 || family >= FAM_COUNT) return fail(SDNS_ERR_ARG, "sdns_profile_read_nvlink: bad argument");
     int e = sdns_profile_read(p, family, nullptr, nullptr, nullptr); if (e) return e;
     *bytes = p->prof_remote[family];
+    return SDNS_OK;
+}
+
+extern "C" int sdns_profile_read_copies(sdns_plan* p, double* busy_ms, double* bytes, long long* ncopies) {
+    if (!p) return fail(SDNS_ERR_ARG, "sdns_profile_read_copies: null plan");
+    int e = sdns_profile_read(p, 0, nullptr, nullptr, nullptr); if (e) return e;
+    double mx = 0; for (int i = 0; i < 32; ++i) mx = std::max(mx, p->copy_ms[i]);
+    if (busy_ms) *busy_ms = mx;
+    if (bytes) *bytes = p->copy_bytes;
+    if (ncopies) *ncopies = p->copy_n;
     return SDNS_OK;
 }

@@ -275,3 +275,10 @@ class Plan(object):
                 _lib.check(self.lib.sdns_profile_read_nvlink(self._p, i, C.byref(r)))
                 out[name] = (ms.value, n.value, b.value, r.value)
         return out
+
+    def profile_read_copies(self):
+        """(busy_ms of the busiest per-peer copy stream, bytes sent over NVLink, number of copies) since
+        profile(True); all zero unless the copy engines carry the exchange (nranks > 1, the default)."""
+        ms, b, n = C.c_double(), C.c_double(), C.c_longlong()
+        _lib.check(self.lib.sdns_profile_read_copies(self._p, C.byref(ms), C.byref(b), C.byref(n)))
+        return ms.value, b.value, n.value
