@@ -114,11 +114,48 @@ static int run_zx(const ZArgs<T>& a, cudaStream_t st) {
     }
 }
 
+template <typename T, int M, int QN>
+static int run_zy_q(const ZArgs<T>& a, cudaStream_t st) {
+    typedef ZYCfg<T, M> C;
+    constexpr size_t smem = C::smem_q(QN);
+    auto kern = zy_kernel<T, M, C::E, QN, C::minBlocks_q(QN)>;
+    static int occ_sm = 0, nsm = 0;
+    if (!occ_sm) {
+        cudaError_t e = set_smem(kern, smem); if (e != cudaSuccess) return (int)e;
+        int dev = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::P, smem);
+        if (e != cudaSuccess) return (int)e;
+        occ_sm = occ > 0 ? occ : 1;
+    }
+    const long long blocks = (long long)((a.grid_cap > 0 && a.grid_cap < occ_sm) ? a.grid_cap : occ_sm) * nsm;
+    dim3 grid((unsigned)(a.nlines < blocks ? a.nlines : blocks));
+    kern<<<grid, C::P, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int M>
+static int run_zy(const ZArgs<T>& a, cudaStream_t st) {
+    typedef ZYCfg<T, M> C;
+    if constexpr (C::ok) {
+        if (a.nin_keep <= C::P * C::QN3) return run_zy_q<T, M, C::QN3>(a, st);
+        return run_zy_q<T, M, C::QN2>(a, st);
+    } else {
+        return -1;
+    }
+}
+
 template <typename T, int M, int MODE>
 static int run_z(const ZArgs<T>& a, cudaStream_t st) {
     if constexpr (MODE == Z_CROSS && ZXCfg<T, M>::ok) {
 #ifndef SDNS_NO_ZX
         return run_zx<T, M>(a, st);
+#endif
+    }
+    if constexpr (MODE == Z_CROSS && ZYCfg<T, M>::ok) {
+#ifndef SDNS_NO_ZY
+        return run_zy<T, M>(a, st);
 #endif
     }
     typedef ZCfg<T, M, MODE> C;

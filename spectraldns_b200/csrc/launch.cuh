@@ -161,6 +161,30 @@ struct ZXCfg {
     static constexpr int minBlocks = cmax(1, cmin(cmin((int)((216 * 1024) / (smem + 1024)), 16), 65536 / (128 * needRegs)));
 };
 
+// CTA-per-line fused z kernel (zy_kernel): two or four warps per line, for the lengths zx_kernel cannot hold in
+// one warp's registers
+constexpr int zy_E(int M) {
+    return (M % 8 == 0 && M / 8 <= 128 && plan_ok(M, 8)) ? 8 :
+           (M % 12 == 0 && M / 12 <= 128 && plan_ok(M, 12)) ? 12 :
+           (M % 16 == 0 && M / 16 <= 128 && plan_ok(M, 16)) ? 16 :
+           (M % 24 == 0 && M / 24 <= 128 && plan_ok(M, 24)) ? 24 : 0;
+}
+template <typename T, int M>
+struct ZYCfg {
+    static constexpr int E = zy_E(M) > 0 ? zy_E(M) : 8;
+    static constexpr int P = M / E;
+    static constexpr bool ok = zy_E(M) > 0 && (P == 64 || P == 128) && !ZXCfg<T, M>::ok;
+    static constexpr int PADW = 128 / (2 * (int)sizeof(T));
+    static constexpr int LP = M + M / PADW + 1;
+    static constexpr int QN3 = (M / 3 + 2 + P - 1) / P;       // covers the 2/3-rule and 3/2-rule mode counts
+    static constexpr int QN2 = (M / 2 + 1 + P - 1) / P;       // all M/2+1 modes
+    static constexpr size_t smem_q(int qn) { return ((size_t)(LP > 2 * qn * P ? LP : 2 * qn * P) + (size_t)2 * E * P) * 2 * sizeof(T); }
+    static constexpr int needRegs = sizeof(T) == 8 ? (E > 12 ? 255 : (E > 8 ? 224 : 168)) : (E > 16 ? 224 : (E > 12 ? 168 : 128));
+    static constexpr int minBlocks_q(int qn) {
+        return cmax(1, cmin(cmin((int)((216 * 1024) / (smem_q(qn) + 1024)), 16), 65536 / (P * needRegs)));
+    }
+};
+
 template <typename K>
 inline cudaError_t set_smem(K kern, size_t smem) {
     if (smem > 48 * 1024)

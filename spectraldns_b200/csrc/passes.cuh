@@ -1067,6 +1067,130 @@ zx_kernel(const ZArgs<T> a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused z-pass, one CTA of P = M/E threads (two or four warps) per line: the zx_kernel scheme for the long lines
+// whose register budget does not allow one warp per line (fp64 M >= 512, fp32 M >= 2048).  Same single HBM read
+// per spectral element, same software pipeline; the Hermitian mirrors travel through the (idle) exchange line in
+// shared memory instead of warp shuffles.
+// ---------------------------------------------------------------------------------------
+template <typename T, int M, int E, int QN, int MINB>
+__global__ void __launch_bounds__(M / E, MINB)
+zy_kernel(const ZArgs<T> a) {
+    typedef typename C2<T>::type V;
+    constexpr int P = M / E;
+    static_assert(P == 64 || P == 128, "two or four warps per line");
+    extern __shared__ __align__(16) unsigned char smraw[];
+    V* sm = reinterpret_cast<V*>(smraw);
+    constexpr int PADW = 128 / (int)sizeof(V);
+    constexpr int LP = M + M / PADW + 1;
+    constexpr int EXN = LP > 2 * QN * P ? LP : 2 * QN * P;
+    const int t = threadIdx.x;
+    const int src = (P - t) % P;
+    V* ex = sm;                                            // exchange line; doubles as mirror staging [slot][thread]
+    V* park = sm + EXN;                                    // parking slots [2E][P]
+    T* park_r = reinterpret_cast<T*>(park);
+    SmemLine<1, PADW> map; map.base = 0;
+    int phase = 0;
+    const V* in = reinterpret_cast<const V*>(a.in);
+    V* out = reinterpret_cast<V*>(a.out);
+    const long long stride = gridDim.x;
+    long long line = blockIdx.x;
+    V nxt[2 * QN];
+    auto load_raw = [&](V (&r)[2 * QN], const V* __restrict__ A, const V* __restrict__ B) {
+#pragma unroll
+        for (int q = 0; q < QN; ++q) {
+            const int kk = t + P * q;
+            if (kk < a.nin_keep) { r[2 * q] = A[kk]; r[2 * q + 1] = B[kk]; }
+            else { r[2 * q] = czero<V>(); r[2 * q + 1] = czero<V>(); }
+        }
+    };
+    if (line < a.nlines) load_raw(nxt, in + line * a.in_ls, in + a.in_fs + line * a.in_ls);
+    for (; line < a.nlines; line += stride) {
+        V x[E];
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+            V raw[2 * QN];
+#pragma unroll
+            for (int i = 0; i < 2 * QN; ++i) raw[i] = nxt[i];
+            if (pr < 2) load_raw(nxt, in + (2 * pr + 2) * a.in_fs + line * a.in_ls, in + (2 * pr + 3) * a.in_fs + line * a.in_ls);
+            else if (line + stride < a.nlines) load_raw(nxt, in + (line + stride) * a.in_ls, in + a.in_fs + (line + stride) * a.in_ls);
+            __syncthreads();                               // the previous transform has left the exchange line
+#pragma unroll
+            for (int i = 0; i < 2 * QN; ++i) ex[i * P + t] = raw[i];
+            __syncthreads();
+            // x[q] = Za[k] + i Zb[k], k = t + P q (load_pair's algebra, mirrors from the staging)
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                V va = czero<V>(), vb = czero<V>();
+                if (q < E / 2) {
+                    if (q < QN) { va = raw[2 * q]; vb = raw[2 * q + 1]; }
+                } else {
+                    const int sq = E - 1 - q;              // k > M/2: element M-k sits in thread (P-t)%P, slot E-1-q ...
+                    V ma = czero<V>(), mb = czero<V>();
+                    if (sq < QN) { ma = ex[(2 * sq) * P + src]; mb = ex[(2 * sq + 1) * P + src]; }
+                    V oa = czero<V>(), ob = czero<V>();    // ... thread 0 holds its own mirror P (E-q) in slot E-q
+                    if (E - q < QN) { oa = raw[2 * (E - q < QN ? E - q : 0)]; ob = raw[2 * (E - q < QN ? E - q : 0) + 1]; }
+                    if (q == E / 2) {
+                        if (t == 0) { va = oa; vb = ob; }  // k = M/2: direct
+                        else { va = cconj(ma); vb = cconj(mb); }
+                    } else {
+                        va = cconj(t == 0 ? oa : ma); vb = cconj(t == 0 ? ob : mb);
+                    }
+                }
+                if (t == 0 && (q == 0 || q == E / 2)) { va.y = 0; vb.y = 0; }
+                x[q].x = va.x - vb.y; x[q].y = va.y + vb.x;
+            }
+            fft_line<T, M, E, +1, 0, 1>(x, t, a.tw, ex, map, 0, phase);
+            if (pr < 2) {
+#pragma unroll
+                for (int q = 0; q < E; ++q) park[(pr * E + q) * P + t] = x[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const V p01 = park[q * P + t], p23 = park[(E + q) * P + t];
+            const T a0 = p01.x, a1 = p01.y, a2 = p23.x;
+            const T b0 = p23.y, b1 = x[q].x, b2 = x[q].y;
+            x[q].x = a1 * b2 - a2 * b1;                      // c = a x b (cross1)
+            x[q].y = a2 * b0 - a0 * b2;
+            park_r[2 * (q * P + t)] = a0 * b1 - a1 * b0;
+        }
+        fft_line<T, M, E, -1, 0, 1>(x, t, a.tw, ex, map, 0, phase);
+        // r2c unpack of the pair (c0, c1): mirrors through the staging
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < E; ++q) ex[q * P + t] = x[q];
+        __syncthreads();
+        {
+            const T h = (T)0.5 * a.scale;
+            V* C = out + line * a.out_ls;
+            V* D = out + a.out_fs + line * a.out_ls;
+#pragma unroll
+            for (int q = 0; q <= E / 2; ++q) {
+                V zm;
+                if (q < E / 2) zm = (t == 0) ? x[(E - q) % E] : ex[(E - 1 - q) * P + src];
+                else zm = x[E / 2];
+                const int k = t + P * q;
+                if ((q < E / 2 || t == 0) && k < a.nout_keep) {
+                    V c, d;
+                    c.x = h * (x[q].x + zm.x); c.y = h * (x[q].y - zm.y);
+                    d.x = h * (x[q].y + zm.y); d.y = -h * (x[q].x - zm.x);
+                    C[k] = c; D[k] = d;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < E; ++q) { x[q].x = park_r[2 * (q * P + t)]; x[q].y = (T)0; }
+        fft_line<T, M, E, -1, 0, 1>(x, t, a.tw, ex, map, 0, phase);
+        V* C2p = out + 2 * a.out_fs + line * a.out_ls;
+#pragma unroll
+        for (int q = 0; q <= E / 2; ++q) {
+            const int k = t + P * q;
+            if ((q < E / 2 || t == 0) && k < a.nout_keep) C2p[k] = cscale<T>(x[q], a.scale);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Hermitian-weighted sum |u_hat|^2 (shenfun.fourier.energy_fourier as used by tests/TG.py:101)
 // ---------------------------------------------------------------------------------------
 template <typename T>

@@ -228,3 +228,23 @@ def test_full_size_properties(cfg):
          torch.fft.rfftfreq(N[2], 1./N[2], device='cuda')]
     div = (k[0][:, None, None]*uh[0] + k[1][None, :, None]*uh[1] + k[2][None, None, :]*uh[2])
     assert float(div.abs().max()) < (1e-12 if prec == 'double' else 1e-5)
+
+
+@pytest.mark.parametrize('cfg', [((16, 16, 512), 'double', '2/3-rule'), ((16, 16, 512), 'double', '3/2-rule'),
+                                 ((16, 16, 1024), 'double', '2/3-rule'), ((16, 16, 2048), 'single', '2/3-rule'),
+                                 ((16, 16, 1024), 'single', '3/2-rule'), ((512, 16, 16), 'double', '2/3-rule'),
+                                 ((16, 512, 16), 'double', '3/2-rule'), ((16, 16, 512), 'double', 'None')])
+def test_long_axis_rhs(cfg):
+    """Transform lengths 512..2048 on one axis (the multi-warp-per-line fused z kernel and the long strided
+    passes) at a size the oracle finishes in seconds: NS ComputeRHS + one RK4 step on a random field."""
+    N, prec, dealias = cfg
+    o = so.Oracle(N, precision=prec, dealias=dealias)
+    p = make_plan(N, precision=prec, dealias=dealias)
+    rng = np.random.RandomState(7)
+    u0 = o.forward(rng.standard_normal((3,)+tuple(N)).astype(o.float)*0.3).astype(o.complex)
+    nu = 0.01
+    rhs = p.to_host(p.compute_rhs(p.empty_spectral(), p.to_device(u0), nu))
+    assert rel_l2(rhs, o.ns_rhs(u0, nu)) < TOL[prec]
+    d_u, u1, u2 = p.to_device(u0), p.empty_spectral(), p.empty_spectral()
+    p.rk4_step(d_u, u1, u2, 0.001, nu)
+    assert rel_l2(p.to_host(d_u), o.solve(u0, 'NS', 1, 0.001, nu)) < TOL[prec]
