@@ -37,7 +37,7 @@ class Oracle(object):
     """
 
     def __init__(self, N, L=(2*np.pi,)*3, precision='double', dealias='2/3-rule',
-                 mask_nyquist=True, workers=-1):
+                 mask_nyquist=True, workers=-1, kcut=None):
         self.N = tuple(int(n) for n in N)
         self.L = tuple(float(l) for l in L)
         # solvers/spectralinit.py:25-29
@@ -81,7 +81,8 @@ class Oracle(object):
         for i, k in enumerate(self.kint):
             s = [1, 1, 1]
             s[i] = len(k)
-            dm = dm & (np.abs(k.reshape(s)) <= dealias_cutoff(self.N[i]))
+            kc = dealias_cutoff(self.N[i]) if (kcut is None or kcut[i] is None or kcut[i] < 0) else int(kcut[i])
+            dm = dm & (np.abs(k.reshape(s)) <= kc)        # kcut: the plan parameter sdns_config.kcut (tests only)
         self.dealias_mask = dm
 
     # ---- transforms (shenfun TensorProductSpace.forward/backward as used at NS.py:93,103,128,135)

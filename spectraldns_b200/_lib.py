@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, 'libsdns_b200.so')
+LIBPATH = os.environ.get('SDNS_LIBPATH') or os.path.join(HERE, 'libsdns_b200.so')     # SDNS_LIBPATH: an experiment variant built with build.py --out
 
 SDNS_ABI_VERSION = 1
 SINGLE, DOUBLE = 0, 1

@@ -45,8 +45,12 @@ def _run(cmd):
     return r.stdout
 
 
-def build(force=False, jobs=None, verbose=False, sizes=None):
+def build(force=False, jobs=None, verbose=False, sizes=None, out=None, precs=(32, 64)):
     """Compile every CUDA translation unit for sm_100a and link libsdns_b200.so."""
+    global OBJ, LIB
+    if out:                                                      # experiment variant: its own objects and library
+        OBJ = os.path.join(HERE, 'build', 'variant_' + os.path.basename(out))
+        LIB = out
     os.makedirs(OBJ, exist_ok=True)
     extra = os.environ.get('SDNS_EXTRA_FLAGS', '').split()      # experiment switches, e.g. -DSDNS_NO_F0X
     if sizes:
@@ -86,5 +90,6 @@ if __name__ == '__main__':
     ap.add_argument('--jobs', type=int, default=None)
     ap.add_argument('--verbose', action='store_true')
     ap.add_argument('--sizes', type=int, nargs='*', default=None)
+    ap.add_argument('--out', default=None, help='write an experiment variant of the library here (with SDNS_EXTRA_FLAGS)')
     a = ap.parse_args()
-    print(build(a.force, a.jobs, a.verbose, a.sizes))
+    print(build(a.force, a.jobs, a.verbose, a.sizes, a.out))

@@ -21,18 +21,78 @@ template <> struct C2<double> { typedef double2 type; };
 template <typename T> __device__ __forceinline__ typename C2<T>::type mk(T x, T y) {
     typename C2<T>::type r; r.x = x; r.y = y; return r;
 }
-template <typename V> __device__ __forceinline__ V cadd(V a, V b) { a.x += b.x; a.y += b.y; return a; }
-template <typename V> __device__ __forceinline__ V csub(V a, V b) { a.x -= b.x; a.y -= b.y; return a; }
-template <typename V> __device__ __forceinline__ V cmul(V a, V b) {
-    V r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+
+// Two adjacent columns of an fp32 array in one register quad: a thread of a strided pass then moves 16 bytes per
+// access, as an fp64 thread does, and every index, twiddle and shared-memory address serves two columns.
+struct __align__(16) float2x2 { float2 a, b; };
+
+// element traits: real type, scalar complex type (twiddles), columns per element
+template <typename V> struct Elt;
+template <> struct Elt<float2>   { typedef float T;  typedef float2 C;  static constexpr int cols = 1; };
+template <> struct Elt<double2>  { typedef double T; typedef double2 C; static constexpr int cols = 1; };
+template <> struct Elt<float2x2> { typedef float T;  typedef float2 C;  static constexpr int cols = 2; };
+
+template <typename A, typename B> struct same_t { static constexpr bool v = false; };
+template <typename A> struct same_t<A, A> { static constexpr bool v = true; };
+
+// Complex arithmetic.  fp32 uses the packed f32x2 pipe of sm_100 (FADD2 / FMUL2 / FFMA2 on a (re, im) register
+// pair; the lane swap and the sign of a multiplication by +-i fold into the operand modifiers), which halves the
+// floating-point instruction count of the fp32 transforms.
+template <typename V> __device__ __forceinline__ V cadd(V a, V b) {
+    if constexpr (same_t<V, float2>::v) return __fadd2_rn(a, b);
+    else if constexpr (same_t<V, float2x2>::v) { V r; r.a = __fadd2_rn(a.a, b.a); r.b = __fadd2_rn(a.b, b.b); return r; }
+    else { a.x += b.x; a.y += b.y; return a; }
+}
+template <typename V> __device__ __forceinline__ V csub(V a, V b) {
+    if constexpr (same_t<V, float2>::v) return __fadd2_rn(a, make_float2(-b.x, -b.y));
+    else if constexpr (same_t<V, float2x2>::v) {
+        V r; r.a = __fadd2_rn(a.a, make_float2(-b.a.x, -b.a.y)); r.b = __fadd2_rn(a.b, make_float2(-b.b.x, -b.b.y)); return r;
+    } else { a.x -= b.x; a.y -= b.y; return a; }
+}
+// a * (-i) and a * (+i)
+template <typename V> __device__ __forceinline__ V mul_mi(V a) {
+    if constexpr (same_t<V, float2x2>::v) { V r; r.a = make_float2(a.a.y, -a.a.x); r.b = make_float2(a.b.y, -a.b.x); return r; }
+    else { V r; r.x = a.y; r.y = -a.x; return r; }
+}
+template <typename V> __device__ __forceinline__ V mul_pi(V a) {
+    if constexpr (same_t<V, float2x2>::v) { V r; r.a = make_float2(-a.a.y, a.a.x); r.b = make_float2(-a.b.y, a.b.x); return r; }
+    else { V r; r.x = -a.y; r.y = a.x; return r; }
+}
+template <typename V> __device__ __forceinline__ V cneg(V a) {
+    if constexpr (same_t<V, float2x2>::v) { V r; r.a = make_float2(-a.a.x, -a.a.y); r.b = make_float2(-a.b.x, -a.b.y); return r; }
+    else { V r; r.x = -a.x; r.y = -a.y; return r; }
 }
 template <typename V> __device__ __forceinline__ V cconj(V a) { a.y = -a.y; return a; }
-// multiply by -i*DIRSIGN... mul_mi: a * (-i) ; mul_pi: a * (+i)
-template <typename V> __device__ __forceinline__ V mul_mi(V a) { V r; r.x = a.y; r.y = -a.x; return r; }
-template <typename V> __device__ __forceinline__ V mul_pi(V a) { V r; r.x = -a.y; r.y = a.x; return r; }
 // rotate by -i for the forward transform (DIR=-1), +i for the backward one (DIR=+1)
 template <int DIR, typename V> __device__ __forceinline__ V rot90(V a) {
     return DIR < 0 ? mul_mi(a) : mul_pi(a);
+}
+// a * s, s real
+template <typename V> __device__ __forceinline__ V cscl(V a, typename Elt<V>::T s) {
+    if constexpr (same_t<V, float2>::v) return __fmul2_rn(a, make_float2(s, s));
+    else if constexpr (same_t<V, float2x2>::v) { V r; r.a = __fmul2_rn(a.a, make_float2(s, s)); r.b = __fmul2_rn(a.b, make_float2(s, s)); return r; }
+    else { a.x *= s; a.y *= s; return a; }
+}
+// acc + x * c, c real
+template <typename V> __device__ __forceinline__ V cfma(V acc, V x, typename Elt<V>::T c) {
+    if constexpr (same_t<V, float2>::v) return __ffma2_rn(x, make_float2(c, c), acc);
+    else if constexpr (same_t<V, float2x2>::v) {
+        V r; r.a = __ffma2_rn(x.a, make_float2(c, c), acc.a); r.b = __ffma2_rn(x.b, make_float2(c, c), acc.b); return r;
+    } else { acc.x += x.x * c; acc.y += x.y * c; return acc; }
+}
+// a * w, w one complex number (a twiddle)
+__device__ __forceinline__ float2 cmul_f2(float2 a, float2 w) {
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
+}
+template <typename V> __device__ __forceinline__ V cmul(V a, typename Elt<V>::C w) {
+    if constexpr (same_t<V, float2>::v) return cmul_f2(a, w);
+    else if constexpr (same_t<V, float2x2>::v) { V r; r.a = cmul_f2(a.a, w); r.b = cmul_f2(a.b, w); return r; }
+    else { V r; r.x = a.x * w.x - a.y * w.y; r.y = a.x * w.y + a.y * w.x; return r; }
+}
+// a * (wr + i wi) with compile-time constants
+template <typename V> __device__ __forceinline__ V cmulc(V a, typename Elt<V>::T wr, typename Elt<V>::T wi) {
+    if constexpr (same_t<V, double2>::v) { V r; r.x = a.x * wr - a.y * wi; r.y = a.x * wi + a.y * wr; return r; }
+    else return cfma(cscl(a, wr), mul_pi(a), wi);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -60,11 +120,8 @@ __device__ __forceinline__ void dft8(V& a0, V& a1, V& a2, V& a3, V& a4, V& a5, V
     dft4<DIR>(e0, e1, e2, e3);
     dft4<DIR>(o0, o1, o2, o3);
     // twiddles W8^k, k=1..3 with sign DIR:  W8^1 = (1 + DIR*i)/sqrt2 ; W8^2 = DIR*i ; W8^3 = (-1 + DIR*i)/sqrt2
-    V w1, w3;
-    if (DIR < 0) { w1 = mk<T>(h * (o1.x + o1.y), h * (o1.y - o1.x));
-                   w3 = mk<T>(h * (o3.y - o3.x), -h * (o3.x + o3.y)); }
-    else         { w1 = mk<T>(h * (o1.x - o1.y), h * (o1.y + o1.x));
-                   w3 = mk<T>(-h * (o3.x + o3.y), h * (o3.x - o3.y)); }
+    V w1 = cscl(cadd(o1, rot90<DIR>(o1)), h);
+    V w3 = cscl(csub(rot90<DIR>(o3), o3), h);
     V w2 = rot90<DIR>(o2);
     a0 = cadd(e0, o0); a4 = csub(e0, o0);
     a1 = cadd(e1, w1); a5 = csub(e1, w1);
@@ -76,10 +133,9 @@ template <int DIR, typename T, typename V>
 __device__ __forceinline__ void dft3(V& a0, V& a1, V& a2) {
     const T s = (T)0.86602540378443864676372317075294L;   // sin(pi/3)
     V t1 = cadd(a1, a2);
-    V t2 = mk<T>(a0.x - (T)0.5 * t1.x, a0.y - (T)0.5 * t1.y);
-    V d = csub(a1, a2);
+    V t2 = cfma(a0, t1, (T)-0.5);
     // forward: X1 = t2 - i*s*d ; backward: X1 = t2 + i*s*d
-    V r = rot90<DIR>(mk<T>(s * d.x, s * d.y));
+    V r = rot90<DIR>(cscl(csub(a1, a2), s));
     a0 = cadd(a0, t1);
     a1 = cadd(t2, r);
     a2 = csub(t2, r);
@@ -93,11 +149,11 @@ __device__ __forceinline__ void dft5(V& a0, V& a1, V& a2, V& a3, V& a4) {
     const T s2 = (T)0.58778525229247312916870595463907L;   // sin(4pi/5)
     V p1 = cadd(a1, a4), m1 = csub(a1, a4);
     V p2 = cadd(a2, a3), m2 = csub(a2, a3);
-    V b1 = mk<T>(a0.x + c1 * p1.x + c2 * p2.x, a0.y + c1 * p1.y + c2 * p2.y);
-    V b2 = mk<T>(a0.x + c2 * p1.x + c1 * p2.x, a0.y + c2 * p1.y + c1 * p2.y);
-    V r1 = rot90<DIR>(mk<T>(s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y));
-    V r2 = rot90<DIR>(mk<T>(s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y));
-    a0 = mk<T>(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
+    V b1 = cfma(cfma(a0, p1, c1), p2, c2);
+    V b2 = cfma(cfma(a0, p1, c2), p2, c1);
+    V r1 = rot90<DIR>(cfma(cscl(m1, s1), m2, s2));
+    V r2 = rot90<DIR>(cfma(cscl(m1, s2), m2, -s1));
+    a0 = cadd(a0, cadd(p1, p2));
     a1 = cadd(b1, r1); a4 = csub(b1, r1);
     a2 = cadd(b2, r2); a3 = csub(b2, r2);
 }
@@ -111,7 +167,7 @@ __device__ __forceinline__ V mulw16(V a) {
     constexpr int mm = m & 15;
     if (mm == 0) return a;
     if (mm == 4) return rot90<DIR>(a);
-    if (mm == 8) { V r; r.x = -a.x; r.y = -a.y; return r; }
+    if (mm == 8) return cneg(a);
     if (mm == 12) return rot90<-DIR>(a);
     // W = cos(th) + i*DIR*sin(th), th = 2*pi*mm/16
     T wr, wi;
@@ -120,7 +176,7 @@ __device__ __forceinline__ V mulw16(V a) {
     else if (mm == 9) { wr = -c; wi = -s; } else if (mm == 10) { wr = -h; wi = -h; } else if (mm == 11) { wr = -s; wi = -c; }
     else if (mm == 13) { wr = s; wi = -c; } else if (mm == 14) { wr = h; wi = -h; } else { wr = c; wi = -s; }
     if (DIR < 0) wi = -wi;
-    V r; r.x = a.x * wr - a.y * wi; r.y = a.x * wi + a.y * wr; return r;
+    return cmulc(a, wr, wi);
 }
 
 // 16-point DFT as 4 x 4: radix-4 over n2 (stride 4), twiddle W16^(n1*k2), radix-4 over n1, transpose
@@ -186,7 +242,8 @@ template <int SYNC> __device__ __forceinline__ void line_sync() {
 }
 
 template <typename T, int N, int E, int DIR, int Ns, int R, typename V>
-__device__ __forceinline__ void fft_stage(V (&x)[E], int t, const V* __restrict__ tw) {
+__device__ __forceinline__ void fft_stage(V (&x)[E], int t, const typename Elt<V>::C* __restrict__ tw) {
+    typedef typename Elt<V>::C W;
     constexpr int P = N / E;
     constexpr int NB = E / R;          // butterflies per thread
     constexpr int TS = N / (Ns * R);   // twiddle table stride
@@ -197,32 +254,32 @@ __device__ __forceinline__ void fft_stage(V (&x)[E], int t, const V* __restrict_
 #ifdef SDNS_TW_TABLE_ALL
 #pragma unroll
             for (int k = 1; k < R; ++k) {
-                V w = __ldg(&tw[(jm * k) * TS]);
+                W w = __ldg(&tw[(jm * k) * TS]);
                 if (DIR > 0) w.y = -w.y;
                 x[m + k * NB] = cmul(x[m + k * NB], w);
             }
 #else
             // one table load per butterfly; the powers w^2..w^(R-1) by multiplication (the L1/LSU path,
             // not the FP pipe, is the busy unit of these kernels)
-            V w1 = __ldg(&tw[jm * TS]);
+            W w1 = __ldg(&tw[jm * TS]);
             if (DIR > 0) w1.y = -w1.y;
             x[m + NB] = cmul(x[m + NB], w1);
             if (R > 2) {
-                const V w2 = cmul(w1, w1);
+                const W w2 = cmul(w1, w1);
                 x[m + 2 * NB] = cmul(x[m + 2 * NB], w2);
                 if (R > 3) {
-                    const V w3 = cmul(w2, w1);
+                    const W w3 = cmul(w2, w1);
                     x[m + 3 * NB] = cmul(x[m + 3 * NB], w3);
                     if (R > 4) {
-                        const V w4 = cmul(w2, w2);
+                        const W w4 = cmul(w2, w2);
                         x[m + 4 * NB] = cmul(x[m + 4 * NB], w4);
                         if (R > 5) {
-                            const V w5 = cmul(w4, w1), w6 = cmul(w3, w3), w7 = cmul(w4, w3);
+                            const W w5 = cmul(w4, w1), w6 = cmul(w3, w3), w7 = cmul(w4, w3);
                             x[m + 5 * NB] = cmul(x[m + 5 * NB], w5);
                             x[m + 6 * NB] = cmul(x[m + 6 * NB], w6);
                             x[m + 7 * NB] = cmul(x[m + 7 * NB], w7);
                             if (R > 8) {
-                                const V w8 = cmul(w4, w4);
+                                const W w8 = cmul(w4, w4);
                                 x[m + 8 * NB] = cmul(x[m + 8 * NB], w8);
                                 x[m + 9 * NB] = cmul(x[m + 9 * NB], cmul(w8, w1));
                                 x[m + 10 * NB] = cmul(x[m + 10 * NB], cmul(w5, w5));
@@ -274,7 +331,7 @@ __device__ __forceinline__ void fft_gather(V (&x)[E], int t, const V* sm, const 
 // NBUF = 2: ping-pong between two regions `bufstride` elements apart (one sync per exchange);
 // NBUF = 1: single region, two syncs per exchange.  `phase` must be CTA-uniform.
 template <typename T, int N, int E, int DIR, int SYNC, int NBUF, int Ns, typename V, typename SM>
-__device__ __forceinline__ void fft_stages(V (&x)[E], int t, const V* __restrict__ tw,
+__device__ __forceinline__ void fft_stages(V (&x)[E], int t, const typename Elt<V>::C* __restrict__ tw,
                                            V* sm, const SM& map, int bufstride, int& phase) {
     if constexpr (Ns < N) {
         constexpr int R = pick_radix(N / Ns, E);
@@ -293,7 +350,7 @@ __device__ __forceinline__ void fft_stages(V (&x)[E], int t, const V* __restrict
 }
 
 template <typename T, int N, int E, int DIR, int SYNC, int NBUF, typename V, typename SM>
-__device__ __forceinline__ void fft_line(V (&x)[E], int t, const V* __restrict__ tw,
+__device__ __forceinline__ void fft_line(V (&x)[E], int t, const typename Elt<V>::C* __restrict__ tw,
                                          V* sm, const SM& map, int bufstride, int& phase) {
     fft_stages<T, N, E, DIR, SYNC, NBUF, 1>(x, t, tw, sm, map, bufstride, phase);
 }

@@ -34,7 +34,13 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
         if (tiles > cap) tiles = cap;
     }
     dim3 grid((unsigned)tiles, ny);
-    kern<<<grid, C::P * C::TC, C::smem, st>>>(a);
+    StridedArgs<T> b = a;
+    b.xuniform = 0;
+    if (a.xchunk > 0 && a.xchunk % C::P == 0 && a.omap.shift % C::P == 0) {
+        const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;     // shift rounded up to whole chunks
+        b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
+    }
+    kern<<<grid, C::P * C::TC, C::smem, st>>>(b);
     return (int)cudaGetLastError();
 }
 
@@ -148,6 +154,9 @@ static int run_zy(const ZArgs<T>& a, cudaStream_t st) {
 
 template <typename T, int M, int MODE>
 static int run_z(const ZArgs<T>& a, cudaStream_t st) {
+#ifdef SDNS_ZY_E4
+    if constexpr (MODE == Z_CROSS && ZYCfg<T, M>::ok && ZYCfg<T, M>::E == 4) return run_zy<T, M>(a, st);
+#endif
     if constexpr (MODE == Z_CROSS && ZXCfg<T, M>::ok) {
 #ifndef SDNS_NO_ZX
         return run_zx<T, M>(a, st);

@@ -53,15 +53,27 @@ template <typename T, int N, int MODE>
 struct SCfg {
     static constexpr bool heavy = (MODE == S_NS_F0 || MODE == S_VV_F0);   // park two fields in smem
     static constexpr bool b0e = (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0);
-#ifdef SDNS_F0_E16
-    static constexpr int E = sizeof(T) == 8 ? (b0e ? pick_E(N, 8) : pick_E64(N)) : pick_E(N, heavy ? 16 : 24);
-#else
-    static constexpr int E = sizeof(T) == 8 ? ((heavy || b0e) ? pick_E(N, 8) : pick_E64(N)) : pick_E(N, heavy ? 16 : 24);
+#ifndef SDNS_F32_EMAX
+#define SDNS_F32_EMAX 24
 #endif
+#ifndef SDNS_F32_EMAX_HEAVY
+#define SDNS_F32_EMAX_HEAVY 16
+#endif
+#ifndef SDNS_F32_MAXT
+#define SDNS_F32_MAXT 256
+#endif
+#ifndef SDNS_F32_MAXT_HEAVY
+#define SDNS_F32_MAXT_HEAVY 512
+#endif
+    static constexpr int E = sizeof(T) == 8 ? ((heavy || b0e) ? pick_E(N, 8) : pick_E64(N))
+                                            : pick_E(N, heavy ? SDNS_F32_EMAX_HEAVY : SDNS_F32_EMAX);
     static constexpr int P = N / E;
     // the passes that store into peer GPUs (B0 family) keep 128-byte rows: NVLink likes the larger packets
     static constexpr bool b0m = (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0);
-    static constexpr int maxThreads = sizeof(T) == 8 ? (b0m ? 512 : 256) : (heavy ? 512 : 1024);
+#ifndef SDNS_B0_MAXT
+#define SDNS_B0_MAXT 512
+#endif
+    static constexpr int maxThreads = sizeof(T) == 8 ? (b0m ? SDNS_B0_MAXT : 256) : (heavy ? SDNS_F32_MAXT_HEAVY : SDNS_F32_MAXT);
     static constexpr int TCfull = 128 / (2 * (int)sizeof(T));
     static constexpr int TC = cmin(TCfull, cmax(1, maxThreads / P));
     static constexpr size_t bytes1 = (size_t)N * TC * 2 * sizeof(T);
@@ -89,7 +101,7 @@ constexpr int fx_blocks(int P, int tc, int csize, int N, int regs) {
     const long long smem = 3LL * N * tc * csize;
     if (smem > 200 * 1024) return 0;
     const int bs = (int)((216 * 1024) / (smem + 1024)), br = 65536 / (threads * regs), bt = 2048 / threads;
-    return cmin(cmin(bs, br), cmin(bt, 3));
+    return cmin(cmin(bs, br), cmin(bt, 4));
 }
 // tile width: the widest one (rows of >= 64 bytes) that still lets two CTAs share an SM, else the widest that fits
 constexpr int fx_tc(int P, int tcfull, int csize, int N, int regs) {
@@ -109,7 +121,11 @@ struct FXCfg {
     static constexpr int P = N / E;
     static constexpr int csize = 2 * (int)sizeof(T);
     static constexpr int needRegs = sizeof(T) == 8 ? (E > 12 ? 128 : 84) : (E > 12 ? 84 : 64);
+#ifdef SDNS_FX_TC
+    static constexpr int TC = fx_blocks(P, SDNS_FX_TC, csize, N, needRegs) >= 1 ? SDNS_FX_TC : fx_tc(P, 128 / csize, csize, N, needRegs);
+#else
     static constexpr int TC = fx_tc(P, 128 / csize, csize, N, needRegs);
+#endif
     static constexpr bool ok = TC > 0 && plan_ok(N, E) && sizeof(T) == 8;   // fp32: the register version is faster
     static constexpr size_t smem = (size_t)3 * N * (TC > 0 ? TC : 1) * csize;
     static constexpr int threads = 3 * P * (TC > 0 ? TC : 1);
@@ -149,8 +165,11 @@ struct ZCfg {
 template <typename T, int M>
 struct ZXCfg {
     static constexpr int E = M / 32;
+#ifndef SDNS_ZX_F32_EMAX
+#define SDNS_ZX_F32_EMAX 32
+#endif
     static constexpr bool ok = (M % 32 == 0) && (E == 8 || E == 12 || E == 16 || E == 24 || E == 32) && plan_ok(M, E)
-                               && (sizeof(T) == 4 || E <= 12);
+                               && (sizeof(T) == 4 ? E <= SDNS_ZX_F32_EMAX : E <= 12);
     static constexpr int LPC = 4;
     static constexpr int PADW = 128 / (2 * (int)sizeof(T));
     static constexpr int LP = M + M / PADW + 1;
@@ -163,7 +182,13 @@ struct ZXCfg {
 
 // CTA-per-line fused z kernel (zy_kernel): two or four warps per line, for the lengths zx_kernel cannot hold in
 // one warp's registers
+#ifndef SDNS_ZY_E4_REGS
+#define SDNS_ZY_E4_REGS 96
+#endif
 constexpr int zy_E(int M) {
+#ifdef SDNS_ZY_E4
+    if (M % 4 == 0 && (M / 4 == 64 || M / 4 == 128) && plan_ok(M, 4)) return 4;
+#endif
     return (M % 8 == 0 && M / 8 <= 128 && plan_ok(M, 8)) ? 8 :
            (M % 12 == 0 && M / 12 <= 128 && plan_ok(M, 12)) ? 12 :
            (M % 16 == 0 && M / 16 <= 128 && plan_ok(M, 16)) ? 16 :
@@ -173,13 +198,17 @@ template <typename T, int M>
 struct ZYCfg {
     static constexpr int E = zy_E(M) > 0 ? zy_E(M) : 8;
     static constexpr int P = M / E;
+#ifdef SDNS_ZY_E4
+    static constexpr bool ok = zy_E(M) > 0 && (P == 64 || P == 128) && (!ZXCfg<T, M>::ok || (sizeof(T) == 8 && E == 4));
+#else
     static constexpr bool ok = zy_E(M) > 0 && (P == 64 || P == 128) && !ZXCfg<T, M>::ok;
+#endif
     static constexpr int PADW = 128 / (2 * (int)sizeof(T));
     static constexpr int LP = M + M / PADW + 1;
     static constexpr int QN3 = (M / 3 + 2 + P - 1) / P;       // covers the 2/3-rule and 3/2-rule mode counts
     static constexpr int QN2 = (M / 2 + 1 + P - 1) / P;       // all M/2+1 modes
     static constexpr size_t smem_q(int qn) { return ((size_t)(LP > 2 * qn * P ? LP : 2 * qn * P) + (size_t)2 * E * P) * 2 * sizeof(T); }
-    static constexpr int needRegs = sizeof(T) == 8 ? (E > 12 ? 255 : (E > 8 ? 224 : 168)) : (E > 16 ? 224 : (E > 12 ? 168 : 128));
+    static constexpr int needRegs = sizeof(T) == 8 ? (E > 12 ? 255 : (E > 8 ? 224 : (E > 4 ? 168 : SDNS_ZY_E4_REGS))) : (E > 16 ? 224 : (E > 12 ? 168 : 128));
     static constexpr int minBlocks_q(int qn) {
         return cmax(1, cmin(cmin((int)((216 * 1024) / (smem_q(qn) + 1024)), 16), 65536 / (P * needRegs)));
     }

@@ -75,6 +75,8 @@ struct StridedArgs {
     int k1_off;                   // global index of local k1 = 0 (Nyquist test in the epilogues)
     int c1_off, c2_off;           // first run / first column of this launch (the multi-GPU pipeline launches a pass in chunks)
     int grid_cap;                 // > 0: launch at most this many CTAs per SM (grid-stride over the tiles)
+    int xuniform;                 // slab stores: P and omap.shift divide into xchunk (destination uniform per q)
+    int xhi_d0, xhi_b0;           // (rank, row in chunk) of transform block q = 0 mapped through the high kept range
     V* peer_out[8];
     int self;                     // destination that uses (out_fs, out_ls, c1_out_off); all others use the second set
     long long out_fs2, out_ls2, c1_out_off2;
@@ -82,7 +84,7 @@ struct StridedArgs {
 
 template <typename V> __device__ __forceinline__ V czero() { V z; z.x = 0; z.y = 0; return z; }
 
-template <typename T, typename V> __device__ __forceinline__ V cscale(V a, T s) { a.x *= s; a.y *= s; return a; }
+template <typename T, typename V> __device__ __forceinline__ V cscale(V a, T s) { return cscl(a, s); }
 
 // i*(ka*b - kb*a) for real ka,kb, complex a,b   (one component of cross2)
 template <typename T, typename V>
@@ -105,40 +107,92 @@ __device__ __forceinline__ void prefetch_line(const V* __restrict__ pin, long lo
     }
 }
 
-// Loads of one transform line: base pointer hoisted, predicated LDG, no branches.
+// Hides how a pointer was formed, so that the compiler keeps it in a register pair and addresses row r as one
+// IMAD.WIDE off it instead of re-deriving a 64-bit element index per access.
+template <typename Q> __device__ __forceinline__ Q* opaque(Q* p) {
+    unsigned long long v = reinterpret_cast<unsigned long long>(p);
+    asm volatile("" : "+l"(v));
+    Q* q = reinterpret_cast<Q*>(v);
+    __builtin_assume(__isGlobal(q));
+    return q;
+}
+
+// Row bookkeeping of one thread of a strided pass.  The thread owns the transform indices j = t + q P, q < E.
+// An AxisMap keeps j < nlo at memory row j (low block) and j >= N - nhi at memory row j - shift (high block), so
+// per thread there are two q-ranges, q < qlo and q >= qhi, two row-base pointers, and one uniform stride P*ls
+// between consecutive q: an access costs a compare pair, a select and one 64-bit add.
+template <int N, int E>
+struct RowSel {
+    int qlo, qhi;
+    __device__ __forceinline__ RowSel(const AxisMap& m, int t, bool valid) {
+        constexpr int P = N / E;
+        qlo = valid ? (m.nlo - t + P - 1) / P : 0;           // q < qlo   <=>  t + q P < nlo
+        qhi = valid ? (N - m.nhi - t + P - 1) / P : E;       // q >= qhi  <=>  t + q P >= N - nhi
+    }
+    __device__ __forceinline__ bool lo(int q) const { return q < qlo; }
+    __device__ __forceinline__ bool ok(int q) const { return q < qlo || q >= qhi; }
+};
+
+// Loads of one transform line.  Row offsets are 32-bit element counts relative to the (64-bit) column base: the
+// host checks N * ls < 2^31.
 template <typename T, int N, int E, typename V>
 __device__ __forceinline__ void load_line(V (&x)[E], const V* __restrict__ pin, long long ls, const AxisMap& m,
                                           int t, bool valid) {
     constexpr int P = N / E;
+    const RowSel<N, E> rs(m, t, valid);
+    const int l = (int)ls;
+    const int olo = t * l, ohi = (t - m.shift) * l, step = P * l;
+    const V* __restrict__ pb = opaque(pin);
 #pragma unroll
     for (int q = 0; q < E; ++q) {
-        const int j = t + q * P;
-        const long long off = (long long)axis_idx(m, j) * ls;
+        const int off = (rs.lo(q) ? olo : ohi) + q * step;
         V v = czero<V>();
-        if (valid && axis_ok(m, N, j)) v = pin[off];
+        if (rs.ok(q)) v = pb[off];
         x[q] = v;
     }
 }
 
-// Stores of one transform line.  Single GPU: pout + i*ls.  Slab decomposition: element i goes to
-// rank i / xchunk (reciprocal multiply, exact for i < 2^22) at line index i % xchunk.
+// Stores of one transform line.  Single GPU: pout + i*ls.  Slab decomposition: element i goes to rank i / xchunk
+// at line index i % xchunk.  When P and the map's shift divide into xchunk (a.xuniform, the normal case) the
+// destination rank and the chunk-local block of every q are the same for all threads of the CTA, so they are
+// computed once in uniform registers; otherwise per element (reciprocal multiply, exact for i < 2^22).
 template <typename T, int N, int E, bool SCALE, typename V>
 __device__ __forceinline__ void store_line(const V (&x)[E], const StridedArgs<T>& a, int f, long long obase,
                                            long long obase2, int t, bool valid, T scale) {
     constexpr int P = N / E;
     const long long fo = f * a.out_fs + obase;
+    const RowSel<N, E> rs(a.omap, t, valid);
     if (a.xchunk == 0) {
-        V* pout = a.out + fo;
+        V* pout = opaque(a.out + fo);
+        const int l = (int)a.out_ls;
+        const int olo = t * l, ohi = (t - a.omap.shift) * l, step = P * l;
 #pragma unroll
         for (int q = 0; q < E; ++q) {
-            const int j = t + q * P;
-            const long long off = (long long)axis_idx(a.omap, j) * a.out_ls;
-            if (valid && axis_ok(a.omap, N, j)) pout[off] = SCALE ? cscale<T>(x[q], scale) : x[q];
+            const int off = (rs.lo(q) ? olo : ohi) + q * step;
+            if (rs.ok(q)) pout[off] = SCALE ? cscale<T>(x[q], scale) : x[q];
         }
-    } else {
+    } else if (a.xuniform) {
         // destination `self` (this rank, or -1) uses the layout of the final array; every other one the second
         // layout (fs2, ls2, obase2): identical to the first for direct peer stores, the send-buffer layout when
         // the copy engines carry the exchange
+        const long long fo2 = f * a.out_fs2 + obase2;
+        const int l1 = (int)a.out_ls, l2 = (int)a.out_ls2;
+        // (destination rank, first row inside its chunk) of block q in the low and in the high kept range: the same
+        // for every thread, advanced by P rows per q
+        int dl = 0, bl = 0, dh = a.xhi_d0, bh = a.xhi_b0;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const bool lo = rs.lo(q);
+            int dest = lo ? dl : dh;
+            dest = dest < 0 ? 0 : dest;
+            const int row = t + (lo ? bl : bh);
+            const bool self = dest == a.self;
+            V* pq = a.peer_out[dest] + (self ? fo : fo2) + row * (self ? l1 : l2);
+            if (rs.ok(q)) *pq = SCALE ? cscale<T>(x[q], scale) : x[q];
+            bl += P; if (bl >= a.xchunk) { bl -= a.xchunk; ++dl; }
+            bh += P; if (bh >= a.xchunk) { bh -= a.xchunk; ++dh; }
+        }
+    } else {
         const float inv = 1.0f / (float)a.xchunk;
         const long long fo2 = f * a.out_fs2 + obase2;
 #pragma unroll
