@@ -20,6 +20,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+import spectraldns_b200  # noqa: E402,F401  (sets CUDA_DEVICE_MAX_CONNECTIONS before the CUDA context exists)
 
 NU, DT = 0.000625, 0.01       # tests/TG.py:131-133 of the reference
 

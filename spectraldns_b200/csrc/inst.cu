@@ -2,6 +2,7 @@
 // Defines sdns_launch_<family>_f<prec>(n, args, stream): picks the kernel compiled for transform
 // length n and launches it.
 #include "launch.cuh"
+#include <algorithm>
 
 #ifndef SDNS_FAMILY
 #error "compile with -DSDNS_FAMILY=n"
@@ -34,6 +35,11 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
         if (tiles > cap) tiles = cap;
     }
     dim3 grid((unsigned)tiles, ny);
+    {   // the passes address rows with 32-bit element offsets relative to the column base
+        auto mag = [](long long v) { return v < 0 ? -v : v; };
+        const long long big = std::max(std::max(mag(a.in_ls), mag(a.out_ls)), mag(a.out_ls2));
+        if ((long long)N * big >= (1LL << 31)) return -1001;
+    }
     StridedArgs<T> b = a;
     b.xuniform = 0;
     if (a.xchunk > 0 && a.xchunk % C::P == 0 && a.omap.shift % C::P == 0) {

@@ -78,9 +78,9 @@ struct sdns_plan {
     // xmode 1: B0 / F1 write per-destination send buffers in chunks and the copy engines move each chunk over
     // NVLink (one stream per peer) while the SMs work on the next chunk.
     int xmode, nchunk, nsplit;      // nsplit: streams (copy engines) per destination rank
-    std::vector<cudaStream_t> ys;   // copy streams, index = destination rank * nsplit + part (own entries unused)
+    std::vector<cudaStream_t> ys;   // copy streams (a few, shared by the destinations) x nsplit parts
     std::vector<cudaEvent_t> ev_k;  // [nchunk] the pass of chunk c has finished
-    std::vector<cudaEvent_t> ev_y;  // [P * nsplit] copy stream drained
+    std::vector<cudaEvent_t> ev_y;  // per copy stream: drained
     size_t off_SF, bytes_SF;        // F1 send buffers (B0's live in the W1 buffer, which is idle at that point)
     bool b0_preissued;              // the B0 chunks (and copies) of the coming right-hand side are already enqueued
     struct CRec { int s; cudaEvent_t a, b; double bytes; };
@@ -242,9 +242,15 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     }
     if (p->xmode) {
         cudaError_t e1 = cudaSuccess;
-        for (int r = 0; r < p->P * p->nsplit && e1 == cudaSuccess; ++r) {
+        // a few copy streams shared by all destinations: one stream already drives the link at its rate
+        // (profiles/tools/p2p_copy_bench.py); more only hide the per-copy start-up cost, and too many streams alias
+        // onto the same hardware queues as the plan stream (CUDA_DEVICE_MAX_CONNECTIONS)
+        const char* cse = getenv("SDNS_COPY_STREAMS");
+        int ncs = cse ? atoi(cse) : 2;
+        ncs = std::max(1, std::min(ncs, std::min(p->P - 1, 8)));
+        for (int r = 0; r < ncs * p->nsplit && e1 == cudaSuccess; ++r) {
             cudaStream_t y = nullptr; cudaEvent_t e = nullptr;
-            if (r / p->nsplit != p->rank) e1 = cudaStreamCreateWithFlags(&y, cudaStreamNonBlocking);
+            e1 = cudaStreamCreateWithFlags(&y, cudaStreamNonBlocking);
             p->ys.push_back(y);
             if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
             p->ev_y.push_back(e);
@@ -474,6 +480,7 @@ static int do_launch(sdns_plan* p, cudaStream_t st, int fam, int n, const void* 
     int e = g_launch[fam][p->prec](n, args, st);
     if (p->prof) { r.b = get_event(p); cudaEventRecord(r.b, st); p->recs.push_back(r); }
     p->launches++;
+    if (e == -1001) return fail(SDNS_ERR_SIZE, "array too large for one pass: transform length x line stride must stay below 2^31 elements per field (use more GPUs)");
     if (e == -1000) { char b[96]; snprintf(b, sizeof b, "no kernel for length %d (family %d)", n, fam); return fail(SDNS_ERR_SIZE, b); }
     if (e != 0) { char b[160]; snprintf(b, sizeof b, "kernel launch (family %d, n=%d): %s", fam, n, cudaGetErrorString((cudaError_t)e)); return fail(SDNS_ERR_CUDA, b); }
     return SDNS_OK;
@@ -724,7 +731,10 @@ static int copy_rows(sdns_plan* p, int r, cudaEvent_t after, void* dst, size_t d
     for (int i = 0; i < p->nsplit; ++i) {
         const size_t h0 = height * i / p->nsplit, h1 = height * (i + 1) / p->nsplit;
         if (h1 == h0) continue;
-        const int si = r * p->nsplit + i;
+        // destinations are visited nearest-neighbour first (rank+1, rank+2, ...) so that no rank is every sender's
+        // first target; destination k of that order uses stream k mod (number of streams)
+        const int ncs = (int)p->ys.size() / p->nsplit;
+        const int si = (((r - p->rank - 1 + p->P) % p->P) % ncs) * p->nsplit + i;
         cudaStream_t y = p->ys[si];
         CUDA_TRY(cudaStreamWaitEvent(y, after, 0));
         sdns_plan::CRec cr; cr.s = si; cr.bytes = (double)width * (h1 - h0);
@@ -784,8 +794,8 @@ static int b0_chunk_ce(sdns_plan* p, Pipe<T>& P, const void* u_hat, bool work_la
     CUDA_TRY(cudaEventRecord(p->ev_k[c], p->stream));
     if (kept.b <= kept.a) return SDNS_OK;
     const size_t cs = p->cs;
-    for (int r = 0; r < p->P; ++r) {
-        if (r == p->rank) continue;
+    for (int k = 1; k < p->P; ++k) {
+        const int r = (p->rank + k) % p->P;
         const V* src = P.B + r * P.b0_slot() + (long long)kept.a * q.K2p;
         V* dst = reinterpret_cast<V*>(p->peer_ws[r] + p->off_A) + ((long long)q.c1off + kept.a) * q.K2p;
         if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.K1n * q.K2p * cs, src, (size_t)q.K1l * q.K2p * cs,
@@ -822,8 +832,8 @@ static int rhs_ce(sdns_plan* p, const void* u_hat, double nu, double eta, const 
         if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true, x0))) return e;
         if ((e = P.f1(nprod, nullptr, x0, true))) return e;
         CUDA_TRY(cudaEventRecord(p->ev_k[c], p->stream));
-        for (int r = 0; r < p->P; ++r) {
-            if (r == p->rank) continue;
+        for (int k = 1; k < p->P; ++k) {
+            const int r = (p->rank + k) % p->P;
             const V* src = P.send_f1() + r * P.f1_slot(nprod) + (long long)x0.a * p->Nhp;
             V* dst = reinterpret_cast<V*>(p->peer_ws[r] + p->off_C) + ((long long)p->rank * q.M0l + x0.a) * p->Nhp;
             if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.M[0] * p->Nhp * cs, src, (size_t)q.M0l * p->Nhp * cs,
