@@ -60,3 +60,74 @@ class SlabLayout(object):
     def forward_destinations(self):
         """F1 output element with global k1 -> owning rank."""
         return np.arange(self.N[1])//self.N1l
+
+
+# ---------------------------------------------------------------------------------------------
+# Copy-engine exchange (csrc/sdns_api.cu: chunk_bound, k1_chunk, b0_chunk_ce, rhs_ce): the passes in front of a
+# transpose run in chunks; a chunk writes the part of every peer into a send slot and one strided 2-D copy per
+# peer moves it.  The functions below are the host mirror of that index arithmetic (elements, not bytes);
+# tests/test_slab_cpu.py replays them with numpy buffers and gloo messages.
+# ---------------------------------------------------------------------------------------------
+def chunk_bound(n, nc, c):
+    """Boundary c (0..nc) of an axis of n entries cut into nc chunks with weights 3,..,3,2,1."""
+    w = [min(nc - i, 3) for i in range(nc)]
+    return (n*sum(w[:c]) + sum(w)//2)//sum(w)
+
+
+class Copy2D(object):
+    """One cudaMemcpy2DAsync: `height` rows of `width` elements, row r at src_off + r*spitch -> dst_off + r*dpitch."""
+    def __init__(self, src_off, spitch, dst_off, dpitch, width, height):
+        self.src_off, self.spitch, self.dst_off, self.dpitch = int(src_off), int(spitch), int(dst_off), int(dpitch)
+        self.width, self.height = int(width), int(height)
+
+    def gather(self, src_flat):
+        rows = self.src_off + self.spitch*np.arange(self.height)[:, None] + np.arange(self.width)[None, :]
+        return src_flat[rows]
+
+    def scatter(self, dst_flat, payload):
+        rows = self.dst_off + self.dpitch*np.arange(self.height)[:, None] + np.arange(self.width)[None, :]
+        dst_flat[rows] = payload
+
+
+class ExchangePlan(object):
+    """Send-slot layouts and per-chunk copies of rank `L.rank` (L: SlabLayout) for nf fields."""
+    def __init__(self, L, nchunk=4):
+        self.L, self.nc = L, int(nchunk)
+        self.K2p = (L.K2n + 1) & ~1
+        self.Nhp = (L.Nh + 1) & ~1
+
+    # B0: slot r holds (6|nf, M0l, K1l, K2p); destination array W0 is (nf, M0l, K1n, K2p) on rank r
+    def b0_slot(self, nf):
+        return nf*self.L.M0l*self.L.K1l*self.K2p
+
+    def b0_kept(self, c):
+        return chunk_bound(self.L.K1l, self.nc, c), chunk_bound(self.L.K1l, self.nc, c+1)
+
+    def b0_send_index(self, nf, r, f, x0l, c1, c2):
+        """element (field f, local x0 of rank r, this rank's compact mode c1, k2) inside the send buffer"""
+        L = self.L
+        return r*self.b0_slot(nf) + ((f*L.M0l + x0l)*L.K1l + c1)*self.K2p + c2
+
+    def b0_copy(self, nf, r, c):
+        L = self.L
+        ka, kb = self.b0_kept(c)
+        return Copy2D(r*self.b0_slot(nf) + ka*self.K2p, L.K1l*self.K2p,
+                      (L.c1off + ka)*self.K2p, L.K1n*self.K2p, (kb - ka)*self.K2p, nf*L.M0l)
+
+    # F1: slot r holds (nf, N1l, M0l, Nhp); destination array W3 is (nf, N1l, M0, Nhp) on rank r
+    def f1_slot(self, nf):
+        L = self.L
+        return nf*L.N1l*L.M0l*self.Nhp
+
+    def f1_planes(self, c):
+        return chunk_bound(self.L.M0l, self.nc, c), chunk_bound(self.L.M0l, self.nc, c+1)
+
+    def f1_send_index(self, nf, r, f, k1l, x0l, c2):
+        L = self.L
+        return r*self.f1_slot(nf) + ((f*L.N1l + k1l)*L.M0l + x0l)*self.Nhp + c2
+
+    def f1_copy(self, nf, r, c):
+        L = self.L
+        xa, xb = self.f1_planes(c)
+        return Copy2D(r*self.f1_slot(nf) + xa*self.Nhp, L.M0l*self.Nhp,
+                      (L.rank*L.M0l + xa)*self.Nhp, L.M[0]*self.Nhp, (xb - xa)*self.Nhp, nf*L.N1l)

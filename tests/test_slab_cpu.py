@@ -142,3 +142,116 @@ def test_slab_layout_matches_c_plan_rules():
 
 def so_cut(n):
     return int(np.ceil(2./3.*(n//2+1))) - 1
+
+
+def _ce_worker(rank, world, port, dealias, N, nchunk, ret):
+    """Copy-engine exchange replayed on CPU: send slots, per-chunk strided 2-D copies (spectraldns_b200.slab's
+    mirror of csrc/sdns_api.cu) delivered as gloo messages, must land every element where the direct slab
+    transpose puts it."""
+    import torch
+    import torch.distributed as dist
+    from spectraldns_b200.slab import SlabLayout, ExchangePlan
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        Ls = [SlabLayout(N, world, r, dealias) for r in range(world)]
+        Xs = [ExchangePlan(L, nchunk) for L in Ls]
+        L, X = Ls[rank], Xs[rank]
+        nf = 2
+
+        def val_b0(f, x0, c1g, c2):      # unique tag of B0 output element (field, global x0, global compact k1, k2)
+            return ((f*L.M[0] + x0)*L.K1n + c1g)*L.K2n + c2 + 1.0
+
+        # ---- B0: own part straight into W0, peers' parts into the send slots
+        W0 = np.zeros(nf*L.M0l*L.K1n*X.K2p)
+        send = np.zeros(world*X.b0_slot(nf))
+        f, x0, c1, c2 = np.meshgrid(np.arange(nf), np.arange(L.M[0]), np.arange(L.K1l), np.arange(L.K2n), indexing='ij')
+        dest, x0l = x0//L.M0l, x0 % L.M0l
+        v = val_b0(f, x0, c1 + L.c1off, c2)
+        own = dest == rank
+        W0[((f[own]*L.M0l + x0l[own])*L.K1n + L.c1off + c1[own])*X.K2p + c2[own]] = v[own]
+        send[X.b0_send_index(nf, dest[~own], f[~own], x0l[~own], c1[~own], c2[~own])] = v[~own]
+        reqs, inbox = [], []
+        for c in range(nchunk):
+            for k in range(1, world):
+                r = (rank + k) % world
+                cp = X.b0_copy(nf, r, c)
+                if cp.width and cp.height:
+                    reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(cp.gather(send))), r, tag=c))
+                s = (rank - k) % world                      # the copy rank s aims at this rank, same chunk
+                cq = Xs[s].b0_copy(nf, rank, c)
+                if cq.width and cq.height:
+                    buf = torch.zeros((cq.height, cq.width), dtype=torch.float64)
+                    reqs.append(dist.irecv(buf, s, tag=c))
+                    inbox.append((cq, buf))
+        for q in reqs:
+            q.wait()
+        for cq, buf in inbox:
+            cq.scatter(W0, buf.numpy())
+        W0 = W0.reshape(nf, L.M0l, L.K1n, X.K2p)[..., :L.K2n]
+        f, x0l, c1g, c2 = np.meshgrid(np.arange(nf), np.arange(L.M0l), np.arange(L.K1n), np.arange(L.K2n), indexing='ij')
+        e_b = float(np.abs(W0 - val_b0(f, x0l + rank*L.M0l, c1g, c2)).max())
+
+        # ---- F1: element (field, global k1, global x0, k2) -> W3 (nf, N1l, M0, Nhp) on the rank owning k1
+        def val_f1(f, k1, x0, c2):
+            return ((f*L.N[1] + k1)*L.M[0] + x0)*L.Nh + c2 + 1.0
+        W3 = np.zeros(nf*L.N1l*L.M[0]*X.Nhp)
+        send = np.zeros(world*X.f1_slot(nf))
+        f, k1, x0l, c2 = np.meshgrid(np.arange(nf), np.arange(L.N[1]), np.arange(L.M0l), np.arange(L.Nh), indexing='ij')
+        dest, k1l = k1//L.N1l, k1 % L.N1l
+        v = val_f1(f, k1, x0l + rank*L.M0l, c2)
+        own = dest == rank
+        W3[((f[own]*L.N1l + k1l[own])*L.M[0] + rank*L.M0l + x0l[own])*X.Nhp + c2[own]] = v[own]
+        send[X.f1_send_index(nf, dest[~own], f[~own], k1l[~own], x0l[~own], c2[~own])] = v[~own]
+        reqs, inbox = [], []
+        for c in range(nchunk):
+            for k in range(1, world):
+                r = (rank + k) % world
+                cp = X.f1_copy(nf, r, c)
+                if cp.width and cp.height:
+                    reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(cp.gather(send))), r, tag=100 + c))
+                s = (rank - k) % world
+                cq = Xs[s].f1_copy(nf, rank, c)
+                if cq.width and cq.height:
+                    buf = torch.zeros((cq.height, cq.width), dtype=torch.float64)
+                    reqs.append(dist.irecv(buf, s, tag=100 + c))
+                    inbox.append((cq, buf))
+        for q in reqs:
+            q.wait()
+        for cq, buf in inbox:
+            cq.scatter(W3, buf.numpy())
+        W3 = W3.reshape(nf, L.N1l, L.M[0], X.Nhp)[..., :L.Nh]
+        f, k1l, x0, c2 = np.meshgrid(np.arange(nf), np.arange(L.N1l), np.arange(L.M[0]), np.arange(L.Nh), indexing='ij')
+        e_f = float(np.abs(W3 - val_f1(f, k1l + rank*L.N1l, x0, c2)).max())
+        ret[rank] = (e_b, e_f, [Ls[r].K1l for r in range(world)])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('cfg', [(2, '2/3-rule', (16, 32, 16), 4), (2, '3/2-rule', (16, 32, 16), 3),
+                                 (4, '2/3-rule', (16, 64, 24), 4), (4, 'None', (8, 16, 8), 2)])
+def test_copy_engine_exchange_layout_gloo(cfg):
+    import torch.multiprocessing as mp
+    world, dealias, N, nchunk = cfg
+    port = 29640 + [2, 4].index(world)*4 + ['2/3-rule', '3/2-rule', 'None'].index(dealias)
+    ctx = mp.get_context('spawn')
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_ce_worker, args=(r, world, port, dealias, N, nchunk, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    for r in range(world):
+        e_b, e_f, K1l = ret[r]
+        assert e_b == 0.0 and e_f == 0.0, (r, e_b, e_f, K1l)
+
+
+def test_chunk_bounds_taper_and_cover():
+    from spectraldns_b200.slab import chunk_bound
+    for n in (0, 1, 5, 43, 64, 128, 341):
+        for nc in (1, 2, 3, 4, 6, 16):
+            b = [chunk_bound(n, nc, c) for c in range(nc+1)]
+            assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+    b = [chunk_bound(90, 4, c) for c in range(5)]
+    assert [y - x for x, y in zip(b, b[1:])] == [30, 30, 20, 10]
