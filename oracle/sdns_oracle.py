@@ -11,7 +11,10 @@ Parity pinning: this restatement is checked (tests/test_oracle.py, oracle/make_g
       (tests/TG.py:125-126), TG-MHD k=0.124565408177, b=0.124637762143 (tests/TGMHD.py:25-26);
   (2) field-level against the reference's UNMODIFIED solvers/{NS,VV,MHD}.py +
       maths/integrators.py imported from /root/reference over the numpy stand-in substrate in
-      oracle/shim (fixtures tests/golden/*.npz written by oracle/make_golden.py).
+      oracle/shim (fixtures tests/golden/*.npz written by oracle/make_golden.py);
+  (3) against the reference's own compiled kernels for this path (optimization/cython_{maths,solvers,
+      integrators}.in built into oracle/_ref by oracle/build_ref_cython.py): cross1, cross2,
+      add_pressure_diffusion_NS, RK4, ForwardEuler, AB2 (tests/test_oracle.py).
 The FFT / padding / truncation arithmetic itself lives in shenfun + mpi4py-fft (pins
 shenfun>=4.0.2, mpi4py-fft>=2.0.3, setup.py:86, conf/conda/meta.yaml:34-35), which are NOT in
 /root/reference; their published algorithm is restated here and the exact 2/3-rule cutoff index
@@ -186,6 +189,17 @@ class Oracle(object):
         rhs *= (-0.5 if convection == 'Skewed' else -1)       # NS.py:170,178,188
         return rhs
 
+    def add_pressure_diffusion(self, rhs, u_hat, nu):
+        """solvers/NS.py:203-217 (Cython: add_pressure_diffusion_NS_, cython_solvers.in:44-80):
+        P_hat = sum_i rhs_i K_i/K^2 ; rhs_i -= P_hat K_i + nu K^2 u_hat_i.  Returns (rhs, P_hat); rhs is
+        updated in place."""
+        nu = self.float(nu)
+        P_hat = np.sum(rhs*self.K_over_K2, 0)
+        for i in range(3):
+            rhs[i] -= P_hat*self.K[i]
+        rhs -= nu*self.K2*u_hat
+        return rhs, P_hat
+
     def ns_rhs(self, u_hat, nu, convection='Vortex', source=None, return_p=False):
         """solvers/NS.py:219-261 with add_pressure_diffusion NS.py:203-217
         (cython_solvers.in:44-80)."""
@@ -193,10 +207,7 @@ class Oracle(object):
         rhs = self.ns_conv(u_hat, convection)
         if self.mask is not None:
             rhs *= self.mask                                   # NS.py:253-254
-        P_hat = np.sum(rhs*self.K_over_K2, 0)
-        for i in range(3):
-            rhs[i] -= P_hat*self.K[i]
-        rhs -= nu*self.K2*u_hat
+        rhs, P_hat = self.add_pressure_diffusion(rhs, u_hat, nu)
         if source is not None:
             rhs += source                                      # NS.py:259
         rhs = rhs.astype(self.complex)

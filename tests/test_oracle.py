@@ -135,3 +135,76 @@ def test_oracle_integrators_reproduce_reference(name):
         u, n, t = o.bs5_solve(u, fn, dt, T, integ == 'BS5_adaptive')
         assert n == int(g['nsteps']) and abs(t - float(g['t_end'])) < 1e-12
     assert rel_l2(u, g['u_hat']) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# second pin: the reference's own COMPILED kernels (Cython templates built by oracle/build_ref_cython.py
+# into oracle/_ref/, from the sources where they lie under /root/reference)
+# ---------------------------------------------------------------------------------------------
+def _ref_cython(precision):
+    import importlib
+    import sys
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(here, 'oracle'))
+    import build_ref_cython as brc
+    if not brc.available() and not brc.build():
+        pytest.skip('oracle/_ref not built and /root/reference absent')
+    if brc.OUT not in sys.path:
+        sys.path.insert(0, brc.OUT)
+    return [importlib.import_module('cython_%s_%s' % (precision, m)) for m in ('maths', 'solvers', 'integrators')]
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_oracle_against_reference_cython_kernels(precision):
+    """cross1 / cross2 / add_pressure_diffusion_NS / RK4 / ForwardEuler / AB2 of the reference's compiled
+    optimisation modules (optimization/cython_{maths,solvers,integrators}.in) against the restatement."""
+    maths, solvers, integ = _ref_cython(precision)
+    N = (8, 6, 10)
+    o = so.Oracle(N, L=(2*np.pi, 4*np.pi, 6*np.pi), precision=precision)
+    tol = 1e-15 if precision == 'double' else 2e-7
+    rng = np.random.RandomState(12)
+    a = rng.standard_normal((3,)+N).astype(o.float)
+    b = rng.standard_normal((3,)+N).astype(o.float)
+    c = maths.cross1(np.zeros_like(a), a, b)
+    assert rel_l2(o.cross1(a, b), c) <= tol
+
+    def cplx(shape):
+        return (rng.standard_normal(shape) + 1j*rng.standard_normal(shape)).astype(o.complex)
+    bh = cplx((3,)+o.sshape)
+    # cross2 with the broadcast wavenumber list (cython _cross3) and with a dense real field (_cross2)
+    c3 = maths.cross2(np.zeros_like(bh), [np.ascontiguousarray(k) for k in o.K], bh)
+    assert rel_l2(o.cross2(o.K, bh), c3) <= tol
+    ad = rng.standard_normal((3,)+o.sshape).astype(o.float)
+    c2 = maths.cross2(np.zeros_like(bh), ad, bh)
+    assert rel_l2(o.cross2(ad, bh), c2) <= tol
+    # add_pressure_diffusion (NS.py:203-217 / cython_solvers.in:40-80)
+    du, uh = cplx((3,)+o.sshape), cplx((3,)+o.sshape)
+    nu = o.float(0.0123)
+    p_ref = np.zeros(o.sshape, dtype=o.complex)
+    du_ref = solvers.add_pressure_diffusion_NS(du.copy(), uh, nu, o.K2, o.K, p_ref, o.K_over_K2)
+    du_or, p_or = o.add_pressure_diffusion(du.copy(), uh, nu)
+    assert rel_l2(du_or, du_ref) <= 4*tol and rel_l2(p_or, p_ref) <= 4*tol
+
+    # integrators: the reference's compiled stage loops around a ComputeRHS supplied by the oracle
+    class Solver(object):
+        @staticmethod
+        def ComputeRHS(dU, U_hat, solver, **ctx):
+            dU[:] = o.ns_rhs(U_hat, 0.01)
+            return dU
+    u0 = (o.forward(so.taylor_green(o)) + 0.05*cplx((3,)+o.sshape)*(o.mask if o.mask is not None else 1)).astype(o.complex)
+    dt = 0.01
+    fn = lambda u: o.ns_rhs(u, 0.01)
+    A = np.array([1./6., 1./3., 1./3., 1./6.], dtype=o.float)
+    B = np.array([0.5, 0.5, 1.], dtype=o.float)
+    U = u0.copy()
+    integ.RK4(U, np.zeros_like(U), np.zeros_like(U), np.zeros_like(U), A, B, o.float(dt), Solver, {})
+    assert rel_l2(o.rk4_step(u0, fn, dt), U) <= 10*tol
+    U = u0.copy()
+    integ.ForwardEuler(U, np.zeros_like(U), np.zeros_like(U), o.float(dt), Solver, {})
+    assert rel_l2(o.forward_euler_step(u0, fn, dt), U) <= 10*tol
+    U, U1 = u0.copy(), np.zeros_like(u0)
+    ref, r1 = u0.copy(), np.zeros_like(u0)
+    for ts in range(3):
+        integ.AB2(U, U1, np.zeros_like(U), o.float(dt), ts, Solver, {})
+        ref, r1 = o.ab2_step(ref, r1, fn, dt, ts)
+    assert rel_l2(ref, U) <= 20*tol and rel_l2(r1, U1) <= 20*tol
