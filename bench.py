@@ -39,6 +39,8 @@ def parse():
                     help='N>1: weak = grid grows with the GPU count (per-GPU work fixed), strong = fixed grid')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
+    ap.add_argument('--timeline', default=None,
+                    help='write PATH.rank<r>.json: start/end of every kernel, peer copy and barrier of one RK4 step')
     return ap.parse_args()
 
 
@@ -266,6 +268,14 @@ def run_ours(a):
     prof = p.profile_read()
     copies = p.profile_read_copies()
     p.profile(False)
+    if a.timeline:
+        barrier()
+        p.profile(True, timeline=True)
+        p.rk4_step(u, u1, u2, DT, NU, eta)
+        rows = p.profile_timeline()
+        p.profile(False)
+        with open('%s.rank%d.json' % (a.timeline, rank), 'w') as f:
+            json.dump([{'what': w, 't0_ms': t0, 't1_ms': t1, 'bytes': b} for w, t0, t1, b in rows], f)
     barrier()
 
     if rank != 0:

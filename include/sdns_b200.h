@@ -183,6 +183,11 @@ int sdns_profile_read_nvlink(sdns_plan* plan, int family, double* bytes);
  * rank sent over NVLink since sdns_profile_enable, the number of strided copies, and the busy time of the busiest
  * per-peer copy stream (the copies to different peers run concurrently) */
 int sdns_profile_read_copies(sdns_plan* plan, double* busy_ms, double* bytes, long long* ncopies);
+/* sdns_profile_enable(plan, 2) additionally keeps a timeline: start and end (ms after the enable call, device clock)
+ * of every kernel launch, peer copy and cross-GPU barrier.  rows receives up to max_rows records of four doubles
+ * (kind, t_start_ms, t_end_ms, bytes); kind = kernel family 0..14, 99 = barrier, 100 + s = copy on copy stream s.
+ * *nrows is the number of records available (rows may be NULL to query it).  sdns_profile_enable clears it. */
+int sdns_profile_timeline(sdns_plan* plan, double* rows, int max_rows, int* nrows);
 
 #ifdef __cplusplus
 }

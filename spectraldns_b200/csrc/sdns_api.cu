@@ -91,6 +91,10 @@ struct sdns_plan {
     std::vector<cudaEvent_t> ev_pool; size_t ev_used;
     struct Rec { int fam; cudaEvent_t a, b; double bytes, remote; };
     std::vector<Rec> recs;
+    // timeline (sdns_profile_enable(plan, 2)): start / end of every launch, copy and barrier relative to tl_base
+    bool tl_on; cudaEvent_t tl_base;
+    std::vector<Rec> brecs;                 // cross-GPU barriers (timeline only)
+    std::vector<double> timeline;           // rows of (kind, t0_ms, t1_ms, bytes)
     double prof_ms[FAM_COUNT]; double prof_bytes[FAM_COUNT]; double prof_remote[FAM_COUNT]; long long prof_n[FAM_COUNT];
 };
 
@@ -225,6 +229,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->rs = p->prec ? 8 : 4; p->cs = 2 * p->rs;
     p->stream = 0; p->ws = nullptr; p->ws_bytes = 0; p->launches = 0;
     p->prof = false; p->ev_used = 0;
+    p->tl_on = false; p->tl_base = nullptr;
     p->xmode = 0; p->nchunk = 1; p->nsplit = 1; p->off_SF = 0; p->bytes_SF = 0; p->b0_preissued = false;
     p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
     if (p->P > 1) {
@@ -317,6 +322,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
 extern "C" int sdns_plan_destroy(sdns_plan* p) {
     if (p) {
         for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+        if (p->tl_base) cudaEventDestroy(p->tl_base);
         for (cudaEvent_t e : p->ev_k) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : p->ev_y) if (e) cudaEventDestroy(e);
         for (cudaStream_t y : p->ys) if (y) cudaStreamDestroy(y);
@@ -416,6 +422,8 @@ __global__ void xbarrier_kernel(const BarrierArgs b) {
 
 }  // namespace sdns
 
+static cudaEvent_t get_event(sdns_plan* p);
+
 static int xbarrier(sdns_plan* p) {
     if (p->P == 1) return SDNS_OK;
     for (int r = 0; r < p->P; ++r) if (!p->peer_ws[r]) return fail(SDNS_ERR_STATE, "peers not opened (sdns_comm_open)");
@@ -424,7 +432,10 @@ static int xbarrier(sdns_plan* p) {
     b.status = reinterpret_cast<unsigned int*>(p->ws + p->off_flags) + 32;
     b.rank = p->rank; b.nranks = p->P; b.epoch = ++p->epoch;
     b.timeout_cycles = 20000000000LL;      // ~10 s: a missing peer must not hang the GPU
+    sdns_plan::Rec r; r.fam = -1; r.bytes = 0; r.remote = 0;
+    if (p->tl_on) { r.a = get_event(p); cudaEventRecord(r.a, p->stream); }
     xbarrier_kernel<<<1, 32, 0, p->stream>>>(b);
+    if (p->tl_on) { r.b = get_event(p); cudaEventRecord(r.b, p->stream); p->brecs.push_back(r); }
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return SDNS_OK;
@@ -1239,7 +1250,12 @@ extern "C" int sdns_profile_enable(sdns_plan* p, int on) {
     if (!p) return fail(SDNS_ERR_ARG, "null plan");
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     for (cudaStream_t y : p->ys) if (y) CUDA_TRY(cudaStreamSynchronize(y));
-    p->prof = on != 0; p->recs.clear(); p->crecs.clear(); p->ev_used = 0;
+    p->prof = on != 0; p->recs.clear(); p->crecs.clear(); p->brecs.clear(); p->ev_used = 0;
+    p->tl_on = on == 2; p->timeline.clear();
+    if (p->tl_on) {
+        if (!p->tl_base) CUDA_TRY(cudaEventCreate(&p->tl_base));
+        CUDA_TRY(cudaEventRecord(p->tl_base, p->stream));
+    }
     for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_remote[i] = 0; p->prof_n[i] = 0; }
     p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
     return SDNS_OK;
@@ -1256,7 +1272,17 @@ extern "C" int sdns_profile_read(sdns_plan* p, int family, double* total_ms, lon
         float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
         p->copy_ms[r.s] += ms; p->copy_bytes += r.bytes; p->copy_n++;
     }
-    p->recs.clear(); p->crecs.clear(); p->ev_used = 0;
+    if (p->tl_on) {
+        auto row = [&](double kind, cudaEvent_t a, cudaEvent_t b, double bytes) {
+            float t0 = 0, t1 = 0;
+            if (cudaEventElapsedTime(&t0, p->tl_base, a) != cudaSuccess || cudaEventElapsedTime(&t1, p->tl_base, b) != cudaSuccess) return;
+            p->timeline.push_back(kind); p->timeline.push_back(t0); p->timeline.push_back(t1); p->timeline.push_back(bytes);
+        };
+        for (const sdns_plan::Rec& r : p->recs) row(r.fam, r.a, r.b, r.bytes);
+        for (const sdns_plan::Rec& r : p->brecs) row(99, r.a, r.b, 0);
+        for (const sdns_plan::CRec& r : p->crecs) row(100 + r.s, r.a, r.b, r.bytes);
+    }
+    p->recs.clear(); p->crecs.clear(); p->brecs.clear(); p->ev_used = 0;
     if (total_ms) *total_ms = p->prof_ms[family];
     if (launches) *launches = p->prof_n[family];
     if (bytes) *bytes = p->prof_bytes[family];
@@ -1277,5 +1303,14 @@ extern "C" int sdns_profile_read_copies(sdns_plan* p, double* busy_ms, double* b
     if (busy_ms) *busy_ms = mx;
     if (bytes) *bytes = p->copy_bytes;
     if (ncopies) *ncopies = p->copy_n;
+    return SDNS_OK;
+}
+
+extern "C" int sdns_profile_timeline(sdns_plan* p, double* rows, int max_rows, int* nrows) {
+    if (!p || !nrows) return fail(SDNS_ERR_ARG, "sdns_profile_timeline: bad argument");
+    int e = sdns_profile_read(p, 0, nullptr, nullptr, nullptr); if (e) return e;
+    const int n = (int)(p->timeline.size() / 4);
+    *nrows = n;
+    if (rows) for (int i = 0; i < 4 * std::min(n, max_rows); ++i) rows[i] = p->timeline[i];
     return SDNS_OK;
 }

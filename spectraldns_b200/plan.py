@@ -261,8 +261,24 @@ class Plan(object):
     FAMILIES = ['plain_fwd_c2c', 'plain_bwd_c2c', 'ns_b0', 'vv_b0', 'ns_f0', 'vv_f0', 'mhd_f0',
                 'c2r', 'r2c', 'z_cross', 'z_mhd', 'ns_grad_b0', 'z_dot', 'z_uu', 'nsdiv_f0']
 
-    def profile(self, on=True):
-        _lib.check(self.lib.sdns_profile_enable(self._p, 1 if on else 0))
+    def profile(self, on=True, timeline=False):
+        _lib.check(self.lib.sdns_profile_enable(self._p, (2 if timeline else 1) if on else 0))
+
+    def profile_timeline(self):
+        """[(kind, t_start_ms, t_end_ms, bytes)] since profile(True, timeline=True); kind is a FAMILIES name,
+        'barrier' or 'copy<stream>'."""
+        n = C.c_int()
+        _lib.check(self.lib.sdns_profile_timeline(self._p, None, 0, C.byref(n)))
+        # the first call consumed the pending records into the timeline; fetch it
+        buf = (C.c_double*(4*max(n.value, 1)))()
+        m = C.c_int()
+        _lib.check(self.lib.sdns_profile_timeline(self._p, buf, n.value, C.byref(m)))
+        out = []
+        for i in range(min(n.value, m.value)):
+            k = int(buf[4*i])
+            name = self.FAMILIES[k] if 0 <= k < len(self.FAMILIES) else ('barrier' if k == 99 else 'copy%d' % (k-100))
+            out.append((name, buf[4*i+1], buf[4*i+2], buf[4*i+3]))
+        return out
 
     def profile_read(self):
         """{family: (total_ms, launches, algorithmic_hbm_bytes, nvlink_bytes_stored)} since profile(True)."""
