@@ -19,9 +19,54 @@ typedef double real_t;
 
 namespace sdns {
 
+#ifdef SDNS_F32_PAIRS
+// fp32 plain pass on column pairs: geometry of the fp64 pass (same bytes per thread), arguments rescaled to pair units
+template <int N, int DIR>
+static int run_plain2(const StridedArgs<float>& a, cudaStream_t st) {
+    typedef SCfg<double, N, S_PLAIN> C;
+    auto kern = plain2_kernel<N, C::E, C::TC, DIR, C::NBUF, C::minBlocks>;
+    static bool once = false;
+    if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
+    StridedArgs<float> b = a;
+    const long long nruns = a.ncols / a.cw;
+    b.cw = (a.cw + 1) / 2; b.ncols = nruns * b.cw; b.c2_off = a.c2_off / 2;
+    b.in_fs /= 2; b.in_ls /= 2; b.in_os /= 2; b.out_fs /= 2; b.out_ls /= 2; b.out_os /= 2; b.out_fs2 /= 2; b.out_ls2 /= 2;
+    long long tiles = (b.ncols + C::TC - 1) / C::TC;
+    if (a.grid_cap > 0) {
+        static int nsm = 0;
+        if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+        const long long cap = ((long long)a.grid_cap * nsm + a.nfields - 1) / a.nfields;
+        if (tiles > cap) tiles = cap;
+    }
+    b.xuniform = 0;
+    if (a.xchunk > 0 && a.xchunk % C::P == 0 && a.omap.shift % C::P == 0) {
+        const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;
+        b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
+    }
+    dim3 grid((unsigned)tiles, a.nfields);
+    kern<<<grid, C::P * C::TC, C::smem, st>>>(b);
+    return (int)cudaGetLastError();
+}
+static bool pair_ok(const StridedArgs<float>& a) {
+    if (!a.pairable || a.cw <= 0 || (a.c2_off & 1)) return false;
+    const long long s[] = {a.in_fs, a.in_ls, a.in_os, a.out_fs, a.out_ls, a.out_os, a.out_fs2, a.out_ls2};
+    for (long long v : s) if (v & 1) return false;
+    if (((uintptr_t)a.in | (uintptr_t)a.out) & 15) return false;
+    if (a.xchunk > 0) for (int r = 0; r < 8; ++r) if (((uintptr_t)a.peer_out[r]) & 15) return false;
+    return true;
+}
+#endif
+
 template <typename T, int N, int MODE, int DIR>
 static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
     typedef SCfg<T, N, MODE> C;
+#ifdef SDNS_F32_PAIRS
+    if constexpr (sizeof(T) == 4 && MODE == S_PLAIN && plan_ok(N, SCfg<double, N, S_PLAIN>::E)) {
+        auto mag = [](long long v) { return v < 0 ? -v : v; };
+        if (pair_ok(a) && (long long)N * std::max(mag(a.in_ls), std::max(mag(a.out_ls), mag(a.out_ls2))) < (1LL << 31))
+            return run_plain2<N, DIR>(a, st);
+    }
+#endif
     static_assert(plan_ok(N, C::E), "no radix plan");
     auto kern = strided_kernel<T, N, C::E, C::TC, DIR, MODE, C::NBUF, C::minBlocks>;
     static bool once = false;

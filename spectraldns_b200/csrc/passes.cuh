@@ -77,12 +77,13 @@ struct StridedArgs {
     int grid_cap;                 // > 0: launch at most this many CTAs per SM (grid-stride over the tiles)
     int xuniform;                 // slab stores: P and omap.shift divide into xchunk (destination uniform per q)
     int xhi_d0, xhi_b0;           // (rank, row in chunk) of transform block q = 0 mapped through the high kept range
+    int pairable;                 // plain passes: the column after the last one of a run is padding in both arrays
     V* peer_out[8];
     int self;                     // destination that uses (out_fs, out_ls, c1_out_off); all others use the second set
     long long out_fs2, out_ls2, c1_out_off2;
 };
 
-template <typename V> __device__ __forceinline__ V czero() { V z; z.x = 0; z.y = 0; return z; }
+template <typename V> __device__ __forceinline__ V czero() { return V(); }
 
 template <typename T, typename V> __device__ __forceinline__ V cscale(V a, T s) { return cscl(a, s); }
 
@@ -163,7 +164,7 @@ __device__ __forceinline__ void store_line(const V (&x)[E], const StridedArgs<T>
     const long long fo = f * a.out_fs + obase;
     const RowSel<N, E> rs(a.omap, t, valid);
     if (a.xchunk == 0) {
-        V* pout = opaque(a.out + fo);
+        V* pout = opaque(reinterpret_cast<V*>(a.out) + fo);
         const int l = (int)a.out_ls;
         const int olo = t * l, ohi = (t - a.omap.shift) * l, step = P * l;
 #pragma unroll
@@ -187,7 +188,7 @@ __device__ __forceinline__ void store_line(const V (&x)[E], const StridedArgs<T>
             dest = dest < 0 ? 0 : dest;
             const int row = t + (lo ? bl : bh);
             const bool self = dest == a.self;
-            V* pq = a.peer_out[dest] + (self ? fo : fo2) + row * (self ? l1 : l2);
+            V* pq = reinterpret_cast<V*>(a.peer_out[dest]) + (self ? fo : fo2) + row * (self ? l1 : l2);
             if (rs.ok(q)) *pq = SCALE ? cscale<T>(x[q], scale) : x[q];
             bl += P; if (bl >= a.xchunk) { bl -= a.xchunk; ++dl; }
             bh += P; if (bh >= a.xchunk) { bh -= a.xchunk; ++dh; }
@@ -203,7 +204,7 @@ __device__ __forceinline__ void store_line(const V (&x)[E], const StridedArgs<T>
             const int il = i - dest * a.xchunk;
             const long long off = dest == a.self ? fo + (long long)il * a.out_ls : fo2 + (long long)il * a.out_ls2;
             if (valid && axis_ok(a.omap, N, j))
-                a.peer_out[dest][off] = SCALE ? cscale<T>(x[q], scale) : x[q];
+                reinterpret_cast<V*>(a.peer_out[dest])[off] = SCALE ? cscale<T>(x[q], scale) : x[q];
         }
     }
 }
@@ -391,6 +392,42 @@ strided_kernel(const StridedArgs<T> a) {
         }
     }
     }   // tile loop
+}
+
+// ---------------------------------------------------------------------------------------
+// Plain strided c2c pass, fp32, two adjacent columns per thread (element type float2x2): the thread moves 16 bytes
+// per access like an fp64 thread, and every row offset, twiddle and shared-memory address serves two columns.
+// `a` arrives with strides, cw, ncols and c2_off in units of column PAIRS (run_plain2 in inst.cu converts them).
+// ROUND-2 CANDIDATE: compiled only with -DSDNS_F32_PAIRS, not yet run on a GPU.
+// ---------------------------------------------------------------------------------------
+template <int N, int E, int TC, int DIR, int NBUF, int MINB>
+__global__ void __launch_bounds__((N / E) * TC, MINB)
+plain2_kernel(const StridedArgs<float> a) {
+    typedef float T;
+    typedef float2x2 V;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    V* sm = reinterpret_cast<V*>(smraw);
+    const int c = threadIdx.x % TC;
+    const int t = threadIdx.x / TC;
+    SmemLine<TC, 0> map; map.base = c;
+    int phase = 0;
+    constexpr int BUFSTRIDE = N * TC;
+    const int f = blockIdx.y;
+    const long long ntiles = (a.ncols + TC - 1) / TC;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long col = tile * TC + c;
+        const bool valid = col < a.ncols;
+        const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;
+        const int c2 = valid ? (int)(col % a.cw) + a.c2_off : 0;
+        const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
+        const long long ibase = (long long)c1m * a.in_os + c2;
+        const long long obase = ((long long)c1 + a.c1_out_off) * a.out_os + c2;
+        const long long obase2 = ((long long)c1 + a.c1_out_off2) * a.out_os + c2;
+        V x[E];
+        load_line<T, N, E>(x, reinterpret_cast<const V*>(a.in) + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
+        fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+        store_line<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -587,6 +587,7 @@ struct Pipe {
         a.omap = all_map(q.M[1]);
         a.out_fs = (long long)q.M0l * q.M[1] * q.K2p; a.out_ls = q.K2p; a.out_os = (long long)q.M[1] * q.K2p;
         a.tw = tw(q.M[1]); a.nfields = nf;
+        a.pairable = (k2.a == 0 && k2.b == q.K2n);      // rows are K2n columns + padding up to the even pitch K2p
         const double bytes = (double)nf * q.M0l * a.cw * ((double)q.K1n + q.M[1]) * p->cs;
         return do_launch(p, st, FAM_PLAIN_BWD, q.M[1], &a, bytes);
     }
@@ -631,6 +632,7 @@ struct Pipe {
         else peers(a, p->off_C, p->N1l);
         a.grid_cap = xcap;
         a.tw = tw(q.M[1]); a.nfields = nf;
+        a.pairable = 1;                                  // rows are Nh columns + padding up to the even pitch Nhp
         const double bytes = (double)nf * (x0.b - x0.a) * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
         const double remote = staged ? 0 : (double)nf * (x0.b - x0.a) * p->Nh * p->N[1] * p->cs * (p->P - 1) / p->P;
         if (a.ncols == 0) return SDNS_OK;
