@@ -9,7 +9,11 @@
 // This replaces the serial FFTW plans that shenfun / mpi4py-fft run underneath the
 // reference's T.forward / T.backward (call sites solvers/NS.py:93,98,103,128,135).
 #pragma once
+#ifdef SDNS_HOST_SHIM          // tests/host/fft_core_harness.cpp: the same templates compiled by g++ for the CPU
+#include "host_shim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace sdns {
