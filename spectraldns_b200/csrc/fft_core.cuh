@@ -9,10 +9,16 @@
 // This replaces the serial FFTW plans that shenfun / mpi4py-fft run underneath the
 // reference's T.forward / T.backward (call sites solvers/NS.py:93,98,103,128,135).
 #pragma once
-#ifdef SDNS_HOST_SHIM          // tests/host/fft_core_harness.cpp: the same templates compiled by g++ for the CPU
-#include "host_shim.h"
+#ifdef SDNS_HOST_SHIM          // tests/host: the same sources compiled by g++ against an emulation of the CUDA execution
+#include "host_shim.h"         // model (kernel-logic tests without a GPU; never part of the product build)
+#define SDNS_LAUNCH(kern, grid, block, smem, stream) sdns_emu::launcher(kern, grid, block, smem)
+#define SDNS_DYN_SMEM(name) unsigned char* name = sdns_emu::dyn_smem()
+#define SDNS_STATIC_SMEM(type, name, n) type* name = reinterpret_cast<type*>(sdns_emu::static_smem())
 #else
 #include <cuda_runtime.h>
+#define SDNS_LAUNCH(kern, grid, block, smem, stream) kern<<<grid, block, smem, stream>>>
+#define SDNS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define SDNS_STATIC_SMEM(type, name, n) __shared__ type name[n]
 #endif
 #include <stdint.h>
 

@@ -44,7 +44,7 @@ static int run_plain2(const StridedArgs<float>& a, cudaStream_t st) {
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
     dim3 grid((unsigned)tiles, a.nfields);
-    kern<<<grid, C::P * C::TC, C::smem, st>>>(b);
+    SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
 static bool pair_ok(const StridedArgs<float>& a) {
@@ -91,7 +91,7 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
         const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;     // shift rounded up to whole chunks
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
-    kern<<<grid, C::P * C::TC, C::smem, st>>>(b);
+    SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
 
@@ -102,7 +102,7 @@ static int run_f0x(const StridedArgs<T>& a, cudaStream_t st) {
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC));
-    kern<<<grid, C::threads, C::smem, st>>>(a);
+    SDNS_LAUNCH(kern, grid, C::threads, C::smem, st)(a);
     return (int)cudaGetLastError();
 }
 
@@ -123,7 +123,7 @@ static int run_mhd_f0(const StridedArgs<T>& a, cudaStream_t st) {
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC));
-    kern<<<grid, C::P * C::TC, C::smem, st>>>(a);
+    SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(a);
     return (int)cudaGetLastError();
 }
 
@@ -135,7 +135,7 @@ static int run_nsdiv_f0(const StridedArgs<T>& a, cudaStream_t st) {
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC));
-    kern<<<grid, C::P * C::TC, C::smem, st>>>(a);
+    SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(a);
     return (int)cudaGetLastError();
 }
 
@@ -156,7 +156,7 @@ static int run_zx_q(const ZArgs<T>& a, cudaStream_t st) {
     const long long blocks_per_sm = (long long)((a.grid_cap > 0 && a.grid_cap < occ_sm) ? a.grid_cap : occ_sm) * nsm;
     const long long want = (a.nlines + C::LPC - 1) / C::LPC;
     dim3 grid((unsigned)(want < blocks_per_sm ? want : blocks_per_sm));
-    kern<<<grid, 32 * C::LPC, C::smem, st>>>(a);
+    SDNS_LAUNCH(kern, grid, 32 * C::LPC, C::smem, st)(a);
     return (int)cudaGetLastError();
 }
 
@@ -188,7 +188,7 @@ static int run_zy_q(const ZArgs<T>& a, cudaStream_t st) {
     }
     const long long blocks = (long long)((a.grid_cap > 0 && a.grid_cap < occ_sm) ? a.grid_cap : occ_sm) * nsm;
     dim3 grid((unsigned)(a.nlines < blocks ? a.nlines : blocks));
-    kern<<<grid, C::P, smem, st>>>(a);
+    SDNS_LAUNCH(kern, grid, C::P, smem, st)(a);
     return (int)cudaGetLastError();
 }
 
@@ -224,7 +224,7 @@ static int run_z(const ZArgs<T>& a, cudaStream_t st) {
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     dim3 grid((unsigned)((a.nlines + C::LPC - 1) / C::LPC));
-    kern<<<grid, C::P * C::LPC, C::smem, st>>>(a);
+    SDNS_LAUNCH(kern, grid, C::P * C::LPC, C::smem, st)(a);
     return (int)cudaGetLastError();
 }
 

@@ -94,7 +94,13 @@ __device__ __forceinline__ V icross(T ka, V b, T kb, V a) {
     V r; r.x = -(ka * b.y - kb * a.y); r.y = ka * b.x - kb * a.x; return r;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef SDNS_HOST_SHIM
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
 // L2 prefetch of one transform line (costs issue slots but no registers): used where a kernel reads
 // several fields one after the other, so that only the first one pays DRAM latency.
@@ -111,11 +117,15 @@ __device__ __forceinline__ void prefetch_line(const V* __restrict__ pin, long lo
 // Hides how a pointer was formed, so that the compiler keeps it in a register pair and addresses row r as one
 // IMAD.WIDE off it instead of re-deriving a 64-bit element index per access.
 template <typename Q> __device__ __forceinline__ Q* opaque(Q* p) {
+#ifndef SDNS_HOST_SHIM
     unsigned long long v = reinterpret_cast<unsigned long long>(p);
     asm volatile("" : "+l"(v));
     Q* q = reinterpret_cast<Q*>(v);
     __builtin_assume(__isGlobal(q));
     return q;
+#else
+    return p;
+#endif
 }
 
 // Row bookkeeping of one thread of a strided pass.  The thread owns the transform indices j = t + q P, q < E.
@@ -217,7 +227,7 @@ template <typename T, int N, int E, int TC, int DIR, int MODE, int NBUF, int MIN
 __global__ void __launch_bounds__((N / E) * TC, MINB)
 strided_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
-    extern __shared__ __align__(16) unsigned char smraw[];
+    SDNS_DYN_SMEM(smraw);
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     const int c = threadIdx.x % TC;
@@ -405,7 +415,7 @@ __global__ void __launch_bounds__((N / E) * TC, MINB)
 plain2_kernel(const StridedArgs<float> a) {
     typedef float T;
     typedef float2x2 V;
-    extern __shared__ __align__(16) unsigned char smraw[];
+    SDNS_DYN_SMEM(smraw);
     V* sm = reinterpret_cast<V*>(smraw);
     const int c = threadIdx.x % TC;
     const int t = threadIdx.x / TC;
@@ -440,7 +450,7 @@ template <typename T, int N, int E, int TC, int MODE, int MINB>
 __global__ void __launch_bounds__(3 * (N / E) * TC, MINB)
 f0x_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
-    extern __shared__ __align__(16) unsigned char smraw[];
+    SDNS_DYN_SMEM(smraw);
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     constexpr int NT = P * TC;
@@ -552,7 +562,7 @@ template <typename T, int N, int E, int TC, int NBUF>
 __global__ void __launch_bounds__((N / E) * TC)
 mhd_f0_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
-    extern __shared__ __align__(16) unsigned char smraw[];
+    SDNS_DYN_SMEM(smraw);
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     const int c = threadIdx.x % TC;
@@ -668,7 +678,7 @@ template <typename T, int N, int E, int TC, int NBUF>
 __global__ void __launch_bounds__((N / E) * TC)
 nsdiv_f0_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
-    extern __shared__ __align__(16) unsigned char smraw[];
+    SDNS_DYN_SMEM(smraw);
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     const int c = threadIdx.x % TC;
@@ -832,7 +842,7 @@ template <typename T, int M, int E, int LPC, int MODE, int SYNC, int NBUF, int M
 __global__ void __launch_bounds__((M / E) * LPC, MINB)
 z_kernel(const ZArgs<T> a) {
     typedef typename C2<T>::type V;
-    extern __shared__ __align__(16) unsigned char smraw[];
+    SDNS_DYN_SMEM(smraw);
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = M / E;
     constexpr int PADW = 128 / (int)sizeof(V);
@@ -1094,7 +1104,7 @@ __global__ void __launch_bounds__(32 * LPC, MINB)
 zx_kernel(const ZArgs<T> a) {
     typedef typename C2<T>::type V;
     static_assert(M / E == 32, "one warp per line");
-    extern __shared__ __align__(16) unsigned char smraw[];
+    SDNS_DYN_SMEM(smraw);
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int PADW = 128 / (int)sizeof(V);
     constexpr int LP = M + M / PADW + 1;
@@ -1169,7 +1179,7 @@ zy_kernel(const ZArgs<T> a) {
     typedef typename C2<T>::type V;
     constexpr int P = M / E;
     static_assert(P == 64 || P == 128, "two or four warps per line");
-    extern __shared__ __align__(16) unsigned char smraw[];
+    SDNS_DYN_SMEM(smraw);
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int PADW = 128 / (int)sizeof(V);
     constexpr int LP = M + M / PADW + 1;
@@ -1296,7 +1306,7 @@ __global__ void energy_kernel(const typename C2<T>::type* __restrict__ u, long l
         s += w * ((double)v.x * v.x + (double)v.y * v.y);
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    __shared__ double ws[32];
+    SDNS_STATIC_SMEM(double, ws, 32);
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x < 32) {

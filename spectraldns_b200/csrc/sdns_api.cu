@@ -3,7 +3,9 @@
 // Host-side equivalent of the reference's get_context() setup (solvers/NS.py:12-72) and of the
 // call sequence ComputeRHS -> conv -> transforms (NS.py:191-261, VV.py:92-146, MHD.py:119-176),
 // re-expressed as five kernel launches per right-hand side (B0, B1, Z, F1, F0).
+#ifndef SDNS_HOST_SHIM
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -14,6 +16,15 @@
 #include "launch.cuh"
 
 using namespace sdns;
+
+// grids of the grid-stride elementwise / reduction kernels: 8 CTAs per SM of a B200 (the emulated build keeps them tiny)
+#ifdef SDNS_HOST_SHIM
+#define SDNS_EW_BLOCKS 2
+#define SDNS_RED_BLOCKS 2
+#else
+#define SDNS_EW_BLOCKS 1184
+#define SDNS_RED_BLOCKS 1024
+#endif
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -296,7 +307,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     }
     p->bytes_A = align_up(a * p->cs, 256); p->bytes_B = align_up(b * p->cs, 256);
     p->bytes_C = align_up(c * p->cs, 256);
-    p->red_blocks = 1024;
+    p->red_blocks = SDNS_RED_BLOCKS;
     p->off_tab = 0;
     p->off_A = align_up(p->host_tables.size(), 256);
     p->off_B = p->off_A + p->bytes_A;
@@ -408,12 +419,20 @@ __global__ void xbarrier_kernel(const BarrierArgs b) {
     if (r >= b.nranks) return;
     __threadfence_system();
     unsigned int* remote = b.peer_flags[r] + b.rank;
+#ifndef SDNS_HOST_SHIM
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(b.epoch) : "memory");
+#else
+    *remote = b.epoch;
+#endif
     const unsigned int* local = b.peer_flags[b.rank] + r;
     const long long t0 = clock64();
     unsigned int v;
     do {
+#ifndef SDNS_HOST_SHIM
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
+#else
+        v = *local;
+#endif
         if ((int)(v - b.epoch) >= 0) break;
         if (clock64() - t0 > b.timeout_cycles) { *b.status = 1u; break; }
     } while (true);
@@ -434,7 +453,7 @@ static int xbarrier(sdns_plan* p) {
     b.timeout_cycles = 20000000000LL;      // ~10 s: a missing peer must not hang the GPU
     sdns_plan::Rec r; r.fam = -1; r.bytes = 0; r.remote = 0;
     if (p->tl_on) { r.a = get_event(p); cudaEventRecord(r.a, p->stream); }
-    xbarrier_kernel<<<1, 32, 0, p->stream>>>(b);
+    SDNS_LAUNCH(xbarrier_kernel, 1, 32, 0, p->stream)(b);
     if (p->tl_on) { r.b = get_event(p); cudaEventRecord(r.b, p->stream); p->brecs.push_back(r); }
     p->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1034,8 +1053,8 @@ extern "C" int sdns_euler_step(sdns_plan* p, void* u_hat, void* rhs, double dt, 
                                const void* source) {
     int e = sdns_compute_rhs(p, rhs, u_hat, nu, eta, source, nullptr); if (e) return e;
     const long long n = (long long)ncomp_state(p) * p->N[0] * p->N1l * p->Nh;
-    if (p->prec) euler_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)u_hat, (const double2*)rhs, dt, n);
-    else euler_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)u_hat, (const float2*)rhs, (float)dt, n);
+    if (p->prec) SDNS_LAUNCH(euler_kernel<double>, SDNS_EW_BLOCKS, 256, 0, p->stream)((double2*)u_hat, (const double2*)rhs, dt, n);
+    else SDNS_LAUNCH(euler_kernel<float>, SDNS_EW_BLOCKS, 256, 0, p->stream)((float2*)u_hat, (const float2*)rhs, (float)dt, n);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return SDNS_OK;
@@ -1045,8 +1064,8 @@ extern "C" int sdns_ab2_step(sdns_plan* p, void* u_hat, void* u1, void* rhs, dou
                              double nu, double eta, const void* source) {
     int e = sdns_compute_rhs(p, rhs, u_hat, nu, eta, source, nullptr); if (e) return e;
     const long long n = (long long)ncomp_state(p) * p->N[0] * p->N1l * p->Nh;
-    if (p->prec) ab2_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)u_hat, (double2*)u1, (const double2*)rhs, dt, tstep == 0, n);
-    else ab2_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)u_hat, (float2*)u1, (const float2*)rhs, (float)dt, tstep == 0, n);
+    if (p->prec) SDNS_LAUNCH(ab2_kernel<double>, SDNS_EW_BLOCKS, 256, 0, p->stream)((double2*)u_hat, (double2*)u1, (const double2*)rhs, dt, tstep == 0, n);
+    else SDNS_LAUNCH(ab2_kernel<float>, SDNS_EW_BLOCKS, 256, 0, p->stream)((float2*)u_hat, (float2*)u1, (const float2*)rhs, (float)dt, tstep == 0, n);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return SDNS_OK;
@@ -1056,11 +1075,11 @@ extern "C" int sdns_cross2(sdns_plan* p, void* c, const void* b, int over_k2) {
     int e = need_ws(p); if (e) return e;
     if (!c || !b || c == b) return fail(SDNS_ERR_ARG, "sdns_cross2: c and b must be distinct arrays");
     if (p->prec)
-        cross2_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)c, (const double2*)b,
+        SDNS_LAUNCH(cross2_kernel<double>, SDNS_EW_BLOCKS, 256, 0, p->stream)((double2*)c, (const double2*)b,
             (const double*)(p->ws + p->kx_off), (const double*)(p->ws + p->ky_off), (const double*)(p->ws + p->kz_off),
             p->N[0], p->N1l, p->Nh, over_k2);
     else
-        cross2_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)c, (const float2*)b,
+        SDNS_LAUNCH(cross2_kernel<float>, SDNS_EW_BLOCKS, 256, 0, p->stream)((float2*)c, (const float2*)b,
             (const float*)(p->ws + p->kx_off), (const float*)(p->ws + p->ky_off), (const float*)(p->ws + p->kz_off),
             p->N[0], p->N1l, p->Nh, over_k2);
     p->launches++;
@@ -1074,8 +1093,8 @@ extern "C" int sdns_energy(sdns_plan* p, const void* u_hat, int nc, double* out)
     const long long n = (long long)nc * p->N[0] * p->N1l * p->Nh;
     double* red = reinterpret_cast<double*>(p->ws + p->off_red);
     const int nb = p->red_blocks;
-    if (p->prec) energy_kernel<double><<<nb, 256, 0, p->stream>>>((const double2*)u_hat, n, p->Nh, p->N[2], red);
-    else energy_kernel<float><<<nb, 256, 0, p->stream>>>((const float2*)u_hat, n, p->Nh, p->N[2], red);
+    if (p->prec) SDNS_LAUNCH(energy_kernel<double>, nb, 256, 0, p->stream)((const double2*)u_hat, n, p->Nh, p->N[2], red);
+    else SDNS_LAUNCH(energy_kernel<float>, nb, 256, 0, p->stream)((const float2*)u_hat, n, p->Nh, p->N[2], red);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     std::vector<double> h(nb);
@@ -1140,8 +1159,8 @@ __global__ void project_kernel(typename C2<T>::type* u, const T* kx, const T* ky
 
 extern "C" int sdns_cross1(sdns_plan* p, void* c, const void* a, const void* b, long long n) {
     if (!p || !c || !a || !b || n < 1) return fail(SDNS_ERR_ARG, "sdns_cross1: bad argument");
-    if (p->prec) cross1_kernel<double><<<1184, 256, 0, p->stream>>>((double*)c, (const double*)a, (const double*)b, n);
-    else cross1_kernel<float><<<1184, 256, 0, p->stream>>>((float*)c, (const float*)a, (const float*)b, n);
+    if (p->prec) SDNS_LAUNCH(cross1_kernel<double>, SDNS_EW_BLOCKS, 256, 0, p->stream)((double*)c, (const double*)a, (const double*)b, n);
+    else SDNS_LAUNCH(cross1_kernel<float>, SDNS_EW_BLOCKS, 256, 0, p->stream)((float*)c, (const float*)a, (const float*)b, n);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return SDNS_OK;
@@ -1149,8 +1168,8 @@ extern "C" int sdns_cross1(sdns_plan* p, void* c, const void* a, const void* b, 
 extern "C" int sdns_cross2_dense(sdns_plan* p, void* c, const void* a, const void* b) {
     if (!p || !c || !a || !b || c == b) return fail(SDNS_ERR_ARG, "sdns_cross2_dense: bad argument");
     const long long n = (long long)p->N[0] * p->N1l * p->Nh;
-    if (p->prec) cross2_dense_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)c, (const double*)a, (const double2*)b, n);
-    else cross2_dense_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)c, (const float*)a, (const float2*)b, n);
+    if (p->prec) SDNS_LAUNCH(cross2_dense_kernel<double>, SDNS_EW_BLOCKS, 256, 0, p->stream)((double2*)c, (const double*)a, (const double2*)b, n);
+    else SDNS_LAUNCH(cross2_dense_kernel<float>, SDNS_EW_BLOCKS, 256, 0, p->stream)((float2*)c, (const float*)a, (const float2*)b, n);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return SDNS_OK;
@@ -1158,9 +1177,9 @@ extern "C" int sdns_cross2_dense(sdns_plan* p, void* c, const void* a, const voi
 extern "C" int sdns_project(sdns_plan* p, void* u) {
     int e = need_ws(p); if (e) return e;
     if (!u) return fail(SDNS_ERR_ARG, "sdns_project: null array");
-    if (p->prec) project_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)u,
+    if (p->prec) SDNS_LAUNCH(project_kernel<double>, SDNS_EW_BLOCKS, 256, 0, p->stream)((double2*)u,
         (const double*)(p->ws + p->kx_off), (const double*)(p->ws + p->ky_off), (const double*)(p->ws + p->kz_off), p->N[0], p->N1l, p->Nh);
-    else project_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)u,
+    else SDNS_LAUNCH(project_kernel<float>, SDNS_EW_BLOCKS, 256, 0, p->stream)((float2*)u,
         (const float*)(p->ws + p->kx_off), (const float*)(p->ws + p->ky_off), (const float*)(p->ws + p->kz_off), p->N[0], p->N1l, p->Nh);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1200,7 +1219,7 @@ __global__ void errnorm_kernel(const typename C2<T>::type* u0, const typename C2
         s += (double)r * (double)r;
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    __shared__ double ws[32];
+    SDNS_STATIC_SMEM(double, ws, 32);
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -1217,8 +1236,8 @@ extern "C" int sdns_lincomb(sdns_plan* p, void* out, const void* base, int nterm
     LinArgs la; la.n = nterms;
     for (int t = 0; t < nterms; ++t) { la.x[t] = arrays[t]; la.c[t] = coeffs[t]; }
     const long long n = (long long)ncomp * p->N[0] * p->N1l * p->Nh;
-    if (p->prec) lincomb_kernel<double><<<1184, 256, 0, p->stream>>>((double2*)out, (const double2*)base, la, n);
-    else lincomb_kernel<float><<<1184, 256, 0, p->stream>>>((float2*)out, (const float2*)base, la, n);
+    if (p->prec) SDNS_LAUNCH(lincomb_kernel<double>, SDNS_EW_BLOCKS, 256, 0, p->stream)((double2*)out, (const double2*)base, la, n);
+    else SDNS_LAUNCH(lincomb_kernel<float>, SDNS_EW_BLOCKS, 256, 0, p->stream)((float2*)out, (const float2*)base, la, n);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return SDNS_OK;
@@ -1233,9 +1252,9 @@ extern "C" int sdns_errnorm(sdns_plan* p, const void* u0, const void* u1, const 
     const int nb = p->red_blocks;
     std::vector<double> h(nb);
     for (int k = 0; k < ncomp; ++k) {
-        if (p->prec) errnorm_kernel<double><<<nb, 256, 0, p->stream>>>((const double2*)u0 + k * n, (const double2*)u1 + k * n,
+        if (p->prec) SDNS_LAUNCH(errnorm_kernel<double>, nb, 256, 0, p->stream)((const double2*)u0 + k * n, (const double2*)u1 + k * n,
                                                                        (const double2*)err + k * n, atol, rtol, n, red);
-        else errnorm_kernel<float><<<nb, 256, 0, p->stream>>>((const float2*)u0 + k * n, (const float2*)u1 + k * n,
+        else SDNS_LAUNCH(errnorm_kernel<float>, nb, 256, 0, p->stream)((const float2*)u0 + k * n, (const float2*)u1 + k * n,
                                                               (const float2*)err + k * n, (float)atol, (float)rtol, n, red);
         p->launches++;
         CUDA_TRY(cudaGetLastError());
