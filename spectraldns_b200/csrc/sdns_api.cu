@@ -422,7 +422,7 @@ __global__ void xbarrier_kernel(const BarrierArgs b) {
 #ifndef SDNS_HOST_SHIM
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(b.epoch) : "memory");
 #else
-    *remote = b.epoch;
+    __atomic_store_n(remote, b.epoch, __ATOMIC_RELEASE);
 #endif
     const unsigned int* local = b.peer_flags[b.rank] + r;
     const long long t0 = clock64();
@@ -431,7 +431,7 @@ __global__ void xbarrier_kernel(const BarrierArgs b) {
 #ifndef SDNS_HOST_SHIM
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
 #else
-        v = *local;
+        v = __atomic_load_n(local, __ATOMIC_ACQUIRE);
 #endif
         if ((int)(v - b.epoch) >= 0) break;
         if (clock64() - t0 > b.timeout_cycles) { *b.status = 1u; break; }
@@ -684,6 +684,9 @@ static int backward_t(sdns_plan* p, int space, int nc, const void* in, void* out
         if ((e = P.b0(FAM_PLAIN_BWD, src, nf))) return e;
         if ((e = xbarrier(p))) return e;
         if ((e = P.b1(nf))) return e;
+        // every rank has finished READING W0 before any rank's next operation stores into it again (a faster
+        // peer could otherwise start its next B0 while this rank is still in B1)
+        if ((e = xbarrier(p))) return e;
         if ((e = P.z(FAM_Z_C2R, P.B, dst, nf, true, false))) return e;
     }
     return SDNS_OK;
@@ -699,6 +702,8 @@ static int forward_t(sdns_plan* p, int space, int nc, const void* in, void* out)
         const T* src = reinterpret_cast<const T*>(in) + (long long)c0 * P.q.M0l * P.q.M[1] * P.q.M[2];
         V* dst = reinterpret_cast<V*>(out) + (long long)c0 * P.dense_fs();
         int e;
+        // no rank may still be reading W3 (the F0 of the previous operation) when the first F1 stores into it
+        if ((e = xbarrier(p))) return e;
         if ((e = P.z(FAM_Z_R2C, src, P.A, nf, false, true))) return e;
         if ((e = P.f1(nf))) return e;
         if ((e = xbarrier(p))) return e;
@@ -909,6 +914,7 @@ static int rhs_t(sdns_plan* p, const void* u_hat, double nu, double eta, const S
                 if ((e = P.b0(FAM_NS_GRAD_B0, u, 3, i, so.in_work_layout))) return e;
                 if ((e = xbarrier(p))) return e;
                 if ((e = P.b1(6))) return e;
+                if ((e = xbarrier(p))) return e;           // W0 is free again on every rank before the next B0 stores into it
                 if ((e = P.z(FAM_Z_DOT, P.B, D + i * dfs, 6, true, true))) return e;
             }
             if ((e = P.f1(3, D))) return e;

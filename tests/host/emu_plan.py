@@ -58,12 +58,29 @@ class EmuPlan(object):
         self.chk(L.sdns_local_shapes(self.p, C.byref(sp), C.byref(ph), C.byref(pd)))
         self.sshape, self.pshape, self.dshape = tuple(sp), tuple(ph), tuple(pd)
         self.ncomp = 6 if solver == 'MHD' else 3
+        self.rank, self.nranks = rank, nranks
+        if nranks > 1:
+            self.chk(L.sdns_comm_alloc(self.p))
         if nranks == 1:
             n = C.c_size_t()
             self.chk(L.sdns_workspace_bytes(self.p, C.byref(n)))
             self._ws = np.full(n.value + 512, 0xFF, dtype=np.uint8)      # NaN bytes: uninitialised reads show up
             base = self._ws.ctypes.data
             self.chk(L.sdns_plan_set_workspace(self.p, vp(base + (-base) % 256), n.value))
+
+    def handle(self):
+        h = (C.c_char*64)()
+        self.chk(self.L.sdns_comm_handle(self.p, h))
+        return bytes(h)
+
+    def open_peers(self, handles):
+        buf = (C.c_char*(64*self.nranks))(*b''.join(handles))
+        self.chk(self.L.sdns_comm_open(self.p, buf, self.nranks))
+
+    def timed_out(self):
+        v = C.c_int()
+        self.chk(self.L.sdns_comm_status(self.p, C.byref(v)))
+        return bool(v.value)
 
     def chk(self, rc):
         if rc:
@@ -101,3 +118,33 @@ class EmuPlan(object):
         for _ in range(nsteps):
             self.chk(self.L.sdns_rk4_step(self.p, u.ctypes.data, u1.ctypes.data, u2.ctypes.data, dt, nu, eta, None))
         return u
+
+
+def run_ranks(world, fn):
+    """Run fn(rank, sync) on `world` threads (the ranks of an emulated multi-GPU run; ctypes releases the GIL inside the
+    library, so the flag barriers between the ranks make progress).  sync(obj) all-gathers obj across the ranks."""
+    import threading
+    bar = threading.Barrier(world)
+    box = [None]*world
+    out, errs = [None]*world, []
+
+    def worker(r):
+        def sync(obj):
+            box[r] = obj
+            bar.wait()
+            got = list(box)
+            bar.wait()
+            return got
+        try:
+            out[r] = fn(r, sync)
+        except BaseException as e:      # noqa: BLE001
+            errs.append((r, e))
+            bar.abort()
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise errs[0][1]
+    return out

@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <barrier>
+#include <chrono>
+#include <functional>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -60,6 +62,14 @@ template <class F> struct Launcher {
     F f; dim3 g, b; size_t smem;
     template <class... A> void operator()(A... args) const {
         const int nt = (int)(b.x * b.y * b.z);
+        // SDNS_EMU_JITTER=<max microseconds>: every launch starts after a random delay, which pulls the ranks of an
+        // emulated multi-GPU run apart and widens the windows of missing cross-rank ordering
+        static const int jitter = std::getenv("SDNS_EMU_JITTER") ? std::atoi(std::getenv("SDNS_EMU_JITTER")) : 0;
+        if (jitter > 0) {
+            static thread_local unsigned long long seed = 88172645463325252ULL ^ (unsigned long long)std::hash<std::thread::id>()(std::this_thread::get_id());
+            seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17;
+            std::this_thread::sleep_for(std::chrono::microseconds(seed % (unsigned long long)jitter));
+        }
         for (unsigned bz = 0; bz < g.z; ++bz) for (unsigned by = 0; by < g.y; ++by) for (unsigned bx = 0; bx < g.x; ++bx) {
             Cta cta(nt, smem);
             std::vector<std::thread> th;
@@ -133,6 +143,7 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nul
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// "IPC": the ranks of an emulated multi-GPU run are threads of one process, the handle carries the pointer
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

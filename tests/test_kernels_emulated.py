@@ -19,6 +19,7 @@ TOL = {'double': 1e-11, 'single': 1e-4}
 
 @pytest.fixture(scope='module')
 def emu():
+    os.environ.setdefault('SDNS_EMU_JITTER', '200')      # random start delay per launch (us): pulls the ranks apart
     import build_emu
     import emu_plan
     return emu_plan.load(build_emu.build()), emu_plan
@@ -44,9 +45,11 @@ def test_emulated_plain_transforms(emu, N, precision):
     p.close()
 
 
-@pytest.mark.parametrize('precision', ['double', 'single'])
-@pytest.mark.parametrize('dealias', ['2/3-rule', '3/2-rule', 'None'])
-@pytest.mark.parametrize('solver,N', [('NS', (16, 16, 16)), ('NS', (32, 16, 8)), ('VV', (16, 32, 16)), ('MHD', (16, 16, 32))])
+@pytest.mark.parametrize('solver,N,dealias,precision', [
+    ('NS', (16, 16, 16), '2/3-rule', 'double'), ('NS', (16, 16, 16), '3/2-rule', 'single'), ('NS', (32, 16, 8), '3/2-rule', 'double'),
+    ('NS', (32, 16, 8), 'None', 'single'), ('NS', (8, 24, 48), '2/3-rule', 'single'),
+    ('VV', (16, 32, 16), '2/3-rule', 'double'), ('VV', (16, 32, 16), '3/2-rule', 'single'), ('VV', (16, 16, 16), 'None', 'double'),
+    ('MHD', (16, 16, 32), '2/3-rule', 'double'), ('MHD', (16, 16, 32), '3/2-rule', 'double'), ('MHD', (16, 16, 16), '2/3-rule', 'single')])
 def test_emulated_rhs_and_rk4(emu, solver, N, dealias, precision):
     L, ep = emu
     o = so.Oracle(N, precision=precision, dealias=dealias)
@@ -69,3 +72,63 @@ def test_emulated_ns_convection_forms(emu, conv):
     f0 = _state(o, 'NS')
     assert rel_l2(p.compute_rhs(f0, 0.005), o.ns_rhs(f0, 0.005, conv)) < 1e-11
     p.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU schedule: the ranks are threads of this process, "peer memory" is each other's host buffer, the
+# device-side flag barrier spins on real flags, the copy-engine copies are memcpys at the point of submission
+# ---------------------------------------------------------------------------------------------
+def _multi_case(emu, world, exchange, case, chunks='4'):
+    L, ep = emu
+    N, prec, dealias, solver = case[:4]
+    kcut = case[4] if len(case) > 4 else None
+    conv = case[5] if len(case) > 5 else None
+    os.environ['SDNS_EXCHANGE'], os.environ['SDNS_CHUNKS'] = exchange, chunks
+    tol = TOL[prec]
+    o = so.Oracle(N, precision=prec, dealias=dealias, kcut=kcut)
+    f0 = _state(o, solver)
+    nu, eta, dt = 0.005, 0.01, 0.002
+    r_ref = {'NS': lambda: o.ns_rhs(f0, nu, conv or 'Vortex'), 'VV': lambda: o.vv_rhs(f0, nu),
+             'MHD': lambda: o.mhd_rhs(f0, nu, eta)}[solver]()
+    s_ref = o.solve(f0, solver, 2, dt, nu, eta=eta, **({'convection': conv} if conv else {}))
+    rng = np.random.RandomState(11)
+    u = rng.standard_normal((3,)+tuple(N)).astype(o.float)
+    uh_ref = o.forward(u)
+
+    def rank_fn(rank, sync):
+        p = ep.EmuPlan(L, N, precision=prec, dealias=dealias, solver=solver, convection=conv, kcut=kcut, rank=rank, nranks=world)
+        p.open_peers(sync(p.handle()))
+        N1l, M0l = N[1]//world, N[0]//world
+        k1s, x0s = slice(rank*N1l, (rank+1)*N1l), slice(rank*M0l, (rank+1)*M0l)
+        e = [rel_l2(p.forward(u[:, x0s]), uh_ref[:, :, k1s]),
+             rel_l2(p.backward(uh_ref[:, :, k1s].astype(o.complex)), u[:, x0s]),
+             rel_l2(p.compute_rhs(f0[:, :, k1s], nu, eta), r_ref[:, :, k1s]),
+             rel_l2(p.rk4(f0[:, :, k1s], 2, dt, nu, eta), s_ref[:, :, k1s])]
+        assert not p.timed_out()
+        sync(None)
+        p.close()
+        return e
+    for rank, e in enumerate(ep.run_ranks(world, rank_fn)):
+        assert all(x < tol for x in e), (world, exchange, case, rank, e)
+
+
+MULTI = [((16, 16, 16), 'double', '2/3-rule', 'NS'), ((16, 16, 16), 'double', '3/2-rule', 'NS'),
+         ((32, 16, 8), 'single', '2/3-rule', 'VV'), ((16, 32, 16), 'double', '2/3-rule', 'MHD'),
+         ((16, 16, 16), 'double', 'None', 'NS'), ((16, 32, 16), 'double', '2/3-rule', 'NS', (-1, 3, -1)),
+         ((16, 16, 16), 'double', '2/3-rule', 'NS', None, 'Skewed'), ((16, 16, 16), 'double', '3/2-rule', 'NS', None, 'Standard')]
+
+
+# (world, cases): every case runs somewhere, 8 ranks get the ones with ranks that own no kept mode
+PICK = {2: (1, 2, 6), 4: (3, 5, 7), 8: (0, 5)}
+
+
+@pytest.mark.parametrize('exchange', ['ce', 'store'])
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_emulated_multi_gpu_schedule(emu, world, exchange):
+    for i in PICK[world]:
+        _multi_case(emu, world, exchange, MULTI[i])
+
+
+def test_emulated_multi_gpu_chunk_counts(emu):
+    _multi_case(emu, 4, 'ce', MULTI[0], '1')
+    _multi_case(emu, 4, 'ce', MULTI[1], '7')
