@@ -1,7 +1,7 @@
 """CPU test of the PRODUCT's FFT core (spectraldns_b200/csrc/fft_core.cuh): the same templates the CUDA kernels
 instantiate -- radix plans, butterflies (radix 2/3/4/5/8/16), twiddle indexing, Stockham exchange maps, and the three
 element types (float2 on the packed f32x2 intrinsics, double2, float2x2 = two columns per thread) -- compiled by g++
-through csrc/host_shim.h and driven with the threads of a line in lockstep (tests/host/fft_core_harness.cpp), for
+through tests/host/host_shim.h and driven with the threads of a line in lockstep (tests/host/fft_core_harness.cpp), for
 every compiled transform length and every elements-per-thread choice, against a long-double DFT."""
 import os
 import subprocess
@@ -16,10 +16,10 @@ SIZES = [8, 12, 16, 32, 64, 128, 256, 512, 1024, 2048, 24, 48, 96, 192, 384, 768
 @pytest.fixture(scope='module')
 def harness():
     deps = [SRC, os.path.join(ROOT, 'spectraldns_b200', 'csrc', 'fft_core.cuh'),
-            os.path.join(ROOT, 'spectraldns_b200', 'csrc', 'host_shim.h')]
+            os.path.join(ROOT, 'tests', 'host', 'host_shim.h')]
     if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(BIN), exist_ok=True)
-        r = subprocess.run(['g++', '-std=c++17', '-O1', '-o', BIN, SRC], stdout=subprocess.PIPE,
+        r = subprocess.run(['g++', '-std=c++20', '-O1', '-pthread', '-I', os.path.join(ROOT, 'tests', 'host'), '-o', BIN, SRC], stdout=subprocess.PIPE,
                            stderr=subprocess.STDOUT, text=True)
         assert r.returncode == 0, r.stdout[-3000:]
     return BIN
