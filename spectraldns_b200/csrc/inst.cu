@@ -20,6 +20,7 @@ typedef double real_t;
 namespace sdns {
 
 #ifdef SDNS_F32_PAIRS
+extern "C" { __attribute__((weak)) long long sdns_debug_pair_launches = 0; }     // how often the pair kernel ran (tests)
 // fp32 plain pass on column pairs: geometry of the fp64 pass (same bytes per thread), arguments rescaled to pair units
 template <int N, int DIR>
 static int run_plain2(const StridedArgs<float>& a, cudaStream_t st) {
@@ -44,6 +45,7 @@ static int run_plain2(const StridedArgs<float>& a, cudaStream_t st) {
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
     dim3 grid((unsigned)tiles, a.nfields);
+    ++sdns_debug_pair_launches;
     SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }

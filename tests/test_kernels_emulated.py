@@ -132,3 +132,47 @@ def test_emulated_multi_gpu_schedule(emu, world, exchange):
 def test_emulated_multi_gpu_chunk_counts(emu):
     _multi_case(emu, 4, 'ce', MULTI[0], '1')
     _multi_case(emu, 4, 'ce', MULTI[1], '7')
+
+
+# ---------------------------------------------------------------------------------------------
+# the kernels that only exist for long lines (warp-per-line zx with shuffle mirrors, CTA-per-line zy, radix-16
+# strided passes, field-parallel F0) on thin grids, and the fp32 column-pair pass that is compiled on request
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def emu_long():
+    import build_emu
+    import emu_plan
+    os.environ.setdefault('SDNS_EMU_JITTER', '200')
+    return emu_plan.load(build_emu.build(lib=os.path.join(build_emu.OUT, 'libsdns_emu_long.so'),
+                                         sizes=(8, 12, 256, 384, 512, 768))), emu_plan
+
+
+@pytest.mark.parametrize('N,precision,dealias', [((8, 8, 256), 'double', '2/3-rule'), ((8, 8, 256), 'single', '3/2-rule'),
+                                                 ((8, 8, 512), 'double', '2/3-rule'), ((256, 8, 8), 'double', '2/3-rule'),
+                                                 ((8, 256, 8), 'single', '3/2-rule')])
+def test_emulated_long_lines(emu_long, N, precision, dealias):
+    L, ep = emu_long
+    o = so.Oracle(N, precision=precision, dealias=dealias)
+    p = ep.EmuPlan(L, N, precision=precision, dealias=dealias)
+    rng = np.random.RandomState(7)
+    u0 = o.forward(rng.standard_normal((3,)+tuple(N)).astype(o.float)*0.3).astype(o.complex)
+    assert rel_l2(p.compute_rhs(u0, 0.01), o.ns_rhs(u0, 0.01)) < TOL[precision]
+    assert rel_l2(p.rk4(u0, 1, 0.001, 0.01), o.solve(u0, 'NS', 1, 0.001, 0.01)) < TOL[precision]
+    p.close()
+
+
+def test_emulated_fp32_pair_kernel():
+    """-DSDNS_F32_PAIRS: the fp32 plain passes on float2x2 column pairs (plain2_kernel); must run and agree."""
+    import ctypes
+    import build_emu
+    import emu_plan
+    L = emu_plan.load(build_emu.build(extra=['-DSDNS_F32_PAIRS'], lib=os.path.join(build_emu.OUT, 'libsdns_emu_pairs.so')))
+    for N, dealias, solver in [((16, 16, 16), '2/3-rule', 'NS'), ((32, 16, 8), '3/2-rule', 'NS'), ((16, 16, 32), '2/3-rule', 'MHD')]:
+        o = so.Oracle(N, precision='single', dealias=dealias)
+        p = emu_plan.EmuPlan(L, N, precision='single', dealias=dealias, solver=solver)
+        f0 = _state(o, solver)
+        ref = o.ns_rhs(f0, 0.005) if solver == 'NS' else o.mhd_rhs(f0, 0.005, 0.01)
+        assert rel_l2(p.compute_rhs(f0, 0.005, 0.01), ref) < 1e-4
+        assert rel_l2(p.rk4(f0, 2, 0.002, 0.005, 0.01), o.solve(f0, solver, 2, 0.002, 0.005, eta=0.01)) < 1e-4
+        p.close()
+    assert ctypes.c_longlong.in_dll(L, 'sdns_debug_pair_launches').value > 50
