@@ -54,7 +54,8 @@ def build(force=False, jobs=None, verbose=False, sizes=None, out=None, precs=(32
     os.makedirs(OBJ, exist_ok=True)
     extra = os.environ.get('SDNS_EXTRA_FLAGS', '').split()      # experiment switches, e.g. -DSDNS_NO_F0X
     if sizes:
-        extra = extra + ['-DSDNS_SIZES(X)=' + ' '.join('X(%d)' % s for s in sizes)]
+        extra = extra + ['-DSDNS_SIZES(X)=' + ' '.join('X(%d)' % s for s in sizes if s % 5),
+                         '-DSDNS_SIZES_5(X)=' + ' '.join('X(%d)' % s for s in sizes if s % 5 == 0)]
     digest = _sources_digest(' '.join(extra))
     stamp = os.path.join(OBJ, 'stamp')
     if (not force and os.path.exists(LIB) and os.path.exists(stamp)

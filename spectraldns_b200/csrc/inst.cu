@@ -265,6 +265,9 @@ int SDNS_FN(int n, const void* args, cudaStream_t st) {
 #define X(N) case N: return run_nsdiv_f0<T, N>(*(const StridedArgs<T>*)args, st);
 #endif
         SDNS_SIZES(X)
+#if SDNS_FAMILY <= 5 || (SDNS_FAMILY >= 7 && SDNS_FAMILY <= 9)
+        SDNS_SIZES_5(X)
+#endif
 #undef X
         default: return -1000;
     }

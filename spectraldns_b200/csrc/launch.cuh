@@ -6,10 +6,17 @@
 
 namespace sdns {
 
-// transform lengths with a compiled kernel: 2^k (8..2048) and 3*2^k (12..3072, the 3/2-rule lengths)
+// transform lengths with a compiled kernel: 2^k (8..2048), 3*2^k (12..3072, the 3/2-rule lengths), and 60 / 90
+// (demo/Isotropic.py's own default grid and its 3/2 padding: radices 2*2*3*5 and 2*3*3*5, 30 elements per thread)
+// 60 / 90 are compiled for the NS / VV Vortex path and the plain transforms only (SDNS_SIZES_5): their kernels are
+// large (30 elements per thread) and MHD / the other NS convection forms report "no kernel for length" there.
 #ifndef SDNS_SIZES
 #define SDNS_SIZES(X) X(8) X(12) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) \
                       X(24) X(48) X(96) X(192) X(384) X(768) X(1536) X(3072)
+#define SDNS_SIZES_5(X) X(60) X(90)
+#endif
+#ifndef SDNS_SIZES_5
+#define SDNS_SIZES_5(X)
 #endif
 
 enum Family {
@@ -25,6 +32,7 @@ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // elements per thread: keep a line inside one warp (P = N/E <= 32) while the register budget
 // allows it (fp32: E <= 32, fp64: E <= 16 for single-field kernels), else 64 or 128 threads per line
 constexpr int pick_E(int N, int emax) {
+    if (N % 5 == 0) return 30;              // a factor 5: every stage radix (2, 3, 5) must divide E
     const int b = (N % 3 == 0) ? 12 : 8;
     int e = b;
     while (N / e > 32 && 2 * e <= emax && plan_ok(N, 2 * e)) e *= 2;
@@ -35,6 +43,7 @@ constexpr int pick_E(int N, int emax) {
 // fp64 strided kernels: P <= 64 threads per line (E up to 16) and CTAs of at most 256 threads, so that
 // three or four CTAs are resident per SM and their load / transform / store phases overlap
 constexpr int pick_E64(int N) {
+    if (N % 5 == 0) return 30;
     const int b = (N % 3 == 0) ? 12 : 8;
 #ifndef SDNS_NO_RADIX16
     if (b == 8 && N >= 256 && N % 256 == 0) {           // 16 x 16 (x 2,4,8): one exchange fewer than 8 x 8 x 4
@@ -135,7 +144,7 @@ struct FXCfg {
 // MHD epilogue: six accumulators per thread -> fewer elements per thread
 template <typename T, int N>
 struct MCfg {
-    static constexpr int E = (N % 3 == 0) ? (sizeof(T) == 8 ? 6 : 12) : (sizeof(T) == 8 ? 4 : 8);
+    static constexpr int E = (N % 5 == 0) ? 30 : (N % 3 == 0) ? (sizeof(T) == 8 ? 6 : 12) : (sizeof(T) == 8 ? 4 : 8);
     static constexpr int P = N / E;
     static constexpr int maxThreads = 512;
     static constexpr int TCfull = 128 / (2 * (int)sizeof(T));
@@ -151,7 +160,7 @@ struct ZCfg {
     static constexpr int E = pick_E(M, sizeof(T) == 8 ? ((MODE == Z_C2R || MODE == Z_R2C) ? 16 : 12) : (MODE == Z_MHD ? 16 : 32));
     static constexpr int P = M / E;
     static constexpr int LPC = cmax(1, 128 / P);
-    static constexpr int SYNC = (P <= 32) ? 1 : 0;
+    static constexpr int SYNC = (P <= 32 && 32 % P == 0) ? 1 : 0;     // __syncwarp only if no line straddles two warps
     static constexpr int NBUF = park ? 1 : 2;
     static constexpr int PADW = 128 / (2 * (int)sizeof(T));
     static constexpr int LP = M + M / PADW + 1;

@@ -43,6 +43,7 @@ static bool size_ok(int n) {
     switch (n) {
 #define X(N) case N: return true;
         SDNS_SIZES(X)
+        SDNS_SIZES_5(X)
 #undef X
         default: return false;
     }
@@ -284,9 +285,17 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
         if (p->sp[s].M[0] % p->P) { delete p; return fail(SDNS_ERR_SIZE, "N[0] (and 3N[0]/2) must be divisible by the number of ranks"); }
     for (int s = 0; s < 2; ++s) for (int i = 0; i < 3; ++i)
         if (!size_ok(p->sp[s].M[i])) {
-            char b[128]; snprintf(b, sizeof b, "no compiled transform of length %d (have 2^k, 3*2^k for 16..3072)", p->sp[s].M[i]);
+            char b[128]; snprintf(b, sizeof b, "no compiled transform of length %d (have 2^k and 3*2^k, 8..3072, and 60, 90)", p->sp[s].M[i]);
             delete p; return fail(SDNS_ERR_SIZE, b);
         }
+    {   // lengths with a factor 5 (60, 90) exist for the NS / VV Vortex path and the plain transforms only
+        const bool vortex = cfg->solver != SDNS_MHD && cfg->convection == SDNS_CONV_VORTEX;
+        for (int s = 0; s < 2 && !vortex; ++s) for (int i = 0; i < 3; ++i)
+            if (p->sp[s].M[i] % 5 == 0) {
+                delete p;
+                return fail(SDNS_ERR_SIZE, "transform lengths 60 / 90 are compiled for the NS / VV Vortex path only");
+            }
+    }
     if (p->prec) fill_tables<double>(p); else fill_tables<float>(p);
     // scratch: A holds W0 (B0 out) and W2 (Z out); B holds W1 (B1 out) and W3 (F1 out)
     const int nz = cfg->solver == SDNS_MHD ? 9 : 6;    // widest field count through the pipeline

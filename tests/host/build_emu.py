@@ -31,7 +31,8 @@ def build(extra=(), lib=LIB, sizes=SIZES, force=False):
         return lib
     tag = os.path.basename(lib).replace('.so', '')
     flags = ['g++', '-std=c++20', '-O1', '-fPIC', '-pthread', '-w', '-DSDNS_HOST_SHIM', '-I', HERE, '-x', 'c++',
-             '-DSDNS_SIZES(X)=' + ' '.join('X(%d)' % s for s in sizes)] + list(extra)
+             '-DSDNS_SIZES(X)=' + ' '.join('X(%d)' % s for s in sizes if s % 5),
+             '-DSDNS_SIZES_5(X)=' + ' '.join('X(%d)' % s for s in sizes if s % 5 == 0)] + list(extra)
     units = []
     for fam in range(NFAM):
         for prec in (32, 64):

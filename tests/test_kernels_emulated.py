@@ -176,3 +176,38 @@ def test_emulated_fp32_pair_kernel():
         assert rel_l2(p.rk4(f0, 2, 0.002, 0.005, 0.01), o.solve(f0, solver, 2, 0.002, 0.005, eta=0.01)) < 1e-4
         p.close()
     assert ctypes.c_longlong.in_dll(L, 'sdns_debug_pair_launches').value > 50
+
+
+@pytest.fixture(scope='module')
+def emu_60():
+    import build_emu
+    import emu_plan
+    return emu_plan.load(build_emu.build(lib=os.path.join(build_emu.OUT, 'libsdns_emu_60.so'), sizes=(8, 12, 60, 90))), emu_plan
+
+
+@pytest.mark.parametrize('N,precision,dealias,solver', [
+    ((60, 8, 8), 'double', '2/3-rule', 'NS'), ((8, 60, 8), 'single', '3/2-rule', 'NS'), ((8, 8, 60), 'double', '3/2-rule', 'NS'),
+    ((8, 60, 8), 'double', '3/2-rule', 'VV'), ((8, 8, 60), 'single', '2/3-rule', 'VV'), ((90, 8, 8), 'double', '2/3-rule', 'NS')])
+def test_emulated_lengths_60_and_90(emu_60, N, precision, dealias, solver):
+    """demo/Isotropic.py's default grid is 60^3 with the 3/2-rule (padded 90): radix-2*2*3*5 / 2*3*3*5 plans with 30
+    elements per thread, on each axis, NS and VV Vortex path plus the plain transforms."""
+    L, ep = emu_60
+    o = so.Oracle(N, precision=precision, dealias=dealias)
+    p = ep.EmuPlan(L, N, precision=precision, dealias=dealias, solver=solver)
+    f0 = _state(o, solver)
+    ref = o.ns_rhs(f0, 0.005) if solver == 'NS' else o.vv_rhs(f0, 0.005)
+    assert rel_l2(p.compute_rhs(f0, 0.005), ref) < TOL[precision]
+    assert rel_l2(p.rk4(f0, 1, 0.002, 0.005), o.solve(f0, solver, 1, 0.002, 0.005)) < TOL[precision]
+    rng = np.random.RandomState(1)
+    u = rng.standard_normal((3,)+tuple(N)).astype(o.float)
+    assert rel_l2(p.forward(u), o.forward(u)) < TOL[precision]
+    assert rel_l2(p.backward(o.forward(u).astype(o.complex)), u) < TOL[precision]
+    p.close()
+
+
+def test_emulated_lengths_60_only_on_the_vortex_path(emu_60):
+    L, ep = emu_60
+    with pytest.raises(RuntimeError, match='Vortex path only'):
+        ep.EmuPlan(L, (60, 8, 8), solver='MHD')
+    with pytest.raises(RuntimeError, match='Vortex path only'):
+        ep.EmuPlan(L, (8, 8, 60), dealias='3/2-rule', convection='Skewed')
