@@ -32,7 +32,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.sdns_abi_version() == 1
     for n in (8, 12, 16, 24, 256, 384, 768, 1024, 2048, 3072):
         assert lib.sdns_size_supported(n, 1) == 0
-    assert lib.sdns_size_supported(60, 1) != 0
+    assert lib.sdns_size_supported(60, 1) == 0 and lib.sdns_size_supported(90, 0) == 0      # demo/Isotropic.py default grid
+    assert lib.sdns_size_supported(100, 1) != 0 and lib.sdns_size_supported(36, 1) != 0
 
 
 def test_plan_fails_loudly_without_gpu():
