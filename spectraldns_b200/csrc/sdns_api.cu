@@ -595,6 +595,7 @@ struct Pipe {
         if (staged) peers(a, p->off_A, q.M0l, B, b0_slot(), (long long)q.M0l * q.K1l * q.K2p, (long long)q.K1l * q.K2p, 0);
         else peers(a, p->off_A, q.M0l);
         a.grid_cap = xcap;
+        a.pairable = (k2.a == 0 && k2.b == q.K2n);      // output rows: K2n columns + padding up to the even pitch K2p
         a.tw = tw(q.M[0]); a.nfields = nf;
         const int nfo = (fam == FAM_PLAIN_BWD) ? nf : 6;
         const double cols = (double)(k1.b - k1.a) * a.cw;
@@ -677,6 +678,7 @@ struct Pipe {
         a.col_nlo = p->N1l; a.col_gap = 0;
         a.imap = all_map(q.M[0]); a.omap = q.fmap[0];
         a.out_fs = dense_fs(); a.out_ls = (long long)p->N1l * p->Nh; a.out_os = p->Nh;
+        a.pairable = (k2.a == 0 && k2.b == p->Nh);       // input rows (W3): Nh columns + padding up to the even pitch Nhp
         a.tw = tw(q.M[0]); a.nfields = nf;
     }
 };

@@ -162,20 +162,21 @@ def test_emulated_long_lines(emu_long, N, precision, dealias):
 
 
 def test_emulated_fp32_pair_kernel():
-    """-DSDNS_F32_PAIRS: the fp32 plain passes on float2x2 column pairs (plain2_kernel); must run and agree."""
+    """-DSDNS_F32_PAIRS: the fp32 strided passes on float2x2 column pairs (plain2 / b02 / f02 kernels); must run and agree."""
     import ctypes
     import build_emu
     import emu_plan
     L = emu_plan.load(build_emu.build(extra=['-DSDNS_F32_PAIRS'], lib=os.path.join(build_emu.OUT, 'libsdns_emu_pairs.so')))
-    for N, dealias, solver in [((16, 16, 16), '2/3-rule', 'NS'), ((32, 16, 8), '3/2-rule', 'NS'), ((16, 16, 32), '2/3-rule', 'MHD')]:
+    for N, dealias, solver in [((16, 16, 16), '2/3-rule', 'NS'), ((32, 16, 8), '3/2-rule', 'NS'), ((16, 32, 16), '3/2-rule', 'VV'),
+                               ((8, 24, 48), '2/3-rule', 'VV'), ((16, 16, 32), '2/3-rule', 'MHD')]:
         o = so.Oracle(N, precision='single', dealias=dealias)
         p = emu_plan.EmuPlan(L, N, precision='single', dealias=dealias, solver=solver)
         f0 = _state(o, solver)
-        ref = o.ns_rhs(f0, 0.005) if solver == 'NS' else o.mhd_rhs(f0, 0.005, 0.01)
+        ref = {'NS': lambda: o.ns_rhs(f0, 0.005), 'VV': lambda: o.vv_rhs(f0, 0.005), 'MHD': lambda: o.mhd_rhs(f0, 0.005, 0.01)}[solver]()
         assert rel_l2(p.compute_rhs(f0, 0.005, 0.01), ref) < 1e-4
         assert rel_l2(p.rk4(f0, 2, 0.002, 0.005, 0.01), o.solve(f0, solver, 2, 0.002, 0.005, eta=0.01)) < 1e-4
         p.close()
-    assert ctypes.c_longlong.in_dll(L, 'sdns_debug_pair_launches').value > 50
+    assert ctypes.c_longlong.in_dll(L, 'sdns_debug_pair_launches').value > 150
 
 
 @pytest.fixture(scope='module')
