@@ -212,3 +212,55 @@ def test_emulated_lengths_60_only_on_the_vortex_path(emu_60):
         ep.EmuPlan(L, (60, 8, 8), solver='MHD')
     with pytest.raises(RuntimeError, match='Vortex path only'):
         ep.EmuPlan(L, (8, 8, 60), dealias='3/2-rule', convection='Skewed')
+
+
+def test_emulated_small_kernels(emu):
+    """energy (shuffle + shared-memory reduction), Euler / AB2 steps, cross2, project, lincomb / errnorm through the C ABI."""
+    import ctypes as C
+    L, ep = emu
+    vp, dbl = C.c_void_p, C.c_double
+    L.sdns_euler_step.argtypes = [vp, vp, vp, dbl, dbl, dbl, vp]
+    L.sdns_ab2_step.argtypes = [vp, vp, vp, vp, dbl, C.c_int, dbl, dbl, vp]
+    L.sdns_cross2.argtypes = [vp, vp, vp, C.c_int]
+    L.sdns_project.argtypes = [vp, vp]
+    L.sdns_lincomb.argtypes = [vp, vp, vp, C.c_int, C.POINTER(dbl), C.POINTER(vp), C.c_int]
+    L.sdns_errnorm.argtypes = [vp, vp, vp, vp, dbl, dbl, C.c_int, C.POINTER(dbl)]
+    N = (16, 16, 16)
+    o = so.Oracle(N)
+    p = ep.EmuPlan(L, N)
+    f0 = _state(o, 'NS')
+    e = C.c_double()
+    p.chk(L.sdns_energy(p.p, f0.ctypes.data, 3, C.byref(e)))
+    assert abs(e.value - o.energy_fourier(f0)) < 1e-12*abs(e.value)
+    nu, dt = 0.005, 0.002
+    fn = lambda u: o.ns_rhs(u, nu)
+    u, rhs = f0.copy(), np.zeros_like(f0)
+    ref = f0.copy()
+    for _ in range(2):
+        p.chk(L.sdns_euler_step(p.p, u.ctypes.data, rhs.ctypes.data, dt, nu, 0.0, None))
+        ref = o.forward_euler_step(ref, fn, dt)
+    assert rel_l2(u, ref) < 1e-11
+    u, u1 = f0.copy(), np.zeros_like(f0)
+    ref, r1 = f0.copy(), np.zeros_like(f0)
+    for ts in range(3):
+        p.chk(L.sdns_ab2_step(p.p, u.ctypes.data, u1.ctypes.data, rhs.ctypes.data, dt, ts, nu, 0.0, None))
+        ref, r1 = o.ab2_step(ref, r1, fn, dt, ts)
+    assert rel_l2(u, ref) < 1e-11
+    c = np.zeros_like(f0)
+    p.chk(L.sdns_cross2(p.p, c.ctypes.data, f0.ctypes.data, 0))
+    assert rel_l2(c, o.cross2(o.K, f0)) < 1e-13
+    v = f0.copy() + 0.1*(np.random.RandomState(2).standard_normal(f0.shape) + 0j)
+    w = v.copy()
+    p.chk(L.sdns_project(p.p, w.ctypes.data))
+    pref = v - np.sum(o.K_over_K2*v, 0)*np.array([np.broadcast_to(k, o.sshape) for k in o.K])
+    assert rel_l2(w, pref) < 1e-13
+    out = np.zeros_like(f0)
+    coeffs = (dbl*2)(0.25, -1.5)
+    arrs = (vp*2)(f0.ctypes.data, c.ctypes.data)
+    p.chk(L.sdns_lincomb(p.p, out.ctypes.data, v.ctypes.data, 2, coeffs, arrs, 3))
+    assert rel_l2(out, v + 0.25*f0 - 1.5*c) < 1e-14
+    en = (dbl*3)()
+    p.chk(L.sdns_errnorm(p.p, f0.ctypes.data, v.ctypes.data, c.ctypes.data, 1e-6, 1e-3, 3, en))
+    sc = 1e-6 + np.maximum(np.abs(f0), np.abs(v))*1e-3
+    assert np.allclose(np.array(en[:]), np.sum(np.abs(c/sc)**2, axis=(1, 2, 3)), rtol=1e-11)
+    p.close()
