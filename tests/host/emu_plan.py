@@ -30,6 +30,9 @@ def load(path):
     L.sdns_comm_handle.argtypes = [vp, vp]
     L.sdns_comm_open.argtypes = [vp, vp, C.c_int]
     L.sdns_comm_status.argtypes = [vp, C.POINTER(C.c_int)]
+    if hasattr(L, 'sdns_emu_set_skew'):
+        L.sdns_emu_set_skew.argtypes = [C.c_int]
+        L.sdns_emu_set_skew.restype = None
     L.sdns_local_shapes.argtypes = [vp, C.POINTER(C.c_int32*3), C.POINTER(C.c_int32*3), C.POINTER(C.c_int32*3)]
     return L
 

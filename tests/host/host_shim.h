@@ -58,6 +58,9 @@ inline Tls& tls() { static thread_local Tls t; return t; }
 inline unsigned char* dyn_smem() { unsigned char* p = tls().cta->dyn.data(); return p + ((256 - (uintptr_t)p % 256) % 256); }
 inline unsigned char* static_smem() { unsigned char* p = tls().cta->stat.data(); return p + ((256 - (uintptr_t)p % 256) % 256); }
 
+// per-rank delay before every launch (set by the rank's host thread through sdns_emu_set_skew): makes one rank
+// systematically slower than its peers, which turns missing cross-rank ordering into wrong results
+inline int& skew_us() { static thread_local int v = 0; return v; }
 template <class F> struct Launcher {
     F f; dim3 g, b; size_t smem;
     template <class... A> void operator()(A... args) const {
@@ -65,6 +68,7 @@ template <class F> struct Launcher {
         // SDNS_EMU_JITTER=<max microseconds>: every launch starts after a random delay, which pulls the ranks of an
         // emulated multi-GPU run apart and widens the windows of missing cross-rank ordering
         static const int jitter = std::getenv("SDNS_EMU_JITTER") ? std::atoi(std::getenv("SDNS_EMU_JITTER")) : 0;
+        if (skew_us() > 0) std::this_thread::sleep_for(std::chrono::microseconds(skew_us()));
         if (jitter > 0) {
             static thread_local unsigned long long seed = 88172645463325252ULL ^ (unsigned long long)std::hash<std::thread::id>()(std::this_thread::get_id());
             seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17;
@@ -147,3 +151,5 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
 inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+extern "C" inline __attribute__((visibility("default"), used)) void sdns_emu_set_skew(int microseconds) { sdns_emu::skew_us() = microseconds; }

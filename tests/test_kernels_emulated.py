@@ -78,7 +78,7 @@ def test_emulated_ns_convection_forms(emu, conv):
 # multi-GPU schedule: the ranks are threads of this process, "peer memory" is each other's host buffer, the
 # device-side flag barrier spins on real flags, the copy-engine copies are memcpys at the point of submission
 # ---------------------------------------------------------------------------------------------
-def _multi_case(emu, world, exchange, case, chunks='4'):
+def _multi_case(emu, world, exchange, case, chunks='4', skew=None):
     L, ep = emu
     N, prec, dealias, solver = case[:4]
     kcut = case[4] if len(case) > 4 else None
@@ -96,14 +96,20 @@ def _multi_case(emu, world, exchange, case, chunks='4'):
     uh_ref = o.forward(u)
 
     def rank_fn(rank, sync):
+        L.sdns_emu_set_skew(int(skew(rank)) if skew else 0)       # this rank's delay before every launch (microseconds)
         p = ep.EmuPlan(L, N, precision=prec, dealias=dealias, solver=solver, convection=conv, kcut=kcut, rank=rank, nranks=world)
         p.open_peers(sync(p.handle()))
         N1l, M0l = N[1]//world, N[0]//world
         k1s, x0s = slice(rank*N1l, (rank+1)*N1l), slice(rank*M0l, (rank+1)*M0l)
+        # the sequence visits every transition between operations that store into the peers
         e = [rel_l2(p.forward(u[:, x0s]), uh_ref[:, :, k1s]),
              rel_l2(p.backward(uh_ref[:, :, k1s].astype(o.complex)), u[:, x0s]),
+             rel_l2(p.backward(uh_ref[:, :, k1s].astype(o.complex)), u[:, x0s]),
              rel_l2(p.compute_rhs(f0[:, :, k1s], nu, eta), r_ref[:, :, k1s]),
-             rel_l2(p.rk4(f0[:, :, k1s], 2, dt, nu, eta), s_ref[:, :, k1s])]
+             rel_l2(p.forward(u[:, x0s]), uh_ref[:, :, k1s]),
+             rel_l2(p.forward(u[:, x0s]), uh_ref[:, :, k1s]),
+             rel_l2(p.rk4(f0[:, :, k1s], 2, dt, nu, eta), s_ref[:, :, k1s]),
+             rel_l2(p.backward(uh_ref[:, :, k1s].astype(o.complex)), u[:, x0s])]
         assert not p.timed_out()
         sync(None)
         p.close()
@@ -127,6 +133,16 @@ PICK = {2: (1, 2, 6), 4: (3, 5, 7), 8: (0, 5)}
 def test_emulated_multi_gpu_schedule(emu, world, exchange):
     for i in PICK[world]:
         _multi_case(emu, world, exchange, MULTI[i])
+
+
+@pytest.mark.parametrize('exchange', ['ce', 'store'])
+def test_emulated_multi_gpu_skewed_ranks(emu, exchange):
+    """One end of the rank range is made systematically slower (a delay before each of its launches): any operation
+    that stores into a peer before that peer has finished reading the buffer shows up as a wrong result."""
+    for case, skew in ((MULTI[0], lambda r: 8000*r), (MULTI[1], lambda r: 8000*(3 - r)), (MULTI[6], lambda r: 8000*r)):
+        _multi_case(emu, 4, exchange, case, skew=skew)
+    L, _ = emu
+    L.sdns_emu_set_skew(0)
 
 
 def test_emulated_multi_gpu_chunk_counts(emu):
