@@ -1,10 +1,10 @@
 # usage: bash profiles/run_timeline.sh <ngpus> [bench args]   (under gpurun --gpus N)
 # One RK4 step with every kernel, peer copy and barrier time-stamped on the device clock (bench.py --timeline), for
-# the copy-engine exchange and for the fused peer stores, then the per-rank summary: how much of the copy time lies
+# the copy-engine exchange, its copy-kernel variant and the fused peer stores, then the per-rank summary: how much of the copy time lies
 # underneath kernels and where the plan stream idles.  First thing to run in round 2.
 NG=${1:-8}; shift
 mkdir -p gpurun_out
-for x in ce store; do
+for x in ce kcopy store; do
   SDNS_EXCHANGE=$x timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29541 \
       bench.py --gpus $NG --no-cpu-baseline --steps 10 --timeline gpurun_out/timeline_${x}_g$NG "$@" > gpurun_out/bench_tl_${x}_g$NG.json 2> gpurun_out/bench_tl_${x}_g$NG.err
   echo "== exchange=$x"; python profiles/tools/timeline_report.py gpurun_out/timeline_${x}_g$NG | head -40

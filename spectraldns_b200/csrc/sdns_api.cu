@@ -90,6 +90,7 @@ struct sdns_plan {
     // xmode 1: B0 / F1 write per-destination send buffers in chunks and the copy engines move each chunk over
     // NVLink (one stream per peer) while the SMs work on the next chunk.
     int xmode, nchunk, nsplit;      // nsplit: streams (copy engines) per destination rank
+    int kcopy, kcopy_ctas;          // xmode 1 variant: a grid-capped copy kernel (peer stores) instead of cudaMemcpy2DAsync
     std::vector<cudaStream_t> ys;   // copy streams (a few, shared by the destinations) x nsplit parts
     std::vector<cudaEvent_t> ev_k;  // [nchunk] the pass of chunk c has finished
     std::vector<cudaEvent_t> ev_y;  // per copy stream: drained
@@ -242,16 +243,19 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->stream = 0; p->ws = nullptr; p->ws_bytes = 0; p->launches = 0;
     p->prof = false; p->ev_used = 0;
     p->tl_on = false; p->tl_base = nullptr;
+    p->kcopy = 0; p->kcopy_ctas = 32;
     p->xmode = 0; p->nchunk = 1; p->nsplit = 1; p->off_SF = 0; p->bytes_SF = 0; p->b0_preissued = false;
     p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
     if (p->P > 1) {
         const char* xm = getenv("SDNS_EXCHANGE");           // "store": peer stores fused into the passes; default: copy engines
         p->xmode = (xm && !strcmp(xm, "store")) ? 0 : 1;
+        p->kcopy = (xm && !strcmp(xm, "kcopy")) ? 1 : 0;    // send slots moved by a small copy kernel instead of the copy engines
         const char* env = getenv("SDNS_CHUNKS");
         p->nchunk = env ? atoi(env) : 4;
         if (p->nchunk < 1) p->nchunk = 1;
         if (p->nchunk > 16) p->nchunk = 16;
         if (!p->xmode) p->nchunk = 1;
+        if (const char* kc = getenv("SDNS_KCOPY_CTAS")) p->kcopy_ctas = std::max(1, atoi(kc));
         const char* sp = getenv("SDNS_SPLIT");
         p->nsplit = sp ? atoi(sp) : 1;      // measured: one copy stream per peer saturates the link (profiles/tools/p2p_copy_bench.py)
         if (p->nsplit < 1) p->nsplit = 1;
@@ -772,6 +776,21 @@ static int launch_f0(sdns_plan* p, Pipe<T>& P, const void* u_hat, double nu, dou
     return do_launch(p, P.st, fam, P.q.M[0], &a, bytes);
 }
 
+namespace sdns {
+// SDNS_EXCHANGE=kcopy: the strided copy of a send slot into the peer's array as a kernel -- 16-byte loads from local
+// HBM, 16-byte stores over NVLink, a few CTAs only (grid-stride) so that it runs beside the passes of the plan
+// stream.  Same rows / pitches as the copy-engine path; an experiment to separate copy-engine behaviour from the
+// schedule.
+__global__ void slot_copy_kernel(uint4* __restrict__ dst, size_t dpitch16, const uint4* __restrict__ src, size_t spitch16,
+                                 size_t width16, size_t height) {
+    const size_t total = width16 * height;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / width16, c = i - r * width16;
+        dst[r * dpitch16 + c] = src[r * spitch16 + c];
+    }
+}
+}  // namespace sdns
+
 // One 2-D copy per destination rank on that rank's copy stream, after `after` has fired
 static int copy_rows(sdns_plan* p, int r, cudaEvent_t after, void* dst, size_t dpitch, const void* src, size_t spitch,
                      size_t width, size_t height) {
@@ -787,6 +806,12 @@ static int copy_rows(sdns_plan* p, int r, cudaEvent_t after, void* dst, size_t d
         CUDA_TRY(cudaStreamWaitEvent(y, after, 0));
         sdns_plan::CRec cr; cr.s = si; cr.bytes = (double)width * (h1 - h0);
         if (p->prof) { cr.a = get_event(p); cudaEventRecord(cr.a, y); }
+        if (p->kcopy && width % 16 == 0 && dpitch % 16 == 0 && spitch % 16 == 0) {
+            SDNS_LAUNCH(slot_copy_kernel, p->kcopy_ctas, 256, 0, y)(reinterpret_cast<uint4*>((char*)dst + h0 * dpitch), dpitch / 16,
+                                                                   reinterpret_cast<const uint4*>((const char*)src + h0 * spitch), spitch / 16,
+                                                                   width / 16, h1 - h0);
+            CUDA_TRY(cudaGetLastError());
+        } else
         CUDA_TRY(cudaMemcpy2DAsync((char*)dst + h0 * dpitch, dpitch, (const char*)src + h0 * spitch, spitch, width, h1 - h0,
                                    cudaMemcpyDeviceToDevice, y));
         if (p->prof) { cr.b = get_event(p); cudaEventRecord(cr.b, y); p->crecs.push_back(cr); }

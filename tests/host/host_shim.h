@@ -29,6 +29,7 @@
 
 struct float2 { float x, y; };
 struct double2 { double x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 // the packed f32x2 intrinsics of sm_100: lane-wise, round to nearest
