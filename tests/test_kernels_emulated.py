@@ -152,10 +152,9 @@ def test_emulated_multi_gpu_skewed_ranks(emu, exchange):
 
 def test_emulated_multi_gpu_kernel_copy(emu):
     """SDNS_EXCHANGE=kcopy: the send slots are moved by slot_copy_kernel (peer stores) instead of the copy engines."""
-    os.environ['SDNS_KCOPY_CTAS'] = '2'
+    os.environ['SDNS_KCOPY_CTAS'] = '1'
     try:
-        _multi_case(emu, 4, 'kcopy', MULTI[1], skew=lambda r: 3000*r)
-        _multi_case(emu, 8, 'kcopy', MULTI[5])
+        _multi_case(emu, 4, 'kcopy', MULTI[1], chunks='2')
     finally:
         os.environ.pop('SDNS_KCOPY_CTAS', None)
 
