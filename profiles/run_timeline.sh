@@ -9,3 +9,15 @@ for x in ce kcopy store; do
       bench.py --gpus $NG --no-cpu-baseline --steps 10 --timeline gpurun_out/timeline_${x}_g$NG "$@" > gpurun_out/bench_tl_${x}_g$NG.json 2> gpurun_out/bench_tl_${x}_g$NG.err
   echo "== exchange=$x"; python profiles/tools/timeline_report.py gpurun_out/timeline_${x}_g$NG | head -40
 done
+# the same bench line with the step replayed as a CUDA graph (no timeline: profiling bypasses the graph)
+SDNS_GRAPH=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29542 \
+    bench.py --gpus $NG --no-cpu-baseline --steps 10 "$@" > gpurun_out/bench_tl_graph_g$NG.json 2> gpurun_out/bench_tl_graph_g$NG.err
+python - <<PY
+import json
+for x in ('ce', 'kcopy', 'store', 'graph'):
+    try:
+        d = json.loads(open('gpurun_out/bench_tl_%s_g$NG.json' % x).read().strip().splitlines()[-1])
+        print('%-6s ms/step %.3f' % (x, d['ms_per_step']))
+    except Exception as e:
+        print(x, 'FAILED', e)
+PY

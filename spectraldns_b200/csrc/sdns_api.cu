@@ -91,6 +91,13 @@ struct sdns_plan {
     // NVLink (one stream per peer) while the SMs work on the next chunk.
     int xmode, nchunk, nsplit;      // nsplit: streams (copy engines) per destination rank
     int kcopy, kcopy_ctas;          // xmode 1 variant: a grid-capped copy kernel (peer stores) instead of cudaMemcpy2DAsync
+    // SDNS_GRAPH=1 (experiment, multi-GPU copy-engine mode): an RK4 step -- kernels, peer copies and their cross-stream
+    // edges -- is captured once per argument set into a CUDA graph on the library's own stream and replayed, which
+    // takes the host out of the schedule.  Barriers inside a graph take their epoch from a device-resident counter.
+    int use_graph; bool capturing, gwarm, ghave;
+    cudaStream_t gstream; cudaEvent_t ev_gin, ev_gout; cudaGraphExec_t gexec;
+    struct GKey { void* u; void* u1; void* u2; const void* src; double dt, nu, eta; } gkey;
+    long long glaunches;
     std::vector<cudaStream_t> ys;   // copy streams (a few, shared by the destinations) x nsplit parts
     std::vector<cudaEvent_t> ev_k;  // [nchunk] the pass of chunk c has finished
     std::vector<cudaEvent_t> ev_y;  // per copy stream: drained
@@ -244,6 +251,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->prof = false; p->ev_used = 0;
     p->tl_on = false; p->tl_base = nullptr;
     p->kcopy = 0; p->kcopy_ctas = 32;
+    p->use_graph = 0; p->capturing = p->gwarm = p->ghave = false; p->gstream = nullptr; p->ev_gin = p->ev_gout = nullptr; p->gexec = nullptr; p->glaunches = 0;
     p->xmode = 0; p->nchunk = 1; p->nsplit = 1; p->off_SF = 0; p->bytes_SF = 0; p->b0_preissued = false;
     p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
     if (p->P > 1) {
@@ -256,6 +264,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
         if (p->nchunk > 16) p->nchunk = 16;
         if (!p->xmode) p->nchunk = 1;
         if (const char* kc = getenv("SDNS_KCOPY_CTAS")) p->kcopy_ctas = std::max(1, atoi(kc));
+        if (const char* g = getenv("SDNS_GRAPH")) p->use_graph = atoi(g) != 0 && p->xmode == 1;
         const char* sp = getenv("SDNS_SPLIT");
         p->nsplit = sp ? atoi(sp) : 1;      // measured: one copy stream per peer saturates the link (profiles/tools/p2p_copy_bench.py)
         if (p->nsplit < 1) p->nsplit = 1;
@@ -280,6 +289,11 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
             cudaEvent_t e = nullptr;
             e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
             p->ev_k.push_back(e);
+        }
+        if (p->use_graph && e1 == cudaSuccess) {
+            e1 = cudaStreamCreateWithFlags(&p->gstream, cudaStreamNonBlocking);
+            if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_gin, cudaEventDisableTiming);
+            if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_gout, cudaEventDisableTiming);
         }
         if (e1 != cudaSuccess) { std::string m = std::string("copy streams/events: ") + cudaGetErrorString(e1); delete p; return fail(SDNS_ERR_CUDA, m); }
     }
@@ -347,6 +361,10 @@ extern "C" int sdns_plan_destroy(sdns_plan* p) {
     if (p) {
         for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
         if (p->tl_base) cudaEventDestroy(p->tl_base);
+        if (p->gexec) cudaGraphExecDestroy(p->gexec);
+        if (p->ev_gin) cudaEventDestroy(p->ev_gin);
+        if (p->ev_gout) cudaEventDestroy(p->ev_gout);
+        if (p->gstream) cudaStreamDestroy(p->gstream);
         for (cudaEvent_t e : p->ev_k) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : p->ev_y) if (e) cudaEventDestroy(e);
         for (cudaStream_t y : p->ys) if (y) cudaStreamDestroy(y);
@@ -452,6 +470,45 @@ __global__ void xbarrier_kernel(const BarrierArgs b) {
     __threadfence_system();
 }
 
+// Barrier for captured (graph) steps: identical handshake, but the epoch comes from a counter in device memory that
+// the kernel itself advances (kernel arguments are frozen in a graph), and it uses its own flag words so that eager
+// and captured barriers never see each other's epochs.
+struct BarrierDevArgs {
+    unsigned int* peer_flags[8];
+    unsigned int* status;
+    unsigned int* counter;
+    int rank, nranks;
+    long long timeout_cycles;
+};
+__global__ void xbarrier_dev_kernel(const BarrierDevArgs b) {
+    SDNS_STATIC_SMEM(unsigned int, sh, 1);
+    if (threadIdx.x == 0) sh[0] = ++(*b.counter);
+    __syncthreads();
+    const unsigned int epoch = sh[0];
+    const int r = threadIdx.x;
+    if (r >= b.nranks) return;
+    __threadfence_system();
+    unsigned int* remote = b.peer_flags[r] + b.rank;
+#ifndef SDNS_HOST_SHIM
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+#else
+    __atomic_store_n(remote, epoch, __ATOMIC_RELEASE);
+#endif
+    const unsigned int* local = b.peer_flags[b.rank] + r;
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+#ifndef SDNS_HOST_SHIM
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
+#else
+        v = __atomic_load_n(local, __ATOMIC_ACQUIRE);
+#endif
+        if ((int)(v - epoch) >= 0) break;
+        if (clock64() - t0 > b.timeout_cycles) { *b.status = 1u; break; }
+    } while (true);
+    __threadfence_system();
+}
+
 }  // namespace sdns
 
 static cudaEvent_t get_event(sdns_plan* p);
@@ -459,6 +516,18 @@ static cudaEvent_t get_event(sdns_plan* p);
 static int xbarrier(sdns_plan* p) {
     if (p->P == 1) return SDNS_OK;
     for (int r = 0; r < p->P; ++r) if (!p->peer_ws[r]) return fail(SDNS_ERR_STATE, "peers not opened (sdns_comm_open)");
+    if (p->capturing) {
+        // flag words 16..23 and the counter at word 40 of the 64-word flag block belong to the captured barriers
+        BarrierDevArgs d;
+        for (int r = 0; r < 8; ++r) d.peer_flags[r] = r < p->P ? reinterpret_cast<unsigned int*>(p->peer_ws[r] + p->off_flags) + 16 : nullptr;
+        d.status = reinterpret_cast<unsigned int*>(p->ws + p->off_flags) + 32;
+        d.counter = reinterpret_cast<unsigned int*>(p->ws + p->off_flags) + 40;
+        d.rank = p->rank; d.nranks = p->P; d.timeout_cycles = 20000000000LL;
+        SDNS_LAUNCH(xbarrier_dev_kernel, 1, 32, 0, p->stream)(d);
+        p->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return SDNS_OK;
+    }
     BarrierArgs b;
     for (int r = 0; r < 8; ++r) b.peer_flags[r] = r < p->P ? reinterpret_cast<unsigned int*>(p->peer_ws[r] + p->off_flags) : nullptr;
     b.status = reinterpret_cast<unsigned int*>(p->ws + p->off_flags) + 32;
@@ -1026,10 +1095,56 @@ static void rk_coeffs(int rk, double dt, double* adt, double* bdt) {
     *bdt = rk < 3 ? (double)(T)(b[rk] * d) : 0.0;
 }
 
+static int rk4_step_eager(sdns_plan* p, void* u_hat, void* u1, void* u2, double dt, double nu, double eta, const void* source);
+
+// SDNS_GRAPH=1: the first step with a given argument set runs eagerly (it also initialises the kernels' attributes),
+// the second one is captured on the library's stream, later ones replay the graph.
+static int rk4_step_graph(sdns_plan* p, void* u_hat, void* u1, void* u2, double dt, double nu, double eta, const void* source) {
+    const sdns_plan::GKey key = {u_hat, u1, u2, source, dt, nu, eta};
+    if (!p->gwarm || memcmp(&key, &p->gkey, sizeof key)) {
+        p->gkey = key; p->gwarm = true; p->ghave = false;
+        if (p->gexec) { cudaGraphExecDestroy(p->gexec); p->gexec = nullptr; }
+        return rk4_step_eager(p, u_hat, u1, u2, dt, nu, eta, source);
+    }
+    cudaStream_t user = p->stream;
+    CUDA_TRY(cudaEventRecord(p->ev_gin, user));
+    CUDA_TRY(cudaStreamWaitEvent(p->gstream, p->ev_gin, 0));
+    if (!p->ghave) {
+        cudaGraph_t graph = nullptr;
+        const long long l0 = p->launches;
+        p->stream = p->gstream; p->capturing = true;
+        cudaError_t ce = cudaStreamBeginCapture(p->gstream, cudaStreamCaptureModeRelaxed);
+        int e = ce == cudaSuccess ? rk4_step_eager(p, u_hat, u1, u2, dt, nu, eta, source) : SDNS_ERR_CUDA;
+        if (ce == cudaSuccess) ce = cudaStreamEndCapture(p->gstream, &graph);
+        p->stream = user; p->capturing = false;
+        if (e) return e;
+        if (ce != cudaSuccess) return fail(SDNS_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+        CUDA_TRY(cudaGraphInstantiate(&p->gexec, graph, 0));
+        CUDA_TRY(cudaGraphDestroy(graph));
+        p->glaunches = p->launches - l0; p->launches = l0;
+        p->ghave = true;
+    }
+    CUDA_TRY(cudaGraphLaunch(p->gexec, p->gstream));
+    p->launches += p->glaunches;
+    CUDA_TRY(cudaEventRecord(p->ev_gout, p->gstream));
+    CUDA_TRY(cudaStreamWaitEvent(user, p->ev_gout, 0));
+#ifdef SDNS_HOST_SHIM
+    p->ghave = false;                 // the emulated runtime executes a "capture" eagerly and cannot replay it
+    if (p->gexec) { cudaGraphExecDestroy(p->gexec); p->gexec = nullptr; }
+#endif
+    return SDNS_OK;
+}
+
 extern "C" int sdns_rk4_step(sdns_plan* p, void* u_hat, void* u1, void* u2, double dt, double nu,
                              double eta, const void* source) {
     int e = need_ws(p); if (e) return e;
     if (!u_hat || !u1 || !u2) return fail(SDNS_ERR_ARG, "sdns_rk4_step: null array");
+    if (p->use_graph && p->P > 1 && p->xmode == 1 && !p->prof) return rk4_step_graph(p, u_hat, u1, u2, dt, nu, eta, source);
+    return rk4_step_eager(p, u_hat, u1, u2, dt, nu, eta, source);
+}
+
+static int rk4_step_eager(sdns_plan* p, void* u_hat, void* u1, void* u2, double dt, double nu, double eta, const void* source) {
+    int e;
     // Between stages the state lives in the workspace in the k1-major work layout (u1, u2 too): the
     // axis-0 passes then read and write it with a stride of one k2 row instead of N1*Nh elements.
     // Stage 0 reads the caller's u_hat (reference layout), stage 3 writes it back in that layout.

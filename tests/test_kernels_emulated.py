@@ -159,6 +159,40 @@ def test_emulated_multi_gpu_kernel_copy(emu):
         os.environ.pop('SDNS_KCOPY_CTAS', None)
 
 
+def test_emulated_multi_gpu_graph_mode_barriers(emu):
+    """SDNS_GRAPH=1: from the second identical step on the library 'captures' the step (executed eagerly here) with
+    the barrier epochs taken from a device-resident counter and separate flag words; eager operations in between keep
+    their own epochs."""
+    L, ep = emu
+    os.environ['SDNS_GRAPH'], os.environ['SDNS_EXCHANGE'] = '1', 'ce'
+    try:
+        N, world = (16, 16, 16), 4
+        o = so.Oracle(N, dealias='3/2-rule')
+        f0 = _state(o, 'NS')
+        ref = o.solve(f0, 'NS', 3, 0.002, 0.005)
+        u = np.random.RandomState(1).standard_normal((3,)+N)
+        uh = o.forward(u)
+
+        def fn(rank, sync):
+            L.sdns_emu_set_skew(2000*rank)
+            p = ep.EmuPlan(L, N, dealias='3/2-rule', rank=rank, nranks=world)
+            p.open_peers(sync(p.handle()))
+            k1s, x0s = slice(rank*4, rank*4+4), slice(rank*4, rank*4+4)
+            e = [rel_l2(p.rk4(f0[:, :, k1s], 3, 0.002, 0.005), ref[:, :, k1s]),
+                 rel_l2(p.backward(uh[:, :, k1s]), u[:, x0s]),
+                 rel_l2(p.rk4(f0[:, :, k1s], 3, 0.002, 0.005), ref[:, :, k1s])]
+            assert not p.timed_out()
+            sync(None)
+            p.close()
+            return e
+        for e in ep.run_ranks(world, fn):
+            assert all(x < 1e-11 for x in e), e
+    finally:
+        os.environ.pop('SDNS_GRAPH', None)
+        os.environ.pop('SDNS_EXCHANGE', None)
+        L.sdns_emu_set_skew(0)
+
+
 def test_emulated_multi_gpu_chunk_counts(emu):
     _multi_case(emu, 4, 'ce', MULTI[0], '1')
     _multi_case(emu, 4, 'ce', MULTI[1], '7')
