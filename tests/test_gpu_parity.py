@@ -248,3 +248,27 @@ def test_long_axis_rhs(cfg):
     d_u, u1, u2 = p.to_device(u0), p.empty_spectral(), p.empty_spectral()
     p.rk4_step(d_u, u1, u2, 0.001, nu)
     assert rel_l2(p.to_host(d_u), o.solve(u0, 'NS', 1, 0.001, nu)) < TOL[prec]
+
+
+@pytest.mark.skipif(not os.environ.get('SDNS_TEST_NEW'), reason='lengths 60 / 90 were added after the round-1 GPU budget was spent and are '
+                    'verified on the emulator only; SDNS_TEST_NEW=1 runs them on the GPU (first call of round 2)')
+@pytest.mark.parametrize('cfg', [((60, 60, 60), 'double', '3/2-rule', 'NS'), ((60, 60, 60), 'single', '2/3-rule', 'NS'),
+                                 ((60, 16, 32), 'double', '2/3-rule', 'VV'), ((16, 90, 16), 'double', 'None', 'NS'),
+                                 ((32, 16, 60), 'single', '3/2-rule', 'VV')])
+def test_lengths_60_and_90(cfg):
+    """demo/Isotropic.py's default grid (60^3, 3/2-rule -> 90^3 padded): NS / VV ComputeRHS + one RK4 step + transforms."""
+    N, prec, dealias, solver = cfg
+    o = so.Oracle(N, precision=prec, dealias=dealias)
+    p = make_plan(N, precision=prec, dealias=dealias, solver=solver)
+    rng = np.random.RandomState(7)
+    u0 = o.forward(rng.standard_normal((3,)+tuple(N)).astype(o.float)*0.3).astype(o.complex)
+    if solver == 'VV':
+        u0 = o.cross2(o.K, u0).astype(o.complex)
+    nu = 0.01
+    ref = o.ns_rhs(u0, nu) if solver == 'NS' else o.vv_rhs(u0, nu)
+    assert rel_l2(p.to_host(p.compute_rhs(p.empty_spectral(), p.to_device(u0), nu)), ref) < TOL[prec]
+    d_u, u1, u2 = p.to_device(u0), p.empty_spectral(), p.empty_spectral()
+    p.rk4_step(d_u, u1, u2, 0.001, nu)
+    assert rel_l2(p.to_host(d_u), o.solve(u0, solver, 1, 0.001, nu)) < TOL[prec]
+    u = rng.standard_normal((3,)+tuple(N)).astype(o.float)
+    assert rel_l2(p.to_host(p.forward(p.to_device(u))), o.forward(u)) < TOL[prec]
