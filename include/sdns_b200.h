@@ -188,6 +188,11 @@ int sdns_profile_read_copies(sdns_plan* plan, double* busy_ms, double* bytes, lo
  * (kind, t_start_ms, t_end_ms, bytes); kind = kernel family 0..14, 99 = barrier, 100 + s = copy on copy stream s.
  * *nrows is the number of records available (rows may be NULL to query it).  sdns_profile_enable clears it. */
 int sdns_profile_timeline(sdns_plan* plan, double* rows, int max_rows, int* nrows);
+/* transfer-role exchange (the default for nranks > 1, csrc/xfer.cuh; replaces mpi4py-fft's Alltoallw Transfer, in-tree
+ * analogue spectralDNS3D_short.py:50-62): bytes this rank has sent over NVLink since plan creation, and how many
+ * transfer-only launches were needed for what no pass kernel could carry.  In the timeline those launches are
+ * kind 98. */
+int sdns_xfer_stats(sdns_plan* plan, double* bytes, long long* flush_launches);
 
 #ifdef __cplusplus
 }

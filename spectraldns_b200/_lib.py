@@ -24,7 +24,7 @@ SYMBOLS = ['sdns_abi_version', 'sdns_last_error', 'sdns_size_supported', 'sdns_p
            'sdns_comm_open', 'sdns_comm_status', 'sdns_forward', 'sdns_backward',
            'sdns_compute_rhs', 'sdns_compute_conv', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2', 'sdns_cross1', 'sdns_cross2_dense', 'sdns_project', 'sdns_lincomb', 'sdns_errnorm',
            'sdns_energy', 'sdns_rk4_steps_host', 'sdns_launch_count',
-           'sdns_profile_enable', 'sdns_profile_read', 'sdns_profile_read_nvlink', 'sdns_profile_read_copies', 'sdns_profile_timeline']
+           'sdns_profile_enable', 'sdns_profile_read', 'sdns_profile_read_nvlink', 'sdns_profile_read_copies', 'sdns_profile_timeline', 'sdns_xfer_stats']
 
 
 class SdnsConfig(C.Structure):
@@ -97,6 +97,7 @@ def lib():
     L.sdns_profile_read_nvlink.argtypes = [vp, i32, C.POINTER(dbl)]
     L.sdns_profile_read_copies.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(C.c_longlong)]
     L.sdns_profile_timeline.argtypes = [vp, C.POINTER(dbl), i32, C.POINTER(i32)]
+    L.sdns_xfer_stats.argtypes = [vp, C.POINTER(dbl), C.POINTER(C.c_longlong)]
     for s in SYMBOLS:
         fn = getattr(L, s)
         if s not in ('sdns_last_error',):

@@ -44,7 +44,8 @@ static int run_plain2(const StridedArgs<float>& a, cudaStream_t st) {
         const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
-    dim3 grid((unsigned)tiles, a.nfields);
+    xfer_prepare(b.x, C::smem);
+    dim3 grid((unsigned)tiles + b.x.nctas, a.nfields);
     ++sdns_debug_pair_launches;
     SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
@@ -72,7 +73,8 @@ static int run_b02(const StridedArgs<float>& a, cudaStream_t st) {
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
     ++sdns_debug_pair_launches;
-    SDNS_LAUNCH(kern, dim3((unsigned)tiles), C::P * C::TC, C::smem, st)(b);
+    xfer_prepare(b.x, C::smem);
+    SDNS_LAUNCH(kern, dim3((unsigned)tiles + b.x.nctas), C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
 static bool pair_ok_out(const StridedArgs<float>& a) {
@@ -96,7 +98,8 @@ static int run_f02(const StridedArgs<float>& a, cudaStream_t st) {
     b.in_fs /= 2; b.in_ls /= 2; b.in_os /= 2;
     const long long tiles = (b.ncols + C::TC - 1) / C::TC;
     ++sdns_debug_pair_launches;
-    SDNS_LAUNCH(kern, dim3((unsigned)tiles), C::P * C::TC, C::smem, st)(b);
+    xfer_prepare(b.x, C::smem);
+    SDNS_LAUNCH(kern, dim3((unsigned)tiles + b.x.nctas), C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
 static bool pair_ok_in(const StridedArgs<float>& a) {
@@ -147,7 +150,6 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
         const long long cap = ((long long)a.grid_cap * nsm + ny - 1) / ny;
         if (tiles > cap) tiles = cap;
     }
-    dim3 grid((unsigned)tiles, ny);
     {   // the passes address rows with 32-bit element offsets relative to the column base
         auto mag = [](long long v) { return v < 0 ? -v : v; };
         const long long big = std::max(std::max(mag(a.in_ls), mag(a.out_ls)), mag(a.out_ls2));
@@ -159,6 +161,8 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
         const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;     // shift rounded up to whole chunks
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
+    xfer_prepare(b.x, C::smem);
+    dim3 grid((unsigned)tiles + b.x.nctas, ny);
     SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
@@ -169,8 +173,10 @@ static int run_f0x(const StridedArgs<T>& a, cudaStream_t st) {
     auto kern = f0x_kernel<T, N, C::E, C::TC, MODE, C::minBlocks>;
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
-    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC));
-    SDNS_LAUNCH(kern, grid, C::threads, C::smem, st)(a);
+    StridedArgs<T> b = a;
+    xfer_prepare(b.x, C::smem);
+    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC) + b.x.nctas);
+    SDNS_LAUNCH(kern, grid, C::threads, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
 
@@ -190,8 +196,10 @@ static int run_mhd_f0(const StridedArgs<T>& a, cudaStream_t st) {
     auto kern = mhd_f0_kernel<T, N, C::E, C::TC, C::NBUF>;
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
-    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC));
-    SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(a);
+    StridedArgs<T> b = a;
+    xfer_prepare(b.x, C::smem);
+    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC) + b.x.nctas);
+    SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
 
@@ -202,8 +210,10 @@ static int run_nsdiv_f0(const StridedArgs<T>& a, cudaStream_t st) {
     auto kern = nsdiv_f0_kernel<T, N, C::E, C::TC, C::NBUF>;
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
-    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC));
-    SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(a);
+    StridedArgs<T> b = a;
+    xfer_prepare(b.x, C::smem);
+    dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC) + b.x.nctas);
+    SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
 
@@ -223,8 +233,12 @@ static int run_zx_q(const ZArgs<T>& a, cudaStream_t st) {
     }
     const long long blocks_per_sm = (long long)((a.grid_cap > 0 && a.grid_cap < occ_sm) ? a.grid_cap : occ_sm) * nsm;
     const long long want = (a.nlines + C::LPC - 1) / C::LPC;
-    dim3 grid((unsigned)(want < blocks_per_sm ? want : blocks_per_sm));
-    SDNS_LAUNCH(kern, grid, 32 * C::LPC, C::smem, st)(a);
+    ZArgs<T> b = a;
+    xfer_prepare(b.x, C::smem);
+    // the transfer CTAs take resident slots of this persistent grid
+    const long long room = std::max(blocks_per_sm - b.x.nctas, (long long)nsm);
+    dim3 grid((unsigned)(want < room ? want : room) + b.x.nctas);
+    SDNS_LAUNCH(kern, grid, 32 * C::LPC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
 
@@ -255,8 +269,11 @@ static int run_zy_q(const ZArgs<T>& a, cudaStream_t st) {
         occ_sm = occ > 0 ? occ : 1;
     }
     const long long blocks = (long long)((a.grid_cap > 0 && a.grid_cap < occ_sm) ? a.grid_cap : occ_sm) * nsm;
-    dim3 grid((unsigned)(a.nlines < blocks ? a.nlines : blocks));
-    SDNS_LAUNCH(kern, grid, C::P, smem, st)(a);
+    ZArgs<T> b = a;
+    xfer_prepare(b.x, smem);
+    const long long room = std::max(blocks - b.x.nctas, (long long)nsm);
+    dim3 grid((unsigned)(a.nlines < room ? a.nlines : room) + b.x.nctas);
+    SDNS_LAUNCH(kern, grid, C::P, smem, st)(b);
     return (int)cudaGetLastError();
 }
 
@@ -291,8 +308,10 @@ static int run_z(const ZArgs<T>& a, cudaStream_t st) {
     auto kern = z_kernel<T, M, C::E, C::LPC, MODE, C::SYNC, C::NBUF, (C::minBlocks < 1 ? 1 : C::minBlocks)>;
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
-    dim3 grid((unsigned)((a.nlines + C::LPC - 1) / C::LPC));
-    SDNS_LAUNCH(kern, grid, C::P * C::LPC, C::smem, st)(a);
+    ZArgs<T> b = a;
+    xfer_prepare(b.x, C::smem);
+    dim3 grid((unsigned)((a.nlines + C::LPC - 1) / C::LPC) + b.x.nctas);
+    SDNS_LAUNCH(kern, grid, C::P * C::LPC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@
 //       update (maths/integrators.py:150-159, cython_integrators.in:8-52).
 #pragma once
 #include "fft_core.cuh"
+#include "xfer.cuh"
 
 namespace sdns {
 
@@ -82,6 +83,7 @@ struct StridedArgs {
     V* peer_out[8];
     int self;                     // destination that uses (out_fs, out_ls, c1_out_off); all others use the second set
     long long out_fs2, out_ls2, c1_out_off2;
+    XferArgs x;                   // transfer role carried by this launch (xfer.cuh); x.nctas == 0: none
 };
 
 template <typename V> __device__ __forceinline__ V czero() { return V(); }
@@ -229,6 +231,7 @@ __global__ void __launch_bounds__((N / E) * TC, MINB)
 strided_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     const int c = threadIdx.x % TC;
@@ -239,7 +242,7 @@ strided_kernel(const StridedArgs<T> a) {
     // One tile of TC columns per CTA; launched with a capped grid (grid_cap, the multi-GPU pipeline) the CTA walks
     // the tiles with a grid stride instead, so that an NVLink-bound pass leaves SM room for the pass beside it.
     const long long ntiles = (a.ncols + TC - 1) / TC;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = bx; tile < ntiles; tile += gx) {
     const long long col = tile * TC + c;
     const bool valid = col < a.ncols;
     const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;      // c1_off / c2_off: chunked launches
@@ -417,6 +420,7 @@ plain2_kernel(const StridedArgs<float> a) {
     typedef float T;
     typedef float2x2 V;
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     const int c = threadIdx.x % TC;
     const int t = threadIdx.x / TC;
@@ -425,7 +429,7 @@ plain2_kernel(const StridedArgs<float> a) {
     constexpr int BUFSTRIDE = N * TC;
     const int f = blockIdx.y;
     const long long ntiles = (a.ncols + TC - 1) / TC;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = bx; tile < ntiles; tile += gx) {
         const long long col = tile * TC + c;
         const bool valid = col < a.ncols;
         const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;
@@ -457,6 +461,7 @@ b02_kernel(const StridedArgs<float> a) {
     typedef float2 C;
     typedef float2x2 V;
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     const int c = threadIdx.x % TC;
@@ -465,7 +470,7 @@ b02_kernel(const StridedArgs<float> a) {
     int phase = 0;
     constexpr int BUFSTRIDE = N * TC;
     const long long ntiles = (a.ncols + TC - 1) / TC;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = bx; tile < ntiles; tile += gx) {
         const long long col = tile * TC + c;
         const bool valid = col < a.ncols;
         const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;
@@ -607,6 +612,7 @@ f02_kernel(const StridedArgs<float> a) {
     typedef float T;
     typedef float2x2 V;
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     constexpr int NT = P * TC;
@@ -616,7 +622,7 @@ f02_kernel(const StridedArgs<float> a) {
     int phase = 0;
     constexpr int BUFSTRIDE = N * TC;
     V* park = sm + NBUF * BUFSTRIDE;
-    const long long col = (long long)blockIdx.x * TC + c;
+    const long long col = (long long)bx * TC + c;
     const bool valid = col < a.ncols;
     const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;
     const int c2p = valid ? (int)(col % a.cw) : 0;
@@ -661,6 +667,7 @@ __global__ void __launch_bounds__(3 * (N / E) * TC, MINB)
 f0x_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     constexpr int NT = P * TC;
@@ -668,7 +675,7 @@ f0x_kernel(const StridedArgs<T> a) {
     const int tid = threadIdx.x - g * NT;
     const int c = tid % TC;
     const int t = tid / TC;
-    const long long col = (long long)blockIdx.x * TC + c;
+    const long long col = (long long)bx * TC + c;
     const bool valid = col < a.ncols;
     const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;      // c1_off / c2_off: chunked launches
     const int c2 = valid ? (int)(col % a.cw) + a.c2_off : 0;
@@ -773,11 +780,12 @@ __global__ void __launch_bounds__((N / E) * TC)
 mhd_f0_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     const int c = threadIdx.x % TC;
     const int t = threadIdx.x / TC;
-    const long long col = (long long)blockIdx.x * TC + c;
+    const long long col = (long long)bx * TC + c;
     const bool valid = col < a.ncols;
     const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;      // c1_off / c2_off: chunked launches
     const int c2 = valid ? (int)(col % a.cw) + a.c2_off : 0;
@@ -889,11 +897,12 @@ __global__ void __launch_bounds__((N / E) * TC)
 nsdiv_f0_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = N / E;
     const int c = threadIdx.x % TC;
     const int t = threadIdx.x / TC;
-    const long long col = (long long)blockIdx.x * TC + c;
+    const long long col = (long long)bx * TC + c;
     const bool valid = col < a.ncols;
     const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;      // c1_off / c2_off: chunked launches
     const int c2 = valid ? (int)(col % a.cw) + a.c2_off : 0;
@@ -1001,7 +1010,9 @@ struct ZArgs {
     const V* tw;
     T scale;                      // applied on the r2c side (and Z_C2R output)
     int grid_cap;                 // persistent kernels: resident CTAs per SM to use (0 = all), leaves room for a concurrent pass
+    XferArgs x;                   // transfer role carried by this launch (xfer.cuh); x.nctas == 0: none
 };
+
 
 template <typename T, int M, int E, typename V>
 __device__ __forceinline__ void load_pair(V (&x)[E], const V* __restrict__ A, const V* __restrict__ B,
@@ -1053,6 +1064,7 @@ __global__ void __launch_bounds__((M / E) * LPC, MINB)
 z_kernel(const ZArgs<T> a) {
     typedef typename C2<T>::type V;
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int P = M / E;
     constexpr int PADW = 128 / (int)sizeof(V);
@@ -1060,7 +1072,7 @@ z_kernel(const ZArgs<T> a) {
     constexpr int BUFSTRIDE = LP * LPC;
     const int t = threadIdx.x % P;
     const int ln = threadIdx.x / P;
-    long long line = (long long)blockIdx.x * LPC + ln;
+    long long line = (long long)bx * LPC + ln;
     const bool valid = line < a.nlines;
     if (!valid) line = a.nlines - 1;               // keep all threads alive for the barriers
     SmemLine<1, PADW> map; map.base = ln * LP;
@@ -1315,6 +1327,7 @@ zx_kernel(const ZArgs<T> a) {
     typedef typename C2<T>::type V;
     static_assert(M / E == 32, "one warp per line");
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int PADW = 128 / (int)sizeof(V);
     constexpr int LP = M + M / PADW + 1;
@@ -1327,8 +1340,8 @@ zx_kernel(const ZArgs<T> a) {
     int phase = 0;
     const V* in = reinterpret_cast<const V*>(a.in);
     V* out = reinterpret_cast<V*>(a.out);
-    const long long stride = (long long)gridDim.x * LPC;
-    long long line = (long long)blockIdx.x * LPC + w;
+    const long long stride = (long long)gx * LPC;
+    long long line = (long long)bx * LPC + w;
     V nxt[2 * QN];
     if (line < a.nlines)
         zx_load_raw<T, QN>(nxt, in + line * a.in_ls, in + a.in_fs + line * a.in_ls, t, a.nin_keep);
@@ -1390,6 +1403,7 @@ zy_kernel(const ZArgs<T> a) {
     constexpr int P = M / E;
     static_assert(P == 64 || P == 128, "two or four warps per line");
     SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
     V* sm = reinterpret_cast<V*>(smraw);
     constexpr int PADW = 128 / (int)sizeof(V);
     constexpr int LP = M + M / PADW + 1;
@@ -1403,8 +1417,8 @@ zy_kernel(const ZArgs<T> a) {
     int phase = 0;
     const V* in = reinterpret_cast<const V*>(a.in);
     V* out = reinterpret_cast<V*>(a.out);
-    const long long stride = gridDim.x;
-    long long line = blockIdx.x;
+    const long long stride = gx;
+    long long line = bx;
     V nxt[2 * QN];
     auto load_raw = [&](V (&r)[2 * QN], const V* __restrict__ A, const V* __restrict__ B) {
 #pragma unroll

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <deque>
 #include "../../include/sdns_b200.h"
 #include "launch.cuh"
 
@@ -90,6 +91,12 @@ struct sdns_plan {
     // xmode 1: B0 / F1 write per-destination send buffers in chunks and the copy engines move each chunk over
     // NVLink (one stream per peer) while the SMs work on the next chunk.
     int xmode, nchunk, nsplit;      // nsplit: streams (copy engines) per destination rank
+    // xmode 2 (default): the send slots are moved by a transfer ROLE inside the following pass kernels (xfer.cuh):
+    // pending 2-D copies wait in `pend`; every launch of the plan stream takes rows worth xratio x its own HBM bytes.
+    std::deque<XferBatch> pend;
+    int xctas, xflush_ctas, xtma;   // transfer CTAs per carrying launch / of a transfer-only launch; bulk-async or ld/st
+    double xratio;                  // NVLink bytes a launch carries per byte of its own HBM traffic
+    double xfer_bytes; long long xfer_flushes;
     int kcopy, kcopy_ctas;          // xmode 1 variant: a grid-capped copy kernel (peer stores) instead of cudaMemcpy2DAsync
     // SDNS_GRAPH=1 (experiment, multi-GPU copy-engine mode): an RK4 step -- kernels, peer copies and their cross-stream
     // edges -- is captured once per argument set into a CUDA graph on the library's own stream and replayed, which
@@ -251,26 +258,38 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->prof = false; p->ev_used = 0;
     p->tl_on = false; p->tl_base = nullptr;
     p->kcopy = 0; p->kcopy_ctas = 32;
+#ifdef SDNS_HOST_SHIM
+    p->xctas = 2; p->xflush_ctas = 3;        // every emulated CUDA thread is an OS thread
+#else
+    p->xctas = 32; p->xflush_ctas = 128;
+#endif
+    p->xtma = 1; p->xratio = 0.16; p->xfer_bytes = 0; p->xfer_flushes = 0;
     p->use_graph = 0; p->capturing = p->gwarm = p->ghave = false; p->gstream = nullptr; p->ev_gin = p->ev_gout = nullptr; p->gexec = nullptr; p->glaunches = 0;
     p->xmode = 0; p->nchunk = 1; p->nsplit = 1; p->off_SF = 0; p->bytes_SF = 0; p->b0_preissued = false;
     p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
     if (p->P > 1) {
         const char* xm = getenv("SDNS_EXCHANGE");           // "store": peer stores fused into the passes; default: copy engines
-        p->xmode = (xm && !strcmp(xm, "store")) ? 0 : 1;
+        // default "tma": send slots + transfer role with bulk-async copies; "ldst": the role with plain loads / stores;
+        // "ce" / "kcopy": copy engines / copy kernels on side streams (round 1); "store": peer stores fused into the passes
+        p->xmode = (xm && !strcmp(xm, "store")) ? 0 : ((xm && (!strcmp(xm, "ce") || !strcmp(xm, "kcopy"))) ? 1 : 2);
+        p->xtma = (xm && !strcmp(xm, "ldst")) ? 0 : 1;
+        if (const char* v = getenv("SDNS_XCTAS")) p->xctas = std::max(1, atoi(v));
+        if (const char* v = getenv("SDNS_XFLUSH_CTAS")) p->xflush_ctas = std::max(1, atoi(v));
+        if (const char* v = getenv("SDNS_XRATIO")) p->xratio = atof(v);
         p->kcopy = (xm && !strcmp(xm, "kcopy")) ? 1 : 0;    // send slots moved by a small copy kernel instead of the copy engines
         const char* env = getenv("SDNS_CHUNKS");
-        p->nchunk = env ? atoi(env) : 4;
+        p->nchunk = env ? atoi(env) : (p->xmode == 2 ? 6 : 4);
         if (p->nchunk < 1) p->nchunk = 1;
         if (p->nchunk > 16) p->nchunk = 16;
         if (!p->xmode) p->nchunk = 1;
         if (const char* kc = getenv("SDNS_KCOPY_CTAS")) p->kcopy_ctas = std::max(1, atoi(kc));
-        if (const char* g = getenv("SDNS_GRAPH")) p->use_graph = atoi(g) != 0 && p->xmode == 1;
+        if (const char* g = getenv("SDNS_GRAPH")) p->use_graph = atoi(g) != 0 && p->xmode >= 1;
         const char* sp = getenv("SDNS_SPLIT");
         p->nsplit = sp ? atoi(sp) : 1;      // measured: one copy stream per peer saturates the link (profiles/tools/p2p_copy_bench.py)
         if (p->nsplit < 1) p->nsplit = 1;
         if (p->nsplit > 4) p->nsplit = 4;
     }
-    if (p->xmode) {
+    if (p->xmode == 1) {
         cudaError_t e1 = cudaSuccess;
         // a few copy streams shared by all destinations: one stream already drives the link at its rate
         // (profiles/tools/p2p_copy_bench.py); more only hide the per-copy start-up cost, and too many streams alias
@@ -290,12 +309,13 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
             e1 = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
             p->ev_k.push_back(e);
         }
-        if (p->use_graph && e1 == cudaSuccess) {
-            e1 = cudaStreamCreateWithFlags(&p->gstream, cudaStreamNonBlocking);
-            if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_gin, cudaEventDisableTiming);
-            if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_gout, cudaEventDisableTiming);
-        }
         if (e1 != cudaSuccess) { std::string m = std::string("copy streams/events: ") + cudaGetErrorString(e1); delete p; return fail(SDNS_ERR_CUDA, m); }
+    }
+    if (p->use_graph) {
+        cudaError_t e1 = cudaStreamCreateWithFlags(&p->gstream, cudaStreamNonBlocking);
+        if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_gin, cudaEventDisableTiming);
+        if (e1 == cudaSuccess) e1 = cudaEventCreateWithFlags(&p->ev_gout, cudaEventDisableTiming);
+        if (e1 != cudaSuccess) { std::string m = std::string("graph stream/events: ") + cudaGetErrorString(e1); delete p; return fail(SDNS_ERR_CUDA, m); }
     }
     for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_remote[i] = 0; p->prof_n[i] = 0; }
     build_spaces(p);
@@ -598,6 +618,71 @@ static int do_launch(sdns_plan* p, cudaStream_t st, int fam, int n, const void* 
     return SDNS_OK;
 }
 
+// ---- transfer role (xmode 2, xfer.cuh) ---------------------------------------------------
+namespace sdns {
+__global__ void __launch_bounds__(128) xfer_kernel(const XferOnlyArgs a) {
+    SDNS_DYN_SMEM(smraw);
+    xfer_role(a.x, smraw, blockIdx.x, gridDim.x);
+}
+}  // namespace sdns
+
+// One 2-D copy per destination, all of the same shape, queued until pass launches of the plan stream carry it.
+static int push_xfer(sdns_plan* p, int ndest, const void* const* src, void* const* dst, size_t spitch, size_t dpitch,
+                     size_t width, size_t height) {
+    if (!ndest || !width || !height) return SDNS_OK;
+    if (ndest > SDNS_XD_MAX || width >= (1ull << 32) || height >= (1ull << 32)) return fail(SDNS_ERR_ARG, "push_xfer: shape");
+    XferBatch b; memset(&b, 0, sizeof b);
+    for (int d = 0; d < ndest; ++d) {
+        b.src[d] = (const char*)src[d]; b.dst[d] = (char*)dst[d];
+        if ((((uintptr_t)src[d]) | ((uintptr_t)dst[d])) & 15) return fail(SDNS_ERR_STATE, "push_xfer: send slots must be 16-byte aligned");
+    }
+    if ((spitch | dpitch | width) & 15) return fail(SDNS_ERR_STATE, "push_xfer: rows must be multiples of 16 bytes");
+    b.spitch = spitch; b.dpitch = dpitch; b.width = (unsigned int)width; b.row0 = 0; b.nrows = (unsigned int)height; b.ndest = ndest;
+    p->pend.push_back(b);
+    p->xfer_bytes += (double)ndest * width * height;
+    return SDNS_OK;
+}
+// the launch about to be made moves `hbm_bytes` through HBM: let it carry xratio times that over NVLink
+static void attach_xfer(sdns_plan* p, XferArgs& x, double hbm_bytes) {
+    x.nctas = 0; x.nbatch = 0; x.tma = p->xtma;
+    if (p->xmode != 2 || p->pend.empty()) return;
+    double budget = hbm_bytes * p->xratio;
+    while (!p->pend.empty() && x.nbatch < SDNS_XB_MAX && budget > 0) {
+        XferBatch& j = p->pend.front();
+        const double per_row = (double)j.width * j.ndest;
+        unsigned int take = (unsigned int)std::min<double>(j.nrows, std::max(1.0, floor(budget / per_row)));
+        XferBatch t = j; t.nrows = take;
+        x.b[x.nbatch++] = t;
+        j.row0 += take; j.nrows -= take; budget -= take * per_row;
+        if (!j.nrows) p->pend.pop_front();
+    }
+    if (x.nbatch) x.nctas = p->xctas;
+}
+// everything still pending, as a launch of its own (before the barrier in front of the pass that needs the data)
+static int flush_xfer(sdns_plan* p) {
+    while (!p->pend.empty()) {
+        XferOnlyArgs a; memset(&a, 0, sizeof a);
+        a.x.tma = p->xtma;
+        while (!p->pend.empty() && a.x.nbatch < SDNS_XB_MAX) { a.x.b[a.x.nbatch++] = p->pend.front(); p->pend.pop_front(); }
+        a.x.nctas = p->xflush_ctas;
+#ifdef SDNS_HOST_SHIM
+        const size_t smem = 4096;
+#else
+        const size_t smem = 96 * 1024;
+        static bool once = false;
+        if (!once) { CUDA_TRY(cudaFuncSetAttribute(xfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
+#endif
+        xfer_prepare(a.x, smem);
+        sdns_plan::Rec r; r.fam = -2; r.bytes = 0; r.remote = 0;
+        if (p->tl_on) { r.a = get_event(p); cudaEventRecord(r.a, p->stream); }
+        SDNS_LAUNCH(xfer_kernel, a.x.nctas, 128, smem, p->stream)(a);
+        if (p->tl_on) { r.b = get_event(p); cudaEventRecord(r.b, p->stream); p->brecs.push_back(r); }
+        p->launches++; p->xfer_flushes++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return SDNS_OK;
+}
+
 // ---- typed pipeline --------------------------------------------------------------------
 struct Rng { int a, b; };     // half-open index range of a chunked launch; a < 0: the whole axis
 
@@ -675,6 +760,7 @@ struct Pipe {
         const double bytes = (nf * cols * (q.bmap[0].nlo + q.bmap[0].nhi) + nfo * cols * q.M[0]) * p->cs;
         if (a.ncols == 0) return SDNS_OK;              // this rank owns no mode that survives the truncation
         const double remote = staged ? 0 : nfo * cols * q.M[0] * p->cs * (p->P - 1) / p->P;   // stored into peers over NVLink
+        attach_xfer(p, a.x, bytes);
         return do_launch(p, st, fam, q.M[0], &a, bytes, remote);
     }
     // B1: A (W0) -> B as W1 (nf, M0l, M1, K2p)
@@ -691,6 +777,7 @@ struct Pipe {
         a.tw = tw(q.M[1]); a.nfields = nf;
         a.pairable = (k2.a == 0 && k2.b == q.K2n);      // rows are K2n columns + padding up to the even pitch K2p
         const double bytes = (double)nf * q.M0l * a.cw * ((double)q.K1n + q.M[1]) * p->cs;
+        attach_xfer(p, a.x, bytes);
         return do_launch(p, st, FAM_PLAIN_BWD, q.M[1], &a, bytes);
     }
     // Z: B (W1) -> A as W2 (nfo, M0l, M1, Nhp)   [fused], or to/from user real arrays [plain].
@@ -715,6 +802,7 @@ struct Pipe {
         const double bin = in_is_W1 ? (double)q.K2n * p->cs : (double)q.M[2] * p->rs;
         const double bout = out_is_W2 ? (double)p->Nh * p->cs : (double)q.M[2] * p->rs;
         if (a.nlines == 0) return SDNS_OK;
+        attach_xfer(p, a.x, (double)a.nlines * (nin * bin + nout * bout));
         return do_launch(p, st, fam, q.M[2], &a, (double)a.nlines * (nin * bin + nout * bout));
     }
     // F1: A (W2) -> W3 (nf, N1l, M0, Nhp) of the rank owning each k1.  x0 is the second-fastest axis of
@@ -738,6 +826,7 @@ struct Pipe {
         const double bytes = (double)nf * (x0.b - x0.a) * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
         const double remote = staged ? 0 : (double)nf * (x0.b - x0.a) * p->Nh * p->N[1] * p->cs * (p->P - 1) / p->P;
         if (a.ncols == 0) return SDNS_OK;
+        attach_xfer(p, a.x, bytes);
         return do_launch(p, st, FAM_PLAIN_FWD, q.M[1], &a, bytes, remote);
     }
     // F0 geometry: W3 -> local dense spectral, k2 columns [k2.a, k2.b)
@@ -842,6 +931,7 @@ static int launch_f0(sdns_plan* p, Pipe<T>& P, const void* u_hat, double nu, dou
     const double dense = (double)p->N[0] * w * p->cs;
     const double bytes = (double)nprod * w * P.q.M[0] * p->cs + stt * ns * dense
                          + (so.source ? ns * dense : 0) + (so.p_hat ? dense : 0);
+    attach_xfer(p, a.x, bytes);
     return do_launch(p, P.st, fam, P.q.M[0], &a, bytes);
 }
 
@@ -889,6 +979,7 @@ static int copy_rows(sdns_plan* p, int r, cudaEvent_t after, void* dst, size_t d
 }
 // the plan stream waits until every copy stream has drained, then the cross-GPU barrier
 static int join_copies(sdns_plan* p) {
+    if (p->xmode == 2) { int e = flush_xfer(p); if (e) return e; return xbarrier(p); }
     for (size_t si = 0; si < p->ys.size(); ++si) {
         if (!p->ys[si]) continue;
         CUDA_TRY(cudaEventRecord(p->ev_y[si], p->ys[si]));
@@ -933,16 +1024,22 @@ static int b0_chunk_ce(sdns_plan* p, Pipe<T>& P, const void* u_hat, bool work_la
     P.st = p->stream;
     if (kept.b > kept.a)
         if ((e = P.b0(fam, reinterpret_cast<const V*>(u_hat), nfin, 0, work_layout, Rng{-1, 0}, kept, true))) return e;
-    CUDA_TRY(cudaEventRecord(p->ev_k[c], p->stream));
+    if (p->xmode == 1) CUDA_TRY(cudaEventRecord(p->ev_k[c], p->stream));
     if (kept.b <= kept.a) return SDNS_OK;
     const size_t cs = p->cs;
+    const void* srcs[SDNS_XD_MAX]; void* dsts[SDNS_XD_MAX];
     for (int k = 1; k < p->P; ++k) {
         const int r = (p->rank + k) % p->P;
         const V* src = P.B + r * P.b0_slot() + (long long)kept.a * q.K2p;
         V* dst = reinterpret_cast<V*>(p->peer_ws[r] + p->off_A) + ((long long)q.c1off + kept.a) * q.K2p;
-        if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.K1n * q.K2p * cs, src, (size_t)q.K1l * q.K2p * cs,
-                           (size_t)(kept.b - kept.a) * q.K2p * cs, (size_t)6 * q.M0l))) return e;
+        srcs[k - 1] = src; dsts[k - 1] = dst;
+        if (p->xmode == 1)
+            if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.K1n * q.K2p * cs, src, (size_t)q.K1l * q.K2p * cs,
+                               (size_t)(kept.b - kept.a) * q.K2p * cs, (size_t)6 * q.M0l))) return e;
     }
+    if (p->xmode == 2)
+        return push_xfer(p, p->P - 1, srcs, dsts, (size_t)q.K1l * q.K2p * cs, (size_t)q.K1n * q.K2p * cs,
+                         (size_t)(kept.b - kept.a) * q.K2p * cs, (size_t)6 * q.M0l);
     return SDNS_OK;
 }
 
@@ -973,14 +1070,20 @@ static int rhs_ce(sdns_plan* p, const void* u_hat, double nu, double eta, const 
         if (x0.b <= x0.a) continue;
         if ((e = P.z(solver == SDNS_MHD ? FAM_Z_MHD : FAM_Z_CROSS, P.B, P.A, 6, true, true, x0))) return e;
         if ((e = P.f1(nprod, nullptr, x0, true))) return e;
-        CUDA_TRY(cudaEventRecord(p->ev_k[c], p->stream));
+        if (p->xmode == 1) CUDA_TRY(cudaEventRecord(p->ev_k[c], p->stream));
+        const void* srcs[SDNS_XD_MAX]; void* dsts[SDNS_XD_MAX];
         for (int k = 1; k < p->P; ++k) {
             const int r = (p->rank + k) % p->P;
             const V* src = P.send_f1() + r * P.f1_slot(nprod) + (long long)x0.a * p->Nhp;
             V* dst = reinterpret_cast<V*>(p->peer_ws[r] + p->off_C) + ((long long)p->rank * q.M0l + x0.a) * p->Nhp;
-            if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.M[0] * p->Nhp * cs, src, (size_t)q.M0l * p->Nhp * cs,
-                               (size_t)(x0.b - x0.a) * p->Nhp * cs, (size_t)nprod * p->N1l))) return e;
+            srcs[k - 1] = src; dsts[k - 1] = dst;
+            if (p->xmode == 1)
+                if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.M[0] * p->Nhp * cs, src, (size_t)q.M0l * p->Nhp * cs,
+                                   (size_t)(x0.b - x0.a) * p->Nhp * cs, (size_t)nprod * p->N1l))) return e;
         }
+        if (p->xmode == 2)
+            if ((e = push_xfer(p, p->P - 1, srcs, dsts, (size_t)q.M0l * p->Nhp * cs, (size_t)q.M[0] * p->Nhp * cs,
+                               (size_t)(x0.b - x0.a) * p->Nhp * cs, (size_t)nprod * p->N1l))) return e;
     }
     if ((e = join_copies(p))) return e;
     for (int c = 0; c < nc; ++c) {
@@ -1139,7 +1242,7 @@ extern "C" int sdns_rk4_step(sdns_plan* p, void* u_hat, void* u1, void* u2, doub
                              double eta, const void* source) {
     int e = need_ws(p); if (e) return e;
     if (!u_hat || !u1 || !u2) return fail(SDNS_ERR_ARG, "sdns_rk4_step: null array");
-    if (p->use_graph && p->P > 1 && p->xmode == 1 && !p->prof) return rk4_step_graph(p, u_hat, u1, u2, dt, nu, eta, source);
+    if (p->use_graph && p->P > 1 && p->xmode >= 1 && !p->prof) return rk4_step_graph(p, u_hat, u1, u2, dt, nu, eta, source);
     return rk4_step_eager(p, u_hat, u1, u2, dt, nu, eta, source);
 }
 
@@ -1457,7 +1560,7 @@ extern "C" int sdns_profile_read(sdns_plan* p, int family, double* total_ms, lon
             p->timeline.push_back(kind); p->timeline.push_back(t0); p->timeline.push_back(t1); p->timeline.push_back(bytes);
         };
         for (const sdns_plan::Rec& r : p->recs) row(r.fam, r.a, r.b, r.bytes);
-        for (const sdns_plan::Rec& r : p->brecs) row(99, r.a, r.b, 0);
+        for (const sdns_plan::Rec& r : p->brecs) row(r.fam == -2 ? 98 : 99, r.a, r.b, 0);
         for (const sdns_plan::CRec& r : p->crecs) row(100 + r.s, r.a, r.b, r.bytes);
     }
     p->recs.clear(); p->crecs.clear(); p->brecs.clear(); p->ev_used = 0;
@@ -1481,6 +1584,13 @@ extern "C" int sdns_profile_read_copies(sdns_plan* p, double* busy_ms, double* b
     if (busy_ms) *busy_ms = mx;
     if (bytes) *bytes = p->copy_bytes;
     if (ncopies) *ncopies = p->copy_n;
+    return SDNS_OK;
+}
+
+extern "C" int sdns_xfer_stats(sdns_plan* p, double* bytes, long long* flushes) {
+    if (!p) return fail(SDNS_ERR_ARG, "sdns_xfer_stats: null plan");
+    if (bytes) *bytes = p->xfer_bytes;
+    if (flushes) *flushes = p->xfer_flushes;
     return SDNS_OK;
 }
 

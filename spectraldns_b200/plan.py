@@ -276,7 +276,7 @@ class Plan(object):
         out = []
         for i in range(min(n.value, m.value)):
             k = int(buf[4*i])
-            name = self.FAMILIES[k] if 0 <= k < len(self.FAMILIES) else ('barrier' if k == 99 else 'copy%d' % (k-100))
+            name = self.FAMILIES[k] if 0 <= k < len(self.FAMILIES) else ('barrier' if k == 99 else ('xfer' if k == 98 else 'copy%d' % (k-100)))
             out.append((name, buf[4*i+1], buf[4*i+2], buf[4*i+3]))
         return out
 
@@ -291,6 +291,12 @@ class Plan(object):
                 _lib.check(self.lib.sdns_profile_read_nvlink(self._p, i, C.byref(r)))
                 out[name] = (ms.value, n.value, b.value, r.value)
         return out
+
+    def xfer_stats(self):
+        """(bytes this rank has sent over NVLink through the transfer role since plan creation, transfer-only launches)."""
+        b, n = C.c_double(), C.c_longlong()
+        _lib.check(self.lib.sdns_xfer_stats(self._p, C.byref(b), C.byref(n)))
+        return b.value, n.value
 
     def profile_read_copies(self):
         """(busy_ms of the busiest per-peer copy stream, bytes sent over NVLink, number of copies) since

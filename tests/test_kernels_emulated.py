@@ -133,14 +133,28 @@ MULTI = [((16, 16, 16), 'double', '2/3-rule', 'NS'), ((16, 16, 16), 'double', '3
 PICK = {2: (2, 6), 4: (3, 7), 8: (1, 5)}
 
 
-@pytest.mark.parametrize('exchange', ['ce', 'store'])
+@pytest.mark.parametrize('exchange', ['tma', 'ce', 'store'])
 @pytest.mark.parametrize('world', [2, 4, 8])
 def test_emulated_multi_gpu_schedule(emu, world, exchange):
+    """'tma' (the default): send slots moved by the transfer role inside the following pass kernels (csrc/xfer.cuh;
+    the bulk-async copies are memcpys here, the ring / piece bookkeeping runs unchanged)."""
     for i in PICK[world][:1 if (world == 8 and exchange == 'store') else None]:
-        _multi_case(emu, world, exchange, MULTI[i])
+        _multi_case(emu, world, exchange, MULTI[i], chunks='6' if exchange == 'tma' else '4')
 
 
-@pytest.mark.parametrize('exchange', ['ce', 'store'])
+def test_emulated_multi_gpu_transfer_role_variants(emu):
+    """plain load / store transfer role; a budget so small that most of the exchange ends up in transfer-only launches;
+    one so large that the first pass after a chunk carries all of it."""
+    _multi_case(emu, 4, 'ldst', MULTI[3], chunks='3')
+    for ratio in ('0.01', '10'):
+        os.environ['SDNS_XRATIO'] = ratio
+        try:
+            _multi_case(emu, 4, 'tma', MULTI[1], chunks='5')
+        finally:
+            os.environ.pop('SDNS_XRATIO', None)
+
+
+@pytest.mark.parametrize('exchange', ['tma', 'ce', 'store'])
 def test_emulated_multi_gpu_skewed_ranks(emu, exchange):
     """One end of the rank range is made systematically slower (a delay before each of its launches): any operation
     that stores into a peer before that peer has finished reading the buffer shows up as a wrong result."""
