@@ -2,13 +2,18 @@
 """bench.py -- time per RK4 step and grid-points*steps/s of the pseudo-spectral NS hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--grid 256] [--precision double|single] [--dealias 2/3-rule|3/2-rule]
+                    [--grid 512] [--precision double|single] [--dealias 2/3-rule|3/2-rule]
                     [--solver NS|VV|MHD]
 
-Default workload = BASELINE.json configs[1]: Taylor-Green NS 256^3 double, RK4, 2/3-rule, 1 B200.
+Default workload: Taylor-Green NS 512^3 double, RK4, 2/3-rule on 1 B200 -- the first size BASELINE.json's metric is
+quoted on (512^3 / 1024^3 / 2048^3); weak scaling doubles one axis per doubling of the GPU count, so N = 8 is the
+1024^3 north-star configuration.  `--grid 256` is BASELINE configs[1].
 One "step" = one RK4 step (4 right-hand sides = 36 scalar 3-D FFTs + fused pointwise work).
-Rank 0 prints ONE JSON line.  --impl reference times the CPU oracle port (numpy + scipy.fft with
-all host threads; the reference's own stack -- shenfun/mpi4py/pyfftw -- is absent from the image).
+Rank 0 prints ONE JSON line.  Before the timed region every rank runs a small parity gate (64^3 NS and MHD, one
+right-hand side and two RK4 steps on a broadband field) against the CPU oracle and the run fails if it is off.
+--impl reference times the reference's OWN solver modules (solvers/NS.py, maths/integrators.py, its Cython kernels
+compiled into oracle/_ref, all staged under baseline/_ref by oracle/stage_reference_scripts.sh) over the numpy
+stand-ins for the absent shenfun / mpi4py-fft (oracle/shim, pocketfft with all host threads).
 """
 import argparse
 import json
@@ -28,10 +33,10 @@ NU, DT = 0.000625, 0.01       # tests/TG.py:131-133 of the reference
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=('ours', 'reference'))
-    ap.add_argument('--grid', type=int, default=256)
+    ap.add_argument('--grid', type=int, default=512)
     ap.add_argument('--precision', default='double', choices=('single', 'double'))
     ap.add_argument('--dealias', default='2/3-rule', choices=('2/3-rule', '3/2-rule', 'None'))
     ap.add_argument('--solver', default='NS', choices=('NS', 'VV', 'MHD'))
@@ -39,6 +44,7 @@ def parse():
                     help='N>1: weak = grid grows with the GPU count (per-GPU work fixed), strong = fixed grid')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
+    ap.add_argument('--no-parity', action='store_true', help='skip the parity gate and the field-level check at size')
     ap.add_argument('--timeline', default=None,
                     help='write PATH.rank<r>.json: start/end of every kernel, peer copy and barrier of one RK4 step')
     return ap.parse_args()
@@ -73,57 +79,206 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU oracle port (also the --impl reference arm)
+# The reference's own CPU implementation of the path (cpu_baseline leg and --impl reference arm)
 # ---------------------------------------------------------------------------------------------
-def cpu_oracle_steps(a, N, max_steps, max_seconds, warm=0):
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+def model_bytes(a, N):
+    """SURVEY.md section 8(d) three-pass model: bytes one RK4 step moves when every scalar 3-D transform is three
+    axis passes that read and write their array once and only the stage update costs extra (276 F for NS / VV with
+    the 2/3 rule, 487.5 F with 3/2 padding, 480 F / 832.5 F for MHD; F = one complex field at the unpadded size)."""
+    F = float(N[0])*N[1]*(N[2]//2+1)*(16 if a.precision == 'double' else 8)
+    per_transform = 11.875 if a.dealias == '3/2-rule' else 6.0
+    ntr, nst = (15, 30.0) if a.solver == 'MHD' else (9, 15.0)
+    return 4*(ntr*per_transform + nst)*F
+
+
+def _reference_modules():
+    """Import the UNMODIFIED reference package staged under baseline/_ref over oracle/shim.  Returns None when it
+    has not been staged (then the callers fall back to the numpy port in oracle/sdns_oracle.py)."""
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.exists(os.path.join(ref, 'spectralDNS', 'solvers', 'NS.py')):
+        return None
+    for p in (ref, os.path.join(ROOT, 'oracle', 'shim')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:
+        import spectralDNS as ref_pkg
+        from spectralDNS import config, get_solver, solve
+    except Exception as e:                                  # pragma: no cover
+        sys.stderr.write('reference package not importable: %r\n' % (e,))
+        return None
+    if 'baseline' not in os.path.abspath(ref_pkg.__file__):
+        return None                                         # the drop-in `spectralDNS` got in first: not the reference
+    return config, get_solver, solve
+
+
+def reference_steps(a, Ns, nsteps, warm, want_state=False):
+    """Run the reference solver (its get_solver / get_context / solve loop, --optimization cython) for warm + nsteps
+    RK4 steps of the Taylor-Green problem on an Ns^3-type grid; per-step wall times from its own Timer hook.
+    Returns (seconds per step over the timed steps, fastest step, kind, final spectral state or None)."""
+    import contextlib
+    import io
     import numpy as np
-    import sdns_oracle as so
-    o = so.Oracle(N, precision=a.precision, dealias=a.dealias)
-    if a.solver == 'MHD':
-        u = o.forward(so.taylor_green_mhd(o))
-    else:
-        u = o.forward(so.taylor_green(o))
+    mods = _reference_modules()
+    M = [int(round(np.log2(n))) for n in Ns]
+    if mods is None or any(2**m != n for m, n in zip(M, Ns)):
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import sdns_oracle as so
+        o = so.Oracle(Ns, precision=a.precision, dealias=a.dealias)
+        u = o.forward(so.taylor_green_mhd(o) if a.solver == 'MHD' else so.taylor_green(o))
         if a.solver == 'VV':
             u = o.cross2(o.K, u)
-    eta = 0.01
-    for _ in range(warm):
-        u = o.solve(u, a.solver, 1, DT, NU, eta=eta)
-    t0 = time.perf_counter()
-    n = 0
-    while n < max_steps:
-        u = o.solve(u, a.solver, 1, DT, NU, eta=eta)
-        n += 1
-        if time.perf_counter() - t0 > max_seconds:
-            break
-    dt = (time.perf_counter() - t0)/n
-    assert np.isfinite(u).all()
-    return dt, n, os.cpu_count()
+        ts = []
+        for _ in range(warm + nsteps):
+            t0 = time.perf_counter()
+            u = o.solve(u, a.solver, 1, DT, NU, eta=0.01)
+            ts.append(time.perf_counter() - t0)
+        ts = ts[warm:]
+        return sum(ts)/len(ts), min(ts), 'port', (u if want_state else None)
+    config, get_solver, solve = mods
+    config.update({'nu': NU, 'dt': DT, 'T': DT*(warm + nsteps), 'eta': 0.01,
+                   'convection': 'Divergence' if a.solver == 'MHD' else 'Vortex'})
+    with contextlib.redirect_stdout(io.StringIO()):
+        solver = get_solver(parse_args=['--M'] + [str(m) for m in M] +
+                            ['--precision', a.precision, '--dealias', a.dealias, '--optimization', 'cython',
+                             '--integrator', 'RK4', a.solver])
+        ctx = solver.get_context()
+    X = ctx.X
+    U = ctx.UB if a.solver == 'MHD' else ctx.U
+    U[:] = 0
+    U[0] = np.sin(X[0])*np.cos(X[1])*np.cos(X[2])
+    U[1] = -np.cos(X[0])*np.sin(X[1])*np.cos(X[2])
+    if a.solver == 'MHD':
+        U[3] = np.sin(X[0])*np.sin(X[1])*np.cos(X[2])
+        U[4] = np.cos(X[0])*np.cos(X[1])*np.cos(X[2])
+    uh = ctx.UB_hat if a.solver == 'MHD' else ctx.U_hat
+    space = ctx.VM if a.solver == 'MHD' else ctx.VT
+    uh[:] = space.forward(U, uh) if hasattr(space, 'forward') else uh
+    if a.solver == 'VV':
+        ctx.W_hat = solver.cross2(ctx.W_hat, ctx.K, ctx.U_hat)
+    stamps = []
+
+    class StepTimer(solver.Timer):                          # the reference's own per-step hook (utilities/__init__.py:33-39)
+        def __call__(self):
+            super().__call__()
+            stamps.append(time.perf_counter())
+    solver.Timer = StepTimer
+    config.params.t = 0.0
+    config.params.tstep = 0
+    t_start = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        solve(solver, ctx)
+    assert len(stamps) == warm + nsteps, (len(stamps), warm, nsteps)
+    ts = [b - a_ for a_, b in zip([t_start] + stamps[:-1], stamps)][warm:]
+    state = None
+    if want_state:
+        state = np.array(ctx.W_hat if a.solver == 'VV' else uh)
+    return sum(ts)/len(ts), min(ts), 'reference', state
+
+
+def sample_grid(a, N, budget_s, nsteps):
+    """Largest grid N / 2^j whose (nsteps) reference steps fit the time budget, from a 64^3-type probe step and
+    N log N scaling (the CPU sample of a workload too large to step on the host within the bench's time box)."""
+    import numpy as np
+    probe = tuple(max(32, n//(N[0]//64)) if N[0] > 64 else n for n in N)
+    t, _, _, _ = reference_steps(a, probe, 1, 1)
+    pts = lambda g: float(g[0])*g[1]*g[2]*np.log2(float(g[0])*g[1]*g[2])
+    g = tuple(N)
+    while g[0] > probe[0] and 1.6*t*pts(g)/pts(probe)*nsteps > budget_s:     # 1.6: large grids fall out of cache
+        g = tuple(n//2 for n in g)
+    return g
 
 
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    # bounded: stop after ~150 s of timed work whatever K is
-    warm = 1 if a.warmup > 0 else 0
     N = grid_for(a, max(1, a.gpus))
-    spt, n, cores = cpu_oracle_steps(a, N, a.steps, 150.0, warm=warm)
-    pts = float(N[0])*N[1]*N[2]
+    warm, steps = max(a.warmup, 0), max(a.steps, 1)
+    Ns = sample_grid(a, N, 150.0, warm + steps)
+    spt, fastest, kind, _ = reference_steps(a, Ns, steps, warm)
+    pts = float(Ns[0])*Ns[1]*Ns[2]
     val = pts/spt
+    note = ('the reference\'s own solvers/%s.py + maths/integrators.py RK4 + its Cython kernels (--optimization cython) over the '
+            'numpy stand-ins for shenfun / mpi4py-fft (scipy.fft pocketfft, all host threads, single rank); the reference\'s '
+            'FFTW / MPI stack is absent from the image' % a.solver) if kind == 'reference' else (
+            'numpy port of the reference path (oracle/sdns_oracle.py): the staged reference package was not found')
     line = {
         'impl': 'reference', 'metric': 'grid_points_steps_per_s', 'value': val, 'unit': 'points*steps/s',
-        'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': spt*1e3,
+        'n_gpus': a.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': spt*1e3,
         'higher_is_better': True, 'scaling': a.scaling if a.gpus > 1 else 'weak', 'vs_baseline': None,
         'dtype': 'f64' if a.precision == 'double' else 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(a, N), 'grid': list(N), 'integrator': 'RK4',
-                   'note': 'CPU oracle port of the reference path (numpy + scipy.fft pocketfft, workers=all cores, '
-                           'single rank); the reference stack shenfun/mpi4py-fft/pyfftw/mpirun is absent from the image'},
-        'cpu_baseline': {'value': val, 'unit': 'points*steps/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d full RK4 steps of the %dx%dx%d workload (%d warm-up)' % (n, N[0], N[1], N[2], warm)},
+        'config': {'workload': workload_name(a, N), 'grid': list(N), 'integrator': 'RK4', 'note': note},
+        'cpu_baseline': {'value': val, 'unit': 'points*steps/s', 'cores': os.cpu_count(), 'kind': kind,
+                         'fastest_step_ms': fastest*1e3,
+                         'sample': ('%d timed + %d warm-up full RK4 steps of the same problem on a %dx%dx%d grid' % ((steps, warm) + tuple(Ns))) +
+                                   ('' if tuple(Ns) == tuple(N) else ' (the %dx%dx%d workload itself does not fit the time box on the '
+                                    'host; points*steps/s is size-normalised)' % tuple(N))},
         'e2e': {'value': val, 'unit': 'points*steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# parity: the CPU oracle as the checker of the GPU path, inside the run the driver makes
+# ---------------------------------------------------------------------------------------------
+def parity_gate(rank, world, local):
+    """64^3 NS (double and single) and MHD: one right-hand side and two RK4 steps on a seeded broadband field, every
+    rank against its slab of the single-process oracle.  Returns {case: rel L2}, the largest ratio err / tol."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import sdns_oracle as so
+    from spectraldns_b200.plan import Plan
+    out, worst = {}, 0.0
+    for N, prec, dealias, solver in (((64, 64, 64), 'double', '2/3-rule', 'NS'), ((64, 64, 64), 'double', '2/3-rule', 'MHD'),
+                                     ((64, 64, 64), 'single', '3/2-rule', 'NS')):
+        tol = 1e-11 if prec == 'double' else 1e-4
+        o = so.Oracle(N, precision=prec, dealias=dealias)
+        p = Plan(N, precision=prec, dealias=dealias, solver=solver, device=local, rank=rank, nranks=world)
+        nc = 6 if solver == 'MHD' else 3
+        f0 = so.isotropic_field(o, seed=3, ncomp=nc).astype(o.complex)
+        N1l = N[1]//world
+        k1s = slice(rank*N1l, (rank+1)*N1l)
+        nu, eta, dt = 0.005, 0.01, 0.002
+        r_ref = o.ns_rhs(f0, nu) if solver == 'NS' else o.mhd_rhs(f0, nu, eta)
+        d_u = p.to_device(f0[:, :, k1s])
+        rhs = p.to_host(p.compute_rhs(p.empty_spectral(), d_u, nu, eta))
+        u1, u2 = p.empty_spectral(), p.empty_spectral()
+        for _ in range(2):
+            p.rk4_step(d_u, u1, u2, dt, nu, eta)
+        s_ref = o.solve(f0, solver, 2, dt, nu, eta=eta)
+        rel = lambda x, y: float(np.linalg.norm((x.astype(np.complex128) - y).ravel())/np.linalg.norm(y.ravel()))
+        e = max(rel(rhs, r_ref[:, :, k1s]), rel(p.to_host(d_u), s_ref[:, :, k1s]))
+        if p.comm_timed_out():
+            e = float('inf')
+        out['%s_%d_%s_%s' % (solver, N[0], prec, dealias)] = e
+        worst = max(worst, e/tol)
+        del p
+    return out, worst
+
+
+def state_parity(a, Ns, ref_state, nsteps):
+    """The same Taylor-Green run on the GPU path (host field -> forward -> nsteps RK4 steps) against the reference
+    solver's final spectral state: relative L2 over the whole field."""
+    import numpy as np
+    from spectraldns_b200.plan import Plan
+    p = Plan(Ns, precision=a.precision, dealias=a.dealias, solver=a.solver)
+    X = np.meshgrid(*[np.arange(n)*2*np.pi/n for n in Ns], indexing='ij')
+    U = np.zeros((p.ncomp,) + tuple(Ns), dtype=p.float)
+    U[0] = np.sin(X[0])*np.cos(X[1])*np.cos(X[2])
+    U[1] = -np.cos(X[0])*np.sin(X[1])*np.cos(X[2])
+    if a.solver == 'MHD':
+        U[3] = np.sin(X[0])*np.sin(X[1])*np.cos(X[2])
+        U[4] = np.cos(X[0])*np.cos(X[1])*np.cos(X[2])
+    u = p.forward(p.to_device(U))
+    if a.solver == 'VV':
+        u = p.cross2(p.empty_spectral(), u)
+    u1, u2 = p.empty_spectral(), p.empty_spectral()
+    for _ in range(nsteps):
+        p.rk4_step(u, u1, u2, DT, NU, 0.01)
+    got = p.to_host(u).astype(np.complex128)
+    err = float(np.linalg.norm((got - ref_state).ravel())/np.linalg.norm(ref_state.ravel()))
+    tol = 1e-11 if a.precision == 'double' else 1e-4
+    return {'grid': list(Ns), 'steps': nsteps, 'rel_l2_vs_reference_solver': err, 'tol': tol, 'ok': bool(err < tol)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -191,6 +346,20 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    parity = None
+    if not a.no_parity:
+        cases, worst = parity_gate(rank, world, local)
+        t = torch.tensor([worst], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity = {'rel_l2': cases, 'tol': {'double': 1e-11, 'single': 1e-4}, 'worst_err_over_tol_all_ranks': float(t.item()),
+                  'what': 'GPU path vs CPU oracle (oracle/sdns_oracle.py), seeded broadband field, 1 RHS + 2 RK4 steps, '
+                          'every rank its slab; rank 0 values shown'}
+        if not float(t.item()) < 1.0:
+            if rank == 0:
+                print(json.dumps({'error': 'parity gate failed', 'parity': parity}))
+            raise SystemExit(3)
 
     N = grid_for(a, world)
     p = Plan(N, precision=a.precision, dealias=a.dealias, solver=a.solver, device=local,
@@ -293,14 +462,9 @@ def run_ours(a):
     kern = max(prof, key=lambda k: prof[k][0])
     kms, kn, kb = prof[kern][:3]
     achieved = kb/kms*1e-6 if kms > 0 else 0.0       # bytes/ms -> GB/s
-    traffic = None
-    tf = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tf):
-        try:
-            traffic = json.load(open(tf)).get('%s_%d_%s' % (kern, a.grid, a.precision))
-        except Exception:
-            traffic = None
+    traffic = None          # DRAM bytes need an ncu capture: the per-round captures are summarised under profiles/
     step_bytes = sum(v[2] for v in prof.values())/npf
+    mbytes = model_bytes(a, N)/world
     line = {
         'metric': 'grid_points_steps_per_s', 'value': value, 'unit': 'points*steps/s',
         'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms,
@@ -323,6 +487,7 @@ def run_ours(a):
                 'h2d_bytes_per_step': state_bytes*world, 'd2h_bytes_per_step': state_bytes*world,
                 'call': 'sdns_rk4_steps_host: pinned host state -> device, one RK4 step, device -> host'},
         'gpu_launches': launches,
+        'parity': parity,
         'roofline': {'bound': 'hbm', 'kernel': kern, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved/peak, 'traffic': traffic, 'peak_source': peak_src,
                      'kernel_share_of_step': kms/tot if tot else None,
@@ -330,6 +495,8 @@ def run_ours(a):
                      'step_algorithmic_GB': step_bytes*1e-9,
                      'step_achieved_GBps': step_bytes*1e-9/(ms*1e-3),
                      'step_frac': step_bytes*1e-9/(ms*1e-3)/peak,
+                     'survey_8d_model_GB_per_gpu': mbytes*1e-9,
+                     'survey_8d_model_frac': mbytes*1e-9/(ms*1e-3)/peak,
                      'all_kernels': {k: {'ms_per_launch': v[0]/v[1], 'launches_per_step': v[1]/npf,
                                          'GBps': v[2]/v[0]*1e-6, 'share': v[0]/tot} for k, v in prof.items()}},
     }
@@ -368,11 +535,20 @@ def run_ours(a):
                           'note': 'transposes are peer stores issued by the FFT pass in front of them, so the '
                                   'kernel time also covers that pass\'s local HBM traffic'}
     if world == 1 and not a.no_cpu_baseline:
-        spt, n, cores = cpu_oracle_steps(a, N, 50, a.cpu_seconds)
-        line['cpu_baseline'] = {'value': pts/spt, 'unit': 'points*steps/s', 'cores': cores, 'kind': 'port',
-                                'ms_per_step': spt*1e3,
-                                'sample': '%d full RK4 steps of the same %d^3 workload with the numpy/scipy.fft '
-                                          'oracle (workers=all cores)' % (n, a.grid)}
+        # the reference's own solver on the host cores, bounded: 2 timed RK4 steps on the largest grid N / 2^j that
+        # fits ~cpu_seconds; its final state is also the field-level parity reference for the GPU path at that size
+        Ns = sample_grid(a, N, a.cpu_seconds, 3)
+        spt, fastest, kind, ref_state = reference_steps(a, Ns, 2, 1, want_state=not a.no_parity)
+        spts = float(Ns[0])*Ns[1]*Ns[2]
+        line['cpu_baseline'] = {'value': spts/spt, 'unit': 'points*steps/s', 'cores': os.cpu_count(), 'kind': kind,
+                                'ms_per_step': spt*1e3, 'fastest_step_ms': fastest*1e3,
+                                'sample': '2 timed + 1 warm-up full RK4 steps of the same Taylor-Green problem on a %dx%dx%d grid '
+                                          'with the reference\'s own solver modules + Cython kernels over scipy.fft (all host '
+                                          'threads); points*steps/s is size-normalised' % tuple(Ns)}
+        if ref_state is not None:
+            del p, u, u1, u2
+            torch.cuda.empty_cache()
+            line['parity']['at_size'] = state_parity(a, Ns, ref_state, 3)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -45,9 +45,12 @@ def _run(cmd):
     return r.stdout
 
 
-def build(force=False, jobs=None, verbose=False, sizes=None, out=None, precs=(32, 64)):
-    """Compile every CUDA translation unit for sm_100a and link libsdns_b200.so."""
+def build(force=False, jobs=None, verbose=False, sizes=None, out=None, precs=(32, 64), families=None):
+    """Compile every CUDA translation unit for sm_100a and link libsdns_b200.so.
+    families (experiment variants only): compile just these kernel families with SDNS_EXTRA_FLAGS and take every
+    other object from the up-to-date default build."""
     global OBJ, LIB
+    main_obj = OBJ
     if out:                                                      # experiment variant: its own objects and library
         OBJ = os.path.join(HERE, 'build', 'variant_' + os.path.basename(out))
         LIB = out
@@ -64,21 +67,28 @@ def build(force=False, jobs=None, verbose=False, sizes=None, out=None, precs=(32
     nvcc = _nvcc()
     jobs = jobs or os.cpu_count() or 4
     units = []
+    reuse = []
     for fam in range(NFAM):
         for prec in (32, 64):
+            if out and families is not None and fam not in families:
+                reuse.append(os.path.join(main_obj, 'inst_%d_f%d.o' % (fam, prec)))
+                continue
             o = os.path.join(OBJ, 'inst_%d_f%d.o' % (fam, prec))
             units.append((o, [nvcc] + ARCH + FLAGS + extra +
                           ['-DSDNS_FAMILY=%d' % fam, '-DSDNS_PREC=%d' % prec,
                            '-c', os.path.join(CSRC, 'inst.cu'), '-o', o]))
     o_api = os.path.join(OBJ, 'sdns_api.o')
-    units.append((o_api, [nvcc] + ARCH + FLAGS + extra + ['-c', os.path.join(CSRC, 'sdns_api.cu'), '-o', o_api]))
+    if out and families is not None and 'api' not in families:
+        reuse.append(os.path.join(main_obj, 'sdns_api.o'))
+    else:
+        units.append((o_api, [nvcc] + ARCH + FLAGS + extra + ['-c', os.path.join(CSRC, 'sdns_api.cu'), '-o', o_api]))
     with ThreadPoolExecutor(max_workers=jobs) as ex:
         outs = list(ex.map(lambda u: _run(u[1]), units))
     if verbose:
         for o in outs:
             if o.strip():
                 print(o)
-    _run([nvcc] + ARCH + ['-shared', '-o', LIB] + [u[0] for u in units])
+    _run([nvcc] + ARCH + ['-shared', '-o', LIB] + [u[0] for u in units] + reuse)
     with open(stamp, 'w') as f:
         f.write(digest)
     return LIB
@@ -92,5 +102,6 @@ if __name__ == '__main__':
     ap.add_argument('--verbose', action='store_true')
     ap.add_argument('--sizes', type=int, nargs='*', default=None)
     ap.add_argument('--out', default=None, help='write an experiment variant of the library here (with SDNS_EXTRA_FLAGS)')
+    ap.add_argument('--families', type=int, nargs='*', default=None, help='variant builds: compile only these kernel families, reuse the default build for the rest')
     a = ap.parse_args()
-    print(build(a.force, a.jobs, a.verbose, a.sizes, a.out))
+    print(build(a.force, a.jobs, a.verbose, a.sizes, a.out, families=a.families))

@@ -44,7 +44,7 @@ static int run_plain2(const StridedArgs<float>& a, cudaStream_t st) {
         const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
-    xfer_prepare(b.x, C::smem);
+    xfer_prepare(b.x, C::smem, C::P * C::TC);
     dim3 grid((unsigned)tiles + b.x.nctas, a.nfields);
     ++sdns_debug_pair_launches;
     SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
@@ -73,7 +73,7 @@ static int run_b02(const StridedArgs<float>& a, cudaStream_t st) {
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
     ++sdns_debug_pair_launches;
-    xfer_prepare(b.x, C::smem);
+    xfer_prepare(b.x, C::smem, C::P * C::TC);
     SDNS_LAUNCH(kern, dim3((unsigned)tiles + b.x.nctas), C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
@@ -98,7 +98,7 @@ static int run_f02(const StridedArgs<float>& a, cudaStream_t st) {
     b.in_fs /= 2; b.in_ls /= 2; b.in_os /= 2;
     const long long tiles = (b.ncols + C::TC - 1) / C::TC;
     ++sdns_debug_pair_launches;
-    xfer_prepare(b.x, C::smem);
+    xfer_prepare(b.x, C::smem, C::P * C::TC);
     SDNS_LAUNCH(kern, dim3((unsigned)tiles + b.x.nctas), C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
@@ -161,7 +161,7 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
         const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;     // shift rounded up to whole chunks
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
-    xfer_prepare(b.x, C::smem);
+    xfer_prepare(b.x, C::smem, C::P * C::TC);
     dim3 grid((unsigned)tiles + b.x.nctas, ny);
     SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
@@ -174,7 +174,7 @@ static int run_f0x(const StridedArgs<T>& a, cudaStream_t st) {
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     StridedArgs<T> b = a;
-    xfer_prepare(b.x, C::smem);
+    xfer_prepare(b.x, C::smem, C::threads);
     dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC) + b.x.nctas);
     SDNS_LAUNCH(kern, grid, C::threads, C::smem, st)(b);
     return (int)cudaGetLastError();
@@ -197,7 +197,7 @@ static int run_mhd_f0(const StridedArgs<T>& a, cudaStream_t st) {
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     StridedArgs<T> b = a;
-    xfer_prepare(b.x, C::smem);
+    xfer_prepare(b.x, C::smem, C::P * C::TC);
     dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC) + b.x.nctas);
     SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
@@ -211,7 +211,7 @@ static int run_nsdiv_f0(const StridedArgs<T>& a, cudaStream_t st) {
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     StridedArgs<T> b = a;
-    xfer_prepare(b.x, C::smem);
+    xfer_prepare(b.x, C::smem, C::P * C::TC);
     dim3 grid((unsigned)((a.ncols + C::TC - 1) / C::TC) + b.x.nctas);
     SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
@@ -234,7 +234,7 @@ static int run_zx_q(const ZArgs<T>& a, cudaStream_t st) {
     const long long blocks_per_sm = (long long)((a.grid_cap > 0 && a.grid_cap < occ_sm) ? a.grid_cap : occ_sm) * nsm;
     const long long want = (a.nlines + C::LPC - 1) / C::LPC;
     ZArgs<T> b = a;
-    xfer_prepare(b.x, C::smem);
+    xfer_prepare(b.x, C::smem, 32 * C::LPC);
     // the transfer CTAs take resident slots of this persistent grid
     const long long room = std::max(blocks_per_sm - b.x.nctas, (long long)nsm);
     dim3 grid((unsigned)(want < room ? want : room) + b.x.nctas);
@@ -248,6 +248,44 @@ static int run_zx(const ZArgs<T>& a, cudaStream_t st) {
     if constexpr (C::ok) {
         if (a.nin_keep <= 32 * C::QN3) return run_zx_q<T, M, C::QN3>(a, st);
         return run_zx_q<T, M, C::QN2>(a, st);
+    } else {
+        return -1;
+    }
+}
+
+template <typename T, int M, int QN>
+static int run_zb_q(const ZArgs<T>& a, cudaStream_t st) {
+    typedef ZBCfg<T, M> C;
+    constexpr size_t smem = C::smem_q(QN);
+    auto kern = zb_kernel<T, M, C::E, C::LPC, QN, C::NST, C::minBlocks_q(QN)>;
+    static int occ_sm = 0, nsm = 0;
+    if (!occ_sm) {
+        cudaError_t e = set_smem(kern, smem); if (e != cudaSuccess) return (int)e;
+        int dev = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * C::LPC, smem);
+        if (e != cudaSuccess) return (int)e;
+        occ_sm = occ > 0 ? occ : 1;
+    }
+    const long long blocks_per_sm = (long long)((a.grid_cap > 0 && a.grid_cap < occ_sm) ? a.grid_cap : occ_sm) * nsm;
+    const long long want = (a.nlines + C::LPC - 1) / C::LPC;
+    ZArgs<T> b = a;
+    xfer_prepare(b.x, smem, 32 * C::LPC);
+    const long long room = std::max(blocks_per_sm - b.x.nctas, (long long)nsm);
+    dim3 grid((unsigned)(want < room ? want : room) + b.x.nctas);
+    SDNS_LAUNCH(kern, grid, 32 * C::LPC, smem, st)(b);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int M>
+static int run_zb(const ZArgs<T>& a, cudaStream_t st) {
+    typedef ZXCfg<T, M> X;
+    if constexpr (ZBCfg<T, M>::ok) {
+        // the staged rows are K2p = in_ls elements long
+        if (a.in_ls <= 32 * X::QN3) return run_zb_q<T, M, X::QN3>(a, st);
+        if (a.in_ls <= 32 * X::QN2) return run_zb_q<T, M, X::QN2>(a, st);
+        return run_zb_q<T, M, X::QN2 + 1>(a, st);
     } else {
         return -1;
     }
@@ -270,7 +308,7 @@ static int run_zy_q(const ZArgs<T>& a, cudaStream_t st) {
     }
     const long long blocks = (long long)((a.grid_cap > 0 && a.grid_cap < occ_sm) ? a.grid_cap : occ_sm) * nsm;
     ZArgs<T> b = a;
-    xfer_prepare(b.x, smem);
+    xfer_prepare(b.x, smem, C::P);
     const long long room = std::max(blocks - b.x.nctas, (long long)nsm);
     dim3 grid((unsigned)(a.nlines < room ? a.nlines : room) + b.x.nctas);
     SDNS_LAUNCH(kern, grid, C::P, smem, st)(b);
@@ -294,6 +332,10 @@ static int run_z(const ZArgs<T>& a, cudaStream_t st) {
     if constexpr (MODE == Z_CROSS && ZYCfg<T, M>::ok && ZYCfg<T, M>::E == 4) return run_zy<T, M>(a, st);
 #endif
     if constexpr (MODE == Z_CROSS && ZXCfg<T, M>::ok) {
+#ifdef SDNS_USE_ZB      // bulk-async staged z pass: measured, not faster than zx_kernel; opt-in
+        if ((a.in_ls * (long long)(2 * sizeof(T))) % 16 == 0 && (a.in_fs * (long long)(2 * sizeof(T))) % 16 == 0 && ((uintptr_t)a.in % 16) == 0)
+            return run_zb<T, M>(a, st);
+#endif
 #ifndef SDNS_NO_ZX
         return run_zx<T, M>(a, st);
 #endif
@@ -309,7 +351,7 @@ static int run_z(const ZArgs<T>& a, cudaStream_t st) {
     static bool once = false;
     if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
     ZArgs<T> b = a;
-    xfer_prepare(b.x, C::smem);
+    xfer_prepare(b.x, C::smem, C::P * C::LPC);
     dim3 grid((unsigned)((a.nlines + C::LPC - 1) / C::LPC) + b.x.nctas);
     SDNS_LAUNCH(kern, grid, C::P * C::LPC, C::smem, st)(b);
     return (int)cudaGetLastError();

@@ -189,6 +189,33 @@ struct ZXCfg {
     static constexpr int minBlocks = cmax(1, cmin(cmin((int)((216 * 1024) / (smem + 1024)), 16), 65536 / (128 * needRegs)));
 };
 
+// zx_kernel with bulk-async input staging (zb_kernel): same lengths; LPC warps per CTA, NST stages per warp
+#ifndef SDNS_ZB_NST
+#define SDNS_ZB_NST 2
+#endif
+#ifndef SDNS_ZB_LPC
+#define SDNS_ZB_LPC 2
+#endif
+#ifndef SDNS_ZB_REGS64
+#define SDNS_ZB_REGS64 128
+#endif
+#ifndef SDNS_ZB_REGS32
+#define SDNS_ZB_REGS32 128
+#endif
+template <typename T, int M>
+struct ZBCfg {
+    static constexpr int E = ZXCfg<T, M>::E;
+    static constexpr bool ok = ZXCfg<T, M>::ok;
+    static constexpr int LPC = SDNS_ZB_LPC, NST = SDNS_ZB_NST;
+    static constexpr int PADW = 128 / (2 * (int)sizeof(T));
+    static constexpr int LP = (M + M / PADW + 2) & ~1;
+    static constexpr size_t smem_q(int qn) { return 128 + (size_t)LPC * (LP + 2 * E * 32 + NST * 6 * 32 * qn) * 2 * sizeof(T); }
+    static constexpr int needRegs = sizeof(T) == 8 ? (E > 8 ? 200 : SDNS_ZB_REGS64) : (E > 16 ? 200 : (E > 8 ? 168 : SDNS_ZB_REGS32));
+    static constexpr int minBlocks_q(int qn) {
+        return cmax(1, cmin(cmin((int)((224 * 1024) / (smem_q(qn) + 1024)), 32), 65536 / (32 * LPC * needRegs)));
+    }
+};
+
 // CTA-per-line fused z kernel (zy_kernel): two or four warps per line, for the lengths zx_kernel cannot hold in
 // one warp's registers
 #ifndef SDNS_ZY_E4_REGS

@@ -1391,6 +1391,110 @@ zx_kernel(const ZArgs<T> a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// zx_kernel with its input staged by the TMA unit: lane 0 of every warp copies the six spectral lines of the NEXT
+// line of the warp into a shared-memory stage with bulk-async copies (cp.async.bulk, mbarrier-tracked; the lines are
+// contiguous K2p-element segments) while the warp transforms the current one.  The raw modes and their Hermitian
+// mirrors are then read from the stage: no prefetch registers (zx_kernel holds 4 QN complex values for them), no
+// shuffles on the c2r side, and the loads are a full line ahead instead of one pair-transform.
+// NST = 2: two stages per warp (the next line is requested before the current one is touched);
+// NST = 1: one stage, refilled as soon as the third pair of the current line has been built from it.
+// ---------------------------------------------------------------------------------------
+template <typename T, int M, int E, int LPC, int QN, int NST, int MINB>
+__global__ void __launch_bounds__(32 * LPC, MINB)
+zb_kernel(const ZArgs<T> a) {
+    typedef typename C2<T>::type V;
+    static_assert(M / E == 32, "one warp per line");
+    static_assert(LPC * NST <= 16, "barrier block");
+    SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
+    constexpr int PADW = 128 / (int)sizeof(V);
+    constexpr int LP = (M + M / PADW + 2) & ~1;            // exchange line, even length (keeps the stage 16-byte aligned)
+    constexpr int SL = 32 * QN;                            // elements per staged field (>= the line pitch K2p)
+    constexpr int WSZ = LP + 2 * E * 32 + NST * 6 * SL;    // elements per warp
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smraw);
+    V* sm = reinterpret_cast<V*>(smraw + 128);
+    const int t = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    V* ex = sm + w * WSZ;                                  // this warp's exchange line
+    V* park = ex + LP;                                     // parking slots [2E][32]
+    V* stage = park + 2 * E * 32;                          // [NST][6][SL]
+    T* park_r = reinterpret_cast<T*>(park);
+    unsigned long long* bar = bars + w * NST;
+    SmemLine<1, PADW> map; map.base = 0;
+    int phase = 0;
+    const V* in = reinterpret_cast<const V*>(a.in);
+    V* out = reinterpret_cast<V*>(a.out);
+    const long long stride = (long long)gx * LPC;
+    long long line = (long long)bx * LPC + w;
+    const unsigned int bytes = (unsigned int)(a.in_ls * (long long)sizeof(V));
+    auto issue = [&](long long ln, int s) {                // lane 0 only
+        mbar_expect_tx(&bar[s], 6u * bytes);
+#pragma unroll
+        for (int f = 0; f < 6; ++f) bulk_g2s(stage + (s * 6 + f) * SL, in + f * a.in_fs + ln * a.in_ls, bytes, &bar[s]);
+    };
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(&bar[s], 1);
+        mbar_init_fence();
+        if (line < a.nlines) issue(line, 0);
+    }
+    __syncwarp();
+    for (int n = 0; line < a.nlines; line += stride, ++n) {
+        const int s = NST == 2 ? (n & 1) : 0;
+        if (NST == 2 && t == 0 && line + stride < a.nlines) issue(line + stride, s ^ 1);
+        mbar_wait(&bar[s], (unsigned int)((NST == 2 ? (n >> 1) : n) & 1));
+        V x[E];
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+            const V* A = stage + (s * 6 + 2 * pr) * SL;
+            const V* B = A + SL;
+            // x[q] = Za[k] + i Zb[k], k = t + 32 q (load_pair's algebra on the staged half spectra)
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const int k = t + 32 * q;
+                const bool lowh = q < E / 2 || (q == E / 2 && t == 0);         // 2 k <= M
+                const int kk = lowh ? k : M - k;
+                V va = czero<V>(), vb = czero<V>();
+                if (kk < a.nin_keep) { va = A[kk]; vb = B[kk]; }
+                if (!lowh) { va.y = -va.y; vb.y = -vb.y; }
+                if (t == 0 && (q == 0 || q == E / 2)) { va.y = 0; vb.y = 0; }   // c2r ignores Im of DC / Nyquist
+                x[q].x = va.x - vb.y; x[q].y = va.y + vb.x;
+            }
+            if (NST == 1 && pr == 2) {
+                __syncwarp();                                   // every lane has read the stage
+                if (t == 0 && line + stride < a.nlines) issue(line + stride, 0);
+            }
+            fft_line<T, M, E, +1, 1, 1>(x, t, a.tw, ex, map, 0, phase);
+            if (pr < 2) {
+#pragma unroll
+                for (int q = 0; q < E; ++q) park[(pr * E + q) * 32 + t] = x[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const V p01 = park[q * 32 + t], p23 = park[(E + q) * 32 + t];
+            const T a0 = p01.x, a1 = p01.y, a2 = p23.x;
+            const T b0 = p23.y, b1 = x[q].x, b2 = x[q].y;
+            x[q].x = a1 * b2 - a2 * b1;                      // c = a x b (cross1)
+            x[q].y = a2 * b0 - a0 * b2;
+            park_r[2 * (q * 32 + t)] = a0 * b1 - a1 * b0;
+        }
+        fft_line<T, M, E, -1, 1, 1>(x, t, a.tw, ex, map, 0, phase);
+        zx_unpack_store<T, E>(x, out + line * a.out_ls, out + a.out_fs + line * a.out_ls, t, a.nout_keep, a.scale);
+#pragma unroll
+        for (int q = 0; q < E; ++q) { x[q].x = park_r[2 * (q * 32 + t)]; x[q].y = (T)0; }
+        fft_line<T, M, E, -1, 1, 1>(x, t, a.tw, ex, map, 0, phase);
+        V* C = out + 2 * a.out_fs + line * a.out_ls;
+#pragma unroll
+        for (int q = 0; q <= E / 2; ++q) {
+            const int k = t + 32 * q;
+            if ((q < E / 2 || t == 0) && k < a.nout_keep) C[k] = cscale<T>(x[q], a.scale);
+        }
+        __syncwarp();                                           // the stage this iteration read may be refilled
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Fused z-pass, one CTA of P = M/E threads (two or four warps) per line: the zx_kernel scheme for the long lines
 // whose register budget does not allow one warp per line (fp64 M >= 512, fp32 M >= 2048).  Same single HBM read
 // per spectral element, same software pipeline; the Hermitian mirrors travel through the (idle) exchange line in

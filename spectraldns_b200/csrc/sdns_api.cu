@@ -96,6 +96,7 @@ struct sdns_plan {
     std::deque<XferBatch> pend;
     int xctas, xflush_ctas, xtma;   // transfer CTAs per carrying launch / of a transfer-only launch; bulk-async or ld/st
     double xratio;                  // NVLink bytes a launch carries per byte of its own HBM traffic
+    unsigned int xinflight;         // ring bytes per carrying launch (sets its number of transfer CTAs); 0: xctas as given
     double xfer_bytes; long long xfer_flushes;
     int kcopy, kcopy_ctas;          // xmode 1 variant: a grid-capped copy kernel (peer stores) instead of cudaMemcpy2DAsync
     // SDNS_GRAPH=1 (experiment, multi-GPU copy-engine mode): an RK4 step -- kernels, peer copies and their cross-stream
@@ -263,7 +264,10 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
 #else
     p->xctas = 32; p->xflush_ctas = 128;
 #endif
-    p->xtma = 1; p->xratio = 0.16; p->xfer_bytes = 0; p->xfer_flushes = 0;
+    p->xtma = 1; p->xinflight = 2u << 20;
+#ifdef SDNS_HOST_SHIM
+    p->xinflight = 0;
+#endif p->xratio = 0.16; p->xfer_bytes = 0; p->xfer_flushes = 0;
     p->use_graph = 0; p->capturing = p->gwarm = p->ghave = false; p->gstream = nullptr; p->ev_gin = p->ev_gout = nullptr; p->gexec = nullptr; p->glaunches = 0;
     p->xmode = 0; p->nchunk = 1; p->nsplit = 1; p->off_SF = 0; p->bytes_SF = 0; p->b0_preissued = false;
     p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
@@ -273,7 +277,8 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
         // "ce" / "kcopy": copy engines / copy kernels on side streams (round 1); "store": peer stores fused into the passes
         p->xmode = (xm && !strcmp(xm, "store")) ? 0 : ((xm && (!strcmp(xm, "ce") || !strcmp(xm, "kcopy"))) ? 1 : 2);
         p->xtma = (xm && !strcmp(xm, "ldst")) ? 0 : 1;
-        if (const char* v = getenv("SDNS_XCTAS")) p->xctas = std::max(1, atoi(v));
+        if (const char* v = getenv("SDNS_XCTAS")) { p->xctas = std::max(1, atoi(v)); p->xinflight = 0; }
+        if (const char* v = getenv("SDNS_XINFLIGHT_KB")) p->xinflight = (unsigned int)std::max(0, atoi(v)) << 10;
         if (const char* v = getenv("SDNS_XFLUSH_CTAS")) p->xflush_ctas = std::max(1, atoi(v));
         if (const char* v = getenv("SDNS_XRATIO")) p->xratio = atof(v);
         p->kcopy = (xm && !strcmp(xm, "kcopy")) ? 1 : 0;    // send slots moved by a small copy kernel instead of the copy engines
@@ -656,7 +661,7 @@ static void attach_xfer(sdns_plan* p, XferArgs& x, double hbm_bytes) {
         j.row0 += take; j.nrows -= take; budget -= take * per_row;
         if (!j.nrows) p->pend.pop_front();
     }
-    if (x.nbatch) x.nctas = p->xctas;
+    if (x.nbatch) { x.nctas = p->xctas; x.inflight = p->xinflight; }
 }
 // everything still pending, as a launch of its own (before the barrier in front of the pass that needs the data)
 static int flush_xfer(sdns_plan* p) {
@@ -672,7 +677,7 @@ static int flush_xfer(sdns_plan* p) {
         static bool once = false;
         if (!once) { CUDA_TRY(cudaFuncSetAttribute(xfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
 #endif
-        xfer_prepare(a.x, smem);
+        xfer_prepare(a.x, smem, 128);
         sdns_plan::Rec r; r.fam = -2; r.bytes = 0; r.remote = 0;
         if (p->tl_on) { r.a = get_event(p); cudaEventRecord(r.a, p->stream); }
         SDNS_LAUNCH(xfer_kernel, a.x.nctas, 128, smem, p->stream)(a);

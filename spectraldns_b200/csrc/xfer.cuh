@@ -33,6 +33,9 @@ struct XferArgs {
     int nbatch;
     int tma;                                // 1: bulk-async copies through the ring; 0: 16-byte loads / stores by the whole CTA
     unsigned int ring_bytes;                // dynamic shared memory available to the role
+    unsigned int stage;                     // bytes per ring stage (>= every batch's piece, multiple of 128)
+    int nrings;                             // warps of a transfer CTA that drive a ring of their own
+    unsigned int inflight;                  // > 0: pick nctas so that the rings of the launch hold about this many bytes
     XferBatch b[SDNS_XB_MAX];
 };
 
@@ -85,100 +88,130 @@ template <int N> inline void bulk_wait_read() {}
 template <int N> inline void bulk_wait_all() {}
 #endif
 
-// piece g (a global index over the batches of this launch) -> addresses.  Within a batch consecutive pieces go to
-// consecutive destinations, starting with the one after this rank, so that at any moment every sender spreads its
-// traffic over all receivers.
-struct XferPiece { const char* src; char* dst; unsigned int bytes; };
-__device__ __forceinline__ unsigned long long xfer_total(const XferArgs& x) {
-    unsigned long long n = 0;
-    for (int i = 0; i < x.nbatch; ++i) n += (unsigned long long)x.b[i].ndest * x.b[i].nrows * x.b[i].nseg;
-    return n;
-}
-__device__ __forceinline__ XferPiece xfer_piece(const XferArgs& x, unsigned long long g) {
-    int i = 0;
-    for (; i < x.nbatch - 1; ++i) {
-        const unsigned long long n = (unsigned long long)x.b[i].ndest * x.b[i].nrows * x.b[i].nseg;
-        if (g < n) break;
-        g -= n;
-    }
-    const XferBatch& b = x.b[i];
-    const unsigned int d = (unsigned int)(g % (unsigned int)b.ndest);
-    const unsigned long long r = g / (unsigned int)b.ndest;
-    const unsigned int seg = (unsigned int)(r % b.nseg);
-    const unsigned long long row = b.row0 + r / b.nseg;
-    const unsigned int off = seg * b.piece;
-    XferPiece p;
-    p.src = b.src[d] + row * b.spitch + off;
-    p.dst = b.dst[d] + row * b.dpitch + off;
-    p.bytes = b.width - off < b.piece ? b.width - off : b.piece;
-    return p;
-}
-
 // The role.  `cta` of `ncta` transfer CTAs; `smem` is the launch's dynamic shared memory (x.ring_bytes of it).
+// Work unit = one row segment (row, seg) of a batch, sent to every destination in turn (the rotation starts at a
+// different destination per unit, so that at any moment the senders spread their traffic over all receivers).  Up to
+// SDNS_XW warps of the CTA drive independent rings (lane 0 of each): one thread's issue rate, not the ring, limits a
+// single ring.  All index arithmetic is 32-bit and incremental -- a 64-bit division per piece costs more than the
+// piece's copy.
+#define SDNS_XW 4
+#define SDNS_XHDR 512        // per ring: 16 mbarriers, 16 destination pointers, 16 byte counts
 __device__ __forceinline__ void xfer_role(const XferArgs& x, unsigned char* smem, int cta, int ncta) {
-    const unsigned long long total = xfer_total(x);
     if (x.tma) {
-        if (threadIdx.x != 0) return;
-        // ring: S stages of `stage` bytes after S mbarriers; lookahead S-2 so that the bulk store issued two pieces
-        // ago may still be reading its stage when the next load is issued
-        unsigned int stage = 0;
-        for (int i = 0; i < x.nbatch; ++i) stage = x.b[i].piece > stage ? x.b[i].piece : stage;
-        stage = (stage + 127u) & ~127u;
-        int S = (int)((x.ring_bytes - 128u) / stage);
+        const int nwarp = (int)((blockDim.x + 31) >> 5);
+        const int nw = nwarp < x.nrings ? nwarp : x.nrings;
+        const int w = (int)(threadIdx.x >> 5);
+        if ((threadIdx.x & 31) != 0 || w >= nw) return;
+        const unsigned int sub = (x.ring_bytes / (unsigned int)nw) & ~127u;
+        unsigned char* base = smem + (size_t)w * sub;
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(base);
+        char** mdst = reinterpret_cast<char**>(base + 128);
+        unsigned int* mbytes = reinterpret_cast<unsigned int*>(base + 256);
+        unsigned char* ring = base + SDNS_XHDR;
+        const unsigned int stage = x.stage;
+        int S = (int)((sub - SDNS_XHDR) / stage);
         if (S > 16) S = 16;
-        unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
-        unsigned char* ring = smem + 128;
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_init_fence();
         const int L = S - 2;                                   // host guarantees S >= 3
-        unsigned long long n = 0;                              // my pieces: g = cta + k * ncta
-        if (total > (unsigned long long)cta) n = (total - cta + ncta - 1) / ncta;
-        for (unsigned long long k = 0; k < n + L; ++k) {
-            if (k < n) {
-                const int s = (int)(k % S);
-                if (k >= (unsigned long long)S) bulk_wait_read<1>();     // the store that last used this stage has read it
-                const XferPiece p = xfer_piece(x, cta + k * ncta);
-                mbar_expect_tx(&bars[s], p.bytes);
-                bulk_g2s(ring + (size_t)s * stage, p.src, p.bytes, &bars[s]);
+        const unsigned int vc = (unsigned int)(cta * nw + w), nvc = (unsigned int)(ncta * nw);
+        // producer cursor
+        int bi = 0;
+        unsigned int u = vc, d = 0, rot = 0, row = 0, off = 0, len = 0;
+        bool have = false;
+        auto seek = [&]() {                                    // position on unit u of batch bi (or run out of batches)
+            while (bi < x.nbatch) {
+                const XferBatch& b = x.b[bi];
+                const unsigned int units = b.nrows * b.nseg;
+                if (u < units) {
+                    const unsigned int r = u / b.nseg, sg = u - r * b.nseg;
+                    row = b.row0 + r; off = sg * b.piece;
+                    len = b.width - off < b.piece ? b.width - off : b.piece;
+                    rot = u % (unsigned int)b.ndest; d = 0; have = true;
+                    return;
+                }
+                ++bi; u = vc;                                  // every batch is dealt out from its first unit
             }
-            if (k >= (unsigned long long)L) {
-                const unsigned long long j = k - L;
-                const int s = (int)(j % S);
-                mbar_wait(&bars[s], (unsigned int)((j / S) & 1));
-                const XferPiece p = xfer_piece(x, cta + j * ncta);
-                bulk_s2g(p.dst, ring + (size_t)s * stage, p.bytes);
+            have = false;
+        };
+        seek();
+        unsigned int k = 0, j = 0;                             // pieces produced / consumed
+        while (have || j < k) {
+            if (have) {
+                const XferBatch& b = x.b[bi];
+                const int s = (int)(k % (unsigned int)S);
+                if (k >= (unsigned int)S) bulk_wait_read<1>();  // the store that last used this stage has read it
+                unsigned int dd = d + rot; if (dd >= (unsigned int)b.ndest) dd -= b.ndest;
+                const char* src = b.src[dd] + (unsigned long long)row * b.spitch + off;
+                mdst[s] = b.dst[dd] + (unsigned long long)row * b.dpitch + off;
+                mbytes[s] = len;
+                mbar_expect_tx(&bars[s], len);
+                bulk_g2s(ring + (size_t)s * stage, src, len, &bars[s]);
+                ++k;
+                if (++d == (unsigned int)b.ndest) { u += nvc; seek(); }
+            }
+            if (k - j > (unsigned int)L || (!have && j < k)) {
+                const int s = (int)(j % (unsigned int)S);
+                mbar_wait(&bars[s], (j / (unsigned int)S) & 1u);
+                bulk_s2g(mdst[s], ring + (size_t)s * stage, mbytes[s]);
                 bulk_commit();
+                ++j;
             }
         }
         bulk_wait_all<0>();                                    // every store has been performed before the CTA retires
     } else {
-        // no TMA (unaligned rows, or SDNS_XFER=ldst): 16-byte loads and peer stores by all threads of the CTA
-        for (unsigned long long g = cta; g < total; g += ncta) {
-            const XferPiece p = xfer_piece(x, g);
-            const uint4* s = reinterpret_cast<const uint4*>(p.src);
-            uint4* d = reinterpret_cast<uint4*>(p.dst);
-            for (unsigned int i = threadIdx.x; i < p.bytes / 16; i += blockDim.x) d[i] = s[i];
+        // no TMA (SDNS_EXCHANGE=ldst, or a ring too small): 16-byte loads and peer stores by all threads of the CTA
+        for (int bi = 0; bi < x.nbatch; ++bi) {
+            const XferBatch& b = x.b[bi];
+            const unsigned int units = b.nrows * b.nseg;
+            for (unsigned int u = (unsigned int)cta; u < units; u += (unsigned int)ncta) {
+                const unsigned int r = u / b.nseg, sg = u - r * b.nseg;
+                const unsigned int off = sg * b.piece;
+                const unsigned int len = b.width - off < b.piece ? b.width - off : b.piece;
+                const unsigned int rot = u % (unsigned int)b.ndest;
+                for (int d = 0; d < b.ndest; ++d) {
+                    int dd = d + (int)rot; if (dd >= b.ndest) dd -= b.ndest;
+                    const uint4* sp = reinterpret_cast<const uint4*>(b.src[dd] + (unsigned long long)(b.row0 + r) * b.spitch + off);
+                    uint4* dp = reinterpret_cast<uint4*>(b.dst[dd] + (unsigned long long)(b.row0 + r) * b.dpitch + off);
+                    for (unsigned int i = threadIdx.x; i < len / 16; i += blockDim.x) dp[i] = sp[i];
+                }
+            }
         }
     }
 }
 
-// Host side, just before the launch: the ring is the launch's dynamic shared memory; about eight stages when it is
-// large enough (pieces of at most 16 KB), at least three, else the role falls back to plain loads / stores.
-inline void xfer_prepare(XferArgs& x, size_t smem) {
+// Host side, just before the launch: the ring is the launch's dynamic shared memory, split over up to SDNS_XW warps;
+// about six stages per ring when it is large enough (pieces of at most 16 KB), at least three, else the role falls
+// back to plain loads / stores.
+inline void xfer_prepare(XferArgs& x, size_t smem, int threads) {
     if (x.nctas <= 0 || x.nbatch <= 0) { x.nctas = 0; x.nbatch = 0; return; }
     x.ring_bytes = (unsigned int)smem;
+    // a ring is latency-bound (its stages in flight per round trip), so the transfer rate of a launch follows the
+    // total ring capacity: small-CTA kernels get more transfer CTAs than the ones with 100 KB of shared memory
+    if (x.inflight > 0 && smem > 0) {
+        long long n = ((long long)x.inflight + (long long)smem - 1) / (long long)smem;
+        x.nctas = (int)(n < 8 ? 8 : (n > 128 ? 128 : n));
+    }
+    int nw = threads / 32 < SDNS_XW ? threads / 32 : SDNS_XW;
+    if (nw < 1) nw = 1;
+    while (nw > 1 && ((smem / nw) & ~(size_t)127) < SDNS_XHDR + 6 * 1024) --nw;     // few large rings rather than many small ones
+    x.nrings = nw;
+    const size_t sub = (smem / nw) & ~(size_t)127;
     unsigned int piece = 0;
-    if (smem >= 128 + 3 * 128) {
-        piece = (unsigned int)((smem - 128) / 8) & ~127u;
+    if (sub >= SDNS_XHDR + 3 * 128) {
+        piece = (unsigned int)((sub - SDNS_XHDR) / 6) & ~127u;
         if (piece < 128) piece = 128;
         if (piece > 16384) piece = 16384;
     }
     if (!x.tma || !piece) { x.tma = 0; piece = 16384; }
+    unsigned int stage = 128;
     for (int i = 0; i < x.nbatch; ++i) {
         XferBatch& b = x.b[i];
         b.piece = b.width < piece ? b.width : piece;
         b.nseg = (b.width + b.piece - 1) / b.piece;
+        stage = std::max(stage, (b.piece + 127u) & ~127u);
     }
+    x.stage = stage;
 }
 
 // A launch made only of the role: what is still pending when a pass needs the transposed data.
