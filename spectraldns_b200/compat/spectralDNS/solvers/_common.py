@@ -15,10 +15,12 @@ def build_spaces(comm, params, float_, solver_name):
                        dtype=(float_ if i == dim-1 else (np.complex64 if float_ == np.float32 else np.complex128)))
          for i in range(dim)]
     conv = params.convection if solver_name == 'NS' else None      # VV: Vortex, MHD: Divergence only
-    if params.decomposition == 'pencil' and comm.Get_size() > 1 and comm.Get_rank() == 0:
-        # one NVSwitch box: a slab needs one exchange per transform where a pencil needs two, and every
-        # GPU reaches every peer at full bandwidth -- the flag is honoured as 'slab' (local shapes are slab shapes)
-        print("spectraldns_b200: --decomposition pencil runs as slab on %d GPUs" % comm.Get_size())
+    if params.decomposition == 'pencil' and comm.Get_size() > 1:
+        # The reference's pencil layout (config.py:194-195; spectral arrays (N0, N1/P0, Nh/P1)) is not built on the
+        # B200 path: on one NVSwitch box a slab needs one exchange per transform where a pencil needs two.  Silently
+        # running slab would hand the caller arrays of a different local shape, so refuse.
+        raise NotImplementedError("spectraldns_b200: --decomposition pencil on %d GPUs is not implemented "
+                                  "(slab is; on a single GPU the flag is accepted because both coincide)" % comm.Get_size())
     eng = Engine.get(params.N, params.L, params.precision, params.dealias, solver_name,
                      params.mask_nyquist, params.decomposition, conv)
     T = TensorProductSpace(comm, V, dtype=float_, slab=(params.decomposition == 'slab'),

@@ -110,7 +110,8 @@ struct sdns_plan {
     std::vector<cudaEvent_t> ev_k;  // [nchunk] the pass of chunk c has finished
     std::vector<cudaEvent_t> ev_y;  // per copy stream: drained
     size_t off_SF, bytes_SF;        // F1 send buffers (B0's live in the W1 buffer, which is idle at that point)
-    bool b0_preissued;              // the B0 chunks (and copies) of the coming right-hand side are already enqueued
+    bool b0_preissued;              // the B0 chunks (and copies) of the coming right-hand side are already enqueued ...
+    const void* b0_pre_u;           // ... for this input array (in the work layout); honoured only for exactly that call
     struct CRec { int s; cudaEvent_t a, b; double bytes; };
     std::vector<CRec> crecs;
     double copy_ms[32]; double copy_bytes; long long copy_n;
@@ -267,9 +268,10 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->xtma = 1; p->xinflight = 2u << 20;
 #ifdef SDNS_HOST_SHIM
     p->xinflight = 0;
-#endif p->xratio = 0.16; p->xfer_bytes = 0; p->xfer_flushes = 0;
+#endif
+    p->xratio = 0.3; p->xfer_bytes = 0; p->xfer_flushes = 0;
     p->use_graph = 0; p->capturing = p->gwarm = p->ghave = false; p->gstream = nullptr; p->ev_gin = p->ev_gout = nullptr; p->gexec = nullptr; p->glaunches = 0;
-    p->xmode = 0; p->nchunk = 1; p->nsplit = 1; p->off_SF = 0; p->bytes_SF = 0; p->b0_preissued = false;
+    p->xmode = 0; p->nchunk = 1; p->nsplit = 1; p->off_SF = 0; p->bytes_SF = 0; p->b0_preissued = false; p->b0_pre_u = nullptr;
     p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
     if (p->P > 1) {
         const char* xm = getenv("SDNS_EXCHANGE");           // "store": peer stores fused into the passes; default: copy engines
@@ -473,6 +475,7 @@ struct BarrierArgs {
 __global__ void xbarrier_kernel(const BarrierArgs b) {
     const int r = threadIdx.x;
     if (r >= b.nranks) return;
+    if (*reinterpret_cast<volatile unsigned int*>(b.status)) return;      // an earlier barrier timed out: the run is lost, do not wait again
     __threadfence_system();
     unsigned int* remote = b.peer_flags[r] + b.rank;
 #ifndef SDNS_HOST_SHIM
@@ -512,6 +515,7 @@ __global__ void xbarrier_dev_kernel(const BarrierDevArgs b) {
     const unsigned int epoch = sh[0];
     const int r = threadIdx.x;
     if (r >= b.nranks) return;
+    if (*reinterpret_cast<volatile unsigned int*>(b.status)) return;
     __threadfence_system();
     unsigned int* remote = b.peer_flags[r] + b.rank;
 #ifndef SDNS_HOST_SHIM
@@ -578,13 +582,25 @@ extern "C" int sdns_comm_status(sdns_plan* p, int* timed_out) {
     return SDNS_OK;
 }
 
+// A barrier timeout means a peer was slow, hung or dead and every later pass ran on partially exchanged data: the
+// fault is sticky (the barriers stop waiting) and fatal at every point where results leave the device.
+static int check_comm(sdns_plan* p) {
+    if (p->P == 1 || !p->ws) return SDNS_OK;
+    unsigned int v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, p->ws + p->off_flags + 32 * sizeof(unsigned int), sizeof v, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (v) return fail(SDNS_ERR_STATE, "cross-GPU barrier timed out (a peer rank is slow, hung or gone): results since then are invalid");
+    return SDNS_OK;
+}
+
 extern "C" int sdns_plan_set_stream(sdns_plan* p, void* s) {
     if (!p) return fail(SDNS_ERR_ARG, "null plan");
     p->stream = (cudaStream_t)s; return SDNS_OK;
 }
 extern "C" int sdns_sync(sdns_plan* p) {
     if (!p) return fail(SDNS_ERR_ARG, "null plan");
-    CUDA_TRY(cudaStreamSynchronize(p->stream)); return SDNS_OK;
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return check_comm(p);
 }
 extern "C" int sdns_local_shapes(const sdns_plan* p, int32_t sp[3], int32_t ph[3], int32_t pd[3]) {
     if (!p) return fail(SDNS_ERR_ARG, "null plan");
@@ -1064,9 +1080,10 @@ static int rhs_ce(sdns_plan* p, const void* u_hat, double nu, double eta, const 
     const int nc = p->nchunk;
     const size_t cs = p->cs;
     int e;
-    if (!p->b0_preissued)
-        for (int c = 0; c < nc; ++c) if ((e = b0_chunk_ce<T>(p, P, u_hat, so.in_work_layout, c))) return e;
+    const bool pre = p->b0_preissued && p->b0_pre_u == u_hat && so.in_work_layout;
     p->b0_preissued = false;
+    if (!pre)
+        for (int c = 0; c < nc; ++c) if ((e = b0_chunk_ce<T>(p, P, u_hat, so.in_work_layout, c))) return e;
     if ((e = join_copies(p))) return e;
     P.st = p->stream;
     if ((e = P.b1(6))) return e;
@@ -1099,7 +1116,7 @@ static int rhs_ce(sdns_plan* p, const void* u_hat, double nu, double eta, const 
                 if ((e = launch_f0<T>(p, P, u_hat, nu, eta, so, nprod, false, (T)1, Rng{-1, 0}, mem[i]))) return e;
         if (so.next_u) if ((e = b0_chunk_ce<T>(p, P, so.next_u, true, c))) return e;
     }
-    if (so.next_u) p->b0_preissued = true;
+    if (so.next_u) { p->b0_preissued = true; p->b0_pre_u = so.next_u; }
     const Rng tr = k1_truncated(p, q);
     P.st = p->stream;
     if (tr.b > tr.a) return launch_f0<T>(p, P, u_hat, nu, eta, so, nprod, false, (T)1, Rng{-1, 0}, tr);
@@ -1253,6 +1270,7 @@ extern "C" int sdns_rk4_step(sdns_plan* p, void* u_hat, void* u1, void* u2, doub
 
 static int rk4_step_eager(sdns_plan* p, void* u_hat, void* u1, void* u2, double dt, double nu, double eta, const void* source) {
     int e;
+    p->b0_preissued = false;            // nothing pre-enqueued survives from an earlier (possibly failed) call
     // Between stages the state lives in the workspace in the k1-major work layout (u1, u2 too): the
     // axis-0 passes then read and write it with a stride of one k2 row instead of N1*Nh elements.
     // Stage 0 reads the caller's u_hat (reference layout), stage 3 writes it back in that layout.
@@ -1367,7 +1385,7 @@ extern "C" int sdns_energy(sdns_plan* p, const void* u_hat, int nc, double* out)
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     double s = 0; for (int i = 0; i < nb; ++i) s += h[i];
     *out = s;
-    return SDNS_OK;
+    return check_comm(p);
 }
 
 extern "C" int sdns_rk4_steps_host(sdns_plan* p, void* host_u, void* du, void* d1, void* d2, int nsteps,
@@ -1379,7 +1397,7 @@ extern "C" int sdns_rk4_steps_host(sdns_plan* p, void* host_u, void* du, void* d
     for (int s = 0; s < nsteps; ++s) { e = sdns_rk4_step(p, du, d1, d2, dt, nu, eta, nullptr); if (e) return e; }
     CUDA_TRY(cudaMemcpyAsync(host_u, du, bytes, cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
-    return SDNS_OK;
+    return check_comm(p);
 }
 
 // ---- standalone pointwise operators of the fine-grained plug-in surface (optimization/__init__.py:12-55)
@@ -1528,7 +1546,7 @@ extern "C" int sdns_errnorm(sdns_plan* p, const void* u0, const void* u1, const 
         double s = 0; for (int i = 0; i < nb; ++i) s += h[i];
         out[k] = s;
     }
-    return SDNS_OK;
+    return check_comm(p);
 }
 
 // ---- profiling ----------------------------------------------------------------------------

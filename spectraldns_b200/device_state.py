@@ -55,6 +55,8 @@ class DeviceState(object):
 
     def sync_to_host(self):
         if self.device_newer:
+            if self.plan.nranks > 1:
+                self.plan.sync()              # raises SdnsError if a cross-GPU barrier timed out: never hand out garbage
             self._d2h(self.host_state, self.u)
             self.device_newer = False
 

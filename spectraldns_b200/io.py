@@ -1,12 +1,22 @@
 """Checkpoint / result files for the solve() loop.
 
 The reference writes HDF5 through shenfun.ShenfunFile + h5py(mpio) (h5io/HDF5File.py:57-120); h5py
-is not in this image, so the same two files per run -- <name>_c (spectral checkpoint with `tstep`,
-`t` attributes) and <name>_w (physical results) -- are stored as numpy .npz archives.  Cadence,
-the kill-file protocol (`killspectraldns`) and the update_components hook are the reference's.
-This is side-band I/O, not part of the timed hot path.
+is not in this image, so the same two streams per run -- <name>_c (spectral checkpoint with `tstep`,
+`t` attributes) and <name>_w (physical results) -- are stored as numpy .npz archives, one archive
+per written time step and rank (nothing earlier than the step being written stays in memory):
+
+    <name>_c[_rank<r>].npz                 latest checkpoint (overwritten), attrs tstep / t
+    <name>_w[_rank<r>]_t<tstep>.npz        results of step tstep
+
+Every archive carries the global shape and this rank's slice of each array (`meta__<key>`), so
+`read_global` reassembles a field written on any number of ranks and `init_from_file` restarts on
+a different rank count (the reference's init_from_file, h5io/HDF5File.py).  Cadence, the
+kill-file protocol (`killspectraldns`, collective over all ranks) and the update_components hook
+are the reference's.  This is side-band I/O, not part of the timed hot path.
 """
+import glob
 import os
+import re
 import sys
 import numpy as np
 
@@ -21,24 +31,28 @@ class _Handle(object):
         self.attrs = attrs
 
 
+def _comm():
+    from mpi4py import MPI          # the torch.distributed-backed stand-in (or the real one)
+    return MPI.COMM_WORLD
+
+
 class ShenfunFile(object):
     """ShenfunFile(name, space, mode=) with .open()/.close()/.f.attrs/.write(tstep, data, as_scalar=)."""
-    def __init__(self, name, space=None, mode='w', **kw):
-        from .spaces import world
-        rank, nranks, _ = world()
-        self.filename = name + ('_rank%d' % rank if nranks > 1 else '') + '.npz'
+    def __init__(self, name, space=None, mode='w', per_step=False, **kw):
+        comm = _comm()
+        self.rank, self.nranks = comm.Get_rank(), comm.Get_size()
+        self.stem = name + ('_rank%d' % self.rank if self.nranks > 1 else '')
+        self.filename = self.stem + '.npz'
+        self.per_step = per_step
         self.space = space
         self.mode = mode
         self._attrs = _Attrs()
-        self._data = {}
         self.f = None
         if mode in ('r', 'a') and os.path.exists(self.filename):
             with np.load(self.filename, allow_pickle=False) as z:
                 for k in z.files:
                     if k.startswith('attr__'):
                         self._attrs[k[6:]] = z[k].item()
-                    else:
-                        self._data[k] = z[k]
 
     def open(self):
         self.f = _Handle(self._attrs)
@@ -46,23 +60,90 @@ class ShenfunFile(object):
     def close(self):
         self.f = None
 
-    def _flush(self):
-        out = dict(self._data)
-        for k, v in self._attrs.items():
-            out['attr__' + k] = np.asarray(v)
-        np.savez(self.filename, **out)
+    def _meta(self, arr):
+        """(global shape, start of this rank's block) of a local array of self.space (None: not distributed)."""
+        sp = self.space
+        try:
+            spectral = np.iscomplexobj(arr)
+            gshape = tuple(sp.global_shape(spectral)) if hasattr(sp, 'global_shape') else None
+            sl = sp.local_slice(spectral)
+            lead = arr.ndim - len(sl)
+            start = (0,)*lead + tuple(int(s.start or 0) for s in sl)
+            if gshape is not None:
+                gshape = tuple(arr.shape[:lead]) + gshape[-len(sl):]
+            return gshape, start
+        except Exception:
+            return None, None
 
     def write(self, tstep, data, as_scalar=False):
         """data: {name: [array, (array, slices), ...]} as in h5io/HDF5File.py:25-52."""
+        self.write_groups({tstep: data}, tstep)
+
+    def write_groups(self, groups, tstep=0):
+        """Several (tstep, data) groups in ONE archive, written once."""
+        out = {}
+        for ts, data in groups.items():
+            self._collect(ts, data, out)
+        for k, v in self._attrs.items():
+            out['attr__' + k] = np.asarray(v)
+        fn = ('%s_t%d.npz' % (self.stem, int(tstep))) if self.per_step else self.filename
+        tmp = fn + '.tmp.npz'
+        np.savez(tmp, **out)
+        os.replace(tmp, fn)                      # a killed run never leaves a truncated checkpoint
+
+    def _collect(self, tstep, data, out):
         for name, items in data.items():
             for item in items:
                 if isinstance(item, tuple):
                     arr, sl = item
-                    key = '%s/slice/%s' % (name, tstep)
-                    self._data[key] = np.array(np.asarray(arr)[tuple(sl)])
+                    out['%s/slice/%s' % (name, tstep)] = np.array(np.asarray(arr)[tuple(sl)])
                 else:
-                    self._data['%s/3D/%s' % (name, tstep)] = np.array(item)
-        self._flush()
+                    a = np.array(item)
+                    key = '%s/3D/%s' % (name, tstep)
+                    out[key] = a
+                    gshape, start = self._meta(a)
+                    if gshape is not None:
+                        out['meta__' + key] = np.array(list(gshape) + list(start), dtype=np.int64)
+
+
+def read_global(name, key_prefix):
+    """Reassemble the arrays whose key starts with key_prefix (e.g. 'U/3D/') from <name>.npz or from the per-rank
+    files <name>_rank*.npz written by any number of ranks.  Returns ({key: global array}, attrs)."""
+    files = sorted(glob.glob(name + '_rank*.npz'), key=lambda f: int(re.search(r'_rank(\d+)', f).group(1)))
+    if not files and os.path.exists(name + '.npz'):
+        files = [name + '.npz']
+    if not files:
+        raise IOError('no checkpoint %s[_rank*].npz' % name)
+    out, attrs = {}, {}
+    for fn in files:
+        with np.load(fn, allow_pickle=False) as z:
+            for k in z.files:
+                if k.startswith('attr__'):
+                    attrs[k[6:]] = z[k].item()
+                elif k.startswith(key_prefix):
+                    a = z[k]
+                    if 'meta__' + k in z.files:
+                        m = z['meta__' + k]
+                        gshape, start = tuple(int(x) for x in m[:a.ndim]), tuple(int(x) for x in m[a.ndim:])
+                        if k not in out:
+                            out[k] = np.zeros(gshape, dtype=a.dtype)
+                        out[k][tuple(slice(s, s + n) for s, n in zip(start, a.shape))] = a
+                    else:
+                        out[k] = a
+    return out, attrs
+
+
+def init_from_file(name, u_hat, space):
+    """Restart: fill this rank's block of the spectral state u_hat from the checkpoint <name>_c written by any
+    number of ranks; returns (tstep, t)."""
+    fields, attrs = read_global(name + '_c', '')
+    keys = sorted(k for k in fields if '/3D/' in k)
+    if not keys:
+        raise IOError('checkpoint %s_c holds no 3D field' % name)
+    g = fields[keys[-1]]
+    sl = space.local_slice(True)
+    u_hat[...] = g[(slice(None),)*(g.ndim - len(sl)) + tuple(sl)]
+    return int(attrs.get('tstep', 0)), float(attrs.get('t', 0.0))
 
 
 class HDF5File(object):
@@ -75,18 +156,22 @@ class HDF5File(object):
         self.checkpoint = checkpoint
         self.results = results
         self.before_host_read = None    # installed by the solver: brings the host mirrors up to date
+        self.before_write = None        # installed by the solver: raises if the GPU exchange reported a fault
 
     def due(self, params):
-        """True when this step writes something (the caller then syncs device -> host first)."""
+        """True when this step may write something (the caller then syncs device -> host first).  Local and cheap:
+        the collective decision is taken in update()."""
         return (params.tstep % params.write_result == 0 or params.tstep % params.checkpoint == 0
-                or 'killspectraldns' in os.listdir(os.getcwd()))
+                or os.path.exists('killspectraldns'))
 
     def update(self, params, **kw):
         write = params.tstep % params.write_result == 0
-        kill = self.check_if_kill(kw.get('comm_', None))
+        kill = self.check_if_kill()
         check = params.tstep % params.checkpoint == 0 or kill
         if not (write or check):
             return
+        if self.before_write is not None:
+            self.before_write()
         if self.before_host_read is not None:
             self.before_host_read()
         if self.cfile is None:
@@ -96,18 +181,17 @@ class HDF5File(object):
             self.cfile.f.attrs.create('t', 0.0)
             self.cfile.close()
         if self.wfile is None:
-            self.wfile = ShenfunFile(self.filename + '_w', self.results.get('space'), mode=params.filemode)
+            self.wfile = ShenfunFile(self.filename + '_w', self.results.get('space'), mode=params.filemode, per_step=True)
         if write:
             self.update_components(**kw)
             self.wfile.write(params.tstep, self.results['data'], as_scalar=True)
         if check:
-            for key, val in self.checkpoint['data'].items():
-                self.cfile.write(int(key), val)
-                self.cfile.open()
-                self.cfile.f.attrs['tstep'] = int(params.tstep)
-                self.cfile.f.attrs['t'] = float(params.t)
-                self.cfile.close()
-                self.cfile._flush()
+            self.cfile.open()
+            self.cfile.f.attrs['tstep'] = int(params.tstep)
+            self.cfile.f.attrs['t'] = float(params.t)
+            self.cfile.close()
+            # every checkpointed group ('0': current state, '1': previous one for multistep integrators) in one archive
+            self.cfile.write_groups({int(key): val for key, val in self.checkpoint['data'].items()})
             if kill:
                 sys.exit(1)
 
@@ -127,15 +211,20 @@ class HDF5File(object):
 
     @staticmethod
     def check_if_kill(comm=None):
-        found = 1 if 'killspectraldns' in os.listdir(os.getcwd()) else 0
-        if comm is not None:
-            found = comm.allreduce(found)
+        """Collective over ALL ranks, like the reference (h5io/HDF5File.py: comm.allreduce(found)): a rank that has
+        not seen the file yet must not keep stepping against peers that stop.  Rank 0 removes the file."""
+        comm = comm if comm is not None else _comm()
+        found = 1 if os.path.exists('killspectraldns') else 0
+        if comm.Get_size() > 1:
+            found = int(comm.allreduce(found))
         if found > 0:
-            if comm is None or comm.Get_rank() == 0:
+            if comm.Get_rank() == 0:
                 try:
                     os.remove('killspectraldns')
                 except OSError:
                     pass
                 print('killspectraldns Found! Stopping simulations cleanly by checkpointing...')
+            if comm.Get_size() > 1:
+                comm.Barrier()
             return True
         return False

@@ -120,7 +120,7 @@ def test_hdf5file_cadence_and_killfile(compat, tmp_path, monkeypatch):
     assert f.cfile is None and f.wfile is None
     P.tstep = 2
     f.update(P)
-    assert os.path.exists('run_w.npz') and not os.path.exists('run_c.npz')
+    assert os.path.exists('run_w_t2.npz') and not os.path.exists('run_c.npz')      # one results archive per written step
     P.tstep, P.t = 4, 0.04
     f.update(P)
     z = np.load('run_c.npz')
@@ -131,6 +131,67 @@ def test_hdf5file_cadence_and_killfile(compat, tmp_path, monkeypatch):
         f.update(P)
     assert not os.path.exists('killspectraldns')
     f.close()
+    # restart from the checkpoint (h5io/HDF5File.py init_from_file): global shape + local slice travel with the data
+    from spectraldns_b200.io import read_global
+    fields, attrs = read_global('run_c', 'U/3D/')
+    assert attrs['tstep'] == 5 and np.array_equal(fields['U/3D/0'], u_hat)
+
+
+_KILL_WORKER = r'''
+import os, sys
+sys.path[:0] = [%(root)r, os.path.join(%(root)r, 'spectraldns_b200', 'compat')]
+import numpy as np
+import torch.distributed as dist
+dist.init_process_group('gloo')
+rank = dist.get_rank()
+os.chdir(%(cwd)r)
+from spectraldns_b200.io import HDF5File, read_global
+from spectralDNS import config
+
+
+class Space(object):           # a slab-distributed spectral space: axis 1 split over the ranks
+    def global_shape(self, spectral=True):
+        return (4, 4, 3)
+    def local_slice(self, spectral=True):
+        return (slice(0, 4), slice(2*rank, 2*rank + 2), slice(0, 3))
+
+
+u_hat = np.full((3, 4, 2, 3), rank + 1, dtype=complex)
+f = HDF5File('run', checkpoint={'space': Space(), 'data': {'0': {'U': [u_hat]}}}, results={'space': None, 'data': {}})
+P = config.AttributeDict(tstep=1, t=0.01, write_result=10**8, checkpoint=10**8, filemode='w')
+f.update(P)
+dist.barrier()
+if rank == 1:                  # only ONE rank sees the file appear before the next update
+    open('killspectraldns', 'w').close()
+dist.barrier()
+P.tstep = 2
+try:
+    f.update(P)
+    print('rank %%d NOT STOPPED' %% rank)
+except SystemExit:
+    print('rank %%d stopped' %% rank)
+dist.barrier()
+if rank == 0:
+    fields, attrs = read_global('run_c', 'U/3D/')
+    g = fields['U/3D/0']
+    assert g.shape == (3, 4, 4, 3) and (g[:, :, :2] == 1).all() and (g[:, :, 2:] == 2).all() and attrs['tstep'] == 2
+    assert not os.path.exists('killspectraldns')
+    print('KILL_WORKER_OK')
+dist.destroy_process_group()
+'''
+
+
+def test_killfile_is_collective_over_ranks(tmp_path):
+    """Two gloo ranks: the kill file is visible to one rank only when update() runs; both must checkpoint and stop
+    (the reference all-reduces `found`, h5io/HDF5File.py), rank 0 removes the file, and the per-rank checkpoint
+    archives reassemble into the global array."""
+    import subprocess
+    script = tmp_path / 'kill_worker.py'
+    script.write_text(_KILL_WORKER % {'root': ROOT, 'cwd': str(tmp_path)})
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29611', str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and 'KILL_WORKER_OK' in r.stdout and r.stdout.count('stopped') == 2 and 'NOT STOPPED' not in r.stdout, r.stdout[-3000:]
 
 
 def test_timer_interface(compat, capsys):

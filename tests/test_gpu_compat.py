@@ -82,7 +82,7 @@ def test_tg_solvers(sdns, name, mesh, tmp_path, monkeypatch):
     assert int(z['attr__tstep']) == 4
     key = 'U/3D/0' if name == 'NS' else 'curl/3D/0'
     assert rel_l2(z[key], np.array(context.u)) == 0.0
-    assert os.path.exists(name + '_w.npz')
+    assert os.path.exists(name + '_w_t4.npz')
     config.params.write_result = config.params.checkpoint = 1e8
     config.params.T = 0.1
 
