@@ -145,6 +145,11 @@ int sdns_cross2(sdns_plan* plan, void* c, const void* b, int over_k2);
 int sdns_cross1(sdns_plan* plan, void* c, const void* a, const void* b, long long n);
 int sdns_cross2_dense(sdns_plan* plan, void* c, const void* a_real, const void* b);
 int sdns_project(sdns_plan* plan, void* u_hat);
+/* add_pressure_diffusion_NS(du, u_hat, nu, ksq, kk, p_hat, k_over_k2)  (solvers/NS.py:203-217; compiled form
+ * optimization/cython_solvers.in:40-80, dispatched at optimization/__init__.py:12-55): in place
+ * p_hat = sum_i du_i K_i/K^2, du_i -= p_hat K_i + nu K^2 u_hat_i.  p_hat (one spectral component) may be NULL.
+ * Stand-alone version of what the F0 pass fuses into sdns_compute_rhs. */
+int sdns_add_pressure_diffusion(sdns_plan* plan, void* du, const void* u_hat, double nu, void* p_hat);
 
 /* Building blocks of adaptiveRK (BS5_adaptive / BS5_fixed, maths/integrators.py:15-147,193-225):
  * out = base + sum_t coeffs[t]*arrays[t] over ncomp spectral components (base may be NULL), and the

@@ -22,7 +22,7 @@ SYMBOLS = ['sdns_abi_version', 'sdns_last_error', 'sdns_size_supported', 'sdns_p
            'sdns_plan_destroy', 'sdns_workspace_bytes', 'sdns_plan_set_workspace',
            'sdns_plan_set_stream', 'sdns_sync', 'sdns_local_shapes', 'sdns_comm_alloc', 'sdns_comm_handle',
            'sdns_comm_open', 'sdns_comm_status', 'sdns_forward', 'sdns_backward',
-           'sdns_compute_rhs', 'sdns_compute_conv', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2', 'sdns_cross1', 'sdns_cross2_dense', 'sdns_project', 'sdns_lincomb', 'sdns_errnorm',
+           'sdns_compute_rhs', 'sdns_compute_conv', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2', 'sdns_cross1', 'sdns_cross2_dense', 'sdns_project', 'sdns_add_pressure_diffusion', 'sdns_lincomb', 'sdns_errnorm',
            'sdns_energy', 'sdns_rk4_steps_host', 'sdns_launch_count',
            'sdns_profile_enable', 'sdns_profile_read', 'sdns_profile_read_nvlink', 'sdns_profile_read_copies', 'sdns_profile_timeline', 'sdns_xfer_stats']
 
@@ -87,6 +87,7 @@ def lib():
     L.sdns_cross1.argtypes = [vp, vp, vp, vp, C.c_longlong]
     L.sdns_cross2_dense.argtypes = [vp, vp, vp, vp]
     L.sdns_project.argtypes = [vp, vp]
+    L.sdns_add_pressure_diffusion.argtypes = [vp, vp, vp, dbl, vp]
     L.sdns_lincomb.argtypes = [vp, vp, vp, i32, C.POINTER(dbl), C.POINTER(vp), i32]
     L.sdns_errnorm.argtypes = [vp, vp, vp, vp, dbl, dbl, i32, C.POINTER(dbl)]
     L.sdns_energy.argtypes = [vp, vp, i32, C.POINTER(dbl)]

@@ -100,8 +100,21 @@ def getConvection(convection):
 
 
 def add_pressure_diffusion(rhs, u_hat, nu, K2, K, P_hat, K_over_K2):
-    """Fused into the last transform pass of ComputeRHS (kernel family ns_f0); not callable alone."""
-    raise NotImplementedError('add_pressure_diffusion is fused into ComputeRHS on the B200 path')
+    """rhs -= P_hat*K + nu*K2*u_hat with P_hat = sum(rhs*K_over_K2, 0) (reference NS.py:203-217,
+    cython_solvers.in:40-80).  ComputeRHS fuses this into its last transform pass (kernel family ns_f0);
+    called on its own -- the fine-grained plug-in surface of optimization/__init__.py:12-55 -- it runs as
+    one launch behind sdns_add_pressure_diffusion on host arrays staged in and out."""
+    from spectralDNS.maths import _engine_for
+    eng = _engine_for(u_hat if hasattr(u_hat, '_space') else rhs)
+    p = eng.plan
+    p.use_current_stream()
+    d_r = eng.upload('apd_rhs', rhs, p.complex, p.tcomplex)
+    d_u = eng.upload('apd_u', u_hat, p.complex, p.tcomplex)
+    d_p = eng.stage('apd_p', p.spectral_shape, p.tcomplex)
+    p.add_pressure_diffusion(d_r, d_u, float(nu), d_p)
+    rhs[...] = d_r.cpu().numpy()
+    P_hat[...] = d_p.cpu().numpy()
+    return rhs
 
 
 add_pressure_diffusion._sdns_builtin = True

@@ -1440,6 +1440,46 @@ __global__ void project_kernel(typename C2<T>::type* u, const T* kx, const T* ky
     }
 }
 
+// add_pressure_diffusion_NS(du, u_hat, nu, ksq, kk, p_hat, k_over_k2)  (solvers/NS.py:203-217, cython_solvers.in:40-80):
+// p_hat = sum_i du_i K_i/K^2 ; du_i -= p_hat K_i + nu K^2 u_hat_i -- the same arithmetic, in the same order, as the F0
+// epilogue that fuses it into the right-hand side
+template <typename T>
+__global__ void pressure_diffusion_kernel(typename C2<T>::type* du, const typename C2<T>::type* uh, typename C2<T>::type* ph,
+                                          T nu, const T* kx, const T* ky, const T* kz, int N0, int N1, int Nh) {
+    typedef typename C2<T>::type V;
+    const long long n = (long long)N0 * N1 * Nh;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int i2 = (int)(i % Nh); const long long r = i / Nh;
+        const int i1 = (int)(r % N1); const int i0 = (int)(r / N1);
+        const T k0 = kx[i0], k1 = ky[i1], k2 = kz[i2];
+        T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;
+        const T ks = ksq == (T)0 ? (T)1 : ksq;
+        const T q0 = k0 / ks, q1 = k1 / ks, q2 = k2 / ks;
+        const T z = nu * ksq;
+        V d0 = du[i], d1 = du[n + i], d2 = du[2 * n + i];
+        const V w0 = uh[i], w1 = uh[n + i], w2 = uh[2 * n + i];
+        V p;
+        p.x = d0.x * q0 + d1.x * q1; p.x += d2.x * q2;
+        p.y = d0.y * q0 + d1.y * q1; p.y += d2.y * q2;
+        if (ph) ph[i] = p;
+        d0.x -= p.x * k0; d0.y -= p.y * k0; d1.x -= p.x * k1; d1.y -= p.y * k1; d2.x -= p.x * k2; d2.y -= p.y * k2;
+        d0.x -= z * w0.x; d0.y -= z * w0.y; d1.x -= z * w1.x; d1.y -= z * w1.y; d2.x -= z * w2.x; d2.y -= z * w2.y;
+        du[i] = d0; du[n + i] = d1; du[2 * n + i] = d2;
+    }
+}
+
+extern "C" int sdns_add_pressure_diffusion(sdns_plan* p, void* du, const void* u_hat, double nu, void* p_hat) {
+    int e = need_ws(p); if (e) return e;
+    if (!du || !u_hat || du == u_hat) return fail(SDNS_ERR_ARG, "sdns_add_pressure_diffusion: du and u_hat must be distinct arrays");
+    if (p->prec) SDNS_LAUNCH(pressure_diffusion_kernel<double>, SDNS_EW_BLOCKS, 256, 0, p->stream)((double2*)du, (const double2*)u_hat, (double2*)p_hat, nu,
+        (const double*)(p->ws + p->kx_off), (const double*)(p->ws + p->ky_off), (const double*)(p->ws + p->kz_off), p->N[0], p->N1l, p->Nh);
+    else SDNS_LAUNCH(pressure_diffusion_kernel<float>, SDNS_EW_BLOCKS, 256, 0, p->stream)((float2*)du, (const float2*)u_hat, (float2*)p_hat, (float)nu,
+        (const float*)(p->ws + p->kx_off), (const float*)(p->ws + p->ky_off), (const float*)(p->ws + p->kz_off), p->N[0], p->N1l, p->Nh);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+
 extern "C" int sdns_cross1(sdns_plan* p, void* c, const void* a, const void* b, long long n) {
     if (!p || !c || !a || !b || n < 1) return fail(SDNS_ERR_ARG, "sdns_cross1: bad argument");
     if (p->prec) SDNS_LAUNCH(cross1_kernel<double>, SDNS_EW_BLOCKS, 256, 0, p->stream)((double*)c, (const double*)a, (const double*)b, n);

@@ -234,6 +234,14 @@ class Plan(object):
         _lib.check(self.lib.sdns_project(self._p, u_hat.data_ptr()))
         return u_hat
 
+    def add_pressure_diffusion(self, du, u_hat, nu, p_hat=None):
+        """add_pressure_diffusion_NS (solvers/NS.py:203-217, cython_solvers.in:40-80) on its own: in place on du."""
+        for t, n in ((du, 'du'), (u_hat, 'u_hat')):
+            assert self._chk(t, self.tcomplex, self.spectral_shape, n) == 3
+        _lib.check(self.lib.sdns_add_pressure_diffusion(self._p, du.data_ptr(), u_hat.data_ptr(), float(nu),
+                                                        p_hat.data_ptr() if p_hat is not None else None))
+        return du
+
     def lincomb(self, out, base, coeffs, arrays):
         """out = base + sum_t coeffs[t]*arrays[t] (base may be None); <= 9 terms."""
         n = len(coeffs)

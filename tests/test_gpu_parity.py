@@ -233,7 +233,13 @@ def test_full_size_properties(cfg):
 @pytest.mark.parametrize('cfg', [((16, 16, 512), 'double', '2/3-rule'), ((16, 16, 512), 'double', '3/2-rule'),
                                  ((16, 16, 1024), 'double', '2/3-rule'), ((16, 16, 2048), 'single', '2/3-rule'),
                                  ((16, 16, 1024), 'single', '3/2-rule'), ((512, 16, 16), 'double', '2/3-rule'),
-                                 ((16, 512, 16), 'double', '3/2-rule'), ((16, 16, 512), 'double', 'None')])
+                                 ((16, 512, 16), 'double', '3/2-rule'), ((16, 16, 512), 'double', 'None'),
+                                 # 1024 / 2048 (and their 3/2 paddings 1536 / 3072) on the strided axes: what the
+                                 # 1024^3 and 2048^3 configurations of BASELINE.json run on axes 0 and 1
+                                 ((1024, 16, 16), 'double', '2/3-rule'), ((16, 1024, 16), 'double', '2/3-rule'),
+                                 ((2048, 16, 16), 'single', '2/3-rule'), ((16, 2048, 16), 'single', '2/3-rule'),
+                                 ((1024, 16, 16), 'single', '3/2-rule'), ((16, 1024, 16), 'double', '3/2-rule'),
+                                 ((2048, 8, 16), 'single', '3/2-rule'), ((2048, 16, 16), 'double', '2/3-rule')])
 def test_long_axis_rhs(cfg):
     """Transform lengths 512..2048 on one axis (the multi-warp-per-line fused z kernel and the long strided
     passes) at a size the oracle finishes in seconds: NS ComputeRHS + one RK4 step on a random field."""
@@ -250,8 +256,6 @@ def test_long_axis_rhs(cfg):
     assert rel_l2(p.to_host(d_u), o.solve(u0, 'NS', 1, 0.001, nu)) < TOL[prec]
 
 
-@pytest.mark.skipif(not os.environ.get('SDNS_TEST_NEW'), reason='lengths 60 / 90 were added after the round-1 GPU budget was spent and are '
-                    'verified on the emulator only; SDNS_TEST_NEW=1 runs them on the GPU (first call of round 2)')
 @pytest.mark.parametrize('cfg', [((60, 60, 60), 'double', '3/2-rule', 'NS'), ((60, 60, 60), 'single', '2/3-rule', 'NS'),
                                  ((60, 16, 32), 'double', '2/3-rule', 'VV'), ((16, 90, 16), 'double', 'None', 'NS'),
                                  ((32, 16, 60), 'single', '3/2-rule', 'VV')])
@@ -272,3 +276,64 @@ def test_lengths_60_and_90(cfg):
     assert rel_l2(p.to_host(d_u), o.solve(u0, solver, 1, 0.001, nu)) < TOL[prec]
     u = rng.standard_normal((3,)+tuple(N)).astype(o.float)
     assert rel_l2(p.to_host(p.forward(p.to_device(u))), o.forward(u)) < TOL[prec]
+
+
+
+def _ref_cython(precision):
+    """The reference's own compiled kernels (oracle/_ref, built in the container from the Cython templates where
+    they lie); None on a box where they are missing."""
+    import importlib
+    import sys
+    import build_ref_cython as brc
+    if not brc.available() and not brc.build():
+        return None
+    if brc.OUT not in sys.path:
+        sys.path.insert(0, brc.OUT)
+    return [importlib.import_module('cython_%s_%s' % (precision, m)) for m in ('maths', 'solvers')]
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_standalone_operators_against_reference_cython(precision):
+    """The fine-grained plug-in surface (optimization/__init__.py:12-55): sdns_cross1, sdns_cross2 (wavenumber form,
+    with and without 1/k^2), sdns_cross2_dense, sdns_project and sdns_add_pressure_diffusion as stand-alone calls,
+    against the reference's compiled Cython (cython_maths.in:8-86, cython_solvers.in:40-80) when oracle/_ref is
+    there, and always against the oracle."""
+    N = (16, 12, 20)
+    Lbox = (2*np.pi, 4*np.pi, 6*np.pi)
+    o = so.Oracle(N, L=Lbox, precision=precision)
+    p = make_plan(N, L=Lbox, precision=precision)
+    tol = 1e-14 if precision == 'double' else 1e-6
+    rng = np.random.RandomState(5)
+    ref = _ref_cython(precision)
+
+    def cplx(shape):
+        return (rng.standard_normal(shape) + 1j*rng.standard_normal(shape)).astype(o.complex)
+    a = rng.standard_normal((3,)+N).astype(o.float)
+    b = rng.standard_normal((3,)+N).astype(o.float)
+    c = p.to_host(p.cross1(p.empty_physical(), p.to_device(a), p.to_device(b)))
+    assert rel_l2(c, o.cross1(a, b)) < tol
+    bh = cplx((3,)+o.sshape)
+    c2 = p.to_host(p.cross2(p.empty_spectral(), p.to_device(bh)))
+    assert rel_l2(c2, o.cross2(o.K, bh)) < tol
+    c2k = p.to_host(p.cross2(p.empty_spectral(), p.to_device(bh), over_k2=True))
+    assert rel_l2(c2k, o.cross2(o.K_over_K2, bh)) < tol
+    ad = rng.standard_normal((3,)+o.sshape).astype(o.float)
+    cd = p.to_host(p.cross2_dense(p.empty_spectral(), p.to_device(ad), p.to_device(bh)))
+    assert rel_l2(cd, o.cross2(ad, bh)) < tol
+    pr = p.to_host(p.project(p.to_device(bh)))
+    pref = bh - np.sum(o.K_over_K2*bh, 0)*np.array([np.broadcast_to(k, o.sshape) for k in o.K])
+    assert rel_l2(pr, pref) < tol
+    du, uh = cplx((3,)+o.sshape), cplx((3,)+o.sshape)
+    nu = 0.0123
+    d_du, d_p = p.to_device(du), p.empty_spectral(0)
+    p.add_pressure_diffusion(d_du, p.to_device(uh), nu, d_p)
+    du_or, p_or = o.add_pressure_diffusion(du.copy(), uh, o.float(nu))
+    assert rel_l2(p.to_host(d_du), du_or) < tol and rel_l2(p.to_host(d_p), p_or) < tol
+    if ref is not None:
+        maths, solvers = ref
+        assert rel_l2(c, maths.cross1(np.zeros_like(a), a, b)) < tol
+        assert rel_l2(c2, maths.cross2(np.zeros_like(bh), [np.ascontiguousarray(k) for k in o.K], bh)) < tol
+        assert rel_l2(cd, maths.cross2(np.zeros_like(bh), ad, bh)) < tol
+        p_ref = np.zeros(o.sshape, dtype=o.complex)
+        du_ref = solvers.add_pressure_diffusion_NS(du.copy(), uh, o.float(nu), o.K2, o.K, p_ref, o.K_over_K2)
+        assert rel_l2(p.to_host(d_du), du_ref) < tol and rel_l2(p.to_host(d_p), p_ref) < tol

@@ -293,7 +293,7 @@ def test_emulated_lengths_60_only_on_the_vortex_path(emu_60):
 
 
 def test_emulated_small_kernels(emu):
-    """energy (shuffle + shared-memory reduction), Euler / AB2 steps, cross2, project, lincomb / errnorm through the C ABI."""
+    """energy (shuffle + shared-memory reduction), Euler / AB2 steps, cross2, project, add_pressure_diffusion, lincomb / errnorm through the C ABI."""
     import ctypes as C
     L, ep = emu
     vp, dbl = C.c_void_p, C.c_double
@@ -332,6 +332,12 @@ def test_emulated_small_kernels(emu):
     p.chk(L.sdns_project(p.p, w.ctypes.data))
     pref = v - np.sum(o.K_over_K2*v, 0)*np.array([np.broadcast_to(k, o.sshape) for k in o.K])
     assert rel_l2(w, pref) < 1e-13
+    # add_pressure_diffusion_NS on its own (cython_solvers.in:40-80)
+    L.sdns_add_pressure_diffusion.argtypes = [vp, vp, vp, dbl, vp]
+    du, ph = v.copy(), np.zeros(o.sshape, dtype=o.complex)
+    p.chk(L.sdns_add_pressure_diffusion(p.p, du.ctypes.data, f0.ctypes.data, 0.0123, ph.ctypes.data))
+    du_ref, p_ref = o.add_pressure_diffusion(v.copy(), f0, 0.0123)
+    assert rel_l2(du, du_ref) < 1e-14 and rel_l2(ph, p_ref) < 1e-14
     out = np.zeros_like(f0)
     coeffs = (dbl*2)(0.25, -1.5)
     arrs = (vp*2)(f0.ctypes.data, c.ctypes.data)
