@@ -26,7 +26,22 @@ def main():
     ap.add_argument('--solver', default='NS')
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--tag', default='')
+    ap.add_argument('--configs', nargs='*', default=None,
+                    help='several configurations in one process, each grid:precision:dealias[:solver], e.g. 512:double:2/3-rule')
+    ap.add_argument('--only', default=None, help='conv | rhs | rk4: time just this call')
     a = ap.parse_args()
+    if a.configs:
+        for c in a.configs:
+            f = c.split(':')
+            a.grid, a.precision, a.dealias = [int(f[0])], f[1], f[2]
+            a.solver = f[3] if len(f) > 3 else 'NS'
+            run(a)
+            torch.cuda.empty_cache()
+    else:
+        run(a)
+
+
+def run(a):
     N = tuple(a.grid*3 if len(a.grid) == 1 else a.grid)
     p = Plan(N, precision=a.precision, dealias=a.dealias, solver=a.solver)
     g = torch.Generator(device='cuda').manual_seed(0)
@@ -39,6 +54,8 @@ def main():
            'lib': os.environ.get('SDNS_LIBPATH', 'default')}
     for name, fn in (('conv', lambda: p.compute_conv(r, u)), ('rhs', lambda: p.compute_rhs(r, u, 1e-3, 1e-3)),
                      ('rk4', lambda: p.rk4_step(u, u1, u2, 1e-4, 1e-3, 1e-3))):
+        if a.only and name != a.only:
+            continue
         for _ in range(2):
             fn()
         torch.cuda.synchronize()

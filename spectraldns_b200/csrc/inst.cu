@@ -168,6 +168,46 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
 }
 
 template <typename T, int N, int MODE>
+static int run_b0x(const StridedArgs<T>& a, cudaStream_t st) {
+    typedef BXCfg<T, N> C;
+    auto kern = a.xchunk > 0 ? b0x_kernel<T, N, C::E, C::TC, MODE, true, C::minBlocks>
+                             : b0x_kernel<T, N, C::E, C::TC, MODE, false, C::minBlocks>;
+    static bool once = false;
+    if (!once) {
+        cudaError_t e = set_smem(b0x_kernel<T, N, C::E, C::TC, MODE, true, C::minBlocks>, C::smem);
+        if (e == cudaSuccess) e = set_smem(b0x_kernel<T, N, C::E, C::TC, MODE, false, C::minBlocks>, C::smem);
+        if (e != cudaSuccess) return (int)e;
+        once = true;
+    }
+    const long long tiles = (a.ncols + C::TC - 1) / C::TC;
+    {   // the passes address rows with 32-bit element offsets relative to the column base
+        auto mag = [](long long v) { return v < 0 ? -v : v; };
+        const long long big = std::max(std::max(mag(a.in_ls), mag(a.out_ls)), mag(a.out_ls2));
+        if ((long long)N * big >= (1LL << 31)) return -1001;
+    }
+    StridedArgs<T> b = a;
+    b.xuniform = 0;
+    if (a.xchunk > 0 && a.xchunk % C::P == 0 && a.omap.shift % C::P == 0) {
+        const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;     // shift rounded up to whole chunks
+        b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
+    }
+    xfer_prepare(b.x, C::smem, C::threads);
+    dim3 grid((unsigned)tiles + b.x.nctas);
+    SDNS_LAUNCH(kern, grid, C::threads, C::smem, st)(b);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int N, int MODE>
+static int run_b0(const StridedArgs<T>& a, cudaStream_t st) {
+    // one tile per CTA: a capped grid (grid_cap, an experiment of the multi-GPU pipeline) and tile counts beyond 32 bits
+    // stay with strided_kernel
+    if constexpr (BXCfg<T, N>::ok) {
+        if (a.grid_cap <= 0 && a.ncols < (1LL << 31)) return run_b0x<T, N, MODE>(a, st);
+    }
+    return run_strided<T, N, MODE, +1>(a, st);
+}
+
+template <typename T, int N, int MODE>
 static int run_f0x(const StridedArgs<T>& a, cudaStream_t st) {
     typedef FXCfg<T, N> C;
     auto kern = f0x_kernel<T, N, C::E, C::TC, MODE, C::minBlocks>;
@@ -365,9 +405,9 @@ int SDNS_FN(int n, const void* args, cudaStream_t st) {
 #elif SDNS_FAMILY == 1
 #define X(N) case N: return run_strided<T, N, S_PLAIN, +1>(*(const StridedArgs<T>*)args, st);
 #elif SDNS_FAMILY == 2
-#define X(N) case N: return run_strided<T, N, S_NS_B0, +1>(*(const StridedArgs<T>*)args, st);
+#define X(N) case N: return run_b0<T, N, S_NS_B0>(*(const StridedArgs<T>*)args, st);
 #elif SDNS_FAMILY == 3
-#define X(N) case N: return run_strided<T, N, S_VV_B0, +1>(*(const StridedArgs<T>*)args, st);
+#define X(N) case N: return run_b0<T, N, S_VV_B0>(*(const StridedArgs<T>*)args, st);
 #elif SDNS_FAMILY == 4
 #define X(N) case N: return run_f0<T, N, S_NS_F0>(*(const StridedArgs<T>*)args, st);
 #elif SDNS_FAMILY == 5

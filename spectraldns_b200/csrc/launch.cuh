@@ -141,6 +141,33 @@ struct FXCfg {
     static constexpr int minBlocks = cmax(1, fx_blocks(P, TC > 0 ? TC : 1, csize, N, needRegs));
 };
 
+// field-parallel B0 (b0x_kernel): 3 thread groups; shared memory = 3 exchange buffers + 3 slot arrays.  Used when a
+// tile of >= 64-byte rows fits (fp64: N <= 512, fp32: N <= 1024); the other lengths keep strided_kernel's B0 branch.
+constexpr int bx_tc(int P, int tcfull, int csize, int N) {
+    for (int tc = tcfull; tc * csize >= 64; tc /= 2)
+        if (3 * P * tc <= 768 && 6LL * N * tc * csize <= 200 * 1024) return tc;
+    return 0;
+}
+template <typename T, int N>
+struct BXCfg {
+    static constexpr int E = sizeof(T) == 8 ? pick_E(N, 8) : pick_E(N, 16);
+    static constexpr int P = N / E;
+    static constexpr int csize = 2 * (int)sizeof(T);
+    static constexpr int TC = bx_tc(P, 128 / csize, csize, N);
+#ifdef SDNS_NO_B0X
+    static constexpr bool ok = false;
+#elif defined(SDNS_F32_PAIRS)
+    static constexpr bool ok = TC > 0 && plan_ok(N, E) && N % 5 != 0 && sizeof(T) == 8;   // experiment build: fp32 B0 on column pairs
+#else
+    static constexpr bool ok = TC > 0 && plan_ok(N, E) && N % 5 != 0;
+#endif
+    static constexpr size_t smem = (size_t)6 * N * (TC > 0 ? TC : 1) * csize;
+    static constexpr int threads = 3 * P * (TC > 0 ? TC : 1);
+    static constexpr int bySmem = (int)((224 * 1024) / (smem + 1024));
+    static constexpr int needRegs = sizeof(T) == 8 ? 84 : 64;
+    static constexpr int minBlocks = cmax(1, cmin(cmin(bySmem, 2048 / threads), cmin(65536 / (threads * needRegs), 4)));
+};
+
 // MHD epilogue: six accumulators per thread -> fewer elements per thread
 template <typename T, int N>
 struct MCfg {
@@ -185,7 +212,10 @@ struct ZXCfg {
     static constexpr size_t smem = ((size_t)LP * LPC + (size_t)2 * E * 32 * LPC) * 2 * sizeof(T);
     static constexpr int QN3 = (M / 3 + 2 + 31) / 32;        // covers the 2/3-rule and 3/2-rule mode counts
     static constexpr int QN2 = E / 2 + 1;                    // all M/2+1 modes
-    static constexpr int needRegs = sizeof(T) == 8 ? (E > 8 ? 255 : 168) : (E > 16 ? 255 : (E > 8 ? 168 : 128));
+#ifndef SDNS_ZX_E8_REGS64
+#define SDNS_ZX_E8_REGS64 168
+#endif
+    static constexpr int needRegs = sizeof(T) == 8 ? (E > 8 ? 255 : SDNS_ZX_E8_REGS64) : (E > 16 ? 255 : (E > 8 ? 168 : 128));
     static constexpr int minBlocks = cmax(1, cmin(cmin((int)((216 * 1024) / (smem + 1024)), 16), 65536 / (128 * needRegs)));
 };
 
@@ -244,7 +274,10 @@ struct ZYCfg {
     static constexpr int QN3 = (M / 3 + 2 + P - 1) / P;       // covers the 2/3-rule and 3/2-rule mode counts
     static constexpr int QN2 = (M / 2 + 1 + P - 1) / P;       // all M/2+1 modes
     static constexpr size_t smem_q(int qn) { return ((size_t)(LP > 2 * qn * P ? LP : 2 * qn * P) + (size_t)2 * E * P) * 2 * sizeof(T); }
-    static constexpr int needRegs = sizeof(T) == 8 ? (E > 12 ? 255 : (E > 8 ? 224 : (E > 4 ? 168 : SDNS_ZY_E4_REGS))) : (E > 16 ? 224 : (E > 12 ? 168 : 128));
+#ifndef SDNS_ZY_E8_REGS64
+#define SDNS_ZY_E8_REGS64 168
+#endif
+    static constexpr int needRegs = sizeof(T) == 8 ? (E > 12 ? 255 : (E > 8 ? 224 : (E > 4 ? SDNS_ZY_E8_REGS64 : SDNS_ZY_E4_REGS))) : (E > 16 ? 224 : (E > 12 ? 168 : 128));
     static constexpr int minBlocks_q(int qn) {
         return cmax(1, cmin(cmin((int)((216 * 1024) / (smem_q(qn) + 1024)), 16), 65536 / (P * needRegs)));
     }

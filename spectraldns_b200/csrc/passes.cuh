@@ -170,13 +170,13 @@ __device__ __forceinline__ void load_line(V (&x)[E], const V* __restrict__ pin, 
 // at line index i % xchunk.  When P and the map's shift divide into xchunk (a.xuniform, the normal case) the
 // destination rank and the chunk-local block of every q are the same for all threads of the CTA, so they are
 // computed once in uniform registers; otherwise per element (reciprocal multiply, exact for i < 2^22).
-template <typename T, int N, int E, bool SCALE, typename V>
+template <typename T, int N, int E, bool SCALE, typename V, bool LOCAL_ONLY = false>
 __device__ __forceinline__ void store_line(const V (&x)[E], const StridedArgs<T>& a, int f, long long obase,
                                            long long obase2, int t, bool valid, T scale) {
     constexpr int P = N / E;
     const long long fo = f * a.out_fs + obase;
     const RowSel<N, E> rs(a.omap, t, valid);
-    if (a.xchunk == 0) {
+    if (LOCAL_ONLY || a.xchunk == 0) {          // LOCAL_ONLY: the kernel variant launched on a single GPU
         V* pout = opaque(reinterpret_cast<V*>(a.out) + fo);
         const int l = (int)a.out_ls;
         const int olo = t * l, ohi = (t - a.omap.shift) * l, step = P * l;
@@ -684,6 +684,28 @@ f0x_kernel(const StridedArgs<T> a) {
     SmemLine<TC, 0> map; map.base = c;
     int phase = 0;
     V* ex = sm + g * (N * TC);
+#ifdef SDNS_F0_PREFETCH
+    // The epilogue moves four times the bytes of the transform input (the RK4 stage update touches u_hat, u1, u2 and
+    // u0).  Ask L2 for this thread's epilogue points now: the state streams in from HBM underneath the W3 loads and
+    // the transform (which has no memory traffic of its own) instead of after them, at no register cost.
+    if (valid && a.out_mode == OUT_STAGE) {
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int j0 = t + q * P;
+            if (q % 3 == g % 3 && axis_ok(a.omap, N, j0)) {
+                const int i0 = axis_idx(a.omap, j0);
+                const long long offu = (long long)i0 * a.uh_ls + (long long)c1 * a.uh_os + c2;
+                const long long offt = (long long)i0 * a.t_ls + (long long)c1 * a.t_os + c2;
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    prefetch_l2(a.u_hat + f * a.st_fs + offu);
+                    if (a.rk > 0) prefetch_l2(a.u2 + f * a.st_fs + offt);
+                    if (a.rk > 0 && a.rk < 3) prefetch_l2(a.u1 + f * a.st_fs + offt);
+                }
+            }
+        }
+    }
+#endif
     {
         V x[E];
         load_line<T, N, E>(x, a.in + (g * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
@@ -700,7 +722,11 @@ f0x_kernel(const StridedArgs<T> a) {
     const int i1 = c1, i2 = c2;
     const T k1 = a.ky[i1], k2 = a.kz[i2];
     const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
+#ifdef SDNS_F0_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int q = g; q < E; q += 3) {
         const int j0 = t + q * P;
         if (!axis_ok(a.omap, N, j0)) continue;
@@ -766,6 +792,82 @@ f0x_kernel(const StridedArgs<T> a) {
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// B0 for NS / VV, field-parallel: three thread groups, group g loads state field g ONCE (one load phase per tile,
+// all three fields in flight together), publishes it in thread-private shared-memory slots, transforms and stores
+// it as the direct field, then forms component g of i k x (.) from the other two groups' slots, transforms and
+// stores that.  strided_kernel's B0 branch runs six load -> transform -> store phases back to back per CTA, the
+// three curl components re-reading their inputs; here a tile has one load phase and two transform phases.
+// Shared memory: three exchange buffers + three slot arrays.  XCH: the output feeds a slab transpose (stores into
+// peer GPUs / send slots); the single-GPU instance leaves that addressing out of its register budget.
+// ---------------------------------------------------------------------------------------
+template <typename T, int N, int E, int TC, int MODE, bool XCH, int MINB>
+__global__ void __launch_bounds__(3 * (N / E) * TC, MINB)
+b0x_kernel(const StridedArgs<T> a) {
+    typedef typename C2<T>::type V;
+    SDNS_DYN_SMEM(smraw);
+    SDNS_XFER_ROLE(a, smraw)
+    V* sm = reinterpret_cast<V*>(smraw);
+    constexpr int P = N / E;
+    constexpr int NT = P * TC;
+    const int g = threadIdx.x / NT;                 // state field loaded by this thread group
+    const int tid = threadIdx.x - g * NT;
+    const int c = tid % TC;
+    const int t = tid / TC;
+    const int ga = (g + 1) % 3, gb = (g + 2) % 3;
+    SmemLine<TC, 0> map; map.base = c;
+    int phase = 0;
+    V* ex = sm + g * (N * TC);                      // this group's exchange buffer
+    V* raw = sm + 3 * (N * TC);                     // [field][q][thread of the group]
+    const int fdir = (MODE == S_VV_B0) ? 3 + g : g; // NS: (u_hat, i k x u_hat); VV: (i k x w_hat / k^2, w_hat)
+    const int fcrs = (MODE == S_VV_B0) ? g : 3 + g;
+    // One tile per CTA (a grid-stride loop's state would stay live across the transforms), 32-bit tile arithmetic
+    // (the host checks ncols < 2^31), and everything a store needs is re-derived from (c1, c2) right before it:
+    // little more than the line itself is live across the transforms, which is what lets 768 threads share an SM.
+    {
+        const unsigned int ncols = (unsigned int)a.ncols;
+        const unsigned int col = (unsigned int)bx * TC + c;
+        const bool valid = col < ncols;
+        const unsigned int run = valid ? col / (unsigned int)a.cw : 0u;
+        const int c1 = (int)run + a.c1_off;
+        const int c2 = (valid ? (int)(col - run * (unsigned int)a.cw) : 0) + a.c2_off;
+        V x[E];
+        {
+            const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
+            load_line<T, N, E>(x, a.in + (g * a.in_fs + (long long)c1m * a.in_os + c2), a.in_ls, a.imap, t, valid);
+        }
+#pragma unroll
+        for (int q = 0; q < E; ++q) raw[(g * E + q) * NT + tid] = x[q];
+        fft_line<T, N, E, +1, 0, 1>(x, t, a.tw, ex, map, 0, phase);
+        store_line<T, N, E, false, V, !XCH>(x, a, fdir, ((long long)c1 + a.c1_out_off) * a.out_os + c2,
+                                   ((long long)c1 + a.c1_out_off2) * a.out_os + c2, t, valid, (T)1);
+        __syncthreads();                            // every group's slots are written
+        {
+            const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
+            const T k1 = valid ? a.ky[c1m] : (T)0;
+            const T k2 = valid ? a.kz[c2] : (T)0;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const int j = t + q * P;
+                const bool ok = valid && axis_ok(a.imap, N, j);
+                const V bb = raw[(gb * E + q) * NT + tid], ba = raw[(ga * E + q) * NT + tid];   // zero where not kept
+                const T k0 = ok ? a.kx[axis_idx(a.imap, j)] : (T)0;
+                T ka = ga == 0 ? k0 : (ga == 1 ? k1 : k2);
+                T kb = gb == 0 ? k0 : (gb == 1 ? k1 : k2);
+                if (MODE == S_VV_B0) {
+                    T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;   // NS.py:42-44
+                    if (ksq == (T)0) ksq = (T)1;                        // NS.py:46-48
+                    ka = ka / ksq; kb = kb / ksq;                       // K_over_K2
+                }
+                x[q] = icross<T, V>(ka, bb, kb, ba);
+            }
+        }
+        fft_line<T, N, E, +1, 0, 1>(x, t, a.tw, ex, map, 0, phase);
+        store_line<T, N, E, false, V, !XCH>(x, a, fcrs, ((long long)c1 + a.c1_out_off) * a.out_os + c2,
+                                   ((long long)c1 + a.c1_out_off2) * a.out_os + c2, t, valid, (T)1);
     }
 }
 
