@@ -165,6 +165,27 @@ int sdns_errnorm(sdns_plan* plan, const void* u0, const void* u1, const void* er
  * Synchronous (returns the value). */
 int sdns_energy(sdns_plan* plan, const void* u_hat, int ncomp, double* out);
 
+/* Diagnostics and low-wavenumber forcing of demo/Isotropic.py, computed where the state lives (the reference does
+ * them with numpy on the context's host arrays).  All reductions cover the LOCAL block and are synchronous; the
+ * caller sums over ranks.
+ *   sdns_energy_weighted : energy_fourier(U_hat*weight, T), weight a real field of the spectral shape or NULL
+ *                          (demo/Isotropic.py:167-169; weight_is_double selects float64 / float32 storage)
+ *   sdns_scale_field     : U_hat *= a*factor + b*(1 - factor), factor a real field broadcast over the components:
+ *                          (a, b) = (1, 0) multiplies by the field; (alpha, 1) with factor = k2_mask is the forcing
+ *                          rescale U_hat *= alpha*k2_mask + (1 - k2_mask) of Isotropic.py:180
+ *   sdns_set_mode        : U_hat[:, i0, i1, i2] = re + i im, i1 local (Isotropic.py:63-64, 162-163: the mean mode)
+ *   sdns_enstrophy       : energy_fourier(cross2(K, U_hat), T), the `dissipation` of Isotropic.py:243-244
+ *   sdns_divergence_norm : sum w |i K.U_hat|^2 = L2_norm(get_divergence(...)) by Parseval (Isotropic.py:245-247)
+ *   sdns_spectrum        : shell sums and point counts of spectrum() (Isotropic.py:88-118): shell i holds the modes
+ *                          with i + 0.5 < |K| <= i + 1.5; sums[i] = sum w sum_c |U_hat_c|^2 (w = 1 on the first and
+ *                          last k2 plane, else 2), counts[i] = number of modes; 2 <= nbins <= 4096, shell nbins-1 unused */
+int sdns_energy_weighted(sdns_plan* plan, const void* u_hat, int ncomp, const void* weight, int weight_is_double, double* out);
+int sdns_scale_field(sdns_plan* plan, void* u_hat, int ncomp, const void* factor, int factor_is_double, double a, double b);
+int sdns_set_mode(sdns_plan* plan, void* u_hat, int ncomp, int i0, int i1, int i2, double re, double im);
+int sdns_enstrophy(sdns_plan* plan, const void* u_hat, double* out);
+int sdns_divergence_norm(sdns_plan* plan, const void* u_hat, double* out);
+int sdns_spectrum(sdns_plan* plan, const void* u_hat, int ncomp, int nbins, double* sums, double* counts);
+
 /* Host-buffer variant of integrate(): copies the state from (pinned) host memory, runs nsteps RK4
  * steps, copies it back.  This is the call a host-array caller (the reference's numpy context)
  * makes; bench.py's e2e number is measured through it. */

@@ -162,6 +162,52 @@ class Oracle(object):
             return 2*np.sum(w[..., 1:-1]) + np.sum(w[..., 0]) + np.sum(w[..., -1])
         return 2*np.sum(w[..., 1:]) + np.sum(w[..., 0])
 
+    # ---- diagnostics and forcing of demo/Isotropic.py (user code of the reference, restated for the device versions)
+    def spectrum(self, u_hat):
+        """demo/Isotropic.py:88-118 on the global array: (Ek, bins).  uiui counts the first and last k2 plane once
+        and the others twice, times 4 pi / 3; shell i holds np.digitize(sqrt(K2), bins, right=True) == i + 1."""
+        u_hat = np.asarray(u_hat)
+        uiui = np.zeros(u_hat[0].shape)
+        uiui[..., 1:-1] = 2*np.sum((u_hat[..., 1:-1]*np.conj(u_hat[..., 1:-1])).real, axis=0)
+        uiui[..., 0] = np.sum((u_hat[..., 0]*np.conj(u_hat[..., 0])).real, axis=0)
+        uiui[..., -1] = np.sum((u_hat[..., -1]*np.conj(u_hat[..., -1])).real, axis=0)
+        uiui *= (4./3.*np.pi)
+        Nb = int(np.sqrt(sum((np.array(self.N)/2)**2)/3))
+        bins = np.array(range(0, Nb))+0.5
+        z = np.digitize(np.sqrt(self.K2), bins, right=True)
+        Ek = np.zeros(Nb)
+        ll = np.zeros(Nb)
+        for i, k in enumerate(bins[1:]):
+            k0 = bins[i]
+            ii = np.where((z > k0) & (z <= k))
+            ll[i] = len(ii[0])
+            Ek[i] = (k**3 - k0**3)*np.sum(uiui[ii])
+        for i in range(Nb):
+            if not ll[i] == 0:
+                Ek[i] = Ek[i] / ll[i]
+        return Ek, bins
+
+    def forcing_rescale(self, u_hat, Kf2, target_energy):
+        """The low-wavenumber forcing of demo/Isotropic.py:161-184 on the global array: returns (u_hat rescaled in
+        place, energy_new, energy_lower, alpha)."""
+        k2_mask = np.where(self.K2 <= Kf2**2, 1, 0)
+        u_hat[:, 0, 0, 0] = 0
+        energy_new = self.energy_fourier(u_hat)
+        energy_lower = self.energy_fourier(u_hat*k2_mask)
+        energy_upper = energy_new - energy_lower
+        alpha = np.sqrt((target_energy - energy_upper)/energy_lower)
+        u_hat *= (alpha*k2_mask + (1-k2_mask))
+        return u_hat, self.energy_fourier(u_hat), energy_lower, alpha
+
+    def enstrophy(self, u_hat):
+        """dissipation = energy_fourier(cross2(K, U_hat)) (demo/Isotropic.py:243-244)."""
+        return self.energy_fourier(self.cross2(self.K, u_hat))
+
+    def divergence_norm(self, u_hat):
+        """L2_norm(get_divergence(...)) (demo/Isotropic.py:78-86, 245-247; solvers/NS.py:107-110): mean of div(u)^2."""
+        d = self.backward(1j*(self.K[0]*u_hat[0] + self.K[1]*u_hat[1] + self.K[2]*u_hat[2]))
+        return float(np.sum(d.astype(np.float64)**2)/np.prod(self.N))
+
     # ---- NS (solvers/NS.py)
     def ns_conv(self, u_hat, convection='Vortex'):
         K = self.K

@@ -23,7 +23,8 @@ SYMBOLS = ['sdns_abi_version', 'sdns_last_error', 'sdns_size_supported', 'sdns_p
            'sdns_plan_set_stream', 'sdns_sync', 'sdns_local_shapes', 'sdns_comm_alloc', 'sdns_comm_handle',
            'sdns_comm_open', 'sdns_comm_status', 'sdns_forward', 'sdns_backward',
            'sdns_compute_rhs', 'sdns_compute_conv', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2', 'sdns_cross1', 'sdns_cross2_dense', 'sdns_project', 'sdns_add_pressure_diffusion', 'sdns_lincomb', 'sdns_errnorm',
-           'sdns_energy', 'sdns_rk4_steps_host', 'sdns_launch_count',
+           'sdns_energy', 'sdns_energy_weighted', 'sdns_scale_field', 'sdns_set_mode', 'sdns_enstrophy',
+           'sdns_divergence_norm', 'sdns_spectrum', 'sdns_rk4_steps_host', 'sdns_launch_count',
            'sdns_profile_enable', 'sdns_profile_read', 'sdns_profile_read_nvlink', 'sdns_profile_read_copies', 'sdns_profile_timeline', 'sdns_xfer_stats']
 
 
@@ -91,6 +92,12 @@ def lib():
     L.sdns_lincomb.argtypes = [vp, vp, vp, i32, C.POINTER(dbl), C.POINTER(vp), i32]
     L.sdns_errnorm.argtypes = [vp, vp, vp, vp, dbl, dbl, i32, C.POINTER(dbl)]
     L.sdns_energy.argtypes = [vp, vp, i32, C.POINTER(dbl)]
+    L.sdns_energy_weighted.argtypes = [vp, vp, i32, vp, i32, C.POINTER(dbl)]
+    L.sdns_scale_field.argtypes = [vp, vp, i32, vp, i32, dbl, dbl]
+    L.sdns_set_mode.argtypes = [vp, vp, i32, i32, i32, i32, dbl, dbl]
+    L.sdns_enstrophy.argtypes = [vp, vp, C.POINTER(dbl)]
+    L.sdns_divergence_norm.argtypes = [vp, vp, C.POINTER(dbl)]
+    L.sdns_spectrum.argtypes = [vp, vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.sdns_rk4_steps_host.argtypes = [vp, vp, vp, vp, vp, i32, dbl, dbl, dbl]
     L.sdns_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.sdns_profile_enable.argtypes = [vp, i32]

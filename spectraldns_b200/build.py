@@ -29,9 +29,13 @@ def _nvcc():
     raise RuntimeError('nvcc not found')
 
 
-def _sources_digest(extra=''):
+def _sources_digest(extra='', kernels_only=False):
+    """Digest of the sources a unit depends on: the kernel instantiation units (inst.cu) do not include sdns_api.cu or
+    the public header, so a change to the plan / C ABI recompiles one file instead of thirty."""
     h = hashlib.sha1()
     for f in sorted(os.listdir(CSRC)) + ['../../include/sdns_b200.h']:
+        if kernels_only and f in ('sdns_api.cu', '../../include/sdns_b200.h'):
+            continue
         with open(os.path.join(CSRC, f), 'rb') as fh:
             h.update(fh.read())
     h.update(extra.encode())
@@ -68,12 +72,18 @@ def build(force=False, jobs=None, verbose=False, sizes=None, out=None, precs=(32
     jobs = jobs or os.cpu_count() or 4
     units = []
     reuse = []
+    kdigest = _sources_digest(' '.join(extra), kernels_only=True)
+    kstamp = os.path.join(OBJ, 'stamp_kernels')
+    kernels_fresh = (not force and os.path.exists(kstamp) and open(kstamp).read().strip() == kdigest)
     for fam in range(NFAM):
         for prec in (32, 64):
             if out and families is not None and fam not in families:
                 reuse.append(os.path.join(main_obj, 'inst_%d_f%d.o' % (fam, prec)))
                 continue
             o = os.path.join(OBJ, 'inst_%d_f%d.o' % (fam, prec))
+            if kernels_fresh and os.path.exists(o):
+                reuse.append(o)
+                continue
             units.append((o, [nvcc] + ARCH + FLAGS + extra +
                           ['-DSDNS_FAMILY=%d' % fam, '-DSDNS_PREC=%d' % prec,
                            '-c', os.path.join(CSRC, 'inst.cu'), '-o', o]))
@@ -91,6 +101,8 @@ def build(force=False, jobs=None, verbose=False, sizes=None, out=None, precs=(32
     _run([nvcc] + ARCH + ['-shared', '-o', LIB] + [u[0] for u in units] + reuse)
     with open(stamp, 'w') as f:
         f.write(digest)
+    with open(kstamp, 'w') as f:
+        f.write(kdigest)
     return LIB
 
 

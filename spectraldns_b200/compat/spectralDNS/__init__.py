@@ -42,14 +42,20 @@ def solve(solver, context):
     integrate = solver.getintegrator(context.dU, context.u, solver, context)
     dev = solver.device_state(context)
     user_update = not getattr(solver.update, '_sdns_default', False)
-    dev.begin_solve()
+    # SDNS_LAZY_STATE=1: the host mirror of the state is refreshed when host code touches it instead of before every
+    # callback, and the forcing expressions of demo/Isotropic.py's update() run on the device (spectraldns_b200/spaces.py)
+    from spectraldns_b200.spaces import lazy_state_enabled
+    lazy = user_update and lazy_state_enabled()
+    dev.begin_solve(lazy)
     dt_in = params.dt
     try:
         while params.t + params.dt <= params.T + 1e-12:
             u, params.dt, dt_took = integrate()
             params.t += dt_took
             params.tstep += 1
-            if user_update:
+            if user_update and lazy:
+                solver.update(context)
+            elif user_update:
                 dev.sync_to_host()
                 solver.update(context)
                 dev.host_touched()

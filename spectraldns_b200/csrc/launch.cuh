@@ -84,7 +84,12 @@ struct SCfg {
 #endif
     static constexpr int maxThreads = sizeof(T) == 8 ? (b0m ? SDNS_B0_MAXT : 256) : (heavy ? SDNS_F32_MAXT_HEAVY : SDNS_F32_MAXT);
     static constexpr int TCfull = 128 / (2 * (int)sizeof(T));
-    static constexpr int TC = cmin(TCfull, cmax(1, maxThreads / P));
+    // widest tile whose buffers (the exchange buffer, plus two parked fields in the epilogue kernels) fit in shared memory
+    static constexpr int tc_fit(int tc) {
+        while (tc > 1 && (size_t)N * tc * 2 * sizeof(T) * (heavy ? 3 : 1) > 200 * 1024) tc /= 2;
+        return tc;
+    }
+    static constexpr int TC = tc_fit(cmin(TCfull, cmax(1, maxThreads / P)));
     static constexpr size_t bytes1 = (size_t)N * TC * 2 * sizeof(T);
 #ifdef SDNS_STRIDED_NBUF
     static constexpr int NBUF = SDNS_STRIDED_NBUF;
@@ -154,7 +159,7 @@ struct BXCfg {
     static constexpr int P = N / E;
     static constexpr int csize = 2 * (int)sizeof(T);
     static constexpr int TC = bx_tc(P, 128 / csize, csize, N);
-#ifdef SDNS_NO_B0X
+#ifndef SDNS_B0X          // opt-in experiment: measured on B200, not faster than strided_kernel's B0 branch
     static constexpr bool ok = false;
 #elif defined(SDNS_F32_PAIRS)
     static constexpr bool ok = TC > 0 && plan_ok(N, E) && N % 5 != 0 && sizeof(T) == 8;   // experiment build: fp32 B0 on column pairs

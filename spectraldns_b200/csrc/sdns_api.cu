@@ -27,6 +27,8 @@ using namespace sdns;
 #define SDNS_RED_BLOCKS 1024
 #endif
 
+#define SDNS_MAX_BINS 4096        // shells of sdns_spectrum (a 4096^3 grid has 2048)
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
@@ -378,7 +380,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->bytes_SF = align_up(sf * p->cs, 256);
     p->off_SF = p->off_U + p->bytes_U;
     p->off_red = p->off_SF + p->bytes_SF;
-    p->off_flags = p->off_red + align_up(sizeof(double) * p->red_blocks, 256);
+    p->off_flags = p->off_red + align_up(sizeof(double) * std::max(p->red_blocks, 2 * SDNS_MAX_BINS), 256);
     p->ws_need = p->off_flags + 256;
     *out = p;
     return SDNS_OK;
@@ -1397,6 +1399,219 @@ extern "C" int sdns_rk4_steps_host(sdns_plan* p, void* host_u, void* du, void* d
     for (int s = 0; s < nsteps; ++s) { e = sdns_rk4_step(p, du, d1, d2, dt, nu, eta, nullptr); if (e) return e; }
     CUDA_TRY(cudaMemcpyAsync(host_u, du, bytes, cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return check_comm(p);
+}
+
+// ---- diagnostics and forcing of demo/Isotropic.py on the device (update(): :161-187, :220-259; spectrum(): :88-118).
+// The reference computes them with numpy on the host arrays of the context; here the state stays on the GPU and each
+// quantity is one reduction kernel over the local spectral block (the caller reduces over ranks).
+enum DiagMode { DIAG_ENERGY_W = 0, DIAG_ENSTROPHY = 1, DIAG_DIVERGENCE = 2 };
+// DIAG_ENERGY_W : sum_c w_h |u_c * weight|^2               energy_fourier(U_hat*k2_mask, T)      (Isotropic.py:168)
+// DIAG_ENSTROPHY: sum_c w_h |(i K x u)_c|^2                 energy_fourier(cross2(K, U_hat), T)   (Isotropic.py:243-244)
+// DIAG_DIVERGENCE: w_h |i K.u|^2                            L2_norm(get_divergence) by Parseval   (Isotropic.py:245-247)
+// w_h = 1 on the k2 = 0 and k2 = N2/2 planes, 2 elsewhere (Hermitian half spectrum)
+template <typename T, typename W, int MODE>
+__global__ void diag_kernel(const typename C2<T>::type* __restrict__ u, const W* __restrict__ weight, long long n1, int ncomp,
+                            const T* kx, const T* ky, const T* kz, int N1, int Nh, int N2, double* __restrict__ out) {
+    typedef typename C2<T>::type V;
+    double s = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (long long)gridDim.x * blockDim.x) {
+        const int i2 = (int)(i % Nh);
+        const double wh = (i2 == 0 || 2 * i2 == N2) ? 1.0 : 2.0;
+        if (MODE == DIAG_ENERGY_W) {
+            const double m = weight ? (double)weight[i] : 1.0;
+            double e = 0;
+            for (int c = 0; c < ncomp; ++c) {
+                const V v = u[c * n1 + i];
+                const double px = (double)v.x * m, py = (double)v.y * m;
+                e += px * px + py * py;
+            }
+            s += wh * e;
+        } else {
+            const long long r = i / Nh;
+            const int i1 = (int)(r % N1), i0 = (int)(r / N1);
+            const T k0 = kx[i0], k1 = ky[i1], k2 = kz[i2];
+            const V a = u[i], b = u[n1 + i], c = u[2 * n1 + i];
+            if (MODE == DIAG_ENSTROPHY) {
+                const V w0 = icross<T, V>(k1, c, k2, b), w1 = icross<T, V>(k2, a, k0, c), w2 = icross<T, V>(k0, b, k1, a);
+                s += wh * ((double)w0.x * w0.x + (double)w0.y * w0.y + (double)w1.x * w1.x + (double)w1.y * w1.y +
+                           (double)w2.x * w2.x + (double)w2.y * w2.y);
+            } else {
+                const T dx = k0 * a.x + k1 * b.x + k2 * c.x, dy = k0 * a.y + k1 * b.y + k2 * c.y;
+                s += wh * ((double)dx * dx + (double)dy * dy);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    SDNS_STATIC_SMEM(double, ws, 32);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[blockIdx.x] = s;
+    }
+}
+
+// U_hat *= a*factor + b*(1 - factor), factor a real field broadcast over the components: with (a, b) = (1, 0) the plain
+// product, with (alpha, 1) and factor = k2_mask the forcing rescale of Isotropic.py:180 without forming its factor array.
+// numpy forms the product in the promoted type and rounds once; so does this.
+template <typename T, typename W>
+__global__ void scale_field_kernel(typename C2<T>::type* u, const W* __restrict__ f, long long n1, int ncomp, double a, double b) {
+    typedef typename C2<T>::type V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (long long)gridDim.x * blockDim.x) {
+        const double fi = (double)f[i];
+        const double m = a * fi + b * (1.0 - fi);          // (a, b) = (1, 0): the field itself; (alpha, 1): alpha*mask + (1 - mask)
+        for (int c = 0; c < ncomp; ++c) {
+            V v = u[c * n1 + i];
+            v.x = (T)((double)v.x * m); v.y = (T)((double)v.y * m);
+            u[c * n1 + i] = v;
+        }
+    }
+}
+template <typename T>
+__global__ void set_mode_kernel(typename C2<T>::type* u, long long n1, int ncomp, long long idx, T re, T im) {
+    const int c = threadIdx.x;
+    if (c < ncomp) { u[c * n1 + idx].x = re; u[c * n1 + idx].y = im; }
+}
+
+#ifdef SDNS_HOST_SHIM
+static inline void sdns_atomic_add(double* p, double v) {
+    unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
+    unsigned long long old = __atomic_load_n(q, __ATOMIC_RELAXED), nw;
+    do { double d; memcpy(&d, &old, 8); d += v; memcpy(&nw, &d, 8); } while (!__atomic_compare_exchange_n(q, &old, nw, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+#else
+static __device__ __forceinline__ void sdns_atomic_add(double* p, double v) { atomicAdd(p, v); }
+#endif
+
+// Shell sums of spectrum() (Isotropic.py:88-118): uiui = w_h * sum_c |u_c|^2 (the 4 pi / 3 factor, the shell volumes
+// k^3 - k0^3 and the division by the point counts are the caller's, after the reduction over ranks); shell i collects
+// the modes with i + 0.5 < |k| <= i + 1.5 -- np.digitize(sqrt(K2), bins, right=True) == i + 1 for bins = 0.5, 1.5, ...
+// hist[0 .. nbins) += uiui, hist[nbins .. 2 nbins) += 1.  Block histogram in shared memory, one flush per block.
+template <typename T>
+__global__ void spectrum_kernel(const typename C2<T>::type* __restrict__ u, long long n1, int ncomp, const T* kx, const T* ky,
+                                const T* kz, int N1, int Nh, int N2, int nbins, double* __restrict__ hist) {
+    typedef typename C2<T>::type V;
+    SDNS_DYN_SMEM(smraw);
+    double* sh = reinterpret_cast<double*>(smraw);
+    for (int b = threadIdx.x; b < 2 * nbins; b += blockDim.x) sh[b] = 0.0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (long long)gridDim.x * blockDim.x) {
+        const int i2 = (int)(i % Nh);
+        const long long r = i / Nh;
+        const int i1 = (int)(r % N1), i0 = (int)(r / N1);
+        const T k0 = kx[i0], k1 = ky[i1], k2 = kz[i2];
+        T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;            // K2 as get_context builds it (NS.py:42-44)
+        const double km = sqrt((double)ksq);
+        // digitize(km, bins, right=True): smallest z with km <= z + 0.5
+        const int z = km <= 0.5 ? 0 : (int)ceil(km - 0.5);
+        const int shell = z - 1;
+        if (shell < 0 || shell >= nbins - 1) continue;
+        double e = 0;
+        for (int c = 0; c < ncomp; ++c) { const V v = u[c * n1 + i]; e += (double)v.x * v.x + (double)v.y * v.y; }
+        const double wh = (i2 == 0 || i2 == Nh - 1) ? 1.0 : 2.0;      // Isotropic.py:90-93: planes 0 and -1 once, the others twice
+        sdns_atomic_add(&sh[shell], wh * e);
+        sdns_atomic_add(&sh[nbins + shell], 1.0);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 2 * nbins; b += blockDim.x) if (sh[b] != 0.0) sdns_atomic_add(&hist[b], sh[b]);
+}
+
+static int reduce_blocks(sdns_plan* p, double* out) {
+    const int nb = p->red_blocks;
+    std::vector<double> h(nb);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), p->ws + p->off_red, sizeof(double) * nb, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    double s = 0; for (int i = 0; i < nb; ++i) s += h[i];
+    *out = s;
+    return check_comm(p);
+}
+
+template <typename T, typename W, int MODE>
+static void launch_diag(sdns_plan* p, const void* u, const void* w, int ncomp) {
+    typedef typename C2<T>::type V;
+    const long long n1 = (long long)p->N[0] * p->N1l * p->Nh;
+    SDNS_LAUNCH((diag_kernel<T, W, MODE>), p->red_blocks, 256, 0, p->stream)((const V*)u, (const W*)w, n1, ncomp,
+        (const T*)(p->ws + p->kx_off), (const T*)(p->ws + p->ky_off), (const T*)(p->ws + p->kz_off), p->N1l, p->Nh, p->N[2],
+        reinterpret_cast<double*>(p->ws + p->off_red));
+    p->launches++;
+}
+
+extern "C" int sdns_energy_weighted(sdns_plan* p, const void* u_hat, int ncomp, const void* weight, int weight_is_double, double* out) {
+    int e = need_ws(p); if (e) return e;
+    if (!u_hat || !out || ncomp < 1) return fail(SDNS_ERR_ARG, "sdns_energy_weighted: bad argument");
+    if (p->prec) { if (weight_is_double) launch_diag<double, double, DIAG_ENERGY_W>(p, u_hat, weight, ncomp); else launch_diag<double, float, DIAG_ENERGY_W>(p, u_hat, weight, ncomp); }
+    else { if (weight_is_double) launch_diag<float, double, DIAG_ENERGY_W>(p, u_hat, weight, ncomp); else launch_diag<float, float, DIAG_ENERGY_W>(p, u_hat, weight, ncomp); }
+    CUDA_TRY(cudaGetLastError());
+    return reduce_blocks(p, out);
+}
+extern "C" int sdns_enstrophy(sdns_plan* p, const void* u_hat, double* out) {
+    int e = need_ws(p); if (e) return e;
+    if (!u_hat || !out) return fail(SDNS_ERR_ARG, "sdns_enstrophy: bad argument");
+    if (p->prec) launch_diag<double, double, DIAG_ENSTROPHY>(p, u_hat, nullptr, 3); else launch_diag<float, float, DIAG_ENSTROPHY>(p, u_hat, nullptr, 3);
+    CUDA_TRY(cudaGetLastError());
+    return reduce_blocks(p, out);
+}
+extern "C" int sdns_divergence_norm(sdns_plan* p, const void* u_hat, double* out) {
+    int e = need_ws(p); if (e) return e;
+    if (!u_hat || !out) return fail(SDNS_ERR_ARG, "sdns_divergence_norm: bad argument");
+    if (p->prec) launch_diag<double, double, DIAG_DIVERGENCE>(p, u_hat, nullptr, 3); else launch_diag<float, float, DIAG_DIVERGENCE>(p, u_hat, nullptr, 3);
+    CUDA_TRY(cudaGetLastError());
+    return reduce_blocks(p, out);
+}
+extern "C" int sdns_scale_field(sdns_plan* p, void* u_hat, int ncomp, const void* factor, int factor_is_double, double a, double b) {
+    int e = need_ws(p); if (e) return e;
+    if (!u_hat || !factor || ncomp < 1) return fail(SDNS_ERR_ARG, "sdns_scale_field: bad argument");
+    const long long n1 = (long long)p->N[0] * p->N1l * p->Nh;
+    if (p->prec) {
+        if (factor_is_double) SDNS_LAUNCH((scale_field_kernel<double, double>), SDNS_EW_BLOCKS, 256, 0, p->stream)((double2*)u_hat, (const double*)factor, n1, ncomp, a, b);
+        else SDNS_LAUNCH((scale_field_kernel<double, float>), SDNS_EW_BLOCKS, 256, 0, p->stream)((double2*)u_hat, (const float*)factor, n1, ncomp, a, b);
+    } else {
+        if (factor_is_double) SDNS_LAUNCH((scale_field_kernel<float, double>), SDNS_EW_BLOCKS, 256, 0, p->stream)((float2*)u_hat, (const double*)factor, n1, ncomp, a, b);
+        else SDNS_LAUNCH((scale_field_kernel<float, float>), SDNS_EW_BLOCKS, 256, 0, p->stream)((float2*)u_hat, (const float*)factor, n1, ncomp, a, b);
+    }
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+extern "C" int sdns_set_mode(sdns_plan* p, void* u_hat, int ncomp, int i0, int i1, int i2, double re, double im) {
+    int e = need_ws(p); if (e) return e;
+    if (!u_hat || ncomp < 1 || ncomp > 32 || i0 < 0 || i0 >= p->N[0] || i1 < 0 || i1 >= p->N1l || i2 < 0 || i2 >= p->Nh)
+        return fail(SDNS_ERR_ARG, "sdns_set_mode: bad argument");
+    const long long n1 = (long long)p->N[0] * p->N1l * p->Nh;
+    const long long idx = ((long long)i0 * p->N1l + i1) * p->Nh + i2;
+    if (p->prec) SDNS_LAUNCH(set_mode_kernel<double>, 1, 32, 0, p->stream)((double2*)u_hat, n1, ncomp, idx, re, im);
+    else SDNS_LAUNCH(set_mode_kernel<float>, 1, 32, 0, p->stream)((float2*)u_hat, n1, ncomp, idx, (float)re, (float)im);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SDNS_OK;
+}
+extern "C" int sdns_spectrum(sdns_plan* p, const void* u_hat, int ncomp, int nbins, double* sums, double* counts) {
+    int e = need_ws(p); if (e) return e;
+    if (!u_hat || !sums || !counts || ncomp < 1 || nbins < 2 || nbins > SDNS_MAX_BINS) return fail(SDNS_ERR_ARG, "sdns_spectrum: bad argument (2 <= nbins <= 4096)");
+    double* hist = reinterpret_cast<double*>(p->ws + p->off_red);
+    CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * 2 * nbins, p->stream));
+    const long long n1 = (long long)p->N[0] * p->N1l * p->Nh;
+    const size_t smem = sizeof(double) * 2 * nbins;
+#ifndef SDNS_HOST_SHIM
+    static bool once = false;
+    if (!once) {
+        CUDA_TRY(cudaFuncSetAttribute(spectrum_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * SDNS_MAX_BINS)));
+        CUDA_TRY(cudaFuncSetAttribute(spectrum_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * SDNS_MAX_BINS)));
+        once = true;
+    }
+#endif
+    if (p->prec) SDNS_LAUNCH(spectrum_kernel<double>, p->red_blocks, 256, smem, p->stream)((const double2*)u_hat, n1, ncomp,
+        (const double*)(p->ws + p->kx_off), (const double*)(p->ws + p->ky_off), (const double*)(p->ws + p->kz_off), p->N1l, p->Nh, p->N[2], nbins, hist);
+    else SDNS_LAUNCH(spectrum_kernel<float>, p->red_blocks, 256, smem, p->stream)((const float2*)u_hat, n1, ncomp,
+        (const float*)(p->ws + p->kx_off), (const float*)(p->ws + p->ky_off), (const float*)(p->ws + p->kz_off), p->N1l, p->Nh, p->N[2], nbins, hist);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> h(2 * nbins);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(double) * 2 * nbins, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    for (int i = 0; i < nbins; ++i) { sums[i] = h[i]; counts[i] = h[nbins + i]; }
     return check_comm(p);
 }
 

@@ -36,10 +36,12 @@ class DeviceState(object):
 
     # -- copies -------------------------------------------------------------
     def _h2d(self, dst, src):
+        src = np.asarray(src).view(np.ndarray) if isinstance(src, np.ndarray) else src
         t = self.torch.from_numpy(np.ascontiguousarray(src))
         dst.copy_(t.reshape(dst.shape), non_blocking=False)
 
     def _d2h(self, dst, src):
+        dst = dst.view(np.ndarray)            # plain view of the same memory: no array-subclass hooks on the way
         t = self.torch.from_numpy(dst) if dst.flags['C_CONTIGUOUS'] else None
         if t is not None:
             t.reshape(src.shape).copy_(src)
@@ -49,16 +51,18 @@ class DeviceState(object):
     def upload_state(self, host=None):
         h = self.host_state if host is None else host
         self._h2d(self.u, h)
+        self.h2d_copies = getattr(self, 'h2d_copies', 0) + 1
         if host is None or host is self.host_state:
             self.host_dirty = False
             self.device_newer = False
 
     def sync_to_host(self):
         if self.device_newer:
+            self.device_newer = False         # first: the copy below may pass through the lazy-mirror hooks of the array
             if self.plan.nranks > 1:
                 self.plan.sync()              # raises SdnsError if a cross-GPU barrier timed out: never hand out garbage
             self._d2h(self.host_state, self.u)
-            self.device_newer = False
+            self.d2h_copies = getattr(self, 'd2h_copies', 0) + 1
 
     def is_state(self, a):
         h = self.host_state
@@ -97,12 +101,22 @@ class DeviceState(object):
 
 
 def _solve_hooks():
-    def begin_solve(self):
+    def begin_solve(self, lazy=False):
         self.managed = True
         self.host_dirty = True
+        self.lazy = bool(lazy)
+        if self.lazy:
+            from .spaces import _LAZY
+            if self not in _LAZY:
+                _LAZY.append(self)
 
     def end_solve(self):
         self.sync_to_host()
+        if getattr(self, 'lazy', False):
+            from .spaces import _LAZY
+            if self in _LAZY:
+                _LAZY.remove(self)
+            self.lazy = False
         self.managed = False
         self.host_dirty = True
 

@@ -265,6 +265,59 @@ class Plan(object):
         _lib.check(self.lib.sdns_energy(self._p, u_hat.data_ptr(), nc, C.byref(out)))
         return out.value
 
+    # -- diagnostics / forcing of demo/Isotropic.py on the device -----------------
+    def _real_field(self, w, name):
+        torch = _torch()
+        if w.dtype not in (torch.float32, torch.float64) or not w.is_cuda or not w.is_contiguous() \
+                or tuple(w.shape) != tuple(self.spectral_shape):
+            raise ValueError('%s: need a contiguous real CUDA tensor of the spectral shape %s' % (name, self.spectral_shape))
+        return 1 if w.dtype == torch.float64 else 0
+
+    def energy_weighted(self, u_hat, weight=None):
+        """energy_fourier(u_hat*weight, T) of the local block (demo/Isotropic.py:168)."""
+        nc = self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat')
+        out = C.c_double()
+        isd = self._real_field(weight, 'weight') if weight is not None else 1
+        _lib.check(self.lib.sdns_energy_weighted(self._p, u_hat.data_ptr(), nc, weight.data_ptr() if weight is not None else None,
+                                                 isd, C.byref(out)))
+        return out.value
+
+    def scale_field(self, u_hat, factor, a=1.0, b=0.0):
+        """u_hat *= a*factor + b*(1 - factor), factor a real field broadcast over the components: the plain product by
+        default, the forcing rescale of demo/Isotropic.py:180 with factor = k2_mask, (a, b) = (alpha, 1)."""
+        nc = self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat')
+        _lib.check(self.lib.sdns_scale_field(self._p, u_hat.data_ptr(), nc, factor.data_ptr(), self._real_field(factor, 'factor'),
+                                             float(a), float(b)))
+        return u_hat
+
+    def set_mode(self, u_hat, index, value=0.0):
+        """u_hat[:, i0, i1, i2] = value (i1 local)."""
+        nc = self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat')
+        v = complex(value)
+        _lib.check(self.lib.sdns_set_mode(self._p, u_hat.data_ptr(), nc, int(index[0]), int(index[1]), int(index[2]), v.real, v.imag))
+        return u_hat
+
+    def enstrophy(self, u_hat):
+        """energy_fourier(1j*K x u_hat, T) of the local block: the `dissipation` of demo/Isotropic.py:243-244."""
+        assert self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat') == 3
+        out = C.c_double()
+        _lib.check(self.lib.sdns_enstrophy(self._p, u_hat.data_ptr(), C.byref(out)))
+        return out.value
+
+    def divergence_norm(self, u_hat):
+        """sum w |1j*K.u_hat|^2 of the local block (= L2_norm(get_divergence) of demo/Isotropic.py:245-247 by Parseval)."""
+        assert self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat') == 3
+        out = C.c_double()
+        _lib.check(self.lib.sdns_divergence_norm(self._p, u_hat.data_ptr(), C.byref(out)))
+        return out.value
+
+    def spectrum_shells(self, u_hat, nbins):
+        """(sums, counts) over the shells of spectrum() (demo/Isotropic.py:88-118), local block."""
+        nc = self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat')
+        s, c = (C.c_double*nbins)(), (C.c_double*nbins)()
+        _lib.check(self.lib.sdns_spectrum(self._p, u_hat.data_ptr(), nc, int(nbins), s, c))
+        return np.array(s[:]), np.array(c[:])
+
     # -- measurement ---------------------------------------------------------
     FAMILIES = ['plain_fwd_c2c', 'plain_bwd_c2c', 'ns_b0', 'vv_b0', 'ns_f0', 'vv_f0', 'mhd_f0',
                 'c2r', 'r2c', 'z_cross', 'z_mhd', 'ns_grad_b0', 'z_dot', 'z_uu', 'nsdiv_f0']

@@ -78,7 +78,11 @@ class Engine(object):
 
     def upload(self, tag, a, dtype_np, tdtype):
         import torch
-        a = np.ascontiguousarray(a, dtype=dtype_np)
+        if _LAZY and isinstance(a, np.ndarray):
+            d = _lazy_dev(a)
+            if d is not None:
+                d.sync_to_host()            # lazily mirrored state: bring the host copy up to date before reading it
+        a = np.ascontiguousarray(np.asarray(a).view(np.ndarray) if isinstance(a, np.ndarray) else a, dtype=dtype_np)
         t = self.stage(tag, a.shape, tdtype)
         t.copy_(torch.from_numpy(a))
         return t
@@ -285,9 +289,190 @@ def _scalar_space(space):
     return space.T if isinstance(space, CompositeSpace) else space
 
 
+# ---- lazy host mirror of the device-resident state (opt-in: SDNS_LAZY_STATE=1) -------------------------------------
+# While solve() runs, the solution lives on the GPU and the context's numpy array is a mirror.  Eagerly, solve()
+# refreshes the mirror before every user callback (one D2H per step) and assumes the callback wrote it (one H2D).  In
+# lazy mode the copy is deferred until host code touches the array through numpy's protocols, and the expressions
+# demo/Isotropic.py's update() uses every step are answered on the device (spectraldns_b200/diagnostics.py), so a
+# forced run moves no state across PCIe.  What numpy does not route through a Python hook (the buffer protocol:
+# memoryview, Cython typed views, views taken before solve()) still sees the mirror as of the last refresh -- hence
+# opt-in.
+_LAZY = []          # DeviceStates whose host mirror may be stale
+
+
+def lazy_state_enabled():
+    import os
+    return os.environ.get('SDNS_LAZY_STATE', '0') not in ('', '0')
+
+
+def _lazy_dev(a):
+    """The DeviceState whose registered host array shares memory with `a`, if its mirror is lazily maintained."""
+    if not _LAZY or not isinstance(a, np.ndarray):
+        return None
+    try:
+        lo = a.__array_interface__['data'][0]
+    except Exception:
+        return None
+    for dev in _LAZY:
+        h = dev.host_state
+        b0 = h.__array_interface__['data'][0]
+        if b0 <= lo < b0 + h.nbytes:
+            return dev
+    return None
+
+
+def _is_whole_state(a, dev):
+    h = dev.host_state
+    return (a.shape == h.shape and a.dtype == h.dtype and a.flags['C_CONTIGUOUS']
+            and a.__array_interface__['data'][0] == h.__array_interface__['data'][0])
+
+
+class _ScaledState(object):
+    """U_hat*weight, not formed: energy_fourier() of it runs on the device; anything else materialises it."""
+    __array_priority__ = 100
+
+    def __init__(self, dev, state, weight):
+        self.dev, self.state, self.weight = dev, state, weight
+
+    def materialise(self):
+        self.dev.sync_to_host()
+        return np.asarray(self.state.view(np.ndarray))*self.weight
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialise()
+        return a.astype(dtype) if dtype is not None else a
+
+    def __getattr__(self, name):            # any ndarray attribute / method: act as the product
+        return getattr(self.materialise(), name)
+
+    def __mul__(self, o):
+        return self.materialise()*o
+    __rmul__ = __mul__
+
+    def __getitem__(self, k):
+        return self.materialise()[k]
+
+
 class _SpaceArray(np.ndarray):
     """ndarray that remembers its function space; slices and views keep it (UB[:3], U_hat[0])."""
     _spectral = False
+
+    # -- lazy mirror hooks (inactive unless a DeviceState registered itself in _LAZY) --
+    def _lazy_read(self):
+        dev = _lazy_dev(self)
+        if dev is not None:
+            dev.sync_to_host()
+        return dev
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kw):
+        if _LAZY:
+            outs = out if isinstance(out, tuple) else ((out,) if out is not None else ())
+            wdev = None
+            for o in outs:
+                d = _lazy_dev(o) if isinstance(o, np.ndarray) else None
+                if d is not None:
+                    wdev = d
+            # U_hat *= real field  (demo/Isotropic.py:180) and U_hat*real field (Isotropic.py:168)
+            if ufunc is np.multiply and method == '__call__' and len(inputs) == 2 and isinstance(inputs[0], _SpaceArray):
+                dev = _lazy_dev(inputs[0])
+                w = inputs[1]
+                if dev is not None and _is_whole_state(inputs[0], dev) and isinstance(w, np.ndarray) and not isinstance(w, _SpaceArray) \
+                        and w.dtype.kind in 'fiub' and w.shape == tuple(dev.plan.spectral_shape):
+                    from . import diagnostics
+                    if len(outs) == 1 and outs[0] is inputs[0]:
+                        if dev.host_dirty:
+                            dev.upload_state()
+                        dev.plan.scale_field(dev.u, diagnostics.real_field(dev, w, 'imul'))
+                        dev.device_newer = True
+                        return inputs[0]
+                    if not outs:
+                        return _ScaledState(dev, inputs[0], w)
+            for a in inputs:
+                if isinstance(a, np.ndarray):
+                    d = _lazy_dev(a)
+                    if d is not None:
+                        d.sync_to_host()
+            if wdev is not None:
+                wdev.sync_to_host()
+                wdev.host_touched()
+        # ndarray's own implementation on plain views, results re-wrapped (the pattern of the numpy subclassing guide)
+        first = next((a for a in inputs if isinstance(a, _SpaceArray)), None)
+        args = [a.view(np.ndarray) if isinstance(a, _SpaceArray) else a for a in inputs]
+        outs_in = out if isinstance(out, tuple) else ((out,) if out is not None else None)
+        if outs_in is not None:
+            kw['out'] = tuple(o.view(np.ndarray) if isinstance(o, _SpaceArray) else o for o in outs_in)
+        res = super().__array_ufunc__(ufunc, method, *args, **kw)
+        if res is NotImplemented or method == 'at':
+            return res
+        many = isinstance(res, tuple)
+        rs = list(res) if many else [res]
+        for i, r in enumerate(rs):
+            if outs_in is not None and i < len(outs_in) and outs_in[i] is not None:
+                rs[i] = outs_in[i]
+            elif isinstance(r, np.ndarray) and first is not None:
+                w = r.view(type(first))
+                w._space = first._space
+                rs[i] = w
+        return tuple(rs) if many else rs[0]
+
+    def __array_function__(self, func, types, args, kwargs):
+        if _LAZY:
+            for a in list(args) + list(kwargs.values()):
+                if isinstance(a, np.ndarray):
+                    d = _lazy_dev(a)
+                    if d is not None:
+                        d.sync_to_host()
+                        d.host_touched()            # conservative: the function may write through the array
+        return super().__array_function__(func, types, args, kwargs)
+
+    def __getitem__(self, key):
+        if _LAZY:
+            self._lazy_read()
+        return super().__getitem__(key)
+
+    def __setitem__(self, key, value):
+        if _LAZY:
+            dev = _lazy_dev(self)
+            if dev is not None:
+                # U_hat[:, i0, i1, i2] = scalar (demo/Isotropic.py:64, 163: the mean mode)
+                if _is_whole_state(self, dev) and isinstance(key, tuple) and len(key) == 4 and isinstance(key[0], slice) \
+                        and key[0] == slice(None) \
+                        and all(isinstance(k, (int, np.integer)) for k in key[1:]) and np.isscalar(value):
+                    if dev.host_dirty:
+                        dev.upload_state()
+                    s = dev.plan.spectral_shape
+                    idx = tuple(int(k) % n for k, n in zip(key[1:], s))
+                    dev.plan.set_mode(dev.u, idx, value)
+                    self.view(np.ndarray)[key] = value       # keep the mirror's entry in step (plain view: no hooks)
+                    return
+                dev.sync_to_host()
+                dev.host_touched()
+                self.view(np.ndarray)[key] = value
+                return
+        super().__setitem__(key, value)
+
+    def copy(self, *a, **k):
+        if _LAZY:
+            self._lazy_read()
+        return super().copy(*a, **k)
+
+    def astype(self, *a, **k):
+        if _LAZY:
+            self._lazy_read()
+        return super().astype(*a, **k)
+
+    def tobytes(self, *a, **k):
+        if _LAZY:
+            self._lazy_read()
+        return super().tobytes(*a, **k)
+
+    def fill(self, v):
+        if _LAZY:
+            dev = _lazy_dev(self)
+            if dev is not None:
+                dev.sync_to_host()
+                dev.host_touched()
+        return super().fill(v)
 
     def __new__(cls, space, val=0, buffer=None, **kw):
         shape = space.shape(cls._spectral)
@@ -359,6 +544,20 @@ def energy_fourier(u_hat, T):
     """Hermitian-weighted sum |u_hat|^2 (tests/TG.py:101; demo/Isotropic.py:67,167-182).
     Host array in, float out; the reduction runs on the GPU (sdns_energy)."""
     S = _scalar_space(T)
+    if _LAZY:
+        # the device-resident state itself, or state*weight (demo/Isotropic.py:167-168): reduce it where it lives
+        st, w = (u_hat.state, u_hat.weight) if isinstance(u_hat, _ScaledState) else (u_hat, None)
+        dev = _lazy_dev(st) if isinstance(st, np.ndarray) else None
+        if dev is not None and _is_whole_state(st, dev):
+            from . import diagnostics
+            if dev.host_dirty:
+                dev.upload_state()
+            dev.plan.use_current_stream()
+            res = dev.plan.energy_weighted(dev.u, diagnostics.real_field(dev, w, 'energy_weight') if w is not None else None)
+            comm = getattr(S, 'comm', None)
+            if comm is not None and hasattr(comm, 'allreduce'):
+                res = comm.allreduce(res)
+            return float(res)
     a = np.asarray(u_hat)
     eng = S.engine
     p = eng.plan

@@ -190,11 +190,15 @@ def test_mhd(sdns, mesh):
     config.update({'convection': 'Vortex'})
 
 
+@pytest.mark.parametrize('lazy', [False, True])
 @pytest.mark.parametrize('precision,dealias', [('double', '3/2-rule'), ('single', '3/2-rule'), ('double', '2/3-rule')])
-def test_forced_isotropic_callback_parity(sdns, precision, dealias):
+def test_forced_isotropic_callback_parity(sdns, precision, dealias, lazy, monkeypatch):
     """demo/Isotropic.py:29-76,150-187 of the reference: broadband initial field, and an update()
-    that rescales the low wavenumber band of c.U_hat ON THE HOST every step (the forcing).  The
-    same sequence is replayed with the CPU oracle; relative L2 of the velocity spectrum."""
+    that rescales the low wavenumber band of c.U_hat every step (the forcing), written with numpy on the
+    context's host array.  The same sequence is replayed with the CPU oracle; relative L2 of the velocity
+    spectrum.  lazy: SDNS_LAZY_STATE=1 -- the same callback, but the state never crosses PCIe inside the
+    time loop (its expressions are answered by sdns_energy_weighted / sdns_scale_field / sdns_set_mode)."""
+    monkeypatch.setenv('SDNS_LAZY_STATE', '1' if lazy else '0')
     config, get_solver, solve = sdns.config, sdns.get_solver, sdns.solve
     from shenfun.fourier import energy_fourier
     config.update({'nu': 0.005428, 'dt': 0.002, 'T': 0.01, 'convection': 'Vortex'})
@@ -226,6 +230,12 @@ def test_forced_isotropic_callback_parity(sdns, precision, dealias):
     config.params.t, config.params.tstep = 0.0, 0
     solve(solver, c)
     assert len(log) == 5
+    dev = c['_dev']
+    if lazy:
+        # one upload of the initial field, one download when solve() hands the result back: nothing per step
+        assert dev.h2d_copies == 1 and dev.d2h_copies == 1, (dev.h2d_copies, dev.d2h_copies)
+    else:
+        assert dev.d2h_copies >= 5 and dev.h2d_copies >= 5
     # oracle replay
     u = u0.copy()
     for _ in range(5):
@@ -241,8 +251,9 @@ def test_forced_isotropic_callback_parity(sdns, precision, dealias):
     config.params.dealias, config.params.precision = '2/3-rule', 'double'
 
 
-def _run(cmd, cwd):
+def _run(cmd, cwd, extra_env=None):
     env = dict(os.environ)
+    env.update(extra_env or {})
     env['PYTHONPATH'] = COMPAT + os.pathsep + ROOT + os.pathsep + env.get('PYTHONPATH', '')
     r = subprocess.run(cmd, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     return r.returncode, r.stdout
@@ -260,9 +271,26 @@ def test_reference_scripts_run_unchanged(tmp_path):
         rc, out = _run([py, os.path.join(ref, script)] + args, str(tmp_path))
         assert rc == 0, (script, args, out[-3000:])
         assert 'Fastest' in out
-    rc, out = _run([py, os.path.join(ref, 'demo', 'Isotropic.py'), '--N', '32', '32', '32', '--T', '0.02',
-                    '--compute_energy', '5', 'NS'], str(tmp_path))
+    iso = [py, os.path.join(ref, 'demo', 'Isotropic.py'), '--N', '32', '32', '32', '--T', '0.02', '--compute_energy', '5', 'NS']
+    rc, out = _run(iso, str(tmp_path))
     assert rc == 0, out[-3000:]
+    # the same unchanged script with the lazily mirrored state: same monitor lines (t, energies, dissipation, Re_lambda)
+    rc, out_lazy = _run(iso, str(tmp_path), {'SDNS_LAZY_STATE': '1'})
+    assert rc == 0, out_lazy[-3000:]
+
+    def monitor(text):
+        rows = []
+        for line in text.splitlines():
+            f = line.split()
+            if len(f) == 9:
+                try:
+                    rows.append([float(x) for x in f])
+                except ValueError:
+                    pass
+        return np.array(rows)
+    m0, m1 = monitor(out), monitor(out_lazy)
+    assert m0.shape == m1.shape and m0.shape[0] >= 1
+    assert np.allclose(m0, m1, rtol=1e-5, atol=1e-9), (m0, m1)
     rc, out = _run([py, '-m', 'pytest', '-x', '-q', os.path.join(ref, 'tests', 'test_NSVV.py'),
                     os.path.join(ref, 'tests', 'test_MHD.py'), '-p', 'no:cacheprovider'], str(tmp_path))
     assert rc == 0, out[-4000:]

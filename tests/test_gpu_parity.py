@@ -337,3 +337,46 @@ def test_standalone_operators_against_reference_cython(precision):
         p_ref = np.zeros(o.sshape, dtype=o.complex)
         du_ref = solvers.add_pressure_diffusion_NS(du.copy(), uh, o.float(nu), o.K2, o.K, p_ref, o.K_over_K2)
         assert rel_l2(p.to_host(d_du), du_ref) < tol and rel_l2(p.to_host(d_p), p_ref) < tol
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_device_diagnostics_match_the_demo(precision):
+    """sdns_spectrum / sdns_enstrophy / sdns_divergence_norm / sdns_energy_weighted / sdns_scale_field / sdns_set_mode
+    against the numpy of demo/Isotropic.py (:88-118 spectrum, :161-184 forcing, :243-247 monitors) restated in the
+    oracle, on a seeded isotropic field."""
+    import torch
+    N = (32, 48, 64)
+    o = so.Oracle(N, precision=precision)
+    p = make_plan(N, precision=precision)
+    tol = 1e-12 if precision == 'double' else 2e-6
+    u0 = so.isotropic_field(o, seed=3)
+    d_u = p.to_device(u0)
+    Ek_ref, bins = o.spectrum(u0)
+    sums, cnts = p.spectrum_shells(d_u, len(bins))
+    Ek = np.zeros(len(bins))
+    for i in range(len(bins)-1):
+        if cnts[i]:
+            Ek[i] = (bins[i+1]**3 - bins[i]**3)*(4./3.*np.pi)*sums[i]/cnts[i]
+    assert np.allclose(Ek, Ek_ref, rtol=tol, atol=0) and Ek_ref.max() > 0
+    assert abs(p.enstrophy(d_u) - o.enstrophy(u0)) < tol*o.enstrophy(u0)
+    ud = (u0 + o.forward(np.random.RandomState(1).standard_normal((3,)+N))*o.mask*1e-3).astype(o.complex)   # not solenoidal
+    assert abs(p.divergence_norm(p.to_device(ud)) - o.divergence_norm(ud)) < 20*tol*o.divergence_norm(ud)
+    # the forcing step, expression by expression
+    g = u0.copy()
+    g[:, 0, 0, 0] = 0.3 - 0.1j
+    d_g = p.to_device(g)
+    k2_mask = np.where(o.K2 <= 3**2, 1, 0)
+    target = 1.05*o.energy_fourier(u0)
+    ref, e_ref, e_low, alpha = o.forcing_rescale(g.copy(), 3, target)
+    p.set_mode(d_g, (0, 0, 0), 0.0)
+    d_m = torch.from_numpy(k2_mask.astype(np.float64)).cuda()
+    assert abs(p.energy_weighted(d_g, d_m) - e_low) < tol*e_low
+    p.scale_field(d_g, d_m, alpha, 1.0)
+    assert rel_l2(p.to_host(d_g), ref) < (1e-15 if precision == 'double' else 2e-7)
+    assert abs(p.energy_weighted(d_g) - e_ref) < tol*e_ref and abs(p.energy(d_g) - e_ref) < tol*e_ref
+    # float32 factor array, plain product
+    f32 = torch.from_numpy((alpha*k2_mask + (1-k2_mask)).astype(np.float32)).cuda()
+    d_h = p.to_device(g)
+    p.set_mode(d_h, (0, 0, 0), 0.0)
+    p.scale_field(d_h, f32)
+    assert rel_l2(p.to_host(d_h), ref) < 2e-7

@@ -338,6 +338,51 @@ def test_emulated_small_kernels(emu):
     p.chk(L.sdns_add_pressure_diffusion(p.p, du.ctypes.data, f0.ctypes.data, 0.0123, ph.ctypes.data))
     du_ref, p_ref = o.add_pressure_diffusion(v.copy(), f0, 0.0123)
     assert rel_l2(du, du_ref) < 1e-14 and rel_l2(ph, p_ref) < 1e-14
+    # diagnostics and forcing of demo/Isotropic.py on the device (Isotropic.py:88-118, 161-184, 243-247)
+    i32 = C.c_int
+    L.sdns_energy_weighted.argtypes = [vp, vp, i32, vp, i32, C.POINTER(dbl)]
+    L.sdns_scale_field.argtypes = [vp, vp, i32, vp, i32, dbl, dbl]
+    L.sdns_set_mode.argtypes = [vp, vp, i32, i32, i32, i32, dbl, dbl]
+    L.sdns_enstrophy.argtypes = [vp, C.c_void_p, C.POINTER(dbl)]
+    L.sdns_divergence_norm.argtypes = [vp, vp, C.POINTER(dbl)]
+    L.sdns_spectrum.argtypes = [vp, vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
+    g = v.copy()
+    g[:, 0, 0, 0] = 1.5 - 0.5j
+    k2_mask = np.where(o.K2 <= 3**2, 1, 0)
+    ref, e_new, e_low, alpha = o.forcing_rescale(g.copy(), 3, 1.1*o.energy_fourier(v))
+    p.chk(L.sdns_set_mode(p.p, g.ctypes.data, 3, 0, 0, 0, 0.0, 0.0))
+    assert np.all(g[:, 0, 0, 0] == 0)
+    wgt = np.ascontiguousarray(k2_mask, dtype=np.float64)
+    p.chk(L.sdns_energy_weighted(p.p, g.ctypes.data, 3, wgt.ctypes.data, 1, C.byref(e)))
+    assert abs(e.value - e_low) < 1e-12*abs(e_low)
+    p.chk(L.sdns_energy_weighted(p.p, g.ctypes.data, 3, None, 1, C.byref(e)))
+    assert abs(e.value - o.energy_fourier(g)) < 1e-12*abs(e.value)
+    fac = np.ascontiguousarray(alpha*k2_mask + (1-k2_mask), dtype=np.float64)
+    g_aff = g.copy()
+    p.chk(L.sdns_scale_field(p.p, g.ctypes.data, 3, fac.ctypes.data, 1, 1.0, 0.0))
+    assert rel_l2(g, ref) < 1e-15
+    p.chk(L.sdns_scale_field(p.p, g_aff.ctypes.data, 3, wgt.ctypes.data, 1, float(alpha), 1.0))      # from the mask itself
+    assert rel_l2(g_aff, ref) < 1e-15
+    fac32 = fac.astype(np.float32)
+    g2 = v.copy()
+    p.chk(L.sdns_scale_field(p.p, g2.ctypes.data, 3, fac32.ctypes.data, 0, 1.0, 0.0))
+    assert rel_l2(g2, v*fac32) < 1e-15
+    p.chk(L.sdns_enstrophy(p.p, v.ctypes.data, C.byref(e)))
+    assert abs(e.value - o.enstrophy(v)) < 1e-12*abs(e.value)
+    # Parseval needs the spectrum of a real field without Nyquist modes (what the solver's mask_nyquist leaves)
+    w_h = (o.forward(np.random.RandomState(3).standard_normal((3,)+tuple(N)))*o.mask).astype(o.complex)
+    p.chk(L.sdns_divergence_norm(p.p, w_h.ctypes.data, C.byref(e)))
+    assert abs(e.value - o.divergence_norm(w_h)) < 1e-11*abs(e.value)
+    Ek_ref, bins = o.spectrum(v)
+    nb = len(bins)
+    sums, cnts = (dbl*nb)(), (dbl*nb)()
+    p.chk(L.sdns_spectrum(p.p, v.ctypes.data, 3, nb, sums, cnts))
+    sums, cnts = np.array(sums[:]), np.array(cnts[:])
+    Ek = np.zeros(nb)
+    for i in range(nb-1):
+        if cnts[i]:
+            Ek[i] = ((bins[i+1])**3 - bins[i]**3)*sums[i]*(4./3.*np.pi)/cnts[i]
+    assert np.allclose(Ek, Ek_ref, rtol=1e-12, atol=0) and cnts.sum() > 0
     out = np.zeros_like(f0)
     coeffs = (dbl*2)(0.25, -1.5)
     arrs = (vp*2)(f0.ctypes.data, c.ctypes.data)
