@@ -220,6 +220,52 @@ int sdns_profile_timeline(sdns_plan* plan, double* rows, int max_rows, int* nrow
  * kind 98. */
 int sdns_xfer_stats(sdns_plan* plan, double* bytes, long long* flush_launches);
 
+/* ---- doubly periodic (2-D) solvers: NS2D (solvers/NS2D.py:13-51) and Bq2D (solvers/Bq2D.py:101-176) -----------------
+ * Same conventions as above.  Spectral arrays are C order (ncomp, N0, N1/2+1) complex, physical arrays (ncomp, M0, M1)
+ * real, ncomp = 2 (NS2D: u) or 3 (Bq2D: u, rho) -- the shapes of Function(VT) / Function(VM) in the reference
+ * (NS.py:51-52 in two dimensions, Bq2D.py:52-63).  Single GPU. */
+enum { SDNS_NS2D = 0, SDNS_BQ2D = 1 };                             /* config.py:256-261 doublyperiodic sub-commands */
+typedef struct sdns2d_config {
+    int32_t abi_version;      /* SDNS_ABI_VERSION */
+    int32_t N[2];             /* params.N */
+    double  L[2];             /* params.L  (config.py:246) */
+    int32_t precision;        /* SDNS_SINGLE | SDNS_DOUBLE */
+    int32_t dealias;          /* SDNS_DEALIAS_* */
+    int32_t solver;           /* SDNS_NS2D | SDNS_BQ2D */
+    int32_t mask_nyquist;     /* params.mask_nyquist */
+    int32_t kcut[2];          /* 2/3-rule cutoff per axis, <0 = default (see sdns_config.kcut) */
+    int32_t device;
+    int32_t reserved[8];
+} sdns2d_config;
+typedef struct sdns2d_plan sdns2d_plan;
+const char* sdns2d_last_error(void);
+/* get_context() of NS2D / Bq2D: spaces T, Tp, wavenumbers (NS2D.py:13-18, Bq2D.py:13-50) */
+int sdns2d_plan_create(sdns2d_plan** plan, const sdns2d_config* cfg);
+int sdns2d_plan_destroy(sdns2d_plan* plan);
+int sdns2d_workspace_bytes(const sdns2d_plan* plan, size_t* bytes);
+int sdns2d_plan_set_workspace(sdns2d_plan* plan, void* device_ptr, size_t bytes);
+int sdns2d_plan_set_stream(sdns2d_plan* plan, void* cuda_stream);
+int sdns2d_sync(sdns2d_plan* plan);
+int sdns2d_shapes(const sdns2d_plan* plan, int32_t spectral[2], int32_t physical[2], int32_t padded[2]);
+int sdns2d_launch_count(const sdns2d_plan* plan, long long* count);
+/* T.forward / T.backward and Tp.forward / Tp.backward of ncomp fields (NS2D.py:20-31, 43-47; tests/TG2D.py:12-16) */
+int sdns2d_forward(sdns2d_plan* plan, int space, int ncomp, const void* real_in, void* cplx_out);
+int sdns2d_backward(sdns2d_plan* plan, int space, int ncomp, const void* cplx_in, void* real_out);
+/* ComputeRHS (NS.py:219-261 with NS2D's Conv, NS2D.py:33-51; Bq2D.py:158-186): conv, Nyquist mask,
+ * add_pressure_diffusion, + Source (NS2D).  Ri and Pr are ignored by NS2D.  source and p_hat may be NULL. */
+int sdns2d_compute_rhs(sdns2d_plan* plan, void* rhs, const void* u_hat, double nu, double Ri, double Pr,
+                       const void* source, void* p_hat);
+/* integrate() for RK4 / ForwardEuler / AB2 (maths/integrators.py:150-175) */
+int sdns2d_rk4_step(sdns2d_plan* plan, void* u_hat, void* u1, void* u2, double dt, double nu, double Ri, double Pr,
+                    const void* source);
+int sdns2d_euler_step(sdns2d_plan* plan, void* u_hat, void* rhs, double dt, double nu, double Ri, double Pr, const void* source);
+int sdns2d_ab2_step(sdns2d_plan* plan, void* u_hat, void* u1, void* rhs, double dt, int tstep, double nu, double Ri, double Pr,
+                    const void* source);
+/* cross2(c, K, u_hat) for a 2-D field: scalar c = 1j*(K0 u1 - K1 u0)  (cython_maths.in:105-147; NS2D.py:21-22) */
+int sdns2d_cross2(sdns2d_plan* plan, void* c, const void* u_hat);
+/* add_pressure_diffusion_NS2D / add_pressure_diffusion_Bq2D on their own, in place on du (cython_solvers.in:82-127) */
+int sdns2d_add_pressure_diffusion(sdns2d_plan* plan, void* du, const void* u_hat, double nu, double Ri, double Pr, void* p_hat);
+
 #ifdef __cplusplus
 }
 #endif

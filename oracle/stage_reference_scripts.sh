@@ -15,8 +15,9 @@ REF=${1:-/root/reference}
 HERE="$(cd "$(dirname "$0")" && pwd)"
 DST="$HERE/../baseline/_ref"
 mkdir -p "$DST/demo" "$DST/tests"
-cp "$REF/demo/TG.py" "$REF/demo/TGMHD.py" "$REF/demo/Isotropic.py" "$DST/demo/"
-cp "$REF/tests/TG.py" "$REF/tests/TGMHD.py" "$REF/tests/test_NSVV.py" "$REF/tests/test_MHD.py" "$DST/tests/"
+cp "$REF/demo/TG.py" "$REF/demo/TGMHD.py" "$REF/demo/Isotropic.py" "$REF/demo/TG2D.py" "$DST/demo/"
+cp "$REF/tests/TG.py" "$REF/tests/TGMHD.py" "$REF/tests/test_NSVV.py" "$REF/tests/test_MHD.py" "$REF/tests/TG2D.py" \
+   "$REF/tests/test_NS2D.py" "$DST/tests/"
 PKG="$DST/spectralDNS"
 rm -rf "$PKG"
 mkdir -p "$PKG/optimization"

@@ -46,6 +46,52 @@ class SdnsConfig(C.Structure):
                 ('reserved', C.c_int32*8)]
 
 
+class Sdns2dConfig(C.Structure):
+    _fields_ = [('abi_version', C.c_int32),
+                ('N', C.c_int32*2),
+                ('L', C.c_double*2),
+                ('precision', C.c_int32),
+                ('dealias', C.c_int32),
+                ('solver', C.c_int32),
+                ('mask_nyquist', C.c_int32),
+                ('kcut', C.c_int32*2),
+                ('device', C.c_int32),
+                ('reserved', C.c_int32*8)]
+
+
+SOLVER2D = {'NS2D': 0, 'Bq2D': 1}
+SYMBOLS2D = ['sdns2d_last_error', 'sdns2d_plan_create', 'sdns2d_plan_destroy', 'sdns2d_workspace_bytes', 'sdns2d_plan_set_workspace',
+             'sdns2d_plan_set_stream', 'sdns2d_sync', 'sdns2d_shapes', 'sdns2d_launch_count', 'sdns2d_forward', 'sdns2d_backward',
+             'sdns2d_compute_rhs', 'sdns2d_rk4_step', 'sdns2d_euler_step', 'sdns2d_ab2_step', 'sdns2d_cross2',
+             'sdns2d_add_pressure_diffusion']
+
+
+def bind2d(L):
+    """argtypes of the sdns2d_* entry points (doubly periodic solvers) on a loaded library."""
+    vp, i32, dbl = C.c_void_p, C.c_int, C.c_double
+    L.sdns2d_last_error.restype = C.c_char_p
+    L.sdns2d_plan_create.argtypes = [C.POINTER(vp), C.POINTER(Sdns2dConfig)]
+    L.sdns2d_plan_destroy.argtypes = [vp]
+    L.sdns2d_workspace_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.sdns2d_plan_set_workspace.argtypes = [vp, vp, C.c_size_t]
+    L.sdns2d_plan_set_stream.argtypes = [vp, vp]
+    L.sdns2d_sync.argtypes = [vp]
+    L.sdns2d_shapes.argtypes = [vp, C.POINTER(C.c_int32*2), C.POINTER(C.c_int32*2), C.POINTER(C.c_int32*2)]
+    L.sdns2d_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.sdns2d_forward.argtypes = [vp, i32, i32, vp, vp]
+    L.sdns2d_backward.argtypes = [vp, i32, i32, vp, vp]
+    L.sdns2d_compute_rhs.argtypes = [vp, vp, vp, dbl, dbl, dbl, vp, vp]
+    L.sdns2d_rk4_step.argtypes = [vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp]
+    L.sdns2d_euler_step.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl, vp]
+    L.sdns2d_ab2_step.argtypes = [vp, vp, vp, vp, dbl, i32, dbl, dbl, dbl, vp]
+    L.sdns2d_cross2.argtypes = [vp, vp, vp]
+    L.sdns2d_add_pressure_diffusion.argtypes = [vp, vp, vp, dbl, dbl, dbl, vp]
+    for s in SYMBOLS2D:
+        if s != 'sdns2d_last_error':
+            getattr(L, s).restype = i32
+    return L
+
+
 class SdnsError(RuntimeError):
     pass
 
@@ -110,6 +156,7 @@ def lib():
         fn = getattr(L, s)
         if s not in ('sdns_last_error',):
             fn.restype = i32
+    bind2d(L)
     if L.sdns_abi_version() != SDNS_ABI_VERSION:
         raise SdnsError('libsdns_b200.so ABI version mismatch')
     _lib = L
@@ -119,3 +166,8 @@ def lib():
 def check(rc):
     if rc != 0:
         raise SdnsError('libsdns_b200: %s (status %d)' % (lib().sdns_last_error().decode(), rc))
+
+
+def check2d(rc):
+    if rc != 0:
+        raise SdnsError('libsdns_b200: %s (status %d)' % (lib().sdns2d_last_error().decode(), rc))

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libsdns_b200.so')
-NFAM = 15
+NFAM = 17
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',
          '-Xfatbin=-compress-all']      # compressed cubins: the .so travels to the GPU box with the tree
@@ -34,7 +34,7 @@ def _sources_digest(extra='', kernels_only=False):
     the public header, so a change to the plan / C ABI recompiles one file instead of thirty."""
     h = hashlib.sha1()
     for f in sorted(os.listdir(CSRC)) + ['../../include/sdns_b200.h']:
-        if kernels_only and f in ('sdns_api.cu', '../../include/sdns_b200.h'):
+        if kernels_only and f in ('sdns_api.cu', 'sdns2d_api.cu', '../../include/sdns_b200.h'):
             continue
         with open(os.path.join(CSRC, f), 'rb') as fh:
             h.update(fh.read())
@@ -87,11 +87,12 @@ def build(force=False, jobs=None, verbose=False, sizes=None, out=None, precs=(32
             units.append((o, [nvcc] + ARCH + FLAGS + extra +
                           ['-DSDNS_FAMILY=%d' % fam, '-DSDNS_PREC=%d' % prec,
                            '-c', os.path.join(CSRC, 'inst.cu'), '-o', o]))
-    o_api = os.path.join(OBJ, 'sdns_api.o')
-    if out and families is not None and 'api' not in families:
-        reuse.append(os.path.join(main_obj, 'sdns_api.o'))
-    else:
-        units.append((o_api, [nvcc] + ARCH + FLAGS + extra + ['-c', os.path.join(CSRC, 'sdns_api.cu'), '-o', o_api]))
+    for api in ('sdns_api', 'sdns2d_api'):          # plan + C ABI of the 3-D path, and of the 2-D solvers
+        o_api = os.path.join(OBJ, api + '.o')
+        if out and families is not None and 'api' not in families:
+            reuse.append(os.path.join(main_obj, api + '.o'))
+        else:
+            units.append((o_api, [nvcc] + ARCH + FLAGS + extra + ['-c', os.path.join(CSRC, api + '.cu'), '-o', o_api]))
     with ThreadPoolExecutor(max_workers=jobs) as ex:
         outs = list(ex.map(lambda u: _run(u[1]), units))
     if verbose:

@@ -9,7 +9,7 @@ from . import config
 
 __version__ = '1.4.0+b200'
 
-_SOLVERS = ('NS', 'VV', 'MHD')
+_SOLVERS = ('NS', 'VV', 'MHD', 'NS2D', 'Bq2D')
 
 
 def get_solver(update=None, regression_test=None, additional_callback=None,

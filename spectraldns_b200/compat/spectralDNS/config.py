@@ -9,7 +9,8 @@ What callers rely on (reference config.py line numbers):
   * config.triplyperiodic: argparse tree, solver name as positional sub-command (:212-239)
   * config.update(new, mesh): change defaults before parsing (:307-314); demos add their own
     arguments with config.triplyperiodic.add_argument (tests/TG.py:139-142)
-Only the 'triplyperiodic' mesh is on the B200 path; 'doublyperiodic' and 'channel' raise.
+  * config.doublyperiodic: the same for the 2-D solvers NS2D / Bq2D (:242-261)
+The 'triplyperiodic' and 'doublyperiodic' meshes are on the B200 path; 'channel' raises.
 """
 import argparse
 import json
@@ -18,7 +19,7 @@ from collections import defaultdict
 import numpy as np
 from numpy import pi
 
-__all__ = ['params', 'triplyperiodic', 'update', 'AttributeDict', 'Params', 'fft_plans']
+__all__ = ['params', 'triplyperiodic', 'doublyperiodic', 'update', 'AttributeDict', 'Params', 'fft_plans']
 
 
 class AttributeDict(dict):
@@ -146,24 +147,45 @@ def _toggle(p, name, default, on_help, off_help):
     p.set_defaults(**{name: default})
 
 
+# reference config.py:242-261
+_DOUBLY = [
+    ('--integrator', dict(default='RK4', choices=('RK4', 'ForwardEuler', 'AB2', 'BS5_fixed', 'BS5_adaptive'),
+                          help='Integrator for doubly periodic domain')),
+    ('--L', dict(default=[2*pi, 2*pi], nargs=2, metavar=('Lx', 'Ly'), help='Physical mesh size')),
+    ('--convection', dict(default='Vortex', choices=('Vortex',), help='Form of the nonlinear convective term')),
+    ('--TOL', dict(type=float, default=1e-6, help='Tolerance for adaptive time integrator')),
+    ('--M', dict(default=[6, 6], nargs=2, metavar=('Mx', 'My'),
+                 help='Mesh size is pow(2, M[i]) in direction i. Used if N is missing.')),
+]
+_SOLVERS_2D = [
+    ('NS2D', 'Regular 2D Navier Stokes solver', []),
+    ('Bq2D', 'Regular 2D Navier Stokes solver with Boussinesq model.',
+     [('--Ri', dict(default=0.1, type=float, help='Richardson number')),
+      ('--Pr', dict(default=1.0, type=float, help='Prandtl number'))]),
+]
+
+
 def _build():
     common = argparse.ArgumentParser(prog='spectralDNS', add_help=False)
     for flag, kw in _COMMON:
         common.add_argument(flag, **kw)
     _toggle(common, 'verbose', True, 'Print timings in the end', 'Do not print timings in the end')
     _toggle(common, 'mask_nyquist', True, 'Eliminate Nyquist frequency', 'Do not eliminate Nyquist frequency')
-    tri = argparse.ArgumentParser(parents=[common])
-    for flag, kw in _TRIPLY:
-        tri.add_argument(flag, **kw)
-    sub = tri.add_subparsers(dest='solver')
-    for name, text, extra in _SOLVERS:
-        sp = sub.add_parser(name, help=text)
-        for flag, kw in extra:
-            sp.add_argument(flag, **kw)
-    return common, tri
+    meshes = []
+    for options, solvers in ((_TRIPLY, _SOLVERS), (_DOUBLY, _SOLVERS_2D)):
+        m = argparse.ArgumentParser(parents=[common])
+        for flag, kw in options:
+            m.add_argument(flag, **kw)
+        sub = m.add_subparsers(dest='solver')
+        for name, text, extra in solvers:
+            sp = sub.add_parser(name, help=text)
+            for flag, kw in extra:
+                sp.add_argument(flag, **kw)
+        meshes.append(m)
+    return common, meshes[0], meshes[1]
 
 
-parser, triplyperiodic = _build()
+parser, triplyperiodic, doublyperiodic = _build()
 
 
 class _Unsupported(object):
@@ -171,11 +193,10 @@ class _Unsupported(object):
         self.name = name
 
     def __getattr__(self, attr):
-        raise NotImplementedError("mesh '%s' is outside the B200 hot path (triply periodic NS/VV/MHD only)"
-                                  % self.name)
+        raise NotImplementedError("mesh '%s' is outside the B200 hot path (triply periodic NS/VV/MHD and doubly "
+                                  "periodic NS2D/Bq2D only)" % self.name)
 
 
-doublyperiodic = _Unsupported('doublyperiodic')
 channel = _Unsupported('channel')
 
 

@@ -37,6 +37,17 @@ def cross2(c, a, b):
     eng = _engine_for(b if hasattr(b, '_space') else c)
     p = eng.plan
     p.use_current_stream()
+    if len(p.spectral_shape) == 2:
+        # 2-D: scalar c = 1j*(a0 b1 - a1 b0) (cython_maths.in:105-147).  With the wavenumber list K this is one launch
+        # (sdns2d_cross2); a dense real `a` is user-side arithmetic and stays numpy.
+        if isinstance(a, (list, tuple)):
+            db = eng.upload('x2b', np.asarray(b)[:2], p.complex, p.tcomplex)
+            dc = eng.stage('x2c', p.spectral_shape, p.tcomplex)
+            p.cross2(dc, db)
+            c[...] = dc.cpu().numpy()
+        else:
+            c[...] = 1j*(a[0]*np.asarray(b)[1] - a[1]*np.asarray(b)[0])
+        return c
     db = eng.upload('x2b', b, p.complex, p.tcomplex)
     dc = eng.stage('x2c', db.shape, p.tcomplex)
     if isinstance(a, (list, tuple)):
@@ -73,6 +84,8 @@ def getintegrator(rhs, u0, solver, context):
         return float(params.eta) if 'eta' in params else 0.0
 
     def before():
+        if hasattr(plan, 'set_physics'):
+            plan.set_physics(params)
         if dev.host_dirty or not dev.managed:
             dev.upload_state()
             dev.refresh_source(context.get('Source', None))
@@ -103,6 +116,9 @@ def getintegrator(rhs, u0, solver, context):
                           float(params.nu), eta(), src)
             after()
             return u0, params.dt, params.dt
+    elif name in ('BS5_adaptive', 'BS5_fixed') and not hasattr(plan, 'lincomb'):
+        raise NotImplementedError('%s is available for the triply periodic solvers; the 2-D solvers provide RK4, '
+                                  'ForwardEuler and AB2' % name)
     elif name in ('BS5_adaptive', 'BS5_fixed'):
         integrate = _bs5(name == 'BS5_adaptive', rhs, u0, solver, context, dev, before, after, eta)
     else:

@@ -10,7 +10,7 @@ from spectraldns_b200.device_state import DeviceState
 def build_spaces(comm, params, float_, solver_name):
     """T and its dealiased companion Tp sharing one CUDA plan (reference solvers/NS.py:14-32)."""
     dim = len(params.N)
-    assert dim == 3, 'the B200 path is triply periodic 3-D'
+    assert dim in (2, 3), 'the B200 path covers the triply and the doubly periodic solvers'
     V = [FunctionSpace(params.N[i], 'F', domain=(0, params.L[i]),
                        dtype=(float_ if i == dim-1 else (np.complex64 if float_ == np.float32 else np.complex128)))
          for i in range(dim)]
@@ -35,16 +35,17 @@ def build_spaces(comm, params, float_, solver_name):
 
 def wavenumber_arrays(T, VT, float_):
     """X, K, K2, K_over_K2 exactly as get_context builds them (solvers/NS.py:36-48)."""
+    dim = len(T.N)
     X = T.local_mesh(True)
     K = T.local_wavenumbers(scaled=True)
-    for i in range(3):
+    for i in range(dim):
         X[i] = X[i].astype(float_)
         K[i] = K[i].astype(float_)
     K2 = np.zeros(T.shape(True), dtype=float_)
-    for i in range(3):
+    for i in range(dim):
         K2 += K[i]*K[i]
     K_over_K2 = np.zeros(VT.shape(True), dtype=float_)
-    for i in range(3):
+    for i in range(dim):
         K_over_K2[i] = K[i] / np.where(K2 == 0, 1, K2)
     return X, K, K2, K_over_K2
 
@@ -78,6 +79,8 @@ def run_rhs(dev, rhs, u_hat, source, want_p):
     if plan.solver == 'NS' and params.convection != plan.convection:
         raise RuntimeError('params.convection changed after get_context(): the CUDA plan was built for %r' % plan.convection)
     plan.use_current_stream()
+    if hasattr(plan, 'set_physics'):
+        plan.set_physics(params)            # Bq2D: Richardson / Prandtl numbers (config.py:260-261)
     d_u = dev.device_input(u_hat)
     src = dev.refresh_source(source)
     d_rhs = dev.rhs_buffer()
@@ -117,6 +120,8 @@ class Convection(object):
         if eng is None:
             raise RuntimeError('conv(): pass the dealiased space Tp/VTp of get_context()')
         p = eng.plan
+        if not hasattr(p, 'compute_conv'):
+            raise NotImplementedError('conv() on its own is not part of the 2-D C ABI; ComputeRHS runs it fused')
         p.use_current_stream()
         d_u = eng.upload('conv_in', u_hat, p.complex, p.tcomplex)
         d_r = eng.stage('conv_out', d_u.shape, p.tcomplex)

@@ -1,4 +1,4 @@
-// inst.cu -- one instantiation unit: compile with -DSDNS_FAMILY=<0..10> -DSDNS_PREC=<32|64>.
+// inst.cu -- one instantiation unit: compile with -DSDNS_FAMILY=<0..16> -DSDNS_PREC=<32|64>.
 // Defines sdns_launch_<family>_f<prec>(n, args, stream): picks the kernel compiled for transform
 // length n and launches it.
 #include "launch.cuh"
@@ -430,6 +430,10 @@ int SDNS_FN(int n, const void* args, cudaStream_t st) {
 #define X(N) case N: return run_z<T, N, Z_UU>(*(const ZArgs<T>*)args, st);
 #elif SDNS_FAMILY == 14
 #define X(N) case N: return run_nsdiv_f0<T, N>(*(const StridedArgs<T>*)args, st);
+#elif SDNS_FAMILY == 15
+#define X(N) case N: return run_z<T, N, Z_NS2D>(*(const ZArgs<T>*)args, st);
+#elif SDNS_FAMILY == 16
+#define X(N) case N: return run_z<T, N, Z_BQ2D>(*(const ZArgs<T>*)args, st);
 #endif
         SDNS_SIZES(X)
 #if SDNS_FAMILY <= 5 || (SDNS_FAMILY >= 7 && SDNS_FAMILY <= 9)

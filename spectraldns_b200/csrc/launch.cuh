@@ -22,7 +22,7 @@ namespace sdns {
 enum Family {
     FAM_PLAIN_FWD = 0, FAM_PLAIN_BWD = 1, FAM_NS_B0 = 2, FAM_VV_B0 = 3, FAM_NS_F0 = 4, FAM_VV_F0 = 5,
     FAM_MHD_F0 = 6, FAM_Z_C2R = 7, FAM_Z_R2C = 8, FAM_Z_CROSS = 9, FAM_Z_MHD = 10,
-    FAM_NS_GRAD_B0 = 11, FAM_Z_DOT = 12, FAM_Z_UU = 13, FAM_NSDIV_F0 = 14, FAM_COUNT = 15
+    FAM_NS_GRAD_B0 = 11, FAM_Z_DOT = 12, FAM_Z_UU = 13, FAM_NSDIV_F0 = 14, FAM_Z_NS2D = 15, FAM_Z_BQ2D = 16, FAM_COUNT = 17
 };
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
@@ -197,7 +197,7 @@ struct ZCfg {
     static constexpr int PADW = 128 / (2 * (int)sizeof(T));
     static constexpr int LP = M + M / PADW + 1;
     static constexpr size_t smem = ((size_t)LP * LPC * NBUF + (park ? (size_t)2 * E * P * LPC : 0)) * 2 * sizeof(T);
-    static constexpr int needRegs = (sizeof(T) == 8 ? (E > 12 ? 200 : 128) : (E > 16 ? 128 : 96)) * ((MODE == Z_MHD || MODE == Z_DOT) ? 2 : 1);
+    static constexpr int needRegs = (sizeof(T) == 8 ? (E > 12 ? 200 : 128) : (E > 16 ? 128 : 96)) * ((MODE == Z_MHD || MODE == Z_DOT || MODE == Z_NS2D || MODE == Z_BQ2D) ? 2 : 1);
     static constexpr int minBlocks = cmax(1, cmin(cmin(cmin((int)((224 * 1024) / (smem + 1024)), 2048 / (P * LPC)),
                                                        65536 / (P * LPC * needRegs)), 4));
 };
@@ -304,7 +304,7 @@ template <typename T> int launch_family(int family, int n, const void* args, cud
     int sdns_launch_##fam##_f64(int n, const void* args, cudaStream_t st);
 SDNS_DECL(0) SDNS_DECL(1) SDNS_DECL(2) SDNS_DECL(3) SDNS_DECL(4) SDNS_DECL(5)
 SDNS_DECL(6) SDNS_DECL(7) SDNS_DECL(8) SDNS_DECL(9) SDNS_DECL(10)
-SDNS_DECL(11) SDNS_DECL(12) SDNS_DECL(13) SDNS_DECL(14)
+SDNS_DECL(11) SDNS_DECL(12) SDNS_DECL(13) SDNS_DECL(14) SDNS_DECL(15) SDNS_DECL(16)
 #undef SDNS_DECL
 
 }  // namespace sdns

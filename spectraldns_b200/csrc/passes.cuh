@@ -30,7 +30,7 @@ __device__ __forceinline__ int axis_idx(const AxisMap& a, int j) { return j < a.
 __device__ __forceinline__ bool axis_ok(const AxisMap& a, int M, int j) { return j < a.nlo || j >= M - a.nhi; }
 
 enum StridedMode { S_PLAIN = 0, S_NS_B0 = 1, S_VV_B0 = 2, S_NS_F0 = 3, S_VV_F0 = 4, S_MHD_F0 = 5, S_NS_GRAD_B0 = 6 };
-enum ZMode { Z_C2R = 0, Z_R2C = 1, Z_CROSS = 2, Z_MHD = 3, Z_DOT = 4, Z_UU = 5 };
+enum ZMode { Z_C2R = 0, Z_R2C = 1, Z_CROSS = 2, Z_MHD = 3, Z_DOT = 4, Z_UU = 5, Z_NS2D = 6, Z_BQ2D = 7 };
 enum OutMode { OUT_RHS = 0, OUT_STAGE = 1, OUT_CONV = 2 };   // OUT_CONV: convection term only (solver.conv)
 
 template <typename T>
@@ -1303,6 +1303,40 @@ z_kernel(const ZArgs<T> a) {
                 fft_line<T, M, E, -1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
                 unpack_store_pair<T, M, E, SYNC, NBUF>(x, out + (2 * pr) * a.out_fs + line * a.out_ls,
                                                        out + (2 * pr + 1) * a.out_fs + line * a.out_ls,
+                                                       t, nk, a.scale, sm, map, BUFSTRIDE, phase);
+            }
+        } else if (MODE == Z_NS2D || MODE == Z_BQ2D) {
+            // 2-D solvers: the contiguous axis of a doubly periodic grid.  NS2D (solvers/NS2D.py:40-48): fields
+            // (u0, u1, curl) -> (u1*curl, -u0*curl).  Bq2D (solvers/Bq2D.py:121-137): fields (u0, u1, rho, curl) ->
+            // (u1*curl, -u0*curl, u0*rho, u1*rho).
+            V p01[E], p23[E];
+            load_pair<T, M, E>(p01, in + 0 * a.in_fs + line * a.in_ls, in + 1 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p01, t, a.tw, sm, map, BUFSTRIDE, phase);
+            if (MODE == Z_BQ2D)        // second pair = curl + i rho
+                load_pair<T, M, E>(p23, in + 3 * a.in_fs + line * a.in_ls, in + 2 * a.in_fs + line * a.in_ls, t, a.nin_keep);
+            else                       // curl alone
+                load_pair<T, M, E>(p23, in + 2 * a.in_fs + line * a.in_ls, (const V*)nullptr, t, a.nin_keep);
+            fft_line<T, M, E, +1, SYNC, NBUF>(p23, t, a.tw, sm, map, BUFSTRIDE, phase);
+            {
+                V x[E];
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    const T u0 = p01[q].x, u1 = p01[q].y, w = p23[q].x;
+                    x[q].x = u1 * w; x[q].y = -u0 * w;
+                }
+                fft_line<T, M, E, -1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+                unpack_store_pair<T, M, E, SYNC, NBUF>(x, out + 0 * a.out_fs + line * a.out_ls, out + 1 * a.out_fs + line * a.out_ls,
+                                                       t, nk, a.scale, sm, map, BUFSTRIDE, phase);
+            }
+            if (MODE == Z_BQ2D) {
+                V x[E];
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    const T u0 = p01[q].x, u1 = p01[q].y, r = p23[q].y;
+                    x[q].x = u0 * r; x[q].y = u1 * r;
+                }
+                fft_line<T, M, E, -1, SYNC, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
+                unpack_store_pair<T, M, E, SYNC, NBUF>(x, out + 2 * a.out_fs + line * a.out_ls, out + 3 * a.out_fs + line * a.out_ls,
                                                        t, nk, a.scale, sm, map, BUFSTRIDE, phase);
             }
         } else {

@@ -35,10 +35,11 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     return fail(SDNS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
 
 typedef int (*launch_fn)(int, const void*, cudaStream_t);
-static launch_fn g_launch[FAM_COUNT][2] = {
+extern launch_fn g_launch[FAM_COUNT][2];
+launch_fn g_launch[FAM_COUNT][2] = {       // also used by sdns2d_api.cu
 #define ROW(f) { sdns_launch_##f##_f32, sdns_launch_##f##_f64 },
     ROW(0) ROW(1) ROW(2) ROW(3) ROW(4) ROW(5) ROW(6) ROW(7) ROW(8) ROW(9) ROW(10)
-    ROW(11) ROW(12) ROW(13) ROW(14)
+    ROW(11) ROW(12) ROW(13) ROW(14) ROW(15) ROW(16)
 #undef ROW
 };
 

@@ -365,3 +365,156 @@ class Plan(object):
         ms, b, n = C.c_double(), C.c_double(), C.c_longlong()
         _lib.check(self.lib.sdns_profile_read_copies(self._p, C.byref(ms), C.byref(b), C.byref(n)))
         return ms.value, b.value, n.value
+
+
+class Plan2D(object):
+    """One doubly periodic grid / precision / solver (NS2D or Bq2D) bound to one GPU: the Python face of sdns2d_plan.
+
+    Mirrors what get_context() of solvers/NS2D.py:13-18 and Bq2D.py:13-50 builds.  Method names follow Plan, so that
+    the host layer (device_state.py, compat/spectralDNS/maths) drives both alike; `eta` arguments are ignored and the
+    Boussinesq numbers Ri, Pr are attributes (set_physics)."""
+
+    def __init__(self, N, L=(2*np.pi,)*2, precision='double', dealias='2/3-rule', solver='NS2D', mask_nyquist=True,
+                 kcut=None, device=0):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.SdnsError('no CUDA device: spectraldns_b200 has no CPU fallback')
+        self.lib = _lib.lib()
+        self.N = tuple(int(n) for n in N)
+        self.L = tuple(float(l) for l in L)
+        self.precision, self.dealias, self.solver = precision, dealias, solver
+        self.convection = 'Vortex'
+        self.float = np.dtype(np.float32 if precision == 'single' else np.float64)
+        self.complex = np.dtype(np.complex64 if precision == 'single' else np.complex128)
+        self.tfloat = torch.float32 if precision == 'single' else torch.float64
+        self.tcomplex = torch.complex64 if precision == 'single' else torch.complex128
+        self.device = torch.device('cuda', device)
+        self.rank, self.nranks = 0, 1
+        self.Ri, self.Pr = 0.1, 1.0                      # config.py:260-261 defaults
+        cfg = _lib.Sdns2dConfig()
+        cfg.abi_version = _lib.SDNS_ABI_VERSION
+        for i in range(2):
+            cfg.N[i], cfg.L[i] = self.N[i], self.L[i]
+            cfg.kcut[i] = -1 if kcut is None else int(kcut[i])
+        cfg.precision = _lib.SINGLE if precision == 'single' else _lib.DOUBLE
+        cfg.dealias = _lib.DEALIAS[dealias]
+        cfg.solver = _lib.SOLVER2D[solver]
+        cfg.mask_nyquist = 1 if mask_nyquist else 0
+        cfg.device = device
+        self._p = C.c_void_p()
+        _lib.check2d(self.lib.sdns2d_plan_create(C.byref(self._p), C.byref(cfg)))
+        sp, ph, pd = (C.c_int32*2)(), (C.c_int32*2)(), (C.c_int32*2)()
+        _lib.check2d(self.lib.sdns2d_shapes(self._p, C.byref(sp), C.byref(ph), C.byref(pd)))
+        self.spectral_shape, self.physical_shape, self.padded_shape = tuple(sp), tuple(ph), tuple(pd)
+        self.ncomp = 3 if solver == 'Bq2D' else 2
+        nb = C.c_size_t()
+        _lib.check2d(self.lib.sdns2d_workspace_bytes(self._p, C.byref(nb)))
+        self.workspace_bytes = nb.value
+        with torch.cuda.device(self.device):
+            self.use_current_stream()
+            self._ws = torch.empty(nb.value + 256, dtype=torch.uint8, device=self.device)
+            off = (-self._ws.data_ptr()) % 256
+            _lib.check2d(self.lib.sdns2d_plan_set_workspace(self._p, self._ws.data_ptr() + off, nb.value))
+
+    def __del__(self):
+        try:
+            if getattr(self, '_p', None):
+                self.lib.sdns2d_plan_destroy(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+    def set_physics(self, params):
+        """Richardson and Prandtl numbers of the Boussinesq solver from the run-time parameters (config.py:260-261)."""
+        if 'Ri' in params:
+            self.Ri = float(params.Ri)
+        if 'Pr' in params:
+            self.Pr = float(params.Pr)
+
+    def use_current_stream(self):
+        s = _torch().cuda.current_stream(self.device).cuda_stream
+        _lib.check2d(self.lib.sdns2d_plan_set_stream(self._p, C.c_void_p(s)))
+
+    def sync(self):
+        _lib.check2d(self.lib.sdns2d_sync(self._p))
+
+    def comm_timed_out(self):
+        return False
+
+    def launch_count(self):
+        c = C.c_longlong()
+        _lib.check2d(self.lib.sdns2d_launch_count(self._p, C.byref(c)))
+        return c.value
+
+    def empty_spectral(self, ncomp=None):
+        shape = self.spectral_shape if ncomp == 0 else ((ncomp or self.ncomp),) + self.spectral_shape
+        return _torch().zeros(shape, dtype=self.tcomplex, device=self.device)
+
+    def empty_physical(self, ncomp=None, padded=False):
+        s = self.padded_shape if padded else self.physical_shape
+        shape = s if ncomp == 0 else ((ncomp or self.ncomp),) + s
+        return _torch().zeros(shape, dtype=self.tfloat, device=self.device)
+
+    to_device = Plan.to_device
+    to_host = staticmethod(Plan.to_host)
+
+    def _chk(self, t, dtype, shape_tail, name):
+        if t.dtype != dtype or not t.is_contiguous() or not t.is_cuda:
+            raise ValueError('%s: need a contiguous CUDA tensor of dtype %s' % (name, dtype))
+        if tuple(t.shape[-2:]) != tuple(shape_tail):
+            raise ValueError('%s: trailing shape %s != %s' % (name, tuple(t.shape[-2:]), tuple(shape_tail)))
+        return t.numel() // int(np.prod(shape_tail))
+
+    def forward(self, u, out=None, padded=False):
+        s = self.padded_shape if padded else self.physical_shape
+        nc = self._chk(u, self.tfloat, s, 'forward input')
+        if out is None:
+            out = _torch().empty(tuple(u.shape[:-2]) + self.spectral_shape, dtype=self.tcomplex, device=self.device)
+        assert self._chk(out, self.tcomplex, self.spectral_shape, 'forward output') == nc
+        _lib.check2d(self.lib.sdns2d_forward(self._p, _lib.SPACE_TP if padded else _lib.SPACE_T, nc, u.data_ptr(), out.data_ptr()))
+        return out
+
+    def backward(self, u_hat, out=None, padded=False, dealias=False):
+        use_tp = padded or dealias
+        s = self.padded_shape if use_tp else self.physical_shape
+        nc = self._chk(u_hat, self.tcomplex, self.spectral_shape, 'backward input')
+        if out is None:
+            out = _torch().empty(tuple(u_hat.shape[:-2]) + s, dtype=self.tfloat, device=self.device)
+        assert self._chk(out, self.tfloat, s, 'backward output') == nc
+        _lib.check2d(self.lib.sdns2d_backward(self._p, _lib.SPACE_TP if use_tp else _lib.SPACE_T, nc, u_hat.data_ptr(), out.data_ptr()))
+        return out
+
+    def compute_rhs(self, rhs, u_hat, nu, eta=0.0, source=None, p_hat=None):
+        assert self._chk(rhs, self.tcomplex, self.spectral_shape, 'rhs') == self.ncomp
+        assert self._chk(u_hat, self.tcomplex, self.spectral_shape, 'u_hat') == self.ncomp
+        _lib.check2d(self.lib.sdns2d_compute_rhs(self._p, rhs.data_ptr(), u_hat.data_ptr(), float(nu), self.Ri, self.Pr,
+                                                 source.data_ptr() if source is not None else None,
+                                                 p_hat.data_ptr() if p_hat is not None else None))
+        return rhs
+
+    def rk4_step(self, u_hat, u1, u2, dt, nu, eta=0.0, source=None):
+        for t, n in ((u_hat, 'u_hat'), (u1, 'u1'), (u2, 'u2')):
+            assert self._chk(t, self.tcomplex, self.spectral_shape, n) == self.ncomp
+        _lib.check2d(self.lib.sdns2d_rk4_step(self._p, u_hat.data_ptr(), u1.data_ptr(), u2.data_ptr(), float(dt), float(nu),
+                                              self.Ri, self.Pr, source.data_ptr() if source is not None else None))
+        return u_hat
+
+    def euler_step(self, u_hat, rhs, dt, nu, eta=0.0, source=None):
+        _lib.check2d(self.lib.sdns2d_euler_step(self._p, u_hat.data_ptr(), rhs.data_ptr(), float(dt), float(nu), self.Ri, self.Pr,
+                                                source.data_ptr() if source is not None else None))
+        return u_hat
+
+    def ab2_step(self, u_hat, u1, rhs, dt, tstep, nu, eta=0.0, source=None):
+        _lib.check2d(self.lib.sdns2d_ab2_step(self._p, u_hat.data_ptr(), u1.data_ptr(), rhs.data_ptr(), float(dt), int(tstep),
+                                              float(nu), self.Ri, self.Pr, source.data_ptr() if source is not None else None))
+        return u_hat
+
+    def cross2(self, c, u_hat):
+        """Scalar c = 1j*(K0 u1 - K1 u0) (solvers/NS2D.py:20-23)."""
+        _lib.check2d(self.lib.sdns2d_cross2(self._p, c.data_ptr(), u_hat.data_ptr()))
+        return c
+
+    def add_pressure_diffusion(self, du, u_hat, nu, p_hat=None):
+        _lib.check2d(self.lib.sdns2d_add_pressure_diffusion(self._p, du.data_ptr(), u_hat.data_ptr(), float(nu), self.Ri, self.Pr,
+                                                            p_hat.data_ptr() if p_hat is not None else None))
+        return du

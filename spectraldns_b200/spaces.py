@@ -11,7 +11,7 @@ demo/Isotropic.py:33-76,159-254.
 """
 import numpy as np
 
-from .plan import Plan
+from .plan import Plan, Plan2D
 from . import _lib
 
 
@@ -51,10 +51,17 @@ class Engine(object):
                     bool(mask_nyquist), decomposition, convection)
         rank, nranks, device = world()
         self.rank, self.nranks = rank, nranks
-        self.plan = Plan(self.key[0], self.key[1], precision, dealias, solver,
-                         convection=convection, mask_nyquist=mask_nyquist,
-                         decomposition='slab' if nranks > 1 else decomposition,
-                         device=device, rank=rank, nranks=nranks)
+        if len(self.key[0]) == 2:
+            # doubly periodic solvers (NS2D / Bq2D): a thousandth of a 3-D problem, single GPU
+            if nranks > 1:
+                raise NotImplementedError('the 2-D solvers run on one GPU (a 2-D grid does not fill one)')
+            self.plan = Plan2D(self.key[0], self.key[1], precision, dealias, solver if solver in ('NS2D', 'Bq2D') else 'NS2D',
+                               mask_nyquist=mask_nyquist, device=device)
+        else:
+            self.plan = Plan(self.key[0], self.key[1], precision, dealias, solver,
+                             convection=convection, mask_nyquist=mask_nyquist,
+                             decomposition='slab' if nranks > 1 else decomposition,
+                             device=device, rank=rank, nranks=nranks)
         self._stage = {}
 
     @classmethod
@@ -132,9 +139,13 @@ class TensorProductSpace(object):
         r, n, _ = world()
         return r, n
 
+    @property
+    def dim(self):
+        return len(self.N)
+
     def global_shape(self, forward_output=False):
         if forward_output:
-            return (self.N[0], self.N[1], self.N[2]//2+1)
+            return tuple(self.N[:-1]) + (self.N[-1]//2+1,)
         return tuple(self.M)
 
     def shape(self, forward_output=False):
@@ -142,29 +153,30 @@ class TensorProductSpace(object):
         (spectralDNS3D_short.py:28-29)."""
         r, n = self._ranks()
         g = self.global_shape(forward_output)
-        if n == 1:
+        if n == 1 or self.dim == 2:
             return g
         return (g[0], g[1]//n, g[2]) if forward_output else (g[0]//n, g[1], g[2])
 
     def local_slice(self, forward_output=False):
         r, n = self._ranks()
         g = self.global_shape(forward_output)
-        ax = 1 if forward_output else 0
         out = [slice(0, m) for m in g]
-        c = g[ax]//n
-        out[ax] = slice(r*c, (r+1)*c)
+        if self.dim == 3:
+            ax = 1 if forward_output else 0
+            c = g[ax]//n
+            out[ax] = slice(r*c, (r+1)*c)
         return tuple(out)
 
     def dims(self):
-        return 3
+        return self.dim
 
     def __len__(self):
-        return 3
+        return self.dim
 
     def local_mesh(self, broadcast=False):
         X = []
-        for i in range(3):
-            s = [1, 1, 1]
+        for i in range(self.dim):
+            s = [1]*self.dim
             s[i] = self.M[i]
             x = (np.arange(self.M[i], dtype=float)*self.L[i]/self.M[i])
             x = x[self.local_slice(False)[i]]
@@ -175,13 +187,13 @@ class TensorProductSpace(object):
 
     def local_wavenumbers(self, broadcast=False, scaled=False, eliminate_highest_freq=False):
         K = []
-        for i in range(3):
+        for i in range(self.dim):
             n = self.N[i]
-            k = np.fft.fftfreq(n, 1./n) if i < 2 else np.fft.rfftfreq(n, 1./n)
+            k = np.fft.fftfreq(n, 1./n) if i < self.dim-1 else np.fft.rfftfreq(n, 1./n)
             if scaled:
                 k = k*2*np.pi/self.L[i]
             k = k[self.local_slice(True)[i]]
-            s = [1, 1, 1]
+            s = [1]*self.dim
             s[i] = len(k)
             k = k.reshape(s)
             K.append(np.broadcast_to(k, self.shape(True)) if broadcast else k)
@@ -191,7 +203,7 @@ class TensorProductSpace(object):
         mask = np.ones(self.global_shape(True), dtype=int)
         for i, n in enumerate(self.N):
             if n % 2 == 0:
-                s = [slice(None)]*3
+                s = [slice(None)]*self.dim
                 s[i] = n//2
                 mask[tuple(s)] = 0
         return np.ascontiguousarray(mask[self.local_slice(True)])
@@ -282,7 +294,7 @@ class CompositeSpace(object):
 
 class VectorSpace(CompositeSpace):
     def __init__(self, T):
-        CompositeSpace.__init__(self, [T]*3)
+        CompositeSpace.__init__(self, [T]*len(T.N))
 
 
 def _scalar_space(space):
@@ -499,7 +511,7 @@ class _SpaceArray(np.ndarray):
     def _transform_space(self):
         """Space whose component count matches this (possibly sliced) array."""
         T = _scalar_space(self._space)
-        return T if self.ndim == 3 else CompositeSpace([T]*self.shape[0])
+        return T if self.ndim == len(T.N) else CompositeSpace([T]*self.shape[0])
 
 
 class Array(_SpaceArray):

@@ -16,7 +16,7 @@ CSRC = os.path.join(ROOT, 'spectraldns_b200', 'csrc')
 OUT = os.path.join(HERE, 'build')
 LIB = os.path.join(OUT, 'libsdns_emu.so')
 SIZES = (8, 12, 16, 24, 32, 48, 64)
-NFAM = 15
+NFAM = 17
 
 
 def build(extra=(), lib=LIB, sizes=SIZES, force=False):
@@ -38,8 +38,9 @@ def build(extra=(), lib=LIB, sizes=SIZES, force=False):
         for prec in (32, 64):
             o = os.path.join(OUT, '%s_inst_%d_f%d.o' % (tag, fam, prec))
             units.append((o, flags + ['-DSDNS_FAMILY=%d' % fam, '-DSDNS_PREC=%d' % prec, '-c', os.path.join(CSRC, 'inst.cu'), '-o', o]))
-    o = os.path.join(OUT, '%s_api.o' % tag)
-    units.append((o, flags + ['-c', os.path.join(CSRC, 'sdns_api.cu'), '-o', o]))
+    for api in ('sdns_api', 'sdns2d_api'):
+        o = os.path.join(OUT, '%s_%s.o' % (tag, api))
+        units.append((o, flags + ['-c', os.path.join(CSRC, api + '.cu'), '-o', o]))
 
     def run(cmd):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -393,3 +393,157 @@ def test_emulated_small_kernels(emu):
     sc = 1e-6 + np.maximum(np.abs(f0), np.abs(v))*1e-3
     assert np.allclose(np.array(en[:]), np.sum(np.abs(c/sc)**2, axis=(1, 2, 3)), rtol=1e-11)
     p.close()
+
+
+# ---- doubly periodic solvers (csrc/sdns2d_api.cu) ----------------------------------------------------------------
+import sdns_oracle2d as so2      # noqa: E402
+
+
+class Emu2D(object):
+    """numpy front end of the sdns2d_* entry points of the emulated library ("device" pointers are numpy buffers)."""
+    def __init__(self, L, N, Lbox=(2*np.pi,)*2, precision='double', dealias='2/3-rule', solver='NS2D', mask_nyquist=True):
+        import ctypes as C
+        from spectraldns_b200 import _lib
+        self.C, self.L = C, _lib.bind2d(L)
+        cfg = _lib.Sdns2dConfig()
+        cfg.abi_version = 1
+        for i in range(2):
+            cfg.N[i], cfg.L[i], cfg.kcut[i] = int(N[i]), float(Lbox[i]), -1
+        cfg.precision = 1 if precision == 'double' else 0
+        cfg.dealias = _lib.DEALIAS[dealias]
+        cfg.solver = _lib.SOLVER2D[solver]
+        cfg.mask_nyquist = int(mask_nyquist)
+        self.p = C.c_void_p()
+        self.chk(L.sdns2d_plan_create(C.byref(self.p), C.byref(cfg)))
+        n = C.c_size_t()
+        self.chk(L.sdns2d_workspace_bytes(self.p, C.byref(n)))
+        self._ws = np.full(n.value + 512, 0xFF, dtype=np.uint8)
+        base = self._ws.ctypes.data
+        self.chk(L.sdns2d_plan_set_workspace(self.p, C.c_void_p(base + (-base) % 256), n.value))
+        sp, ph, pd = (C.c_int32*2)(), (C.c_int32*2)(), (C.c_int32*2)()
+        self.chk(L.sdns2d_shapes(self.p, C.byref(sp), C.byref(ph), C.byref(pd)))
+        self.sshape, self.pshape, self.dshape = tuple(sp), tuple(ph), tuple(pd)
+        self.real = np.float64 if precision == 'double' else np.float32
+        self.cplx = np.complex128 if precision == 'double' else np.complex64
+
+    def chk(self, rc):
+        if rc:
+            raise RuntimeError(self.L.sdns2d_last_error().decode())
+
+    def forward(self, u, padded=False):
+        u = np.ascontiguousarray(u, dtype=self.real)
+        out = np.full(u.shape[:-2]+self.sshape, np.nan, dtype=self.cplx)
+        self.chk(self.L.sdns2d_forward(self.p, int(padded), u.shape[0], u.ctypes.data, out.ctypes.data))
+        return out
+
+    def backward(self, uh, padded=False):
+        uh = np.ascontiguousarray(uh, dtype=self.cplx)
+        out = np.full(uh.shape[:-2]+(self.dshape if padded else self.pshape), np.nan, dtype=self.real)
+        self.chk(self.L.sdns2d_backward(self.p, int(padded), uh.shape[0], uh.ctypes.data, out.ctypes.data))
+        return out
+
+    def compute_rhs(self, uh, nu, Ri=0.0, Pr=1.0, source=None, want_p=False):
+        uh = np.ascontiguousarray(uh, dtype=self.cplx)
+        rhs = np.full(uh.shape, np.nan, dtype=self.cplx)
+        ph = np.full(self.sshape, np.nan, dtype=self.cplx)
+        self.chk(self.L.sdns2d_compute_rhs(self.p, rhs.ctypes.data, uh.ctypes.data, nu, Ri, Pr,
+                                           source.ctypes.data if source is not None else None, ph.ctypes.data if want_p else None))
+        return (rhs, ph) if want_p else rhs
+
+    def rk4(self, uh, nsteps, dt, nu, Ri=0.0, Pr=1.0):
+        u = np.ascontiguousarray(uh, dtype=self.cplx).copy()
+        u1, u2 = np.full(u.shape, np.nan, dtype=self.cplx), np.full(u.shape, np.nan, dtype=self.cplx)
+        for _ in range(nsteps):
+            self.chk(self.L.sdns2d_rk4_step(self.p, u.ctypes.data, u1.ctypes.data, u2.ctypes.data, dt, nu, Ri, Pr, None))
+        return u
+
+    def close(self):
+        self.L.sdns2d_plan_destroy(self.p)
+
+
+def _state2d(o, ncomp, seed=5):
+    rng = np.random.RandomState(seed)
+    U = rng.standard_normal((ncomp,)+o.N)
+    X = o.mesh()
+    U[0] += 2*np.sin(X[0])*np.cos(X[1])
+    U[1] -= 2*np.sin(X[1])*np.cos(X[0])
+    uh = o.forward(U.astype(o.float))
+    if o.mask is not None:
+        uh = uh*o.mask
+    return uh.astype(o.complex)
+
+
+@pytest.mark.parametrize('solver,N,Lbox,dealias,precision', [
+    ('NS2D', (16, 16), (2*np.pi, 2*np.pi), '2/3-rule', 'double'), ('NS2D', (32, 16), (6*np.pi, 4*np.pi), '3/2-rule', 'double'),
+    ('NS2D', (16, 48), (2*np.pi, 2*np.pi), 'None', 'single'), ('NS2D', (8, 32), (2*np.pi, 4*np.pi), '2/3-rule', 'single'),
+    ('Bq2D', (16, 16), (2*np.pi, 2*np.pi), '2/3-rule', 'double'), ('Bq2D', (16, 32), (6*np.pi, 4*np.pi), '3/2-rule', 'double'),
+    ('Bq2D', (32, 16), (2*np.pi, 2*np.pi), '3/2-rule', 'single')])
+def test_emulated_2d_solvers(emu, solver, N, Lbox, dealias, precision):
+    """NS2D (solvers/NS2D.py:13-51) and Bq2D (solvers/Bq2D.py:101-186): transforms on T and Tp, ComputeRHS with the
+    pressure, two RK4 steps, Forward Euler / AB2 and the stand-alone 2-D operators against oracle/sdns_oracle2d.py."""
+    import ctypes as C
+    L, _ = emu
+    o = so2.Oracle2D(N, L=Lbox, precision=precision, dealias=dealias)
+    p = Emu2D(L, N, Lbox, precision, dealias, solver)
+    tol = TOL[precision]
+    nc = 3 if solver == 'Bq2D' else 2
+    rng = np.random.RandomState(2)
+    u = rng.standard_normal((nc,)+tuple(N)).astype(o.float)
+    assert rel_l2(p.forward(u), o.forward(u)) < tol
+    assert rel_l2(p.backward(o.forward(u).astype(o.complex)), u) < tol
+    f0 = _state2d(o, nc)
+    assert rel_l2(p.backward(f0, padded=True), o._bwd_p(f0)) < tol
+    up = rng.standard_normal((nc,)+tuple(o.M)).astype(o.float)
+    assert rel_l2(p.forward(up, padded=True), o._fwd_p(up)) < tol
+    nu, Ri, Pr, dt = 0.01, 0.1, 0.7, 0.01
+    if solver == 'NS2D':
+        ref, pref = o.ns2d_rhs(f0, nu, return_p=True)
+        fn = lambda v: o.ns2d_rhs(v, nu)
+    else:
+        ref, pref = o.bq2d_rhs(f0, nu, Ri, Pr, return_p=True)
+        fn = lambda v: o.bq2d_rhs(v, nu, Ri, Pr)
+    rhs, ph = p.compute_rhs(f0, nu, Ri, Pr, want_p=True)
+    assert rel_l2(rhs, ref) < tol and rel_l2(ph, pref) < tol
+    assert rel_l2(p.rk4(f0, 2, dt, nu, Ri, Pr), o.solve(f0, solver, 2, dt, nu, Ri, Pr)) < tol
+    # ForwardEuler and AB2 (maths/integrators.py:161-175)
+    uu, rr = f0.copy(), np.zeros_like(f0)
+    p.chk(p.L.sdns2d_euler_step(p.p, uu.ctypes.data, rr.ctypes.data, dt, nu, Ri, Pr, None))
+    assert rel_l2(uu, o.forward_euler_step(f0, fn, dt)) < tol
+    uu, u1 = f0.copy(), np.zeros_like(f0)
+    refu, r1 = f0.copy(), np.zeros_like(f0)
+    for ts in range(3):
+        p.chk(p.L.sdns2d_ab2_step(p.p, uu.ctypes.data, u1.ctypes.data, rr.ctypes.data, dt, ts, nu, Ri, Pr, None))
+        refu, r1 = o.ab2_step(refu, r1, fn, dt, ts)
+    assert rel_l2(uu, refu) < tol
+    # stand-alone operators
+    c = np.zeros(o.sshape, dtype=o.complex)
+    p.chk(p.L.sdns2d_cross2(p.p, c.ctypes.data, f0.ctypes.data))
+    assert rel_l2(c, o.cross2(f0[:2])) < (1e-14 if precision == 'double' else 1e-6)
+    du = (f0[::-1]*0.3).astype(o.complex).copy()
+    ph = np.zeros(o.sshape, dtype=o.complex)
+    p.chk(p.L.sdns2d_add_pressure_diffusion(p.p, du.ctypes.data, f0.ctypes.data, nu, Ri, Pr, ph.ctypes.data))
+    if solver == 'NS2D':
+        dref, pr = o.add_pressure_diffusion_ns2d((f0[::-1]*0.3).astype(o.complex), f0, nu)
+    else:
+        dref, pr = o.add_pressure_diffusion_bq2d((f0[::-1]*0.3).astype(o.complex), f0, nu, Ri, Pr)
+    assert rel_l2(du, dref) < (1e-14 if precision == 'double' else 1e-6) and rel_l2(ph, pr) < (1e-14 if precision == 'double' else 1e-6)
+    if solver == 'NS2D':
+        src = (0.1*f0[::-1]).astype(o.complex).copy()
+        assert rel_l2(p.compute_rhs(f0, nu, source=src), o.ns2d_rhs(f0, nu, source=src)) < tol
+    p.close()
+
+
+def test_emulated_2d_taylor_green_known_answer(emu):
+    """tests/TG2D.py:41-52 through the C ABI: kinetic energy of the 2-D Taylor-Green vortex after 20 RK4 steps against
+    the analytic decay, to the reference's ntol = 7 digits."""
+    L, _ = emu
+    N = (32, 32)
+    o = so2.Oracle2D(N)
+    p = Emu2D(L, N)
+    nu, dt, nsteps = 0.01, 0.05, 20
+    u = p.rk4(so2.taylor_green_2d(o), nsteps, dt, nu)
+    U = p.backward(u)
+    k = np.sum(U.astype(np.float64)**2)/np.prod(N)/2
+    ke = 0.25*np.exp(-2*nu*nsteps*dt)**2
+    assert round(float(k - ke), 7) == 0
+    p.close()
