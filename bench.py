@@ -507,7 +507,7 @@ def run_ours(a):
         line['nvlink'] = {'bytes_per_step_per_gpu': xfer_bytes_step, 'sustained_GBps_per_direction': sus,
                           'peak_measured_GBps': 770.0, 'peak_nominal_GBps': 900.0, 'frac': sus/770.0,
                           'frac_of_nominal': sus/900.0, 'transfer_only_launches_per_step': xfer_flushes_step,
-                          'exchange': os.environ.get('SDNS_EXCHANGE', 'tma'),
+                          'exchange': os.environ.get('SDNS_EXCHANGE', 'tma (default for 3 or more GPUs)'),
                           'note': 'send slots moved by bulk-async (TMA) copies issued from a transfer role inside the FFT pass '
                                   'kernels (csrc/xfer.cuh); frac = sustained over the whole step / 770 GB/s measured peer copy'}
     elif world > 1 and copies[2]:
@@ -516,12 +516,15 @@ def run_ours(a):
         xbytes, xms = copies[1]/npf, copies[0]/npf
         line['nvlink'] = {'bytes_per_step_per_gpu': xbytes, 'copies_per_step': copies[2]/npf,
                           'copy_stream_busy_ms_per_step': xms,
-                          'achieved_GBps_per_direction': xbytes*1e-9/(xms*1e-3) if xms else None,
-                          'sustained_over_step_GBps': xbytes*1e-9/(ms*1e-3),
+                          'while_busy_GBps_per_direction': xbytes*1e-9/(xms*1e-3) if xms else None,
+                          'sustained_GBps_per_direction': xbytes*1e-9/(ms*1e-3),
                           'peak_measured_GBps': 770.0, 'peak_nominal_GBps': 900.0,
-                          'frac_of_measured': (xbytes*1e-9/(xms*1e-3))/770.0 if xms else None,
+                          'frac': xbytes*1e-9/(ms*1e-3)/770.0,
+                          'while_busy_frac_of_measured': (xbytes*1e-9/(xms*1e-3))/770.0 if xms else None,
+                          'exchange': 'ce',
                           'note': 'strided cudaMemcpy2DAsync per peer and chunk on per-peer streams, concurrent with '
-                                  'the FFT passes; busy time = summed copy durations of the busiest stream'}
+                                  'the FFT passes; frac = bytes sent per step / step time / 770 GB/s measured peer copy '
+                                  '(sustained); while_busy = rate while the busiest copy stream is busy'}
     elif world > 1:
         # NVLink side of the roofline (rank 0's view): bytes the exchange passes store into peers
         xk = {k: v for k, v in prof.items() if v[3] > 0}

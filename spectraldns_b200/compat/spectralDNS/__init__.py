@@ -57,6 +57,7 @@ def solve(solver, context):
                 solver.update(context)
             elif user_update:
                 dev.sync_to_host()
+                dev.host_touched()          # the callback may change the host state and then call ComputeRHS / transforms on it
                 solver.update(context)
                 dev.host_touched()
             context.hdf5file.update(params, **context)

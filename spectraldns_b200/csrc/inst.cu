@@ -19,125 +19,9 @@ typedef double real_t;
 
 namespace sdns {
 
-#ifdef SDNS_F32_PAIRS
-extern "C" { __attribute__((weak)) long long sdns_debug_pair_launches = 0; }     // how often the pair kernel ran (tests)
-// fp32 plain pass on column pairs: geometry of the fp64 pass (same bytes per thread), arguments rescaled to pair units
-template <int N, int DIR>
-static int run_plain2(const StridedArgs<float>& a, cudaStream_t st) {
-    typedef SCfg<double, N, S_PLAIN> C;
-    auto kern = plain2_kernel<N, C::E, C::TC, DIR, C::NBUF, C::minBlocks>;
-    static bool once = false;
-    if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
-    StridedArgs<float> b = a;
-    const long long nruns = a.ncols / a.cw;
-    b.cw = (a.cw + 1) / 2; b.ncols = nruns * b.cw; b.c2_off = a.c2_off / 2;
-    b.in_fs /= 2; b.in_ls /= 2; b.in_os /= 2; b.out_fs /= 2; b.out_ls /= 2; b.out_os /= 2; b.out_fs2 /= 2; b.out_ls2 /= 2;
-    long long tiles = (b.ncols + C::TC - 1) / C::TC;
-    if (a.grid_cap > 0) {
-        static int nsm = 0;
-        if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-        const long long cap = ((long long)a.grid_cap * nsm + a.nfields - 1) / a.nfields;
-        if (tiles > cap) tiles = cap;
-    }
-    b.xuniform = 0;
-    if (a.xchunk > 0 && a.xchunk % C::P == 0 && a.omap.shift % C::P == 0) {
-        const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;
-        b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
-    }
-    xfer_prepare(b.x, C::smem, C::P * C::TC);
-    dim3 grid((unsigned)tiles + b.x.nctas, a.nfields);
-    ++sdns_debug_pair_launches;
-    SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
-    return (int)cudaGetLastError();
-}
-// B0 on column pairs: output side (W0 / send slots) in pairs, input side (dense state) stays scalar
-template <int N, int MODE>
-static int run_b02(const StridedArgs<float>& a, cudaStream_t st) {
-    typedef SCfg<double, N, MODE> C;
-    auto kern = b02_kernel<N, C::E, C::TC, MODE, C::NBUF, C::minBlocks>;
-    static bool once = false;
-    if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
-    StridedArgs<float> b = a;
-    const long long nruns = a.ncols / a.cw;
-    b.cw_sc = a.cw; b.cw = (a.cw + 1) / 2; b.ncols = nruns * b.cw;
-    b.out_fs /= 2; b.out_ls /= 2; b.out_os /= 2; b.out_fs2 /= 2; b.out_ls2 /= 2;
-    long long tiles = (b.ncols + C::TC - 1) / C::TC;
-    if (a.grid_cap > 0) {
-        static int nsm = 0;
-        if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-        if (tiles > (long long)a.grid_cap * nsm) tiles = (long long)a.grid_cap * nsm;
-    }
-    b.xuniform = 0;
-    if (a.xchunk > 0 && a.xchunk % C::P == 0 && a.omap.shift % C::P == 0) {
-        const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;
-        b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
-    }
-    ++sdns_debug_pair_launches;
-    xfer_prepare(b.x, C::smem, C::P * C::TC);
-    SDNS_LAUNCH(kern, dim3((unsigned)tiles + b.x.nctas), C::P * C::TC, C::smem, st)(b);
-    return (int)cudaGetLastError();
-}
-static bool pair_ok_out(const StridedArgs<float>& a) {
-    if (!a.pairable || a.cw <= 0 || a.c2_off) return false;
-    const long long s[] = {a.out_fs, a.out_ls, a.out_os, a.out_fs2, a.out_ls2};
-    for (long long v : s) if (v & 1) return false;
-    if (((uintptr_t)a.out) & 15) return false;
-    if (a.xchunk > 0) for (int r = 0; r < 8; ++r) if (((uintptr_t)a.peer_out[r]) & 15) return false;
-    return true;
-}
-// F0 on column pairs: input side (W3) in pairs, the epilogue's state arrays stay scalar
-template <int N, int MODE>
-static int run_f02(const StridedArgs<float>& a, cudaStream_t st) {
-    typedef SCfg<double, N, MODE> C;
-    auto kern = f02_kernel<N, C::E, C::TC, MODE, C::NBUF, C::minBlocks>;
-    static bool once = false;
-    if (!once) { cudaError_t e = set_smem(kern, C::smem); if (e != cudaSuccess) return (int)e; once = true; }
-    StridedArgs<float> b = a;
-    const long long nruns = a.ncols / a.cw;
-    b.cw_sc = a.cw; b.cw = (a.cw + 1) / 2; b.ncols = nruns * b.cw;
-    b.in_fs /= 2; b.in_ls /= 2; b.in_os /= 2;
-    const long long tiles = (b.ncols + C::TC - 1) / C::TC;
-    ++sdns_debug_pair_launches;
-    xfer_prepare(b.x, C::smem, C::P * C::TC);
-    SDNS_LAUNCH(kern, dim3((unsigned)tiles + b.x.nctas), C::P * C::TC, C::smem, st)(b);
-    return (int)cudaGetLastError();
-}
-static bool pair_ok_in(const StridedArgs<float>& a) {
-    if (!a.pairable || a.cw <= 0 || a.c2_off) return false;
-    const long long s[] = {a.in_fs, a.in_ls, a.in_os};
-    for (long long v : s) if (v & 1) return false;
-    return (((uintptr_t)a.in) & 15) == 0;
-}
-static bool pair_ok(const StridedArgs<float>& a) {
-    if (!a.pairable || a.cw <= 0 || (a.c2_off & 1)) return false;
-    const long long s[] = {a.in_fs, a.in_ls, a.in_os, a.out_fs, a.out_ls, a.out_os, a.out_fs2, a.out_ls2};
-    for (long long v : s) if (v & 1) return false;
-    if (((uintptr_t)a.in | (uintptr_t)a.out) & 15) return false;
-    if (a.xchunk > 0) for (int r = 0; r < 8; ++r) if (((uintptr_t)a.peer_out[r]) & 15) return false;
-    return true;
-}
-#endif
-
 template <typename T, int N, int MODE, int DIR>
 static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
     typedef SCfg<T, N, MODE> C;
-#ifdef SDNS_F32_PAIRS
-    if constexpr (sizeof(T) == 4 && MODE == S_PLAIN && plan_ok(N, SCfg<double, N, S_PLAIN>::E)) {
-        auto mag = [](long long v) { return v < 0 ? -v : v; };
-        if (pair_ok(a) && (long long)N * std::max(mag(a.in_ls), std::max(mag(a.out_ls), mag(a.out_ls2))) < (1LL << 31))
-            return run_plain2<N, DIR>(a, st);
-    }
-    if constexpr (sizeof(T) == 4 && (MODE == S_NS_B0 || MODE == S_VV_B0) && plan_ok(N, SCfg<double, N, MODE>::E)) {
-        auto mag = [](long long v) { return v < 0 ? -v : v; };
-        if (pair_ok_out(a) && (long long)N * std::max(mag(a.in_ls), std::max(mag(a.out_ls), mag(a.out_ls2))) < (1LL << 31))
-            return run_b02<N, MODE>(a, st);
-    }
-    if constexpr (sizeof(T) == 4 && (MODE == S_NS_F0 || MODE == S_VV_F0) && plan_ok(N, SCfg<double, N, MODE>::E)) {
-        auto mag = [](long long v) { return v < 0 ? -v : v; };
-        if (pair_ok_in(a) && (long long)N * mag(a.in_ls) < (1LL << 31))
-            return run_f02<N, MODE>(a, st);
-    }
-#endif
     static_assert(plan_ok(N, C::E), "no radix plan");
     auto kern = strided_kernel<T, N, C::E, C::TC, DIR, MODE, C::NBUF, C::minBlocks>;
     static bool once = false;

@@ -161,8 +161,6 @@ struct BXCfg {
     static constexpr int TC = bx_tc(P, 128 / csize, csize, N);
 #ifndef SDNS_B0X          // opt-in experiment: measured on B200, not faster than strided_kernel's B0 branch
     static constexpr bool ok = false;
-#elif defined(SDNS_F32_PAIRS)
-    static constexpr bool ok = TC > 0 && plan_ok(N, E) && N % 5 != 0 && sizeof(T) == 8;   // experiment build: fp32 B0 on column pairs
 #else
     static constexpr bool ok = TC > 0 && plan_ok(N, E) && N % 5 != 0;
 #endif

@@ -78,8 +78,6 @@ struct StridedArgs {
     int grid_cap;                 // > 0: launch at most this many CTAs per SM (grid-stride over the tiles)
     int xuniform;                 // slab stores: P and omap.shift divide into xchunk (destination uniform per q)
     int xhi_d0, xhi_b0;           // (rank, row in chunk) of transform block q = 0 mapped through the high kept range
-    int pairable;                 // plain passes: the column after the last one of a run is padding in both arrays
-    int cw_sc;                    // column-pair kernels: number of (scalar) columns per run; the last pair may be half valid
     V* peer_out[8];
     int self;                     // destination that uses (out_fs, out_ls, c1_out_off); all others use the second set
     long long out_fs2, out_ls2, c1_out_off2;
@@ -406,254 +404,6 @@ strided_kernel(const StridedArgs<T> a) {
         }
     }
     }   // tile loop
-}
-
-// ---------------------------------------------------------------------------------------
-// Plain strided c2c pass, fp32, two adjacent columns per thread (element type float2x2): the thread moves 16 bytes
-// per access like an fp64 thread, and every row offset, twiddle and shared-memory address serves two columns.
-// `a` arrives with strides, cw, ncols and c2_off in units of column PAIRS (run_plain2 in inst.cu converts them).
-// ROUND-2 CANDIDATE: compiled only with -DSDNS_F32_PAIRS, not yet run on a GPU.
-// ---------------------------------------------------------------------------------------
-template <int N, int E, int TC, int DIR, int NBUF, int MINB>
-__global__ void __launch_bounds__((N / E) * TC, MINB)
-plain2_kernel(const StridedArgs<float> a) {
-    typedef float T;
-    typedef float2x2 V;
-    SDNS_DYN_SMEM(smraw);
-    SDNS_XFER_ROLE(a, smraw)
-    V* sm = reinterpret_cast<V*>(smraw);
-    const int c = threadIdx.x % TC;
-    const int t = threadIdx.x / TC;
-    SmemLine<TC, 0> map; map.base = c;
-    int phase = 0;
-    constexpr int BUFSTRIDE = N * TC;
-    const int f = blockIdx.y;
-    const long long ntiles = (a.ncols + TC - 1) / TC;
-    for (long long tile = bx; tile < ntiles; tile += gx) {
-        const long long col = tile * TC + c;
-        const bool valid = col < a.ncols;
-        const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;
-        const int c2 = valid ? (int)(col % a.cw) + a.c2_off : 0;
-        const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
-        const long long ibase = (long long)c1m * a.in_os + c2;
-        const long long obase = ((long long)c1 + a.c1_out_off) * a.out_os + c2;
-        const long long obase2 = ((long long)c1 + a.c1_out_off2) * a.out_os + c2;
-        V x[E];
-        load_line<T, N, E>(x, reinterpret_cast<const V*>(a.in) + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
-        fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-        store_line<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// Column-pair versions (fp32, element type float2x2) of the two fused axis-0 passes.  ROUND-2 CANDIDATES: compiled
-// only with -DSDNS_F32_PAIRS; logic verified on the CUDA-model emulator (tests/test_kernels_emulated.py), not yet
-// run on a GPU.
-//
-// B0: the three dense state fields are read with 8-byte loads (their rows are Nh = N2/2+1 elements, not 16-byte
-// aligned), the six output fields go out as 16-byte pairs.  Input strides / ibase are in scalar elements, output
-// strides, cw, ncols and obase in column pairs (run_b02 in inst.cu converts them).
-// ---------------------------------------------------------------------------------------
-template <int N, int E, int TC, int MODE, int NBUF, int MINB>
-__global__ void __launch_bounds__((N / E) * TC, MINB)
-b02_kernel(const StridedArgs<float> a) {
-    typedef float T;
-    typedef float2 C;
-    typedef float2x2 V;
-    SDNS_DYN_SMEM(smraw);
-    SDNS_XFER_ROLE(a, smraw)
-    V* sm = reinterpret_cast<V*>(smraw);
-    constexpr int P = N / E;
-    const int c = threadIdx.x % TC;
-    const int t = threadIdx.x / TC;
-    SmemLine<TC, 0> map; map.base = c;
-    int phase = 0;
-    constexpr int BUFSTRIDE = N * TC;
-    const long long ntiles = (a.ncols + TC - 1) / TC;
-    for (long long tile = bx; tile < ntiles; tile += gx) {
-        const long long col = tile * TC + c;
-        const bool valid = col < a.ncols;
-        const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;
-        const int c2p = valid ? (int)(col % a.cw) : 0;
-        const int c2 = 2 * c2p;                                   // first (scalar) column of the pair
-        const bool ok2 = valid && c2 + 1 < a.cw_sc;
-        const int c1m = c1 < a.col_nlo ? c1 : c1 + a.col_gap;
-        const long long ibase = (long long)c1m * a.in_os + c2;
-        const long long obase = ((long long)c1 + a.c1_out_off) * a.out_os + c2p;
-        const long long obase2 = ((long long)c1 + a.c1_out_off2) * a.out_os + c2p;
-        const T k1 = valid ? a.ky[c1m] : (T)0;
-        const T k2a = valid ? a.kz[c2] : (T)0;
-        const T k2b = ok2 ? a.kz[c2 + 1] : (T)0;
-        const C* pin = a.in + ibase;
-        const RowSel<N, E> rs(a.imap, t, valid);
-        const int l = (int)a.in_ls;
-        const int olo = t * l, ohi = (t - a.imap.shift) * l, step = P * l;
-#pragma unroll 1
-        for (int f = 0; f < 6; ++f) {
-            V x[E];
-            const bool direct = (MODE == S_VV_B0) ? (f >= 3) : (f < 3);
-            const int g = f % 3;
-            const int ga = (g + 1) % 3, gb = (g + 2) % 3;
-            if (direct) {
-                const C* pg = pin + g * a.in_fs;
-#pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    const int off = (rs.lo(q) ? olo : ohi) + q * step;
-                    C va = czero<C>(), vb = czero<C>();
-                    if (rs.ok(q)) { va = pg[off]; if (ok2) vb = pg[off + 1]; }
-                    x[q].a = va; x[q].b = vb;
-                }
-            } else {
-                const C* pa = pin + ga * a.in_fs;
-                const C* pb = pin + gb * a.in_fs;
-#pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    const int off = (rs.lo(q) ? olo : ohi) + q * step;
-                    const bool ok = rs.ok(q);
-                    C ba0 = czero<C>(), bb0 = czero<C>(), ba1 = czero<C>(), bb1 = czero<C>();
-                    T k0 = (T)0;
-                    if (ok) {
-                        const int i = (rs.lo(q) ? t : t - a.imap.shift) + q * P;      // memory row = axis-0 index
-                        k0 = a.kx[i];
-                        ba0 = pa[off]; bb0 = pb[off];
-                        if (ok2) { ba1 = pa[off + 1]; bb1 = pb[off + 1]; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const T k2 = j ? k2b : k2a;
-                        T ka = ga == 0 ? k0 : (ga == 1 ? k1 : k2);
-                        T kb = gb == 0 ? k0 : (gb == 1 ? k1 : k2);
-                        if (MODE == S_VV_B0) {
-                            T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;   // NS.py:42-44
-                            if (ksq == (T)0) ksq = (T)1;                        // NS.py:46-48
-                            ka = ka / ksq; kb = kb / ksq;                       // K_over_K2
-                        }
-                        const C r = icross<T, C>(ka, j ? bb1 : bb0, kb, j ? ba1 : ba0);
-                        if (j) x[q].b = r; else x[q].a = r;
-                    }
-                }
-            }
-            fft_line<T, N, E, +1, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-            store_line<T, N, E, false>(x, a, f, obase, obase2, t, valid, (T)1);
-        }
-    }
-}
-
-// F0 on column pairs: W3 is read as 16-byte pairs (strides / ibase in pairs), the three transformed fields are
-// parked in shared memory as in strided_kernel's F0 branch, the epilogue runs per lane on the dense state arrays
-// (scalar strides).  Same arithmetic as the S_NS_F0 / S_VV_F0 epilogue of strided_kernel.
-template <int MODE>
-__device__ __forceinline__ void f0_point(const StridedArgs<float>& a, float2 d0, float2 d1, float2 d2,
-                                         int i0, int c1, int c2, float k0, float k1, float k2, bool nyq) {
-    typedef float T;
-    typedef float2 V;
-    const long long off = (long long)i0 * a.out_ls + (long long)c1 * a.out_os + c2;
-    T ksq = k0 * k0; ksq += k1 * k1; ksq += k2 * k2;
-    if (MODE == S_VV_F0) {
-        V e0 = icross<T, V>(k1, d2, k2, d1);
-        V e1 = icross<T, V>(k2, d0, k0, d2);
-        V e2 = icross<T, V>(k0, d1, k1, d0);
-        d0 = e0; d1 = e1; d2 = e2;
-    }
-    if (a.out_mode == OUT_CONV) {
-        a.rhs[off] = d0; a.rhs[a.st_fs + off] = d1; a.rhs[2 * a.st_fs + off] = d2;
-        return;
-    }
-    if (nyq) { d0 = czero<V>(); d1 = czero<V>(); d2 = czero<V>(); }
-    const long long offu = (long long)i0 * a.uh_ls + (long long)c1 * a.uh_os + c2;
-    const long long offt = (long long)i0 * a.t_ls + (long long)c1 * a.t_os + c2;
-    const V w0 = a.u_hat[offu], w1 = a.u_hat[a.st_fs + offu], w2 = a.u_hat[2 * a.st_fs + offu];
-    const T z = a.nu * ksq;
-    if (MODE == S_NS_F0) {
-        const T ks = ksq == (T)0 ? (T)1 : ksq;
-        const T q0 = k0 / ks, q1 = k1 / ks, q2 = k2 / ks;
-        V p;
-        p.x = d0.x * q0 + d1.x * q1; p.x += d2.x * q2;
-        p.y = d0.y * q0 + d1.y * q1; p.y += d2.y * q2;
-        if (a.p_hat) a.p_hat[off] = p;
-        d0.x -= p.x * k0; d0.y -= p.y * k0;
-        d1.x -= p.x * k1; d1.y -= p.y * k1;
-        d2.x -= p.x * k2; d2.y -= p.y * k2;
-    }
-    d0.x -= z * w0.x; d0.y -= z * w0.y;
-    d1.x -= z * w1.x; d1.y -= z * w1.y;
-    d2.x -= z * w2.x; d2.y -= z * w2.y;
-    if (a.source) {
-        d0 = cadd(d0, a.source[off]); d1 = cadd(d1, a.source[a.st_fs + off]);
-        d2 = cadd(d2, a.source[2 * a.st_fs + off]);
-    }
-    V dd[3] = {d0, d1, d2};
-    V ww[3] = {w0, w1, w2};
-    if (a.out_mode == OUT_RHS) {
-#pragma unroll
-        for (int f = 0; f < 3; ++f) a.rhs[f * a.st_fs + off] = dd[f];
-    } else {
-#pragma unroll
-        for (int f = 0; f < 3; ++f) {
-            const long long o = f * a.st_fs + offt;
-            V b1, b2;
-            if (a.rk == 0) { b1 = ww[f]; b2 = ww[f]; a.u1[o] = b1; }
-            else { b2 = a.u2[o]; if (a.rk < 3) b1 = a.u1[o]; }
-            b2.x += a.adt * dd[f].x; b2.y += a.adt * dd[f].y;
-            if (a.rk < 3) {
-                a.u2[o] = b2;
-                V n; n.x = b1.x + a.bdt * dd[f].x; n.y = b1.y + a.bdt * dd[f].y;
-                a.u0[o] = n;
-            } else {
-                a.u0[f * a.st_fs + off] = b2;
-            }
-        }
-    }
-}
-
-template <int N, int E, int TC, int MODE, int NBUF, int MINB>
-__global__ void __launch_bounds__((N / E) * TC, MINB)
-f02_kernel(const StridedArgs<float> a) {
-    typedef float T;
-    typedef float2x2 V;
-    SDNS_DYN_SMEM(smraw);
-    SDNS_XFER_ROLE(a, smraw)
-    V* sm = reinterpret_cast<V*>(smraw);
-    constexpr int P = N / E;
-    constexpr int NT = P * TC;
-    const int c = threadIdx.x % TC;
-    const int t = threadIdx.x / TC;
-    SmemLine<TC, 0> map; map.base = c;
-    int phase = 0;
-    constexpr int BUFSTRIDE = N * TC;
-    V* park = sm + NBUF * BUFSTRIDE;
-    const long long col = (long long)bx * TC + c;
-    const bool valid = col < a.ncols;
-    const int c1 = valid ? (int)(col / a.cw) + a.c1_off : 0;
-    const int c2p = valid ? (int)(col % a.cw) : 0;
-    const int c2 = 2 * c2p;
-    const bool ok2 = valid && c2 + 1 < a.cw_sc;
-    const long long ibase = (long long)c1 * a.in_os + c2p;
-    V x[E];
-#pragma unroll 1
-    for (int f = 0; f < 3; ++f) {
-        load_line<T, N, E>(x, reinterpret_cast<const V*>(a.in) + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
-        fft_line<T, N, E, -1, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-        if (f < 2) {
-#pragma unroll
-            for (int q = 0; q < E; ++q) park[(f * E + q) * NT + threadIdx.x] = x[q];
-        }
-    }
-    if (!valid) return;
-    const T k1 = a.ky[c1];
-    const bool nyq1 = a.mask_nyquist && (2 * (c1 + a.k1_off) == a.N1);
-#pragma unroll
-    for (int q = 0; q < E; ++q) {
-        const int i0 = axis_mem(a.omap, N, t + q * P);
-        if (i0 < 0) continue;
-        const T k0 = a.kx[i0];
-        const bool nyq01 = nyq1 || (a.mask_nyquist && 2 * i0 == a.N0);
-        const V p0 = cscale<T>(park[q * NT + threadIdx.x], a.scale), p1 = cscale<T>(park[(E + q) * NT + threadIdx.x], a.scale),
-                p2 = cscale<T>(x[q], a.scale);
-        f0_point<MODE>(a, p0.a, p1.a, p2.a, i0, c1, c2, k0, k1, a.kz[c2], nyq01 || (a.mask_nyquist && 2 * c2 == a.N2));
-        if (ok2)
-            f0_point<MODE>(a, p0.b, p1.b, p2.b, i0, c1, c2 + 1, k0, k1, a.kz[c2 + 1], nyq01 || (a.mask_nyquist && 2 * (c2 + 1) == a.N2));
-    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -277,10 +277,14 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->xmode = 0; p->nchunk = 1; p->nsplit = 1; p->off_SF = 0; p->bytes_SF = 0; p->b0_preissued = false; p->b0_pre_u = nullptr;
     p->copy_bytes = 0; p->copy_n = 0; for (int i = 0; i < 32; ++i) p->copy_ms[i] = 0;
     if (p->P > 1) {
-        const char* xm = getenv("SDNS_EXCHANGE");           // "store": peer stores fused into the passes; default: copy engines
-        // default "tma": send slots + transfer role with bulk-async copies; "ldst": the role with plain loads / stores;
+        const char* xm = getenv("SDNS_EXCHANGE");
+        // "tma" (default for 3 or more ranks): send slots + transfer role with bulk-async copies; "ldst": the role with plain loads / stores;
         // "ce" / "kcopy": copy engines / copy kernels on side streams (round 1); "store": peer stores fused into the passes
         p->xmode = (xm && !strcmp(xm, "store")) ? 0 : ((xm && (!strcmp(xm, "ce") || !strcmp(xm, "kcopy"))) ? 1 : 2);
+        // measured (profiles/r2): with ONE peer the copy engines hide the exchange best (512^3 per GPU: 57.5 ms against
+        // 67-70 ms for the transfer role); with seven destinations per chunk the transfer role does (1024^3 on 8 GPUs:
+        // 75 ms against 91-96 ms)
+        if (!xm && p->P == 2) p->xmode = 1;
         p->xtma = (xm && !strcmp(xm, "ldst")) ? 0 : 1;
         if (const char* v = getenv("SDNS_XCTAS")) { p->xctas = std::max(1, atoi(v)); p->xinflight = 0; }
         if (const char* v = getenv("SDNS_XINFLIGHT_KB")) p->xinflight = (unsigned int)std::max(0, atoi(v)) << 10;
@@ -777,7 +781,6 @@ struct Pipe {
         if (staged) peers(a, p->off_A, q.M0l, B, b0_slot(), (long long)q.M0l * q.K1l * q.K2p, (long long)q.K1l * q.K2p, 0);
         else peers(a, p->off_A, q.M0l);
         a.grid_cap = xcap;
-        a.pairable = (k2.a == 0 && k2.b == q.K2n);      // output rows: K2n columns + padding up to the even pitch K2p
         a.tw = tw(q.M[0]); a.nfields = nf;
         const int nfo = (fam == FAM_PLAIN_BWD) ? nf : 6;
         const double cols = (double)(k1.b - k1.a) * a.cw;
@@ -799,7 +802,6 @@ struct Pipe {
         a.omap = all_map(q.M[1]);
         a.out_fs = (long long)q.M0l * q.M[1] * q.K2p; a.out_ls = q.K2p; a.out_os = (long long)q.M[1] * q.K2p;
         a.tw = tw(q.M[1]); a.nfields = nf;
-        a.pairable = (k2.a == 0 && k2.b == q.K2n);      // rows are K2n columns + padding up to the even pitch K2p
         const double bytes = (double)nf * q.M0l * a.cw * ((double)q.K1n + q.M[1]) * p->cs;
         attach_xfer(p, a.x, bytes);
         return do_launch(p, st, FAM_PLAIN_BWD, q.M[1], &a, bytes);
@@ -846,7 +848,6 @@ struct Pipe {
         else peers(a, p->off_C, p->N1l);
         a.grid_cap = xcap;
         a.tw = tw(q.M[1]); a.nfields = nf;
-        a.pairable = 1;                                  // rows are Nh columns + padding up to the even pitch Nhp
         const double bytes = (double)nf * (x0.b - x0.a) * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
         const double remote = staged ? 0 : (double)nf * (x0.b - x0.a) * p->Nh * p->N[1] * p->cs * (p->P - 1) / p->P;
         if (a.ncols == 0) return SDNS_OK;
@@ -864,7 +865,6 @@ struct Pipe {
         a.col_nlo = p->N1l; a.col_gap = 0;
         a.imap = all_map(q.M[0]); a.omap = q.fmap[0];
         a.out_fs = dense_fs(); a.out_ls = (long long)p->N1l * p->Nh; a.out_os = p->Nh;
-        a.pairable = (k2.a == 0 && k2.b == p->Nh);       // input rows (W3): Nh columns + padding up to the even pitch Nhp
         a.tw = tw(q.M[0]); a.nfields = nf;
     }
 };

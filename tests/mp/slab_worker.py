@@ -29,13 +29,19 @@ def main():
              ((16, 32, 64), 'double', '2/3-rule', 'MHD'), ((32, 16, 32), 'double', 'None', 'NS'),
              ((128, 128, 128), 'double', '2/3-rule', 'NS'),
              # low axis-1 cutoff: with 4 or more ranks the middle ones own no mode that survives the truncation
-             ((32, 32, 32), 'double', '2/3-rule', 'NS', (-1, 3, -1)), ((32, 64, 32), 'single', '2/3-rule', 'MHD', (-1, 5, -1))]
+             ((32, 32, 32), 'double', '2/3-rule', 'NS', (-1, 3, -1)), ((32, 64, 32), 'single', '2/3-rule', 'MHD', (-1, 5, -1)),
+             # the other convection forms of NS.getConvection (NS.py:164-201), VV with padding, MHD in single precision
+             ((32, 32, 32), 'double', '2/3-rule', 'NS', None, 'Standard'), ((32, 32, 16), 'double', '3/2-rule', 'NS', None, 'Divergence'),
+             ((16, 32, 32), 'double', '2/3-rule', 'NS', None, 'Skewed'), ((32, 32, 32), 'single', '3/2-rule', 'NS', None, 'Skewed'),
+             ((32, 32, 32), 'double', '3/2-rule', 'VV'), ((32, 32, 32), 'single', '3/2-rule', 'MHD')]
     for case in cases:
         N, prec, dealias, solver = case[:4]
         kcut = case[4] if len(case) > 4 else None
+        conv = case[5] if len(case) > 5 else None
         tol = 1e-11 if prec == 'double' else 1e-4
         o = so.Oracle(N, precision=prec, dealias=dealias, kcut=kcut)
-        p = Plan(N, precision=prec, dealias=dealias, solver=solver, device=local, rank=rank, nranks=world, kcut=kcut)
+        p = Plan(N, precision=prec, dealias=dealias, solver=solver, device=local, rank=rank, nranks=world, kcut=kcut,
+                 convection=conv)
         N1l = N[1]//world
         k1s = slice(rank*N1l, (rank+1)*N1l)
         M0l, Mp0l = N[0]//world, o.M[0]//world
@@ -60,7 +66,7 @@ def main():
             f0 = o.cross2(o.K, f0)
         nu, eta, dt = 0.005, 0.01, 0.002
         if solver == 'NS':
-            r_ref = o.ns_rhs(f0, nu)
+            r_ref = o.ns_rhs(f0, nu, convection=conv or 'Vortex')
         elif solver == 'VV':
             r_ref = o.vv_rhs(f0, nu)
         else:
@@ -71,7 +77,7 @@ def main():
         u1, u2 = p.empty_spectral(), p.empty_spectral()
         for _ in range(2):
             p.rk4_step(d_u, u1, u2, dt, nu, eta)
-        s_ref = o.solve(f0, solver, 2, dt, nu, eta=eta)
+        s_ref = o.solve(f0, solver, 2, dt, nu, eta=eta, convection=conv or 'Vortex')
         e5 = rel(p.to_host(d_u), s_ref[:, :, k1s])
         # energy: local parts sum to the global value
         t = torch.tensor([p.energy(d_u)], dtype=torch.float64, device='cuda')
@@ -80,7 +86,7 @@ def main():
         errs = (e1, e2, e3, e4, e5, e6)
         ok = all(e < tol for e in errs) and not p.comm_timed_out()
         if rank == 0 or not ok:
-            print('rank %d %s %s %s %s: %s %s' % (rank, N, prec, dealias, solver, ' '.join('%.1e' % e for e in errs),
+            print('rank %d %s %s %s %s: %s %s' % (rank, N, prec, dealias, solver + ('/' + conv if conv else ''), ' '.join('%.1e' % e for e in errs),
                                                   'OK' if ok else 'FAIL'), flush=True)
         if not ok:
             fails.append((N, prec, dealias, solver, errs))

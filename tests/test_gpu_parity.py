@@ -298,7 +298,7 @@ def test_standalone_operators_against_reference_cython(precision):
     with and without 1/k^2), sdns_cross2_dense, sdns_project and sdns_add_pressure_diffusion as stand-alone calls,
     against the reference's compiled Cython (cython_maths.in:8-86, cython_solvers.in:40-80) when oracle/_ref is
     there, and always against the oracle."""
-    N = (16, 12, 20)
+    N = (16, 12, 24)
     Lbox = (2*np.pi, 4*np.pi, 6*np.pi)
     o = so.Oracle(N, L=Lbox, precision=precision)
     p = make_plan(N, L=Lbox, precision=precision)

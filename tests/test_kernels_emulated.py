@@ -214,7 +214,7 @@ def test_emulated_multi_gpu_chunk_counts(emu):
 
 # ---------------------------------------------------------------------------------------------
 # the kernels that only exist for long lines (warp-per-line zx with shuffle mirrors, CTA-per-line zy, radix-16
-# strided passes, field-parallel F0) on thin grids, and the fp32 column-pair pass that is compiled on request
+# strided passes, field-parallel F0) on thin grids
 # ---------------------------------------------------------------------------------------------
 @pytest.fixture(scope='module')
 def emu_long():
@@ -237,24 +237,6 @@ def test_emulated_long_lines(emu_long, N, precision, dealias):
     assert rel_l2(p.compute_rhs(u0, 0.01), o.ns_rhs(u0, 0.01)) < TOL[precision]
     assert rel_l2(p.rk4(u0, 1, 0.001, 0.01), o.solve(u0, 'NS', 1, 0.001, 0.01)) < TOL[precision]
     p.close()
-
-
-def test_emulated_fp32_pair_kernel():
-    """-DSDNS_F32_PAIRS: the fp32 strided passes on float2x2 column pairs (plain2 / b02 / f02 kernels); must run and agree."""
-    import ctypes
-    import build_emu
-    import emu_plan
-    L = emu_plan.load(build_emu.build(extra=['-DSDNS_F32_PAIRS'], lib=os.path.join(build_emu.OUT, 'libsdns_emu_pairs.so')))
-    for N, dealias, solver in [((16, 16, 16), '2/3-rule', 'NS'), ((32, 16, 8), '3/2-rule', 'NS'), ((16, 32, 16), '3/2-rule', 'VV'),
-                               ((8, 24, 48), '2/3-rule', 'VV'), ((16, 16, 32), '2/3-rule', 'MHD')]:
-        o = so.Oracle(N, precision='single', dealias=dealias)
-        p = emu_plan.EmuPlan(L, N, precision='single', dealias=dealias, solver=solver)
-        f0 = _state(o, solver)
-        ref = {'NS': lambda: o.ns_rhs(f0, 0.005), 'VV': lambda: o.vv_rhs(f0, 0.005), 'MHD': lambda: o.mhd_rhs(f0, 0.005, 0.01)}[solver]()
-        assert rel_l2(p.compute_rhs(f0, 0.005, 0.01), ref) < 1e-4
-        assert rel_l2(p.rk4(f0, 2, 0.002, 0.005, 0.01), o.solve(f0, solver, 2, 0.002, 0.005, eta=0.01)) < 1e-4
-        p.close()
-    assert ctypes.c_longlong.in_dll(L, 'sdns_debug_pair_launches').value > 150
 
 
 @pytest.fixture(scope='module')
