@@ -211,11 +211,62 @@ __device__ __forceinline__ void dft16(V& a0, V& a1, V& a2, V& a3, V& a4, V& a5, 
     t = a6; a6 = a9; a9 = t;      t = a7; a7 = a13; a13 = t;    t = a11; a11 = a14; a14 = t;
 }
 
+// cos / sin of 2 pi m / 24 (the twiddles inside the composite radix-12 and radix-24 butterflies)
+template <typename T> __host__ __device__ constexpr T cos24(int m) {
+    switch (((m % 24) + 24) % 24) {
+        case 0: return (T)1; case 1: case 23: return (T)0.96592582628906828674974319972890L;
+        case 2: case 22: return (T)0.86602540378443864676372317075294L; case 3: case 21: return (T)0.70710678118654752440084436210485L;
+        case 4: case 20: return (T)0.5; case 5: case 19: return (T)0.25881904510252076234889883762405L;
+        case 6: case 18: return (T)0; case 7: case 17: return (T)-0.25881904510252076234889883762405L;
+        case 8: case 16: return (T)-0.5; case 9: case 15: return (T)-0.70710678118654752440084436210485L;
+        case 10: case 14: return (T)-0.86602540378443864676372317075294L; case 11: case 13: return (T)-0.96592582628906828674974319972890L;
+        default: return (T)-1;      // 12
+    }
+}
+template <typename T> __host__ __device__ constexpr T sin24(int m) { return cos24<T>(m - 6); }
+
+// R-point DFT with R = R1 * 3 (R1 = 4 or 8) entirely in registers, natural order in and out: Cooley-Tukey with
+// n = 3 n1 + n2, k = k1 + R1 k2 -- three DFT-R1 over n1, the twiddles W_R^(n2 k1), R1 DFT-3 over n2.  Lets the lengths
+// 3 * 2^k (the 3/2-rule paddings) take a factor 12 or 24 per stage instead of 4 / 8 and a separate factor 3, i.e. one
+// shared-memory exchange fewer per line.
+template <int DIR, int R1, typename T, typename V>
+__device__ __forceinline__ void dft_x3(V (&a)[R1 * 3]) {
+    constexpr int R = R1 * 3;
+#pragma unroll
+    for (int n2 = 0; n2 < 3; ++n2) {
+        if constexpr (R1 == 8) dft8<DIR, T>(a[n2], a[3 + n2], a[6 + n2], a[9 + n2], a[12 + n2], a[15 + n2], a[18 + n2], a[21 + n2]);
+        else dft4<DIR>(a[n2], a[3 + n2], a[6 + n2], a[9 + n2]);
+    }
+    // slot 3 k1 + n2 now holds Y[k1][n2]
+#pragma unroll
+    for (int k1 = 1; k1 < R1; ++k1)
+#pragma unroll
+        for (int n2 = 1; n2 < 3; ++n2) {
+            const int m = (24 / R) * n2 * k1;                       // W_R^(n2 k1) = W_24^m
+            a[3 * k1 + n2] = cmulc(a[3 * k1 + n2], cos24<T>(m), (DIR < 0 ? -1 : 1) * sin24<T>(m));
+        }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) dft3<DIR, T>(a[3 * k1], a[3 * k1 + 1], a[3 * k1 + 2]);
+    // slot 3 k1 + k2 holds X[k1 + R1 k2]
+    V b[R];
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1)
+#pragma unroll
+        for (int k2 = 0; k2 < 3; ++k2) b[k1 + R1 * k2] = a[3 * k1 + k2];
+#pragma unroll
+    for (int i = 0; i < R; ++i) a[i] = b[i];
+}
+
 // ---------------------------------------------------------------------------------------
-// radix plan: largest radix in {16,8,4,2,3,5} dividing both what is left of N and E
+// radix plan: largest radix in {24,16,12,8,4,2,3,5} dividing both what is left of N and E
 // ---------------------------------------------------------------------------------------
 __host__ __device__ constexpr int pick_radix(int rem, int E) {
-    return (rem % 16 == 0 && E % 16 == 0) ? 16 :
+    return
+#ifndef SDNS_NO_RADIX_X3
+           (rem % 24 == 0 && E % 24 == 0) ? 24 :
+           (rem % 12 == 0 && E % 12 == 0 && E % 8 != 0) ? 12 :
+#endif
+           (rem % 16 == 0 && E % 16 == 0) ? 16 :
            (rem % 8 == 0 && E % 8 == 0) ? 8 :
            (rem % 4 == 0 && E % 4 == 0) ? 4 :
            (rem % 2 == 0 && E % 2 == 0) ? 2 :
@@ -274,6 +325,8 @@ __device__ __forceinline__ void fft_stage(V (&x)[E], int t, const typename Elt<V
             W w1 = __ldg(&tw[jm * TS]);
             if (DIR > 0) w1.y = -w1.y;
             x[m + NB] = cmul(x[m + NB], w1);
+            // (the composite radices 12 / 24 only ever form the FIRST stage of the compiled lengths, which has no twiddles)
+            static_assert(!(R == 12 || R == 24) || Ns == 1, "composite radix beyond the first stage");
             if (R > 2) {
                 const W w2 = cmul(w1, w1);
                 x[m + 2 * NB] = cmul(x[m + 2 * NB], w2);
@@ -305,6 +358,14 @@ __device__ __forceinline__ void fft_stage(V (&x)[E], int t, const typename Elt<V
             }
 #endif
         }
+        if constexpr (R == 12 || R == 24) {
+            V a[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) a[k] = x[m + k * NB];
+            dft_x3<DIR, R / 3, T>(a);
+#pragma unroll
+            for (int k = 0; k < R; ++k) x[m + k * NB] = a[k];
+        } else
         if (R == 2) dft2<DIR>(x[m], x[m + NB]);
         else if (R == 4) dft4<DIR>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB]);
         else if (R == 8) dft8<DIR, T>(x[m], x[m + NB], x[m + 2 * NB], x[m + 3 * NB],
