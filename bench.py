@@ -42,6 +42,9 @@ def parse():
     ap.add_argument('--solver', default='NS', choices=('NS', 'VV', 'MHD'))
     ap.add_argument('--scaling', default='weak', choices=('weak', 'strong'),
                     help='N>1: weak = grid grows with the GPU count (per-GPU work fixed), strong = fixed grid')
+    ap.add_argument('--k1-layout', default='auto', choices=('auto', 'blocks', 'cyclic'),
+                    help='N>1: which axis-1 modes a rank owns (include/sdns_b200.h).  auto = cyclic on 3 or more GPUs under the '
+                         '2/3 rule (every rank keeps the same number of modes), else the reference\'s contiguous blocks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
     ap.add_argument('--no-parity', action='store_true', help='skip the parity gate and the field-level check at size')
@@ -61,6 +64,12 @@ def grid_for(a, world):
             w //= 2
             i += 1
     return tuple(N)
+
+
+def k1_layout_for(a, world):
+    if a.k1_layout != 'auto':
+        return a.k1_layout if world > 1 else 'blocks'
+    return 'cyclic' if (world >= 3 and a.dealias == '2/3-rule') else 'blocks'
 
 
 def workload_name(a, N=None):
@@ -221,7 +230,7 @@ def run_reference(a):
 # ---------------------------------------------------------------------------------------------
 # parity: the CPU oracle as the checker of the GPU path, inside the run the driver makes
 # ---------------------------------------------------------------------------------------------
-def parity_gate(rank, world, local):
+def parity_gate(rank, world, local, layout='blocks'):
     """64^3 NS (double and single) and MHD: one right-hand side and two RK4 steps on a seeded broadband field, every
     rank against its slab of the single-process oracle.  Returns {case: rel L2}, the largest ratio err / tol."""
     import numpy as np
@@ -233,11 +242,10 @@ def parity_gate(rank, world, local):
                                      ((64, 64, 64), 'single', '3/2-rule', 'NS')):
         tol = 1e-11 if prec == 'double' else 1e-4
         o = so.Oracle(N, precision=prec, dealias=dealias)
-        p = Plan(N, precision=prec, dealias=dealias, solver=solver, device=local, rank=rank, nranks=world)
+        p = Plan(N, precision=prec, dealias=dealias, solver=solver, device=local, rank=rank, nranks=world, k1_layout=layout)
         nc = 6 if solver == 'MHD' else 3
         f0 = so.isotropic_field(o, seed=3, ncomp=nc).astype(o.complex)
-        N1l = N[1]//world
-        k1s = slice(rank*N1l, (rank+1)*N1l)
+        k1s = p.k1_slice
         nu, eta, dt = 0.005, 0.01, 0.002
         r_ref = o.ns_rhs(f0, nu) if solver == 'NS' else o.mhd_rhs(f0, nu, eta)
         d_u = p.to_device(f0[:, :, k1s])
@@ -349,7 +357,7 @@ def run_ours(a):
 
     parity = None
     if not a.no_parity:
-        cases, worst = parity_gate(rank, world, local)
+        cases, worst = parity_gate(rank, world, local, k1_layout_for(a, world))
         t = torch.tensor([worst], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -363,7 +371,7 @@ def run_ours(a):
 
     N = grid_for(a, world)
     p = Plan(N, precision=a.precision, dealias=a.dealias, solver=a.solver, device=local,
-             rank=rank, nranks=world)
+             rank=rank, nranks=world, k1_layout=k1_layout_for(a, world))
     # synthetic Taylor-Green field generated on the device (tests/TG.py:23-28 / tests/TGMHD.py:4-12)
     X = [torch.arange(n, dtype=torch.float64, device='cuda')*2*np.pi/n for n in N]
     M0l = N[0]//world
@@ -479,6 +487,9 @@ def run_ours(a):
                        '(no NCCL on the data path)' if copies[2] else
                        'transposes are peer-memory stores fused into the FFT passes (no NCCL on the data path)'),
                        a.scaling)) if world > 1 else 'single GPU',
+                   'k1_layout': (p.k1_layout + (' (rank r owns the axis-1 modes r, r + P, ...: every rank keeps the same number of '
+                                                'modes under the 2/3 rule; same global field as the reference\'s contiguous blocks)'
+                                                if p.k1_layout == 'cyclic' else ' (the reference\'s contiguous axis-1 blocks)')) if world > 1 else None,
                    'l2': 'inputs larger than L2 (state %.0f MB, scratch %.0f MB)' % (state_bytes/1e6, p.workspace_bytes/1e6),
                    'timing': 'CUDA events on the launch stream, max over ranks',
                    'kinetic_energy_after_run': energy},

@@ -48,6 +48,13 @@ enum { SDNS_NS = 0, SDNS_VV = 1, SDNS_MHD = 2 };                   /* config.py:
 enum { SDNS_CONV_VORTEX = 0, SDNS_CONV_DIVERGENCE = 1,
        SDNS_CONV_STANDARD = 2, SDNS_CONV_SKEWED = 3 };             /* config.py:214-216 --convection   */
 enum { SDNS_SLAB = 0, SDNS_PENCIL = 1 };                           /* config.py:194-195 --decomposition */
+/* Slab ownership of the spectral axis 1.  BLOCKS is the reference's layout: rank r owns k1 in
+ * [r*N1/P, (r+1)*N1/P) (solvers/spectralinit.py:19-21, spectralDNS3D_short.py:29), i.e. the slice
+ * [r*N1l : (r+1)*N1l].  CYCLIC deals the modes out round robin, rank r owns the slice [r::P]: under the
+ * 2/3 rule every rank then holds the same number of kept modes (with BLOCKS the ranks at the ends of the
+ * k1 range hold 1.5x the average and the middle ones none).  Same global field either way;
+ * sdns_k1_layout reports the slice. */
+enum { SDNS_K1_BLOCKS = 0, SDNS_K1_CYCLIC = 1 };
 enum { SDNS_SPACE_T = 0, SDNS_SPACE_TP = 1 };                      /* solvers/NS.py:21-32  T/VT vs Tp/VTp */
 
 typedef struct sdns_config {
@@ -65,7 +72,8 @@ typedef struct sdns_config {
     int32_t prune;            /* 1: skip transform lines that the truncation zeroes (same result) */
     int32_t rank, nranks;     /* slab position of this process (solvers/spectralinit.py:19-21) */
     int32_t device;           /* CUDA device ordinal */
-    int32_t reserved[8];
+    int32_t k1_layout;        /* SDNS_K1_BLOCKS | SDNS_K1_CYCLIC: which axis-1 modes a rank owns (nranks > 1) */
+    int32_t reserved[7];
 } sdns_config;
 
 typedef struct sdns_plan sdns_plan;
@@ -102,6 +110,8 @@ int sdns_comm_status(sdns_plan* plan, int* timed_out);
 
 /* local array extents of this rank (T.shape(True), T.shape(False), Tp.shape(False)) */
 int sdns_local_shapes(const sdns_plan* plan, int32_t spectral[3], int32_t physical[3], int32_t padded[3]);
+/* axis-1 mode index of local spectral index j: first + j*step (the local_slice of T.local_slice(True)[1]) */
+int sdns_k1_layout(const sdns_plan* plan, int32_t* first, int32_t* step);
 
 /* T.forward / VT.forward (space = SDNS_SPACE_T) and Tp.forward / VTp.forward (SDNS_SPACE_TP):
  * rfftn/prod(M) incl. 3/2-rule truncation.  Call sites NS.py:103,135; MHD.py:107. */

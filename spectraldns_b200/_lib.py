@@ -20,7 +20,7 @@ SPACE_T, SPACE_TP = 0, 1
 # every symbol include/sdns_b200.h declares (tests check that the library exports them all)
 SYMBOLS = ['sdns_abi_version', 'sdns_last_error', 'sdns_size_supported', 'sdns_plan_create',
            'sdns_plan_destroy', 'sdns_workspace_bytes', 'sdns_plan_set_workspace',
-           'sdns_plan_set_stream', 'sdns_sync', 'sdns_local_shapes', 'sdns_comm_alloc', 'sdns_comm_handle',
+           'sdns_plan_set_stream', 'sdns_sync', 'sdns_local_shapes', 'sdns_k1_layout', 'sdns_comm_alloc', 'sdns_comm_handle',
            'sdns_comm_open', 'sdns_comm_status', 'sdns_forward', 'sdns_backward',
            'sdns_compute_rhs', 'sdns_compute_conv', 'sdns_rk4_step', 'sdns_euler_step', 'sdns_ab2_step', 'sdns_cross2', 'sdns_cross1', 'sdns_cross2_dense', 'sdns_project', 'sdns_add_pressure_diffusion', 'sdns_lincomb', 'sdns_errnorm',
            'sdns_energy', 'sdns_energy_weighted', 'sdns_scale_field', 'sdns_set_mode', 'sdns_enstrophy',
@@ -43,7 +43,11 @@ class SdnsConfig(C.Structure):
                 ('rank', C.c_int32),
                 ('nranks', C.c_int32),
                 ('device', C.c_int32),
-                ('reserved', C.c_int32*8)]
+                ('k1_layout', C.c_int32),
+                ('reserved', C.c_int32*7)]
+
+
+K1_LAYOUT = {'blocks': 0, 'cyclic': 1}
 
 
 class Sdns2dConfig(C.Structure):
@@ -146,6 +150,7 @@ def lib():
     L.sdns_spectrum.argtypes = [vp, vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.sdns_rk4_steps_host.argtypes = [vp, vp, vp, vp, vp, i32, dbl, dbl, dbl]
     L.sdns_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.sdns_k1_layout.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.sdns_profile_enable.argtypes = [vp, i32]
     L.sdns_profile_read.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(C.c_longlong), C.POINTER(dbl)]
     L.sdns_profile_read_nvlink.argtypes = [vp, i32, C.POINTER(dbl)]

@@ -102,7 +102,10 @@ struct SCfg {
     static constexpr int bySmem = (int)((224 * 1024) / (smem + 1024));
     static constexpr int byThreads = 2048 / (P * TC);
     static constexpr bool b0 = (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0);
-    static constexpr int needRegs = sizeof(T) == 8 ? (heavy ? 128 : (E > 12 ? (b0 ? 168 : 128) : (b0 ? 96 : 80)))
+#ifndef SDNS_PLAIN64_REGS
+#define SDNS_PLAIN64_REGS 128
+#endif
+    static constexpr int needRegs = sizeof(T) == 8 ? (heavy ? 128 : (E > 12 ? (b0 ? 168 : SDNS_PLAIN64_REGS) : (b0 ? 96 : 80)))
                                                    : (heavy ? (E > 12 ? 128 : 100) : (E > 16 ? 80 : (b0 ? 72 : 64)));
     static constexpr int byRegs = 65536 / (P * TC * needRegs);
     static constexpr int minBlocks = cmax(1, cmin(cmin(cmin(bySmem, byThreads), byRegs), heavy ? 2 : 4));

@@ -73,7 +73,10 @@ struct StridedArgs {
     T cfac;                       // divergence-form epilogue: factor on the convection (-1 or -0.5)
     int xchunk;
     long long c1_out_off;         // added to the run index of the output base (global x0 / compact k1)
-    int k1_off;                   // global index of local k1 = 0 (Nyquist test in the epilogues)
+    int k1_off, k1_mul;           // global axis-1 index of local column j: k1_off + j*k1_mul (Nyquist test in the epilogues)
+    // SDNS_K1_CYCLIC (sdns_api.cu fill_tables): row of W0 that holds transform index j of the axis-1 backward pass, and
+    // (owner rank << 24 | local row) of output j of the axis-1 forward pass; -1: not kept.  Null: the AxisMaps apply.
+    const int* itab; const int* otab;
     int c1_off, c2_off;           // first run / first column of this launch (the multi-GPU pipeline launches a pass in chunks)
     int grid_cap;                 // > 0: launch at most this many CTAs per SM (grid-stride over the tiles)
     int xuniform;                 // slab stores: P and omap.shift divide into xchunk (destination uniform per q)
@@ -161,6 +164,39 @@ __device__ __forceinline__ void load_line(V (&x)[E], const V* __restrict__ pin, 
         V v = czero<V>();
         if (rs.ok(q)) v = pb[off];
         x[q] = v;
+    }
+}
+
+// Table-driven variants for the cyclic slab ownership of axis 1: the row of every transform index comes from a small
+// table (L1-resident, shared by all columns) instead of the two-range AxisMap.
+template <typename T, int N, int E, typename V>
+__device__ __forceinline__ void load_line_tab(V (&x)[E], const V* __restrict__ pin, long long ls,
+                                              const int* __restrict__ tab, int t, bool valid) {
+    constexpr int P = N / E;
+    const int l = (int)ls;
+    const V* __restrict__ pb = opaque(pin);
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int r = valid ? tab[t + q * P] : -1;
+        V v = czero<V>();
+        if (r >= 0) v = pb[r * l];
+        x[q] = v;
+    }
+}
+template <typename T, int N, int E, bool SCALE, typename V>
+__device__ __forceinline__ void store_line_tab(const V (&x)[E], const StridedArgs<T>& a, int f, long long obase,
+                                               long long obase2, int t, bool valid, T scale) {
+    constexpr int P = N / E;
+    const long long fo = f * a.out_fs + obase, fo2 = f * a.out_fs2 + obase2;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int e = valid ? a.otab[t + q * P] : -1;
+        if (e >= 0) {
+            const int dest = e >> 24, row = e & 0xffffff;
+            const bool self = dest == a.self;
+            V* pq = reinterpret_cast<V*>(a.peer_out[dest]) + (self ? fo : fo2) + (long long)row * (self ? a.out_ls : a.out_ls2);
+            *pq = SCALE ? cscale<T>(x[q], scale) : x[q];
+        }
     }
 }
 
@@ -253,9 +289,11 @@ strided_kernel(const StridedArgs<T> a) {
     if (MODE == S_PLAIN) {
         const int f = blockIdx.y;
         V x[E];
-        load_line<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
+        if (a.itab) load_line_tab<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.itab, t, valid);
+        else load_line<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
         fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-        store_line<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
+        if (a.otab) store_line_tab<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
+        else store_line<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
     } else if (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0) {
         // in: 3 dense spectral fields.  out: 6 fields (NS: u_hat, i k x u_hat ; VV: i k x w_hat / k^2, w_hat)
         const T k1 = valid ? a.ky[c1m] : (T)0;
@@ -333,7 +371,7 @@ strided_kernel(const StridedArgs<T> a) {
         if (!valid) continue;
         const int i1 = c1, i2 = c2;
         const T k1 = a.ky[i1], k2 = a.kz[i2];
-        const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
+        const bool nyq12 = a.mask_nyquist && ((2 * (i1 * a.k1_mul + a.k1_off) == a.N1) || (2 * i2 == a.N2));
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int i0 = axis_mem(a.omap, N, t + q * P);
@@ -471,7 +509,7 @@ f0x_kernel(const StridedArgs<T> a) {
     const V* pk2 = sm + 2 * N * TC;
     const int i1 = c1, i2 = c2;
     const T k1 = a.ky[i1], k2 = a.kz[i2];
-    const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
+    const bool nyq12 = a.mask_nyquist && ((2 * (i1 * a.k1_mul + a.k1_off) == a.N1) || (2 * i2 == a.N2));
 #ifdef SDNS_F0_UNROLL
 #pragma unroll
 #else
@@ -676,7 +714,7 @@ mhd_f0_kernel(const StridedArgs<T> a) {
     }
     if (!valid) return;
     const int i1 = c1, i2 = c2;
-    const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
+    const bool nyq12 = a.mask_nyquist && ((2 * (i1 * a.k1_mul + a.k1_off) == a.N1) || (2 * i2 == a.N2));
     const T hs = (T)0.5 * a.scale;
 #pragma unroll
     for (int q = 0; q < E; ++q) {
@@ -788,7 +826,7 @@ nsdiv_f0_kernel(const StridedArgs<T> a) {
     }
     if (!valid) return;
     const int i1 = c1, i2 = c2;
-    const bool nyq12 = a.mask_nyquist && ((2 * (i1 + a.k1_off) == a.N1) || (2 * i2 == a.N2));
+    const bool nyq12 = a.mask_nyquist && ((2 * (i1 * a.k1_mul + a.k1_off) == a.N1) || (2 * i2 == a.N2));
 #pragma unroll
     for (int q = 0; q < E; ++q) {
         const int j0 = t + q * P;

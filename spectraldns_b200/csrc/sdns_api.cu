@@ -62,18 +62,20 @@ struct Space {
     int col_nlo, col_gap;  // compact axis-1 index -> memory index
     int K2n, K2p;          // axis-2 modes entering the backward transform, padded pitch
     double scale;          // 1/prod(M)
-    // slab decomposition: this rank owns spectral k1 in [rank*N1l, (rank+1)*N1l) and physical x0 in
-    // [rank*M0l, (rank+1)*M0l)  (spectralDNS3D_short.py:28-29)
+    // slab decomposition: this rank owns spectral k1 in [rank*N1l, (rank+1)*N1l) (SDNS_K1_BLOCKS) or the modes
+    // rank, rank + P, ... (SDNS_K1_CYCLIC) and physical x0 in [rank*M0l, (rank+1)*M0l)  (spectralDNS3D_short.py:28-29)
     int M0l;               // local physical planes
     int K1l;               // kept axis-1 modes owned by this rank
     int lcol_nlo, lcol_gap;// local compact axis-1 index -> local memory index
-    int c1off;             // global compact index of this rank's first kept axis-1 mode
+    int c1off;             // position of this rank's first kept axis-1 mode in W0's compact axis 1 (rank-major order)
+    size_t itab_off, otab_off;   // CYCLIC: B1 row table (transform index -> W0 row) and F1 store table (-> rank, row)
 };
 
 struct sdns_plan {
     sdns_config cfg;
     int N[3], Nh, Nhp;
     int P, rank, N1l;       // ranks, this rank, local spectral extent of axis 1
+    int k1cyc;              // 1: SDNS_K1_CYCLIC (local index j holds mode rank + j*P), 0: SDNS_K1_BLOCKS
     size_t off_C, bytes_C, off_flags, off_D, bytes_D, off_S, bytes_S, off_U, bytes_U;
     bool own_ws;            // workspace cudaMalloc'ed by the library (multi-GPU: IPC-shared)
     char* peer_ws[8];       // base of every rank's workspace (peer_ws[rank] == ws)
@@ -134,6 +136,29 @@ static AxisMap all_map(int n) { AxisMap m; m.nlo = n; m.nhi = 0; m.shift = 0; re
 
 static int default_kcut(int n) { return (int)ceil(2.0 / 3.0 * (n / 2 + 1)) - 1; }
 
+// Kept axis-1 modes of rank r in space q: local indices [0, a1) (low run) and [a1 + gap, a1 + gap + nb) (high run).
+// The kept global modes are [0, col_nlo) and [N1 - (K1n - col_nlo), N1).
+struct K1Own { int a1, nb, gap; };
+static K1Own k1_own(const sdns_plan* p, const Space& q, int r) {
+    const int N1 = p->N[1], N1l = p->N1l, P = p->P;
+    const int nlo = q.col_nlo, nhi = q.K1n - q.col_nlo, hstart = N1 - nhi;
+    K1Own o;
+    if (!p->k1cyc) {
+        const int lo = r * N1l, hi = lo + N1l;
+        o.a1 = std::max(0, std::min(hi, nlo) - lo);
+        const int b0 = std::max(lo, hstart);
+        o.nb = (nhi > 0 && hi > b0) ? hi - b0 : 0;
+        o.gap = o.nb > 0 ? (b0 - lo) - o.a1 : 0;
+    } else {
+        // local index j holds mode j*P + r
+        o.a1 = nlo > r ? (nlo - r + P - 1) / P : 0;                     // j*P + r < nlo
+        const int jh = hstart > r ? (hstart - r + P - 1) / P : 0;       // first j with j*P + r >= hstart
+        o.nb = nhi > 0 ? std::max(0, N1l - jh) : 0;
+        o.gap = o.nb > 0 ? jh - o.a1 : 0;
+    }
+    return o;
+}
+
 static void build_spaces(sdns_plan* p) {
     const int* N = p->N;
     // T: plain space
@@ -168,16 +193,15 @@ static void build_spaces(sdns_plan* p) {
         q.K2p = (q.K2n + 1) & ~1;
         q.scale = 1.0 / ((double)q.M[0] * q.M[1] * q.M[2]);
         q.M0l = q.M[0] / p->P;
-        // kept axis-1 modes (global memory indices [0,col_nlo) and [N1-(K1n-col_nlo), N1)) owned here
-        const int lo = p->rank * p->N1l, hi = lo + p->N1l;
-        const int nlo = q.col_nlo, nhi = q.K1n - q.col_nlo, hstart = N[1] - nhi;
-        const int a1 = std::max(0, std::min(hi, nlo) - lo);                  // low run: local [0, a1)
-        const int b0 = std::max(lo, hstart), b1 = hi;                         // high run: global [b0, b1)
-        const int nb = (nhi > 0 && b1 > b0) ? b1 - b0 : 0;
-        q.K1l = a1 + nb;
-        q.lcol_nlo = a1;
-        q.lcol_gap = nb > 0 ? (b0 - lo) - a1 : 0;
-        q.c1off = a1 > 0 ? lo : (nb > 0 ? b0 - (N[1] - q.K1n) : 0);
+        // kept axis-1 modes owned here; W0's compact axis 1 lists the ranks' kept modes one rank after the other
+        // (for SDNS_K1_BLOCKS that is the natural order)
+        const K1Own o = k1_own(p, q, p->rank);
+        q.K1l = o.a1 + o.nb;
+        q.lcol_nlo = o.a1;
+        q.lcol_gap = o.gap;
+        q.c1off = 0;
+        for (int r = 0; r < p->rank; ++r) { const K1Own x = k1_own(p, q, r); q.c1off += x.a1 + x.nb; }
+        q.itab_off = q.otab_off = 0;
     }
 }
 
@@ -199,12 +223,12 @@ static void fill_tables(sdns_plan* p) {
         p->tw_off[n] = off;
     };
     for (int s = 0; s < 2; ++s) for (int i = 0; i < 3; ++i) add_tw(p->sp[s].M[i]);
-    auto add_k = [&](int n, int len, double L, bool real_axis, int first = 0) {
+    auto add_k = [&](int n, int len, double L, bool real_axis, int first = 0, int step = 1) {
         size_t off = align_up(h.size(), 256);
         h.resize(off + sizeof(T) * len);
         T* k = reinterpret_cast<T*>(h.data() + off);
         for (int j = 0; j < len; ++j) {
-            const int i = j + first;
+            const int i = j * step + first;
             int kk = real_axis ? i : (i < (n + 1) / 2 ? i : i - n);
             // same evaluation order as the oracle: k*2*pi/L in double, then cast (NS.py:38-41)
             k[j] = (T)(((double)kk * 2.0 * M_PI) / L);
@@ -212,8 +236,40 @@ static void fill_tables(sdns_plan* p) {
         return off;
     };
     p->kx_off = add_k(p->N[0], p->N[0], p->cfg.L[0], false);
-    p->ky_off = add_k(p->N[1], p->N1l, p->cfg.L[1], false, p->rank * p->N1l);
+    if (p->k1cyc) p->ky_off = add_k(p->N[1], p->N1l, p->cfg.L[1], false, p->rank, p->P);
+    else p->ky_off = add_k(p->N[1], p->N1l, p->cfg.L[1], false, p->rank * p->N1l);
     p->kz_off = add_k(p->N[2], p->Nh, p->cfg.L[2], true);
+    // SDNS_K1_CYCLIC: the axis-1 passes on either side of a transpose see the modes in rank-major order.  B1 finds the
+    // W0 row of transform index j in itab (-1: not an input), F1 finds (owner << 24 | local row) of output j in otab.
+    for (int s = 0; s < 2 && p->k1cyc && p->P > 1; ++s) {
+        Space& q = p->sp[s];
+        const int M1 = q.M[1], P = p->P;
+        std::vector<int> first(P, 0);
+        std::vector<K1Own> own(P);
+        for (int r = 0, c = 0; r < P; ++r) { own[r] = k1_own(p, q, r); first[r] = c; c += own[r].a1 + own[r].nb; }
+        size_t off = align_up(h.size(), 256);
+        h.resize(off + sizeof(int) * 2 * M1);
+        q.itab_off = off; q.otab_off = off + sizeof(int) * M1;
+        std::vector<int> it(M1), ot(M1);
+        for (int j = 0; j < M1; ++j) {
+            const AxisMap& bm = q.bmap[1];
+            it[j] = -1;
+            if (j < bm.nlo || j >= M1 - bm.nhi) {
+                const int idx = j < bm.nlo ? j : j - bm.shift;                // natural compact index
+                const int m = idx < q.col_nlo ? idx : idx + q.col_gap;        // mode index in [0, N1)
+                const int r = m % P, jl = m / P;
+                it[j] = first[r] + (jl < own[r].a1 ? jl : jl - own[r].gap);
+            }
+            const AxisMap& fm = q.fmap[1];
+            ot[j] = -1;
+            if (j < fm.nlo || j >= M1 - fm.nhi) {
+                const int i = j < fm.nlo ? j : j - fm.shift;
+                ot[j] = ((i % P) << 24) | (i / P);
+            }
+        }
+        memcpy(h.data() + q.itab_off, it.data(), sizeof(int) * M1);
+        memcpy(h.data() + q.otab_off, ot.data(), sizeof(int) * M1);
+    }
 }
 
 extern "C" int sdns_abi_version(void) { return SDNS_ABI_VERSION; }
@@ -257,6 +313,8 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     for (int r = 0; r < 8; ++r) p->peer_ws[r] = nullptr;
     if (p->N[1] % p->P) { delete p; return fail(SDNS_ERR_SIZE, "N[1] must be divisible by the number of ranks"); }
     p->N1l = p->N[1] / p->P;
+    if (cfg->k1_layout != SDNS_K1_BLOCKS && cfg->k1_layout != SDNS_K1_CYCLIC) { delete p; return fail(SDNS_ERR_ARG, "k1_layout"); }
+    p->k1cyc = (cfg->k1_layout == SDNS_K1_CYCLIC && p->P > 1) ? 1 : 0;
     p->prec = cfg->precision;
     p->rs = p->prec ? 8 : 4; p->cs = 2 * p->rs;
     p->stream = 0; p->ws = nullptr; p->ws_bytes = 0; p->launches = 0;
@@ -428,6 +486,14 @@ extern "C" int sdns_plan_set_workspace(sdns_plan* p, void* dptr, size_t bytes) {
     return SDNS_OK;
 }
 
+// flag-barrier timeout in clock64() ticks: ~10 s of SM clock.  The CPU emulation of the tests counts nanoseconds and
+// runs every CUDA thread as an OS thread, so a rank can legitimately be tens of seconds behind on a loaded machine.
+#ifdef SDNS_HOST_SHIM
+#define SDNS_BARRIER_TIMEOUT 300000000000LL
+#else
+#define SDNS_BARRIER_TIMEOUT 20000000000LL
+#endif
+
 // ---- slab decomposition over NVLink peer memory (one process per GPU) -----------------------
 // The all-to-all of mpi4py-fft's Transfer (MPI_Alltoallw; in-tree analogue spectralDNS3D_short.py:53,59)
 // has no kernel of its own here: B0 and F1 store each output element directly into the owning rank's
@@ -558,7 +624,7 @@ static int xbarrier(sdns_plan* p) {
         for (int r = 0; r < 8; ++r) d.peer_flags[r] = r < p->P ? reinterpret_cast<unsigned int*>(p->peer_ws[r] + p->off_flags) + 16 : nullptr;
         d.status = reinterpret_cast<unsigned int*>(p->ws + p->off_flags) + 32;
         d.counter = reinterpret_cast<unsigned int*>(p->ws + p->off_flags) + 40;
-        d.rank = p->rank; d.nranks = p->P; d.timeout_cycles = 20000000000LL;
+        d.rank = p->rank; d.nranks = p->P; d.timeout_cycles = SDNS_BARRIER_TIMEOUT;
         SDNS_LAUNCH(xbarrier_dev_kernel, 1, 32, 0, p->stream)(d);
         p->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -568,7 +634,7 @@ static int xbarrier(sdns_plan* p) {
     for (int r = 0; r < 8; ++r) b.peer_flags[r] = r < p->P ? reinterpret_cast<unsigned int*>(p->peer_ws[r] + p->off_flags) : nullptr;
     b.status = reinterpret_cast<unsigned int*>(p->ws + p->off_flags) + 32;
     b.rank = p->rank; b.nranks = p->P; b.epoch = ++p->epoch;
-    b.timeout_cycles = 20000000000LL;      // ~10 s: a missing peer must not hang the GPU
+    b.timeout_cycles = SDNS_BARRIER_TIMEOUT;      // ~10 s: a missing peer must not hang the GPU
     sdns_plan::Rec r; r.fam = -1; r.bytes = 0; r.remote = 0;
     if (p->tl_on) { r.a = get_event(p); cudaEventRecord(r.a, p->stream); }
     SDNS_LAUNCH(xbarrier_kernel, 1, 32, 0, p->stream)(b);
@@ -614,6 +680,12 @@ extern "C" int sdns_local_shapes(const sdns_plan* p, int32_t sp[3], int32_t ph[3
     sp[0] = p->N[0]; sp[1] = p->N1l; sp[2] = p->Nh;
     for (int i = 0; i < 3; ++i) { ph[i] = p->sp[0].M[i]; pd[i] = p->sp[1].M[i]; }
     ph[0] = p->sp[0].M0l; pd[0] = p->sp[1].M0l;
+    return SDNS_OK;
+}
+extern "C" int sdns_k1_layout(const sdns_plan* p, int32_t* first, int32_t* step) {
+    if (!p || !first || !step) return fail(SDNS_ERR_ARG, "null argument");
+    *first = p->k1cyc ? p->rank : p->rank * p->N1l;
+    *step = p->k1cyc ? p->P : 1;
     return SDNS_OK;
 }
 extern "C" int sdns_launch_count(const sdns_plan* p, long long* c) {
@@ -737,7 +809,7 @@ struct Pipe {
         a.mask_nyquist = p->cfg.mask_nyquist;
         a.scale = (T)1;
         a.st_fs = dense_fs();
-        a.k1_off = p->rank * p->N1l;
+        a.k1_off = p->k1cyc ? p->rank : p->rank * p->N1l; a.k1_mul = p->k1cyc ? p->P : 1;
         a.uh_ls = (long long)p->N1l * p->Nh; a.uh_os = p->Nh;          // reference layout (N0, N1l, Nh)
         a.t_ls = p->Nh; a.t_os = (long long)p->N[0] * p->Nh;           // work layout (N1l, N0, Nh)
     }
@@ -799,6 +871,7 @@ struct Pipe {
         a.cw = k2.b - k2.a; a.c2_off = k2.a; a.ncols = (long long)q.M0l * a.cw;
         a.col_nlo = q.M0l; a.col_gap = 0;
         a.imap = q.bmap[1];
+        if (p->k1cyc) a.itab = reinterpret_cast<const int*>(p->ws + p->off_tab + q.itab_off);
         a.omap = all_map(q.M[1]);
         a.out_fs = (long long)q.M0l * q.M[1] * q.K2p; a.out_ls = q.K2p; a.out_os = (long long)q.M[1] * q.K2p;
         a.tw = tw(q.M[1]); a.nfields = nf;
@@ -846,6 +919,7 @@ struct Pipe {
         a.c1_out_off = (long long)p->rank * q.M0l;
         if (staged) peers(a, p->off_C, p->N1l, send_f1(), f1_slot(nf), (long long)p->N1l * q.M0l * p->Nhp, (long long)q.M0l * p->Nhp, 0);
         else peers(a, p->off_C, p->N1l);
+        if (p->k1cyc) a.otab = reinterpret_cast<const int*>(p->ws + p->off_tab + q.otab_off);
         a.grid_cap = xcap;
         a.tw = tw(q.M[1]); a.nfields = nf;
         const double bytes = (double)nf * (x0.b - x0.a) * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;

@@ -4,6 +4,7 @@ PyTorch is used only to allocate device buffers and to name the CUDA stream; eve
 operation goes through the C ABI into the hand-written sm_100a kernels.  There is no CPU path.
 """
 import ctypes as C
+import os
 import numpy as np
 
 from . import _lib
@@ -23,7 +24,7 @@ class Plan(object):
 
     def __init__(self, N, L=(2*np.pi,)*3, precision='double', dealias='2/3-rule', solver='NS',
                  convection=None, mask_nyquist=True, decomposition='slab', kcut=None, device=0,
-                 rank=0, nranks=1):
+                 rank=0, nranks=1, k1_layout=None):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.SdnsError('no CUDA device: spectraldns_b200 has no CPU fallback')
@@ -56,10 +57,20 @@ class Plan(object):
         cfg.prune = 1
         cfg.rank, cfg.nranks, cfg.device = int(rank), int(nranks), device
         self.rank, self.nranks = int(rank), int(nranks)
+        # which axis-1 modes a rank owns: 'blocks' = the reference's contiguous slabs (spectralinit.py:19-21),
+        # 'cyclic' = rank r owns [r::P] (balances the modes the 2/3 rule keeps; include/sdns_b200.h)
+        if k1_layout is None:
+            k1_layout = os.environ.get('SDNS_K1_LAYOUT', 'blocks')
+        cfg.k1_layout = _lib.K1_LAYOUT[k1_layout]
+        self.k1_layout = k1_layout if self.nranks > 1 else 'blocks'
         self._p = C.c_void_p()
         _lib.check(self.lib.sdns_plan_create(C.byref(self._p), C.byref(cfg)))
         sp, ph, pd = (C.c_int32*3)(), (C.c_int32*3)(), (C.c_int32*3)()
         _lib.check(self.lib.sdns_local_shapes(self._p, C.byref(sp), C.byref(ph), C.byref(pd)))
+        k1a, k1s = C.c_int32(), C.c_int32()
+        _lib.check(self.lib.sdns_k1_layout(self._p, C.byref(k1a), C.byref(k1s)))
+        # T.local_slice(True)[1]: the axis-1 modes of this rank as a slice of the global axis
+        self.k1_slice = slice(k1a.value, self.N[1] if k1s.value > 1 else k1a.value + sp[1], k1s.value)
         self.spectral_shape = tuple(sp)
         self.physical_shape = tuple(ph)
         self.padded_shape = tuple(pd)

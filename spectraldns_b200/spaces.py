@@ -9,6 +9,7 @@ resident on the device (see compat/spectralDNS/solvers/_device.py).
 Call sites this serves: solvers/NS.py:17-64,86-110; MHD.py:18-66,79-87; tests/TG.py:24-36,100-102;
 demo/Isotropic.py:33-76,159-254.
 """
+import os
 import numpy as np
 
 from .plan import Plan, Plan2D
@@ -165,6 +166,8 @@ class TensorProductSpace(object):
             ax = 1 if forward_output else 0
             c = g[ax]//n
             out[ax] = slice(r*c, (r+1)*c)
+            if forward_output and n > 1 and os.environ.get('SDNS_K1_LAYOUT', 'blocks') == 'cyclic':
+                out[ax] = slice(r, g[ax], n)       # Plan(k1_layout='cyclic'): rank r owns the axis-1 modes r, r + n, ...
         return tuple(out)
 
     def dims(self):

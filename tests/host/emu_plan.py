@@ -34,12 +34,13 @@ def load(path):
         L.sdns_emu_set_skew.argtypes = [C.c_int]
         L.sdns_emu_set_skew.restype = None
     L.sdns_local_shapes.argtypes = [vp, C.POINTER(C.c_int32*3), C.POINTER(C.c_int32*3), C.POINTER(C.c_int32*3)]
+    L.sdns_k1_layout.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     return L
 
 
 class EmuPlan(object):
     def __init__(self, L, N, Lbox=(2*np.pi,)*3, precision='double', dealias='2/3-rule', solver='NS',
-                 convection=None, mask_nyquist=True, kcut=None, rank=0, nranks=1):
+                 convection=None, mask_nyquist=True, kcut=None, rank=0, nranks=1, k1_layout='blocks'):
         self.L = L
         cfg = _lib.SdnsConfig()
         cfg.abi_version = 1
@@ -53,6 +54,7 @@ class EmuPlan(object):
         cfg.convection = _lib.CONVECTION[conv]
         cfg.mask_nyquist = int(mask_nyquist)
         cfg.rank, cfg.nranks = rank, nranks
+        cfg.k1_layout = _lib.K1_LAYOUT[k1_layout]
         self.p = vp()
         self.chk(L.sdns_plan_create(C.byref(self.p), C.byref(cfg)))
         self.real = np.float64 if precision == 'double' else np.float32
@@ -60,6 +62,9 @@ class EmuPlan(object):
         sp, ph, pd = (C.c_int32*3)(), (C.c_int32*3)(), (C.c_int32*3)()
         self.chk(L.sdns_local_shapes(self.p, C.byref(sp), C.byref(ph), C.byref(pd)))
         self.sshape, self.pshape, self.dshape = tuple(sp), tuple(ph), tuple(pd)
+        a, b = C.c_int32(), C.c_int32()
+        self.chk(L.sdns_k1_layout(self.p, C.byref(a), C.byref(b)))
+        self.k1_slice = slice(a.value, int(N[1]) if b.value > 1 else a.value + sp[1], b.value)     # this rank's axis-1 modes
         self.ncomp = 6 if solver == 'MHD' else 3
         self.rank, self.nranks = rank, nranks
         if nranks > 1:

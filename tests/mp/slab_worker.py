@@ -24,6 +24,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     fails = []
+    # SLAB_K1_LAYOUT=cyclic: rank r owns the axis-1 modes [r::P] instead of the reference's contiguous block
+    layout = os.environ.get('SLAB_K1_LAYOUT', 'blocks')
     cases = [((32, 32, 32), 'double', '2/3-rule', 'NS'), ((32, 32, 32), 'double', '3/2-rule', 'NS'),
              ((64, 32, 16), 'double', '2/3-rule', 'VV'), ((32, 32, 32), 'single', '2/3-rule', 'NS'),
              ((16, 32, 64), 'double', '2/3-rule', 'MHD'), ((32, 16, 32), 'double', 'None', 'NS'),
@@ -41,9 +43,10 @@ def main():
         tol = 1e-11 if prec == 'double' else 1e-4
         o = so.Oracle(N, precision=prec, dealias=dealias, kcut=kcut)
         p = Plan(N, precision=prec, dealias=dealias, solver=solver, device=local, rank=rank, nranks=world, kcut=kcut,
-                 convection=conv)
+                 convection=conv, k1_layout=layout)
         N1l = N[1]//world
-        k1s = slice(rank*N1l, (rank+1)*N1l)
+        k1s = p.k1_slice
+        assert k1s == (slice(rank, N[1], world) if layout == 'cyclic' else slice(rank*N1l, (rank+1)*N1l)), k1s
         M0l, Mp0l = N[0]//world, o.M[0]//world
         x0s, x0ps = slice(rank*M0l, (rank+1)*M0l), slice(rank*Mp0l, (rank+1)*Mp0l)
         assert p.spectral_shape == (N[0], N1l, N[2]//2+1), p.spectral_shape

@@ -14,14 +14,18 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
+@pytest.mark.parametrize('layout', ['blocks', 'cyclic'])
 @pytest.mark.parametrize('world', [2, 4, 8])
-def test_slab_parity(world):
+def test_slab_parity(world, layout):
+    """layout: which axis-1 modes a rank owns -- the reference's contiguous blocks, or [rank::P] (Plan(k1_layout='cyclic'),
+    the balanced ownership bench.py uses on 3 or more GPUs under the 2/3 rule)."""
     if _ngpu() < world:
         pytest.skip('needs %d GPUs' % world)
+    env = dict(os.environ, SLAB_K1_LAYOUT=layout)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
            '--master-addr', '127.0.0.1', '--master-port', str(29500 + world),
            os.path.join(ROOT, 'tests', 'mp', 'slab_worker.py')]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0 and 'SLAB_WORKER_RESULT fails=0' in r.stdout, r.stdout[-6000:]
 
 

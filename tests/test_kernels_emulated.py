@@ -78,7 +78,7 @@ def test_emulated_ns_convection_forms(emu, conv):
 # multi-GPU schedule: the ranks are threads of this process, "peer memory" is each other's host buffer, the
 # device-side flag barrier spins on real flags, the copy-engine copies are memcpys at the point of submission
 # ---------------------------------------------------------------------------------------------
-def _multi_case(emu, world, exchange, case, chunks='4', skew=None):
+def _multi_case(emu, world, exchange, case, chunks='4', skew=None, k1_layout='blocks'):
     L, ep = emu
     N, prec, dealias, solver = case[:4]
     kcut = case[4] if len(case) > 4 else None
@@ -97,10 +97,12 @@ def _multi_case(emu, world, exchange, case, chunks='4', skew=None):
 
     def rank_fn(rank, sync):
         L.sdns_emu_set_skew(int(skew(rank)) if skew else 0)       # this rank's delay before every launch (microseconds)
-        p = ep.EmuPlan(L, N, precision=prec, dealias=dealias, solver=solver, convection=conv, kcut=kcut, rank=rank, nranks=world)
+        p = ep.EmuPlan(L, N, precision=prec, dealias=dealias, solver=solver, convection=conv, kcut=kcut, rank=rank, nranks=world,
+                       k1_layout=k1_layout)
         p.open_peers(sync(p.handle()))
         N1l, M0l = N[1]//world, N[0]//world
-        k1s, x0s = slice(rank*N1l, (rank+1)*N1l), slice(rank*M0l, (rank+1)*M0l)
+        k1s, x0s = p.k1_slice, slice(rank*M0l, (rank+1)*M0l)
+        assert k1s == (slice(rank, N[1], world) if k1_layout == 'cyclic' else slice(rank*N1l, (rank+1)*N1l))
         # the sequence visits every transition between operations that store into the peers
         e = [rel_l2(p.forward(u[:, x0s]), uh_ref[:, :, k1s]),
              rel_l2(p.backward(uh_ref[:, :, k1s].astype(o.complex)), u[:, x0s]),
@@ -140,6 +142,16 @@ def test_emulated_multi_gpu_schedule(emu, world, exchange):
     the bulk-async copies are memcpys here, the ring / piece bookkeeping runs unchanged)."""
     for i in PICK[world][:1 if (world == 8 and exchange == 'store') else None]:
         _multi_case(emu, world, exchange, MULTI[i], chunks='6' if exchange == 'tma' else '4')
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_emulated_multi_gpu_cyclic_k1(emu, world):
+    """Plan(k1_layout='cyclic'): rank r owns the axis-1 modes [r::P], so that the 2/3 rule leaves every rank the same number
+    of kept modes.  Same global results; every exchange mode, the three dealias modes, the convection forms, MHD."""
+    cases = {2: (('tma', 0), ('ce', 7), ('store', 3)), 4: (('tma', 1), ('ce', 5), ('store', 6), ('tma', 3)),
+             8: (('tma', 5), ('ce', 0), ('tma', 2))}[world]
+    for exchange, i in cases:
+        _multi_case(emu, world, exchange, MULTI[i], chunks='6' if exchange == 'tma' else '4', k1_layout='cyclic')
 
 
 def test_emulated_multi_gpu_transfer_role_variants(emu):

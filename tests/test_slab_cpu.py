@@ -255,3 +255,31 @@ def test_chunk_bounds_taper_and_cover():
             assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
     b = [chunk_bound(90, 4, c) for c in range(5)]
     assert [y - x for x, y in zip(b, b[1:])] == [30, 30, 20, 10]
+
+
+def test_cyclic_k1_ownership_host_side(monkeypatch):
+    """Plan(k1_layout='cyclic') / SDNS_K1_LAYOUT=cyclic: rank r owns the axis-1 modes [r::P].  The host mirror reports it
+    through T.local_slice(True), and the local wavenumbers / Nyquist mask follow from that slice.  Under the 2/3 rule the
+    kept modes are then spread evenly, while the reference's contiguous blocks leave the end ranks 1.5x the average."""
+    from spectraldns_b200 import spaces
+    N, P = (16, 32, 8), 4
+    bases = [spaces.FunctionSpace(n, 'F') for n in N]
+    kept = lambda k: np.count_nonzero(np.abs(k) < 2./3*(N[1]//2 + 1))
+    counts = {}
+    for layout in ('blocks', 'cyclic'):
+        monkeypatch.setenv('SDNS_K1_LAYOUT', layout)
+        seen, counts[layout] = [], []
+        for r in range(P):
+            monkeypatch.setattr(spaces, 'world', lambda r=r: (r, P, 0))
+            T = spaces.TensorProductSpace(None, bases)
+            sl = T.local_slice(True)
+            assert sl[1] == (slice(r, N[1], P) if layout == 'cyclic' else slice(r*8, r*8 + 8))
+            assert T.shape(True) == (16, 8, 5)
+            k = T.local_wavenumbers()[1].ravel()
+            assert np.array_equal(k, np.fft.fftfreq(N[1], 1./N[1])[sl[1]])
+            assert T.get_mask_nyquist().shape == T.shape(True)
+            seen.extend(range(N[1])[sl[1]])
+            counts[layout].append(kept(k))
+        assert sorted(seen) == list(range(N[1]))          # a partition of the axis
+    assert max(counts['cyclic']) - min(counts['cyclic']) <= 1
+    assert max(counts['blocks']) == 8 and min(counts['blocks']) < 4
