@@ -36,6 +36,8 @@ def main():
              ((32, 32, 32), 'double', '2/3-rule', 'NS', None, 'Standard'), ((32, 32, 16), 'double', '3/2-rule', 'NS', None, 'Divergence'),
              ((16, 32, 32), 'double', '2/3-rule', 'NS', None, 'Skewed'), ((32, 32, 32), 'single', '3/2-rule', 'NS', None, 'Skewed'),
              ((32, 32, 32), 'double', '3/2-rule', 'VV'), ((32, 32, 32), 'single', '3/2-rule', 'MHD')]
+    if os.environ.get('SLAB_CASES'):            # a subset, by index (the 8-GPU box is paid by the second)
+        cases = [cases[int(i)] for i in os.environ['SLAB_CASES'].split(',')]
     for case in cases:
         N, prec, dealias, solver = case[:4]
         kcut = case[4] if len(case) > 4 else None
