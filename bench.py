@@ -27,7 +27,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import spectraldns_b200  # noqa: E402,F401  (sets CUDA_DEVICE_MAX_CONNECTIONS before the CUDA context exists)
 
-NU, DT = 0.000625, 0.01       # tests/TG.py:131-133 of the reference
+NU, DT = 0.000625, 0.01       # tests/TG.py:131-133 of the reference (32^3)
+
+
+def dt_for(a, N):
+    """The reference's dt = 0.01 where RK4 is stable with it, else the largest stable one with a margin: the advection term
+    has eigenvalues up to i*sum_i kc_i*max|v_i| (kc_i = N_i/3 kept modes; |v| <= 1 for the Taylor-Green velocity, 2 for the
+    Elsasser fields of TG-MHD), and RK4 is stable on the imaginary axis below 2.83.  dt = 0.01 on 1024^3 (MHD: 512^3) grows
+    round-off in the highest modes by a factor > 3 (> 50) per step.  The work per step does not depend on dt."""
+    vmax = 2.0 if a.solver == 'MHD' else 1.0
+    return min(DT, 1.4/(vmax*sum(n/3.0 for n in N)))
 
 
 def parse():
@@ -139,12 +148,12 @@ def reference_steps(a, Ns, nsteps, warm, want_state=False):
         ts = []
         for _ in range(warm + nsteps):
             t0 = time.perf_counter()
-            u = o.solve(u, a.solver, 1, DT, NU, eta=0.01)
+            u = o.solve(u, a.solver, 1, dt_for(a, Ns), NU, eta=0.01)
             ts.append(time.perf_counter() - t0)
         ts = ts[warm:]
         return sum(ts)/len(ts), min(ts), 'port', (u if want_state else None)
     config, get_solver, solve = mods
-    config.update({'nu': NU, 'dt': DT, 'T': DT*(warm + nsteps), 'eta': 0.01,
+    config.update({'nu': NU, 'dt': dt_for(a, Ns), 'T': dt_for(a, Ns)*(warm + nsteps), 'eta': 0.01,
                    'convection': 'Divergence' if a.solver == 'MHD' else 'Vortex'})
     with contextlib.redirect_stdout(io.StringIO()):
         solver = get_solver(parse_args=['--M'] + [str(m) for m in M] +
@@ -282,7 +291,7 @@ def state_parity(a, Ns, ref_state, nsteps):
         u = p.cross2(p.empty_spectral(), u)
     u1, u2 = p.empty_spectral(), p.empty_spectral()
     for _ in range(nsteps):
-        p.rk4_step(u, u1, u2, DT, NU, 0.01)
+        p.rk4_step(u, u1, u2, dt_for(a, Ns), NU, 0.01)
     got = p.to_host(u).astype(np.complex128)
     err = float(np.linalg.norm((got - ref_state).ravel())/np.linalg.norm(ref_state.ravel()))
     tol = 1e-11 if a.precision == 'double' else 1e-4
@@ -391,11 +400,11 @@ def run_ours(a):
         w = p.cross2(p.empty_spectral(), u)
         u = w
     u1, u2 = p.empty_spectral(), p.empty_spectral()
-    eta = 0.01
+    eta, dt = 0.01, dt_for(a, N)
     state_bytes = u.numel()*u.element_size()
 
     for _ in range(max(a.warmup, 3)):
-        p.rk4_step(u, u1, u2, DT, NU, eta)
+        p.rk4_step(u, u1, u2, dt, NU, eta)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = p.launch_count()
@@ -404,7 +413,7 @@ def run_ours(a):
     barrier()
     e0.record()
     for _ in range(a.steps):
-        p.rk4_step(u, u1, u2, DT, NU, eta)
+        p.rk4_step(u, u1, u2, dt, NU, eta)
     e1.record()
     torch.cuda.synchronize()
     barrier()
@@ -428,11 +437,11 @@ def run_ours(a):
     host = torch.empty(u.shape, dtype=u.dtype, pin_memory=True)
     host.copy_(u)
     ne = max(3, min(a.steps, 10))
-    p.rk4_steps_host(host, u, u1, u2, 1, DT, NU, eta)       # warm
+    p.rk4_steps_host(host, u, u1, u2, 1, dt, NU, eta)       # warm
     barrier()
     t0 = time.perf_counter()
     for _ in range(ne):
-        p.rk4_steps_host(host, u, u1, u2, 1, DT, NU, eta)
+        p.rk4_steps_host(host, u, u1, u2, 1, dt, NU, eta)
     torch.cuda.synchronize()
     te = (time.perf_counter() - t0)/ne
     t = torch.tensor([te], dtype=torch.float64, device='cuda')
@@ -444,14 +453,14 @@ def run_ours(a):
     p.profile(True)
     npf = max(2, min(a.steps, 5))
     for _ in range(npf):
-        p.rk4_step(u, u1, u2, DT, NU, eta)
+        p.rk4_step(u, u1, u2, dt, NU, eta)
     prof = p.profile_read()
     copies = p.profile_read_copies()
     p.profile(False)
     if a.timeline:
         barrier()
         p.profile(True, timeline=True)
-        p.rk4_step(u, u1, u2, DT, NU, eta)
+        p.rk4_step(u, u1, u2, dt, NU, eta)
         rows = p.profile_timeline()
         p.profile(False)
         with open('%s.rank%d.json' % (a.timeline, rank), 'w') as f:
@@ -492,6 +501,7 @@ def run_ours(a):
                                                 if p.k1_layout == 'cyclic' else ' (the reference\'s contiguous axis-1 blocks)')) if world > 1 else None,
                    'l2': 'inputs larger than L2 (state %.0f MB, scratch %.0f MB)' % (state_bytes/1e6, p.workspace_bytes/1e6),
                    'timing': 'CUDA events on the launch stream, max over ranks',
+                   'dt': dt, 'nu': NU,
                    'kinetic_energy_after_run': energy},
         'clocks': clocks,
         'e2e': {'value': pts/te, 'unit': 'points*steps/s', 'ms_per_step': te*1e3,

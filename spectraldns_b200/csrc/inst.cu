@@ -34,10 +34,11 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
         const long long cap = ((long long)a.grid_cap * nsm + ny - 1) / ny;
         if (tiles > cap) tiles = cap;
     }
-    {   // the passes address rows with 32-bit element offsets relative to the column base
+    {   // the passes address rows with 32-bit element offsets relative to the column base; a pass that stores into the
+        // slab owners (xchunk > 0) offsets each destination's base by the row inside that destination's chunk only
         auto mag = [](long long v) { return v < 0 ? -v : v; };
-        const long long big = std::max(std::max(mag(a.in_ls), mag(a.out_ls)), mag(a.out_ls2));
-        if ((long long)N * big >= (1LL << 31)) return -1001;
+        const long long orows = a.xchunk > 0 ? a.xchunk : N;
+        if ((long long)N * mag(a.in_ls) >= (1LL << 31) || orows * std::max(mag(a.out_ls), mag(a.out_ls2)) >= (1LL << 31)) return -1001;
     }
     StridedArgs<T> b = a;
     b.xuniform = 0;
@@ -45,6 +46,12 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
         const int sp = (a.omap.shift + a.xchunk - 1) / a.xchunk * a.xchunk;     // shift rounded up to whole chunks
         b.xuniform = 1; b.xhi_d0 = -(sp / a.xchunk); b.xhi_b0 = sp - a.omap.shift;
     }
+    // cyclic axis-1 ownership: closed-form rows when the ranks divide the threads of a line, else the tables
+    b.icyc = (a.itab && a.cycP > 0 && C::P % a.cycP == 0) ? 1 : 0;
+    b.ocyc = (a.otab && a.cycP > 0 && C::P % a.cycP == 0) ? 1 : 0;
+#ifdef SDNS_CYC_TABLES
+    b.icyc = b.ocyc = 0;
+#endif
     xfer_prepare(b.x, C::smem, C::P * C::TC);
     dim3 grid((unsigned)tiles + b.x.nctas, ny);
     SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
@@ -64,10 +71,11 @@ static int run_b0x(const StridedArgs<T>& a, cudaStream_t st) {
         once = true;
     }
     const long long tiles = (a.ncols + C::TC - 1) / C::TC;
-    {   // the passes address rows with 32-bit element offsets relative to the column base
+    {   // the passes address rows with 32-bit element offsets relative to the column base; a pass that stores into the
+        // slab owners (xchunk > 0) offsets each destination's base by the row inside that destination's chunk only
         auto mag = [](long long v) { return v < 0 ? -v : v; };
-        const long long big = std::max(std::max(mag(a.in_ls), mag(a.out_ls)), mag(a.out_ls2));
-        if ((long long)N * big >= (1LL << 31)) return -1001;
+        const long long orows = a.xchunk > 0 ? a.xchunk : N;
+        if ((long long)N * mag(a.in_ls) >= (1LL << 31) || orows * std::max(mag(a.out_ls), mag(a.out_ls2)) >= (1LL << 31)) return -1001;
     }
     StridedArgs<T> b = a;
     b.xuniform = 0;

@@ -82,7 +82,10 @@ struct SCfg {
 #ifndef SDNS_B0_MAXT
 #define SDNS_B0_MAXT 512
 #endif
-    static constexpr int maxThreads = sizeof(T) == 8 ? (b0m ? SDNS_B0_MAXT : 256) : (heavy ? SDNS_F32_MAXT_HEAVY : SDNS_F32_MAXT);
+#ifndef SDNS_F64_MAXT_HEAVY
+#define SDNS_F64_MAXT_HEAVY 256
+#endif
+    static constexpr int maxThreads = sizeof(T) == 8 ? (b0m ? SDNS_B0_MAXT : (heavy ? SDNS_F64_MAXT_HEAVY : 256)) : (heavy ? SDNS_F32_MAXT_HEAVY : SDNS_F32_MAXT);
     static constexpr int TCfull = 128 / (2 * (int)sizeof(T));
     // widest tile whose buffers (the exchange buffer, plus two parked fields in the epilogue kernels) fit in shared memory
     static constexpr int tc_fit(int tc) {

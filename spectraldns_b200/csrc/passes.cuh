@@ -77,6 +77,12 @@ struct StridedArgs {
     // SDNS_K1_CYCLIC (sdns_api.cu fill_tables): row of W0 that holds transform index j of the axis-1 backward pass, and
     // (owner rank << 24 | local row) of output j of the axis-1 forward pass; -1: not kept.  Null: the AxisMaps apply.
     const int* itab; const int* otab;
+    // the same maps in closed form, used when the ranks P divide the threads per line (run_strided decides): a thread's
+    // rows then belong to one rank per kept range and advance by (threads per line)/P.  cyc_first[r]: first W0 row of
+    // rank r's kept modes, cyc_hi[r]: the same minus the rows its truncated gap skips, cyc_dm: transform index - mode
+    // index in the high range.
+    int icyc, ocyc, cycP, cyc_dm;
+    int cyc_first[8], cyc_hi[8];
     int c1_off, c2_off;           // first run / first column of this launch (the multi-GPU pipeline launches a pass in chunks)
     int grid_cap;                 // > 0: launch at most this many CTAs per SM (grid-stride over the tiles)
     int xuniform;                 // slab stores: P and omap.shift divide into xchunk (destination uniform per q)
@@ -183,6 +189,48 @@ __device__ __forceinline__ void load_line_tab(V (&x)[E], const V* __restrict__ p
         x[q] = v;
     }
 }
+// Closed-form variants (P | threads per line): the loads keep load_line's shape -- two row bases, one stride.
+template <typename T, int N, int E, typename V>
+__device__ __forceinline__ void load_line_cyc(V (&x)[E], const V* __restrict__ pin, long long ls, const StridedArgs<T>& a,
+                                              int t, bool valid) {
+    constexpr int P = N / E;
+    const RowSel<N, E> rs(a.imap, t, valid);
+    const int R = a.cycP, l = (int)ls;
+    const int rl = t % R;
+    const int th = t - a.cyc_dm;
+    const int rh = ((th % R) + R) % R;
+    const int olo = (a.cyc_first[rl] + t / R) * l, ohi = (a.cyc_hi[rh] + (th - rh) / R) * l, step = (P / R) * l;
+    const V* __restrict__ pb = opaque(pin);
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int off = (rs.lo(q) ? olo : ohi) + q * step;
+        V v = czero<V>();
+        if (rs.ok(q)) v = pb[off];
+        x[q] = v;
+    }
+}
+template <typename T, int N, int E, bool SCALE, typename V>
+__device__ __forceinline__ void store_line_cyc(const V (&x)[E], const StridedArgs<T>& a, int f, long long obase,
+                                               long long obase2, int t, bool valid, T scale) {
+    constexpr int P = N / E;
+    const RowSel<N, E> rs(a.omap, t, valid);
+    const int R = a.cycP;
+    const long long fo = f * a.out_fs + obase, fo2 = f * a.out_fs2 + obase2;
+    const int dl = t % R;                                    // owner of this thread's outputs in the low kept range
+    const int th = t - a.omap.shift;
+    const int dh = ((th % R) + R) % R;                       // ... and in the high one
+    const bool sl = dl == a.self, sh = dh == a.self;
+    const int ll = (int)(sl ? a.out_ls : a.out_ls2), lh = (int)(sh ? a.out_ls : a.out_ls2);
+    V* plo = opaque(reinterpret_cast<V*>(a.peer_out[dl]) + (sl ? fo : fo2) + (long long)(t / R) * ll);
+    V* phi = opaque(reinterpret_cast<V*>(a.peer_out[dh]) + (sh ? fo : fo2)) + (long long)((th - dh) / R) * lh;
+    const int slo = (P / R) * ll, shi = (P / R) * lh;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        V* pq = rs.lo(q) ? plo + q * slo : phi + (long long)q * shi;
+        if (rs.ok(q)) *pq = SCALE ? cscale<T>(x[q], scale) : x[q];
+    }
+}
+
 template <typename T, int N, int E, bool SCALE, typename V>
 __device__ __forceinline__ void store_line_tab(const V (&x)[E], const StridedArgs<T>& a, int f, long long obase,
                                                long long obase2, int t, bool valid, T scale) {
@@ -289,10 +337,12 @@ strided_kernel(const StridedArgs<T> a) {
     if (MODE == S_PLAIN) {
         const int f = blockIdx.y;
         V x[E];
-        if (a.itab) load_line_tab<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.itab, t, valid);
+        if (a.icyc) load_line_cyc<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a, t, valid);
+        else if (a.itab) load_line_tab<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.itab, t, valid);
         else load_line<T, N, E>(x, a.in + (f * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
         fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-        if (a.otab) store_line_tab<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
+        if (a.ocyc) store_line_cyc<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
+        else if (a.otab) store_line_tab<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
         else store_line<T, N, E, true>(x, a, f, obase, obase2, t, valid, a.scale);
     } else if (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0) {
         // in: 3 dense spectral fields.  out: 6 fields (NS: u_hat, i k x u_hat ; VV: i k x w_hat / k^2, w_hat)

@@ -69,6 +69,7 @@ struct Space {
     int lcol_nlo, lcol_gap;// local compact axis-1 index -> local memory index
     int c1off;             // position of this rank's first kept axis-1 mode in W0's compact axis 1 (rank-major order)
     size_t itab_off, otab_off;   // CYCLIC: B1 row table (transform index -> W0 row) and F1 store table (-> rank, row)
+    int cyc_first[8], cyc_hi[8], cyc_dm;   // the same map in closed form (StridedArgs, passes.cuh)
 };
 
 struct sdns_plan {
@@ -247,6 +248,8 @@ static void fill_tables(sdns_plan* p) {
         std::vector<int> first(P, 0);
         std::vector<K1Own> own(P);
         for (int r = 0, c = 0; r < P; ++r) { own[r] = k1_own(p, q, r); first[r] = c; c += own[r].a1 + own[r].nb; }
+        for (int r = 0; r < 8; ++r) { q.cyc_first[r] = r < P ? first[r] : 0; q.cyc_hi[r] = r < P ? first[r] - own[r].gap : 0; }
+        q.cyc_dm = q.bmap[1].shift - q.col_gap;
         size_t off = align_up(h.size(), 256);
         h.resize(off + sizeof(int) * 2 * M1);
         q.itab_off = off; q.otab_off = off + sizeof(int) * M1;
@@ -871,7 +874,11 @@ struct Pipe {
         a.cw = k2.b - k2.a; a.c2_off = k2.a; a.ncols = (long long)q.M0l * a.cw;
         a.col_nlo = q.M0l; a.col_gap = 0;
         a.imap = q.bmap[1];
-        if (p->k1cyc) a.itab = reinterpret_cast<const int*>(p->ws + p->off_tab + q.itab_off);
+        if (p->k1cyc) {
+            a.itab = reinterpret_cast<const int*>(p->ws + p->off_tab + q.itab_off);
+            a.cycP = p->P; a.cyc_dm = q.cyc_dm;
+            for (int r = 0; r < 8; ++r) { a.cyc_first[r] = q.cyc_first[r]; a.cyc_hi[r] = q.cyc_hi[r]; }
+        }
         a.omap = all_map(q.M[1]);
         a.out_fs = (long long)q.M0l * q.M[1] * q.K2p; a.out_ls = q.K2p; a.out_os = (long long)q.M[1] * q.K2p;
         a.tw = tw(q.M[1]); a.nfields = nf;
@@ -919,7 +926,7 @@ struct Pipe {
         a.c1_out_off = (long long)p->rank * q.M0l;
         if (staged) peers(a, p->off_C, p->N1l, send_f1(), f1_slot(nf), (long long)p->N1l * q.M0l * p->Nhp, (long long)q.M0l * p->Nhp, 0);
         else peers(a, p->off_C, p->N1l);
-        if (p->k1cyc) a.otab = reinterpret_cast<const int*>(p->ws + p->off_tab + q.otab_off);
+        if (p->k1cyc) { a.otab = reinterpret_cast<const int*>(p->ws + p->off_tab + q.otab_off); a.cycP = p->P; }
         a.grid_cap = xcap;
         a.tw = tw(q.M[1]); a.nfields = nf;
         const double bytes = (double)nf * (x0.b - x0.a) * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;

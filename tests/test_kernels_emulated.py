@@ -152,6 +152,12 @@ def test_emulated_multi_gpu_cyclic_k1(emu, world):
              8: (('tma', 5), ('ce', 0), ('tma', 2))}[world]
     for exchange, i in cases:
         _multi_case(emu, world, exchange, MULTI[i], chunks='6' if exchange == 'tma' else '4', k1_layout='cyclic')
+    # the axis-1 passes find their rows in closed form when the ranks divide the threads of a line (64 / 8 = 8 threads for
+    # 8 ranks, 48 / 12 = 4 for 4 ranks and the padded length), through the tables otherwise (the 8-rank cases above)
+    if world == 8:
+        _multi_case(emu, 8, 'tma', ((16, 64, 8), 'double', '2/3-rule', 'NS'), chunks='3', k1_layout='cyclic')
+    if world == 4:
+        _multi_case(emu, 4, 'tma', ((16, 32, 8), 'double', '3/2-rule', 'NS'), chunks='3', k1_layout='cyclic')
 
 
 def test_emulated_multi_gpu_transfer_role_variants(emu):
