@@ -180,7 +180,10 @@ struct BXCfg {
 // MHD epilogue: six accumulators per thread -> fewer elements per thread
 template <typename T, int N>
 struct MCfg {
-    static constexpr int E = (N % 5 == 0) ? 30 : (N % 3 == 0) ? (sizeof(T) == 8 ? 6 : 12) : (sizeof(T) == 8 ? 4 : 8);
+#ifndef SDNS_MHD_F32_E3
+#define SDNS_MHD_F32_E3 12      // fp32, 3*2^k lengths: elements per thread (six accumulators of E complex values per thread)
+#endif
+    static constexpr int E = (N % 5 == 0) ? 30 : (N % 3 == 0) ? (sizeof(T) == 8 ? 6 : SDNS_MHD_F32_E3) : (sizeof(T) == 8 ? 4 : 8);
     static constexpr int P = N / E;
     static constexpr int maxThreads = 512;
     static constexpr int TCfull = 128 / (2 * (int)sizeof(T));

@@ -744,11 +744,29 @@ mhd_f0_kernel(const StridedArgs<T> a) {
 
     // R_ij = FFT0(ZZ[i][j]); S_a = sum_b K_b (R_ab + R_ba) ; D_a = sum_b K_b (R_ba - R_ab)
     // R_ij contributes  K_j*R_ij to S_i,  K_i*R_ij to S_j,  K_i*R_ij to D_j,  -K_j*R_ij to D_i
+    // The nine fields stream through one work array.  fp64: the NEXT field's line is loaded into a second register set (E
+    // is small here) before the current one is transformed, so that its DRAM latency runs under the transform and the
+    // accumulation instead of in front of them (one CTA per SM: nothing else would hide it).  Measured on B200
+    // (profiles/r2/final_1gpu/passbench_mhd_pipe.txt): fp64 256^3 1776 -> 1683 us, 512^3 14.9 -> 14.7 ms; fp32 (E = 8, twice
+    // the registers per set, already spilling) 1494 -> 1730 us, so fp32 keeps the serial order.
+#ifndef SDNS_NO_MHD_F0_PIPE
+    constexpr bool PIPE = sizeof(T) == 8;
+#else
+    constexpr bool PIPE = false;
+#endif
+    V xn[PIPE ? E : 1];
+    if constexpr (PIPE) load_line<T, N, E>(xn, a.in + ibase, a.in_ls, a.imap, t, valid);
 #pragma unroll
     for (int ij = 0; ij < 9; ++ij) {
         const int i = ij / 3, j = ij % 3;
         V x[E];
-        load_line<T, N, E>(x, a.in + (ij * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
+        if constexpr (PIPE) {
+#pragma unroll
+            for (int q = 0; q < E; ++q) x[q] = xn[q];
+            if (ij < 8) load_line<T, N, E>(xn, a.in + ((ij + 1) * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
+        } else {
+            load_line<T, N, E>(x, a.in + (ij * a.in_fs + ibase), a.in_ls, a.imap, t, valid);
+        }
         fft_line<T, N, E, -1, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
 #pragma unroll
         for (int q = 0; q < E; ++q) {

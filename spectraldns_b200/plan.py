@@ -70,7 +70,7 @@ class Plan(object):
         k1a, k1s = C.c_int32(), C.c_int32()
         _lib.check(self.lib.sdns_k1_layout(self._p, C.byref(k1a), C.byref(k1s)))
         # T.local_slice(True)[1]: the axis-1 modes of this rank as a slice of the global axis
-        self.k1_slice = slice(k1a.value, self.N[1] if k1s.value > 1 else k1a.value + sp[1], k1s.value)
+        self.k1_slice = (slice(k1a.value, self.N[1], k1s.value) if k1s.value > 1 else slice(k1a.value, k1a.value + sp[1]))
         self.spectral_shape = tuple(sp)
         self.physical_shape = tuple(ph)
         self.padded_shape = tuple(pd)

@@ -64,7 +64,7 @@ class EmuPlan(object):
         self.sshape, self.pshape, self.dshape = tuple(sp), tuple(ph), tuple(pd)
         a, b = C.c_int32(), C.c_int32()
         self.chk(L.sdns_k1_layout(self.p, C.byref(a), C.byref(b)))
-        self.k1_slice = slice(a.value, int(N[1]) if b.value > 1 else a.value + sp[1], b.value)     # this rank's axis-1 modes
+        self.k1_slice = slice(a.value, int(N[1]), b.value) if b.value > 1 else slice(a.value, a.value + sp[1])     # this rank's axis-1 modes
         self.ncomp = 6 if solver == 'MHD' else 3
         self.rank, self.nranks = rank, nranks
         if nranks > 1:

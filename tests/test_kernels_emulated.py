@@ -257,6 +257,19 @@ def test_emulated_long_lines(emu_long, N, precision, dealias):
     p.close()
 
 
+@pytest.mark.parametrize('N', [(8, 8, 512), (512, 8, 8)])
+def test_emulated_long_lines_mhd(emu_long, N):
+    """TG-MHD 512^3 (BASELINE configs[3]) runs the MHD kernels on 512-point lines: z_kernel<Z_MHD> with CTA barriers (a line
+    straddles two warps) and mhd_f0_kernel with its software-pipelined loads."""
+    L, ep = emu_long
+    o = so.Oracle(N, precision='double', dealias='2/3-rule')
+    p = ep.EmuPlan(L, N, precision='double', dealias='2/3-rule', solver='MHD')
+    rng = np.random.RandomState(7)
+    u0 = o.forward(rng.standard_normal((6,)+tuple(N))*0.3).astype(o.complex)
+    assert rel_l2(p.compute_rhs(u0, 0.01, 0.02), o.mhd_rhs(u0, 0.01, 0.02)) < 1e-11
+    assert rel_l2(p.rk4(u0, 1, 0.001, 0.01, 0.02), o.solve(u0, 'MHD', 1, 0.001, 0.01, eta=0.02)) < 1e-11
+
+
 @pytest.fixture(scope='module')
 def emu_60():
     import build_emu
