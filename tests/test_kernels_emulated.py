@@ -15,6 +15,11 @@ import sdns_oracle as so          # noqa: E402
 from conftest import rel_l2      # noqa: E402
 
 TOL = {'double': 1e-11, 'single': 1e-4}
+# The emulated multi-rank matrix takes a quarter of an hour on 8 cores.  The default run keeps one representative of every
+# mechanism (each exchange mode, each rank count, both axis-1 layouts, the skewed-rank race detector); SDNS_EMU_FULL=1 runs
+# all of it (what every change to the exchange was developed against).
+FULL = os.environ.get('SDNS_EMU_FULL') == '1'
+full_only = pytest.mark.skipif(not FULL, reason='part of the full emulated matrix: SDNS_EMU_FULL=1')
 
 
 @pytest.fixture(scope='module')
@@ -140,7 +145,9 @@ PICK = {2: (2, 6), 4: (3, 7), 8: (1, 5)}
 def test_emulated_multi_gpu_schedule(emu, world, exchange):
     """'tma' (the default): send slots moved by the transfer role inside the following pass kernels (csrc/xfer.cuh;
     the bulk-async copies are memcpys here, the ring / piece bookkeeping runs unchanged)."""
-    for i in PICK[world][:1 if (world == 8 and exchange == 'store') else None]:
+    if not FULL and world > 2 and exchange != 'tma':
+        pytest.skip('default run: the copy-engine and peer-store modes on 2 ranks, the transfer role on 2, 4 and 8')
+    for i in PICK[world][:1 if (world == 8 and (exchange == 'store' or not FULL)) else None]:
         _multi_case(emu, world, exchange, MULTI[i], chunks='6' if exchange == 'tma' else '4')
 
 
@@ -150,7 +157,7 @@ def test_emulated_multi_gpu_cyclic_k1(emu, world):
     of kept modes.  Same global results; every exchange mode, the three dealias modes, the convection forms, MHD."""
     cases = {2: (('tma', 0), ('ce', 7), ('store', 3)), 4: (('tma', 1), ('ce', 5), ('store', 6), ('tma', 3)),
              8: (('tma', 5), ('ce', 0), ('tma', 2))}[world]
-    for exchange, i in cases:
+    for exchange, i in (cases if FULL else cases[:2 if world == 2 else 1]):
         _multi_case(emu, world, exchange, MULTI[i], chunks='6' if exchange == 'tma' else '4', k1_layout='cyclic')
     # the axis-1 passes find their rows in closed form when the ranks divide the threads of a line (64 / 8 = 8 threads for
     # 8 ranks, 48 / 12 = 4 for 4 ranks and the padded length), through the tables otherwise (the 8-rank cases above)
@@ -164,7 +171,7 @@ def test_emulated_multi_gpu_transfer_role_variants(emu):
     """plain load / store transfer role; a budget so small that most of the exchange ends up in transfer-only launches;
     one so large that the first pass after a chunk carries all of it."""
     _multi_case(emu, 4, 'ldst', MULTI[3], chunks='3')
-    for ratio in ('0.01', '10'):
+    for ratio in (('0.01', '10') if FULL else ()):
         os.environ['SDNS_XRATIO'] = ratio
         try:
             _multi_case(emu, 4, 'tma', MULTI[1], chunks='5')
@@ -176,12 +183,15 @@ def test_emulated_multi_gpu_transfer_role_variants(emu):
 def test_emulated_multi_gpu_skewed_ranks(emu, exchange):
     """One end of the rank range is made systematically slower (a delay before each of its launches): any operation
     that stores into a peer before that peer has finished reading the buffer shows up as a wrong result."""
-    for case, skew in ((MULTI[1], lambda r: 8000*(3 - r)), (MULTI[6], lambda r: 8000*r)):
+    if not FULL and exchange != 'tma':
+        pytest.skip('default run: the transfer role only')
+    for case, skew in ((MULTI[1], lambda r: 8000*(3 - r)), (MULTI[6], lambda r: 8000*r))[:None if FULL else 1]:
         _multi_case(emu, 4, exchange, case, skew=skew)
     L, _ = emu
     L.sdns_emu_set_skew(0)
 
 
+@full_only
 def test_emulated_multi_gpu_kernel_copy(emu):
     """SDNS_EXCHANGE=kcopy: the send slots are moved by slot_copy_kernel (peer stores) instead of the copy engines."""
     os.environ['SDNS_KCOPY_CTAS'] = '1'
@@ -191,6 +201,7 @@ def test_emulated_multi_gpu_kernel_copy(emu):
         os.environ.pop('SDNS_KCOPY_CTAS', None)
 
 
+@full_only
 def test_emulated_multi_gpu_graph_mode_barriers(emu):
     """SDNS_GRAPH=1: from the second identical step on the library 'captures' the step (executed eagerly here) with
     the barrier epochs taken from a device-resident counter and separate flag words; eager operations in between keep
@@ -257,7 +268,7 @@ def test_emulated_long_lines(emu_long, N, precision, dealias):
     p.close()
 
 
-@pytest.mark.parametrize('N', [(8, 8, 512), (512, 8, 8)])
+@pytest.mark.parametrize('N', [(8, 8, 512), (512, 8, 8)] if FULL else [(512, 8, 8)])
 def test_emulated_long_lines_mhd(emu_long, N):
     """TG-MHD 512^3 (BASELINE configs[3]) runs the MHD kernels on 512-point lines: z_kernel<Z_MHD> with CTA barriers (a line
     straddles two warps) and mhd_f0_kernel with its software-pipelined loads."""
