@@ -61,7 +61,8 @@ class ShenfunFile(object):
         self.f = None
 
     def _meta(self, arr):
-        """(global shape, start of this rank's block) of a local array of self.space (None: not distributed)."""
+        """(global shape, start, step of this rank's slice) of a local array of self.space (None: not distributed).  The step
+        is 1 for the reference's contiguous slabs and the rank count on the axis-1 of a cyclic ownership (SDNS_K1_LAYOUT)."""
         sp = self.space
         try:
             spectral = np.iscomplexobj(arr)
@@ -69,11 +70,12 @@ class ShenfunFile(object):
             sl = sp.local_slice(spectral)
             lead = arr.ndim - len(sl)
             start = (0,)*lead + tuple(int(s.start or 0) for s in sl)
+            step = (1,)*lead + tuple(int(s.step or 1) for s in sl)
             if gshape is not None:
                 gshape = tuple(arr.shape[:lead]) + gshape[-len(sl):]
-            return gshape, start
+            return gshape, start, step
         except Exception:
-            return None, None
+            return None, None, None
 
     def write(self, tstep, data, as_scalar=False):
         """data: {name: [array, (array, slices), ...]} as in h5io/HDF5File.py:25-52."""
@@ -101,9 +103,9 @@ class ShenfunFile(object):
                     a = np.array(item)
                     key = '%s/3D/%s' % (name, tstep)
                     out[key] = a
-                    gshape, start = self._meta(a)
+                    gshape, start, step = self._meta(a)
                     if gshape is not None:
-                        out['meta__' + key] = np.array(list(gshape) + list(start), dtype=np.int64)
+                        out['meta__' + key] = np.array(list(gshape) + list(start) + list(step), dtype=np.int64)
 
 
 def read_global(name, key_prefix):
@@ -124,10 +126,11 @@ def read_global(name, key_prefix):
                     a = z[k]
                     if 'meta__' + k in z.files:
                         m = z['meta__' + k]
-                        gshape, start = tuple(int(x) for x in m[:a.ndim]), tuple(int(x) for x in m[a.ndim:])
+                        gshape, start = tuple(int(x) for x in m[:a.ndim]), tuple(int(x) for x in m[a.ndim:2*a.ndim])
+                        step = tuple(int(x) for x in m[2*a.ndim:]) or (1,)*a.ndim        # older archives: contiguous blocks
                         if k not in out:
                             out[k] = np.zeros(gshape, dtype=a.dtype)
-                        out[k][tuple(slice(s, s + n) for s, n in zip(start, a.shape))] = a
+                        out[k][tuple(slice(s, s + (n - 1)*st + 1, st) for s, n, st in zip(start, a.shape, step))] = a
                     else:
                         out[k] = a
     return out, attrs

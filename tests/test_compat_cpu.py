@@ -248,3 +248,33 @@ def test_slab_and_plan_size_rules_agree():
         except ValueError:
             good = False
         assert good == ok, (N, P)
+
+
+def test_checkpoint_metadata_carries_the_slice_step(tmp_path, monkeypatch):
+    """Cyclic axis-1 ownership (SDNS_K1_LAYOUT=cyclic): a rank's block is the strided slice [r::P].  The archives record
+    start AND step per axis, read_global reassembles them, and archives without a step (contiguous blocks) still read."""
+    monkeypatch.chdir(tmp_path)
+    from spectraldns_b200.io import ShenfunFile, read_global
+    g = (np.arange(3*4*6*3).reshape(3, 4, 6, 3) + 1j).astype(complex)
+
+    class Space(object):
+        def __init__(self, r):
+            self.r = r
+
+        def global_shape(self, spectral=True):
+            return (4, 6, 3)
+
+        def local_slice(self, spectral=True):
+            return (slice(0, 4), slice(self.r, 6, 2), slice(0, 3))
+    for r in range(2):
+        gshape, start, step = ShenfunFile('unused', Space(r))._meta(g[:, :, r::2])       # what the writer records
+        assert gshape == (3, 4, 6, 3) and start == (0, 0, r, 0) and step == (1, 1, 2, 1)
+        m = np.array([3, 4, 6, 3, 0, 0, r, 0, 1, 1, 2, 1], dtype=np.int64)
+        np.savez('cyc_c_rank%d.npz' % r, **{'U/3D/0': g[:, :, r::2], 'meta__U/3D/0': m, 'attr__tstep': np.array(7)})
+    fields, attrs = read_global('cyc_c', 'U/3D/')
+    assert np.array_equal(fields['U/3D/0'], g) and attrs['tstep'] == 7
+    for r in range(2):                  # the older layout of the metadata: shape + start, contiguous blocks
+        m = np.array([3, 4, 6, 3, 0, 0, 3*r, 0], dtype=np.int64)
+        np.savez('blk_c_rank%d.npz' % r, **{'U/3D/0': g[:, :, 3*r:3*r + 3], 'meta__U/3D/0': m})
+    fields, _ = read_global('blk_c', 'U/3D/')
+    assert np.array_equal(fields['U/3D/0'], g)
