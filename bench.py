@@ -383,8 +383,7 @@ def run_ours(a):
              rank=rank, nranks=world, k1_layout=k1_layout_for(a, world))
     # synthetic Taylor-Green field generated on the device (tests/TG.py:23-28 / tests/TGMHD.py:4-12)
     X = [torch.arange(n, dtype=torch.float64, device='cuda')*2*np.pi/n for n in N]
-    M0l = N[0]//world
-    X[0] = X[0][rank*M0l:(rank+1)*M0l]          # this rank's slab of physical space
+    X[0] = X[0][p.x0_slice]                      # this rank's slab of physical space
     s0, c0 = torch.sin(X[0])[:, None, None], torch.cos(X[0])[:, None, None]
     s1, c1 = torch.sin(X[1])[None, :, None], torch.cos(X[1])[None, :, None]
     c2 = torch.cos(X[2])[None, None, :]

@@ -70,7 +70,8 @@ typedef struct sdns_config {
     int32_t kcut[3];          /* 2/3-rule: largest kept |k| per axis; <0 = default
                                  ceil(2/3*(N/2+1))-1  (spectralDNS3D_short.py:44-46) */
     int32_t prune;            /* 1: skip transform lines that the truncation zeroes (same result) */
-    int32_t rank, nranks;     /* slab position of this process (solvers/spectralinit.py:19-21) */
+    int32_t rank, nranks;     /* slab position of this process (solvers/spectralinit.py:19-21); an extent the rank count
+                                 does not divide is split N / P per rank, the first N % P ranks one more (mpi4py-fft) */
     int32_t device;           /* CUDA device ordinal */
     int32_t k1_layout;        /* SDNS_K1_BLOCKS | SDNS_K1_CYCLIC: which axis-1 modes a rank owns (nranks > 1) */
     int32_t reserved[7];

@@ -54,6 +54,15 @@ static int run_strided(const StridedArgs<T>& a, cudaStream_t st) {
 #endif
     xfer_prepare(b.x, C::smem, C::P * C::TC);
     dim3 grid((unsigned)tiles + b.x.nctas, ny);
+    if constexpr (MODE == S_NS_B0 || MODE == S_VV_B0 || MODE == S_NS_GRAD_B0) {
+        if (a.otab) {       // uneven split of the x0 planes: the instantiation that looks every output's owner up
+            auto kx = strided_kernel<T, N, C::E, C::TC, DIR, MODE, C::NBUF, C::minBlocks, true>;
+            static bool oncex = false;
+            if (!oncex) { cudaError_t e = set_smem(kx, C::smem); if (e != cudaSuccess) return (int)e; oncex = true; }
+            SDNS_LAUNCH(kx, grid, C::P * C::TC, C::smem, st)(b);
+            return (int)cudaGetLastError();
+        }
+    }
     SDNS_LAUNCH(kern, grid, C::P * C::TC, C::smem, st)(b);
     return (int)cudaGetLastError();
 }
@@ -94,7 +103,7 @@ static int run_b0(const StridedArgs<T>& a, cudaStream_t st) {
     // one tile per CTA: a capped grid (grid_cap, an experiment of the multi-GPU pipeline) and tile counts beyond 32 bits
     // stay with strided_kernel
     if constexpr (BXCfg<T, N>::ok) {
-        if (a.grid_cap <= 0 && a.ncols < (1LL << 31)) return run_b0x<T, N, MODE>(a, st);
+        if (a.grid_cap <= 0 && a.ncols < (1LL << 31) && !a.otab) return run_b0x<T, N, MODE>(a, st);
     }
     return run_strided<T, N, MODE, +1>(a, st);
 }

@@ -76,6 +76,8 @@ struct StridedArgs {
     int k1_off, k1_mul;           // global axis-1 index of local column j: k1_off + j*k1_mul (Nyquist test in the epilogues)
     // SDNS_K1_CYCLIC (sdns_api.cu fill_tables): row of W0 that holds transform index j of the axis-1 backward pass, and
     // (owner rank << 24 | local row) of output j of the axis-1 forward pass; -1: not kept.  Null: the AxisMaps apply.
+    // otab also serves the uneven slab splits (N1 or M0 not divisible by the ranks): (owner, row) of F1's axis-1 outputs
+    // and of B0's x0 outputs.
     const int* itab; const int* otab;
     // the same maps in closed form, used when the ranks P divide the threads per line (run_strided decides): a thread's
     // rows then belong to one rank per kept range and advance by (threads per line)/P.  cyc_first[r]: first W0 row of
@@ -308,7 +310,9 @@ __device__ __forceinline__ void store_line(const V (&x)[E], const StridedArgs<T>
 // Strided c2c pass over a tile of TC adjacent columns (TC*sizeof(V) = 128 bytes -> every
 // global access of a warp covers whole 128-byte lines; thread index = column + TC*t).
 // ---------------------------------------------------------------------------------------
-template <typename T, int N, int E, int TC, int DIR, int MODE, int NBUF, int MINB>
+// XTAB (B0 modes): the x0 planes are split unevenly over the ranks and every output finds (owner, local plane) in
+// a.otab; a separate instantiation, so that the kernels of the even split stay exactly as they were measured.
+template <typename T, int N, int E, int TC, int DIR, int MODE, int NBUF, int MINB, bool XTAB = false>
 __global__ void __launch_bounds__((N / E) * TC, MINB)
 strided_kernel(const StridedArgs<T> a) {
     typedef typename C2<T>::type V;
@@ -399,7 +403,8 @@ strided_kernel(const StridedArgs<T> a) {
                 }
             }
             fft_line<T, N, E, DIR, 0, NBUF>(x, t, a.tw, sm, map, BUFSTRIDE, phase);
-            store_line<T, N, E, false>(x, a, f, obase, obase2, t, valid, (T)1);
+            if (XTAB) store_line_tab<T, N, E, false>(x, a, f, obase, obase2, t, valid, (T)1);       // uneven split of x0
+            else store_line<T, N, E, false>(x, a, f, obase, obase2, t, valid, (T)1);
         }
     } else if (MODE == S_NS_F0 || MODE == S_VV_F0) {
         // Three forward transforms; the results of the first two are parked in thread-private

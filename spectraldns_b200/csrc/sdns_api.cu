@@ -64,7 +64,9 @@ struct Space {
     double scale;          // 1/prod(M)
     // slab decomposition: this rank owns spectral k1 in [rank*N1l, (rank+1)*N1l) (SDNS_K1_BLOCKS) or the modes
     // rank, rank + P, ... (SDNS_K1_CYCLIC) and physical x0 in [rank*M0l, (rank+1)*M0l)  (spectralDNS3D_short.py:28-29)
-    int M0l;               // local physical planes
+    int M0l;               // local physical planes (this rank's share of M[0]: M0/P + (rank < M0 % P), spectralinit's split)
+    int M0p, s0;           // ceil(M0/P): the plane pitch of every rank's W0 and send slots; first plane of this rank
+    size_t xtab_off;       // uneven split of M[0]: B0 store table, x0 -> (owner << 24 | local plane)
     int K1l;               // kept axis-1 modes owned by this rank
     int lcol_nlo, lcol_gap;// local compact axis-1 index -> local memory index
     int c1off;             // position of this rank's first kept axis-1 mode in W0's compact axis 1 (rank-major order)
@@ -75,7 +77,9 @@ struct Space {
 struct sdns_plan {
     sdns_config cfg;
     int N[3], Nh, Nhp;
-    int P, rank, N1l;       // ranks, this rank, local spectral extent of axis 1
+    int P, rank, N1l;       // ranks, this rank, local spectral extent of axis 1 (N1/P + (rank < N1 % P))
+    int N1p, s1;            // ceil(N1/P): the row pitch of every rank's W3 and send slots; first axis-1 mode of this rank
+    int uneven1;            // N1 % P != 0: the axis-1 forward pass finds (owner, row) in a table
     int k1cyc;              // 1: SDNS_K1_CYCLIC (local index j holds mode rank + j*P), 0: SDNS_K1_BLOCKS
     size_t off_C, bytes_C, off_flags, off_D, bytes_D, off_S, bytes_S, off_U, bytes_U;
     bool own_ws;            // workspace cudaMalloc'ed by the library (multi-GPU: IPC-shared)
@@ -137,6 +141,11 @@ static AxisMap all_map(int n) { AxisMap m; m.nlo = n; m.nhi = 0; m.shift = 0; re
 
 static int default_kcut(int n) { return (int)ceil(2.0 / 3.0 * (n / 2 + 1)) - 1; }
 
+// Share of rank r of an axis of n entries split over P ranks: n/P + (r < n % P), the remainder going to the first ranks
+// (mpi4py-fft's decomposition).  start = first index of the share.
+static int share_count(int n, int P, int r) { return n / P + (r < n % P ? 1 : 0); }
+static int share_start(int n, int P, int r) { return r * (n / P) + std::min(r, n % P); }
+
 // Kept axis-1 modes of rank r in space q: local indices [0, a1) (low run) and [a1 + gap, a1 + gap + nb) (high run).
 // The kept global modes are [0, col_nlo) and [N1 - (K1n - col_nlo), N1).
 struct K1Own { int a1, nb, gap; };
@@ -145,7 +154,7 @@ static K1Own k1_own(const sdns_plan* p, const Space& q, int r) {
     const int nlo = q.col_nlo, nhi = q.K1n - q.col_nlo, hstart = N1 - nhi;
     K1Own o;
     if (!p->k1cyc) {
-        const int lo = r * N1l, hi = lo + N1l;
+        const int lo = share_start(N1, P, r), hi = lo + share_count(N1, P, r);
         o.a1 = std::max(0, std::min(hi, nlo) - lo);
         const int b0 = std::max(lo, hstart);
         o.nb = (nhi > 0 && hi > b0) ? hi - b0 : 0;
@@ -193,7 +202,10 @@ static void build_spaces(sdns_plan* p) {
         Space& q = p->sp[s];
         q.K2p = (q.K2n + 1) & ~1;
         q.scale = 1.0 / ((double)q.M[0] * q.M[1] * q.M[2]);
-        q.M0l = q.M[0] / p->P;
+        q.M0l = share_count(q.M[0], p->P, p->rank);
+        q.M0p = (q.M[0] + p->P - 1) / p->P;
+        q.s0 = share_start(q.M[0], p->P, p->rank);
+        q.xtab_off = 0;
         // kept axis-1 modes owned here; W0's compact axis 1 lists the ranks' kept modes one rank after the other
         // (for SDNS_K1_BLOCKS that is the natural order)
         const K1Own o = k1_own(p, q, p->rank);
@@ -237,8 +249,9 @@ static void fill_tables(sdns_plan* p) {
         return off;
     };
     p->kx_off = add_k(p->N[0], p->N[0], p->cfg.L[0], false);
-    if (p->k1cyc) p->ky_off = add_k(p->N[1], p->N1l, p->cfg.L[1], false, p->rank, p->P);
-    else p->ky_off = add_k(p->N[1], p->N1l, p->cfg.L[1], false, p->rank * p->N1l);
+    // N1p entries on every rank (the table region has the same size everywhere); the entries past this rank's share are unused
+    if (p->k1cyc) p->ky_off = add_k(p->N[1], p->N1p, p->cfg.L[1], false, p->rank, p->P);
+    else p->ky_off = add_k(p->N[1], p->N1p, p->cfg.L[1], false, p->s1);
     p->kz_off = add_k(p->N[2], p->Nh, p->cfg.L[2], true);
     // SDNS_K1_CYCLIC: the axis-1 passes on either side of a transpose see the modes in rank-major order.  B1 finds the
     // W0 row of transform index j in itab (-1: not an input), F1 finds (owner << 24 | local row) of output j in otab.
@@ -272,6 +285,39 @@ static void fill_tables(sdns_plan* p) {
         }
         memcpy(h.data() + q.itab_off, it.data(), sizeof(int) * M1);
         memcpy(h.data() + q.otab_off, ot.data(), sizeof(int) * M1);
+    }
+    // Uneven splits (N1 or M0 not divisible by P): the owner of an index is no longer index / chunk, so the pass in front
+    // of a transpose finds (owner << 24 | row inside the owner's share) in a table: F1 for its axis-1 outputs, B0 for its x0.
+    for (int s = 0; s < 2 && p->P > 1; ++s) {
+        Space& q = p->sp[s];
+        const int P = p->P;
+        auto owner_tab = [&](int n, const std::vector<int>& idx) {      // idx[j]: global index of entry j, or -1
+            std::vector<int> t(idx.size());
+            for (size_t j = 0; j < idx.size(); ++j) {
+                t[j] = -1;
+                if (idx[j] < 0) continue;
+                int r = 0;
+                while (r + 1 < P && share_start(n, P, r + 1) <= idx[j]) ++r;
+                t[j] = (r << 24) | (idx[j] - share_start(n, P, r));
+            }
+            const size_t off = align_up(h.size(), 256);
+            h.resize(off + sizeof(int) * t.size());
+            memcpy(h.data() + off, t.data(), sizeof(int) * t.size());
+            return off;
+        };
+        if (p->uneven1) {
+            const int M1 = q.M[1];
+            const AxisMap& fm = q.fmap[1];
+            std::vector<int> idx(M1, -1);
+            for (int j = 0; j < M1; ++j)
+                if (j < fm.nlo || j >= M1 - fm.nhi) idx[j] = j < fm.nlo ? j : j - fm.shift;
+            q.otab_off = owner_tab(p->N[1], idx);
+        }
+        if (q.M[0] % P) {
+            std::vector<int> idx(q.M[0]);
+            for (int j = 0; j < q.M[0]; ++j) idx[j] = j;
+            q.xtab_off = owner_tab(q.M[0], idx);
+        }
     }
 }
 
@@ -314,10 +360,15 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->P = cfg->nranks; p->rank = cfg->rank;
     p->own_ws = false; p->epoch = 0;
     for (int r = 0; r < 8; ++r) p->peer_ws[r] = nullptr;
-    if (p->N[1] % p->P) { delete p; return fail(SDNS_ERR_SIZE, "N[1] must be divisible by the number of ranks"); }
-    p->N1l = p->N[1] / p->P;
+    if (p->N[1] < p->P) { delete p; return fail(SDNS_ERR_SIZE, "N[1] must be at least the number of ranks"); }
+    // spectral axis 1 split like mpi4py-fft's slabs: N1/P modes per rank, the first N1 % P ranks one more
+    p->N1l = share_count(p->N[1], p->P, p->rank);
+    p->N1p = (p->N[1] + p->P - 1) / p->P;
+    p->s1 = share_start(p->N[1], p->P, p->rank);
+    p->uneven1 = p->N[1] % p->P != 0;
     if (cfg->k1_layout != SDNS_K1_BLOCKS && cfg->k1_layout != SDNS_K1_CYCLIC) { delete p; return fail(SDNS_ERR_ARG, "k1_layout"); }
     p->k1cyc = (cfg->k1_layout == SDNS_K1_CYCLIC && p->P > 1) ? 1 : 0;
+    if (p->k1cyc && p->uneven1) { delete p; return fail(SDNS_ERR_SIZE, "k1_layout cyclic needs N[1] divisible by the number of ranks"); }
     p->prec = cfg->precision;
     p->rs = p->prec ? 8 : 4; p->cs = 2 * p->rs;
     p->stream = 0; p->ws = nullptr; p->ws_bytes = 0; p->launches = 0;
@@ -395,7 +446,7 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     for (int i = 0; i < FAM_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_bytes[i] = 0; p->prof_remote[i] = 0; p->prof_n[i] = 0; }
     build_spaces(p);
     for (int s = 0; s < 2; ++s)
-        if (p->sp[s].M[0] % p->P) { delete p; return fail(SDNS_ERR_SIZE, "N[0] (and 3N[0]/2) must be divisible by the number of ranks"); }
+        if (p->sp[s].M[0] < p->P) { delete p; return fail(SDNS_ERR_SIZE, "N[0] must be at least the number of ranks"); }
     for (int s = 0; s < 2; ++s) for (int i = 0; i < 3; ++i)
         if (!size_ok(p->sp[s].M[i])) {
             char b[128]; snprintf(b, sizeof b, "no compiled transform of length %d (have 2^k and 3*2^k, 8..3072, and 60, 90)", p->sp[s].M[i]);
@@ -412,19 +463,23 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     if (p->prec) fill_tables<double>(p); else fill_tables<float>(p);
     // scratch: A holds W0 (B0 out) and W2 (Z out); B holds W1 (B1 out) and W3 (F1 out)
     const int nz = cfg->solver == SDNS_MHD ? 9 : 6;    // widest field count through the pipeline
+    // Every region is sized with the padded shares (M0p, N1p, the largest K1l of any rank) so that the workspace layout --
+    // the offsets peers add to each other's base pointer -- is the same on all ranks, whatever their own shares are.
     size_t a = 0, b = 0, c = 0, sf = 0;
     for (int s = 0; s < 2; ++s) {
         const Space& q = p->sp[s];
-        size_t w0 = (size_t)6 * q.M0l * q.K1n * q.K2p;
-        size_t w1 = (size_t)6 * q.M0l * q.M[1] * q.K2p;
-        size_t w2 = (size_t)nz * q.M0l * q.M[1] * p->Nhp;
-        size_t w3 = (size_t)nz * q.M[0] * p->N1l * p->Nhp;
+        int k1lmax = 0;
+        for (int r = 0; r < p->P; ++r) { const K1Own x = k1_own(p, q, r); k1lmax = std::max(k1lmax, x.a1 + x.nb); }
+        size_t w0 = (size_t)6 * q.M0p * q.K1n * q.K2p;
+        size_t w1 = (size_t)6 * q.M0p * q.M[1] * q.K2p;
+        size_t w2 = (size_t)nz * q.M0p * q.M[1] * p->Nhp;
+        size_t w3 = (size_t)nz * q.M[0] * p->N1p * p->Nhp;
         a = std::max(a, std::max(w0, w2));
         if (p->P == 1) b = std::max(b, std::max(w1, w3));      // single GPU: W3 reuses W1's buffer
         else { b = std::max(b, w1); c = std::max(c, w3); }      // multi GPU: peers write W3 while W1 is live
         if (p->xmode) {
-            b = std::max(b, (size_t)6 * q.M[0] * q.K1l * q.K2p);             // B0 send buffers: P slots of (6, M0l, K1l, K2p)
-            sf = std::max(sf, (size_t)nz * p->N[1] * q.M0l * p->Nhp);        // F1 send buffers: P slots of (nz, N1l, M0l, Nhp)
+            b = std::max(b, (size_t)6 * p->P * q.M0p * k1lmax * q.K2p);      // B0 send buffers: P slots of (6, M0p, K1l, K2p)
+            sf = std::max(sf, (size_t)nz * p->P * p->N1p * q.M0p * p->Nhp);  // F1 send buffers: P slots of (nz, N1p, M0l, Nhp)
         }
     }
     p->bytes_A = align_up(a * p->cs, 256); p->bytes_B = align_up(b * p->cs, 256);
@@ -436,12 +491,12 @@ extern "C" int sdns_plan_create(sdns_plan** out, const sdns_config* cfg) {
     p->off_C = p->P == 1 ? p->off_B : p->off_B + p->bytes_B;
     const bool needD = cfg->solver == SDNS_NS && (cfg->convection == SDNS_CONV_STANDARD || cfg->convection == SDNS_CONV_SKEWED);
     const bool needS = cfg->solver == SDNS_NS && cfg->convection == SDNS_CONV_SKEWED;
-    p->bytes_D = needD ? align_up((size_t)3 * p->sp[1].M0l * p->sp[1].M[1] * p->Nhp * p->cs, 256) : 0;
-    p->bytes_S = needS ? align_up((size_t)3 * p->N[0] * p->N1l * p->Nh * p->cs, 256) : 0;
+    p->bytes_D = needD ? align_up((size_t)3 * p->sp[1].M0p * p->sp[1].M[1] * p->Nhp * p->cs, 256) : 0;
+    p->bytes_S = needS ? align_up((size_t)3 * p->N[0] * p->N1p * p->Nh * p->cs, 256) : 0;
     p->off_D = p->off_B + p->bytes_B + p->bytes_C;
     p->off_S = p->off_D + p->bytes_D;
     // inter-stage copy of the RK4 state in the k1-major work layout
-    p->bytes_U = align_up((size_t)(cfg->solver == SDNS_MHD ? 6 : 3) * p->N[0] * p->N1l * p->Nh * p->cs, 256);
+    p->bytes_U = align_up((size_t)(cfg->solver == SDNS_MHD ? 6 : 3) * p->N[0] * p->N1p * p->Nh * p->cs, 256);
     p->off_U = p->off_S + p->bytes_S;
     p->bytes_SF = align_up(sf * p->cs, 256);
     p->off_SF = p->off_U + p->bytes_U;
@@ -687,7 +742,7 @@ extern "C" int sdns_local_shapes(const sdns_plan* p, int32_t sp[3], int32_t ph[3
 }
 extern "C" int sdns_k1_layout(const sdns_plan* p, int32_t* first, int32_t* step) {
     if (!p || !first || !step) return fail(SDNS_ERR_ARG, "null argument");
-    *first = p->k1cyc ? p->rank : p->rank * p->N1l;
+    *first = p->k1cyc ? p->rank : p->s1;
     *step = p->k1cyc ? p->P : 1;
     return SDNS_OK;
 }
@@ -812,7 +867,7 @@ struct Pipe {
         a.mask_nyquist = p->cfg.mask_nyquist;
         a.scale = (T)1;
         a.st_fs = dense_fs();
-        a.k1_off = p->k1cyc ? p->rank : p->rank * p->N1l; a.k1_mul = p->k1cyc ? p->P : 1;
+        a.k1_off = p->k1cyc ? p->rank : p->s1; a.k1_mul = p->k1cyc ? p->P : 1;
         a.uh_ls = (long long)p->N1l * p->Nh; a.uh_os = p->Nh;          // reference layout (N0, N1l, Nh)
         a.t_ls = p->Nh; a.t_os = (long long)p->N[0] * p->Nh;           // work layout (N1l, N0, Nh)
     }
@@ -835,8 +890,8 @@ struct Pipe {
 
     // B0: local dense spectral (nf, N0, N1l, Nh) -> W0 (nfo, M0l, K1n, K2p) of the rank owning each x0.
     // k2: the k2 columns of this launch.
-    long long b0_slot() const { return (long long)6 * q.M0l * q.K1l * q.K2p; }
-    long long f1_slot(int nf) const { return (long long)nf * p->N1l * q.M0l * p->Nhp; }
+    long long b0_slot() const { return (long long)6 * q.M0p * q.K1l * q.K2p; }
+    long long f1_slot(int nf) const { return (long long)nf * p->N1p * q.M0l * p->Nhp; }
     V* send_f1() const { return reinterpret_cast<V*>(p->ws + p->off_SF); }
 
     int b0(int fam, const V* in, int nf, int comp = 0, bool work_layout = false, Rng k2 = Rng{-1, 0},
@@ -851,10 +906,11 @@ struct Pipe {
         a.cw = k2.b - k2.a; a.c2_off = k2.a; a.c1_off = k1.a; a.ncols = (long long)(k1.b - k1.a) * a.cw;
         a.col_nlo = q.lcol_nlo; a.col_gap = q.lcol_gap;
         a.imap = q.bmap[0]; a.omap = all_map(q.M[0]);
-        a.out_fs = (long long)q.M0l * q.K1n * q.K2p; a.out_ls = (long long)q.K1n * q.K2p; a.out_os = q.K2p;
+        a.out_fs = (long long)q.M0p * q.K1n * q.K2p; a.out_ls = (long long)q.K1n * q.K2p; a.out_os = q.K2p;
         a.c1_out_off = q.c1off;
-        if (staged) peers(a, p->off_A, q.M0l, B, b0_slot(), (long long)q.M0l * q.K1l * q.K2p, (long long)q.K1l * q.K2p, 0);
-        else peers(a, p->off_A, q.M0l);
+        if (staged) peers(a, p->off_A, q.M0p, B, b0_slot(), (long long)q.M0p * q.K1l * q.K2p, (long long)q.K1l * q.K2p, 0);
+        else peers(a, p->off_A, q.M0p);
+        if (p->P > 1 && q.M[0] % p->P) a.otab = reinterpret_cast<const int*>(p->ws + p->off_tab + q.xtab_off);
         a.grid_cap = xcap;
         a.tw = tw(q.M[0]); a.nfields = nf;
         const int nfo = (fam == FAM_PLAIN_BWD) ? nf : 6;
@@ -870,7 +926,7 @@ struct Pipe {
         k2 = whole(k2, q.K2n);
         StridedArgs<T> a; base(a);
         a.in = A; a.out = B;
-        a.in_fs = (long long)q.M0l * q.K1n * q.K2p; a.in_ls = q.K2p; a.in_os = (long long)q.K1n * q.K2p;
+        a.in_fs = (long long)q.M0p * q.K1n * q.K2p; a.in_ls = q.K2p; a.in_os = (long long)q.K1n * q.K2p;
         a.cw = k2.b - k2.a; a.c2_off = k2.a; a.ncols = (long long)q.M0l * a.cw;
         a.col_nlo = q.M0l; a.col_gap = 0;
         a.imap = q.bmap[1];
@@ -922,11 +978,12 @@ struct Pipe {
         a.cw = p->Nh; a.c1_off = x0.a; a.ncols = (long long)(x0.b - x0.a) * p->Nh;
         a.col_nlo = q.M0l; a.col_gap = 0;
         a.imap = all_map(q.M[1]); a.omap = q.fmap[1];
-        a.out_fs = (long long)p->N1l * q.M[0] * p->Nhp; a.out_ls = (long long)q.M[0] * p->Nhp; a.out_os = p->Nhp;
-        a.c1_out_off = (long long)p->rank * q.M0l;
-        if (staged) peers(a, p->off_C, p->N1l, send_f1(), f1_slot(nf), (long long)p->N1l * q.M0l * p->Nhp, (long long)q.M0l * p->Nhp, 0);
-        else peers(a, p->off_C, p->N1l);
+        a.out_fs = (long long)p->N1p * q.M[0] * p->Nhp; a.out_ls = (long long)q.M[0] * p->Nhp; a.out_os = p->Nhp;
+        a.c1_out_off = q.s0;
+        if (staged) peers(a, p->off_C, p->N1p, send_f1(), f1_slot(nf), (long long)p->N1p * q.M0l * p->Nhp, (long long)q.M0l * p->Nhp, 0);
+        else peers(a, p->off_C, p->N1p);
         if (p->k1cyc) { a.otab = reinterpret_cast<const int*>(p->ws + p->off_tab + q.otab_off); a.cycP = p->P; }
+        else if (p->uneven1 && p->P > 1) a.otab = reinterpret_cast<const int*>(p->ws + p->off_tab + q.otab_off);
         a.grid_cap = xcap;
         a.tw = tw(q.M[1]); a.nfields = nf;
         const double bytes = (double)nf * (x0.b - x0.a) * p->Nh * ((double)q.M[1] + p->N[1]) * p->cs;
@@ -941,7 +998,7 @@ struct Pipe {
         k1 = whole(k1, p->N1l);
         base(a);
         a.in = C;
-        a.in_fs = (long long)p->N1l * q.M[0] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[0] * p->Nhp;
+        a.in_fs = (long long)p->N1p * q.M[0] * p->Nhp; a.in_ls = p->Nhp; a.in_os = (long long)q.M[0] * p->Nhp;
         a.cw = k2.b - k2.a; a.c2_off = k2.a; a.c1_off = k1.a; a.ncols = (long long)(k1.b - k1.a) * a.cw;
         a.col_nlo = p->N1l; a.col_gap = 0;
         a.imap = all_map(q.M[0]); a.omap = q.fmap[0];
@@ -1140,11 +1197,11 @@ static int b0_chunk_ce(sdns_plan* p, Pipe<T>& P, const void* u_hat, bool work_la
         srcs[k - 1] = src; dsts[k - 1] = dst;
         if (p->xmode == 1)
             if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.K1n * q.K2p * cs, src, (size_t)q.K1l * q.K2p * cs,
-                               (size_t)(kept.b - kept.a) * q.K2p * cs, (size_t)6 * q.M0l))) return e;
+                               (size_t)(kept.b - kept.a) * q.K2p * cs, (size_t)6 * q.M0p))) return e;
     }
     if (p->xmode == 2)
         return push_xfer(p, p->P - 1, srcs, dsts, (size_t)q.K1l * q.K2p * cs, (size_t)q.K1n * q.K2p * cs,
-                         (size_t)(kept.b - kept.a) * q.K2p * cs, (size_t)6 * q.M0l);
+                         (size_t)(kept.b - kept.a) * q.K2p * cs, (size_t)6 * q.M0p);
     return SDNS_OK;
 }
 
@@ -1181,15 +1238,15 @@ static int rhs_ce(sdns_plan* p, const void* u_hat, double nu, double eta, const 
         for (int k = 1; k < p->P; ++k) {
             const int r = (p->rank + k) % p->P;
             const V* src = P.send_f1() + r * P.f1_slot(nprod) + (long long)x0.a * p->Nhp;
-            V* dst = reinterpret_cast<V*>(p->peer_ws[r] + p->off_C) + ((long long)p->rank * q.M0l + x0.a) * p->Nhp;
+            V* dst = reinterpret_cast<V*>(p->peer_ws[r] + p->off_C) + ((long long)q.s0 + x0.a) * p->Nhp;
             srcs[k - 1] = src; dsts[k - 1] = dst;
             if (p->xmode == 1)
                 if ((e = copy_rows(p, r, p->ev_k[c], dst, (size_t)q.M[0] * p->Nhp * cs, src, (size_t)q.M0l * p->Nhp * cs,
-                                   (size_t)(x0.b - x0.a) * p->Nhp * cs, (size_t)nprod * p->N1l))) return e;
+                                   (size_t)(x0.b - x0.a) * p->Nhp * cs, (size_t)nprod * p->N1p))) return e;
         }
         if (p->xmode == 2)
             if ((e = push_xfer(p, p->P - 1, srcs, dsts, (size_t)q.M0l * p->Nhp * cs, (size_t)q.M[0] * p->Nhp * cs,
-                               (size_t)(x0.b - x0.a) * p->Nhp * cs, (size_t)nprod * p->N1l))) return e;
+                               (size_t)(x0.b - x0.a) * p->Nhp * cs, (size_t)nprod * p->N1p))) return e;
     }
     if ((e = join_copies(p))) return e;
     for (int c = 0; c < nc; ++c) {

@@ -74,6 +74,13 @@ class Plan(object):
         self.spectral_shape = tuple(sp)
         self.physical_shape = tuple(ph)
         self.padded_shape = tuple(pd)
+        # this rank's planes of the physical axis 0, plain and dealiased space (M0 // P per rank, the first M0 % P one more)
+        def share(m):
+            c, rem = divmod(m, self.nranks)
+            lo = self.rank*c + min(self.rank, rem)
+            return slice(lo, lo + c + (1 if self.rank < rem else 0))
+        M0p = self.N[0]*3//2 if dealias == '3/2-rule' else self.N[0]
+        self.x0_slice, self.x0p_slice = share(self.N[0]), share(M0p)
         self.ncomp = 6 if solver == 'MHD' else 3
         nb = C.c_size_t()
         _lib.check(self.lib.sdns_workspace_bytes(self._p, C.byref(nb)))

@@ -22,7 +22,7 @@ class SlabLayout(object):
         self.Nh = N2//2+1
         self.M = tuple(3*n//2 for n in self.N) if dealias == '3/2-rule' else self.N
         if N1 % self.P or self.M[0] % self.P or N0 % self.P:
-            raise ValueError('N[0], N[1] (and 3N[0]/2) must be divisible by the number of ranks')
+            raise ValueError('this numpy replay covers the even split only: N[0], N[1] (and 3N[0]/2) divisible by the number of ranks')
         self.N1l = N1//self.P
         self.M0l = self.M[0]//self.P
         self.k1_slice = slice(rank*self.N1l, (rank+1)*self.N1l)

@@ -156,16 +156,19 @@ class TensorProductSpace(object):
         g = self.global_shape(forward_output)
         if n == 1 or self.dim == 2:
             return g
-        return (g[0], g[1]//n, g[2]) if forward_output else (g[0]//n, g[1], g[2])
+        sl = self.local_slice(forward_output)
+        return tuple(len(range(*s.indices(m))) for s, m in zip(sl, g))
 
     def local_slice(self, forward_output=False):
         r, n = self._ranks()
         g = self.global_shape(forward_output)
         out = [slice(0, m) for m in g]
         if self.dim == 3:
+            # mpi4py-fft's slabs: m // n entries per rank, the first m % n ranks one more
             ax = 1 if forward_output else 0
-            c = g[ax]//n
-            out[ax] = slice(r*c, (r+1)*c)
+            c, rem = divmod(g[ax], n)
+            lo = r*c + min(r, rem)
+            out[ax] = slice(lo, lo + c + (1 if r < rem else 0))
             if forward_output and n > 1 and os.environ.get('SDNS_K1_LAYOUT', 'blocks') == 'cyclic':
                 out[ax] = slice(r, g[ax], n)       # Plan(k1_layout='cyclic'): rank r owns the axis-1 modes r, r + n, ...
         return tuple(out)

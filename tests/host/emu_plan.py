@@ -67,6 +67,13 @@ class EmuPlan(object):
         self.k1_slice = slice(a.value, int(N[1]), b.value) if b.value > 1 else slice(a.value, a.value + sp[1])     # this rank's axis-1 modes
         self.ncomp = 6 if solver == 'MHD' else 3
         self.rank, self.nranks = rank, nranks
+
+        def share(m):                       # mpi4py-fft's slabs: m // P per rank, the first m % P ranks one more
+            c, rem = divmod(m, nranks)
+            lo = rank*c + min(rank, rem)
+            return slice(lo, lo + c + (1 if rank < rem else 0))
+        self.x0_slice, self.x0p_slice = share(int(N[0])), share(int(N[0])*3//2 if dealias == '3/2-rule' else int(N[0]))
+        assert self.pshape[0] == len(range(*self.x0_slice.indices(int(N[0])))), (self.pshape, self.x0_slice)
         if nranks > 1:
             self.chk(L.sdns_comm_alloc(self.p))
         if nranks == 1:

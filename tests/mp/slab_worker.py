@@ -35,7 +35,10 @@ def main():
              # the other convection forms of NS.getConvection (NS.py:164-201), VV with padding, MHD in single precision
              ((32, 32, 32), 'double', '2/3-rule', 'NS', None, 'Standard'), ((32, 32, 16), 'double', '3/2-rule', 'NS', None, 'Divergence'),
              ((16, 32, 32), 'double', '2/3-rule', 'NS', None, 'Skewed'), ((32, 32, 32), 'single', '3/2-rule', 'NS', None, 'Skewed'),
-             ((32, 32, 32), 'double', '3/2-rule', 'VV'), ((32, 32, 32), 'single', '3/2-rule', 'MHD')]
+             ((32, 32, 32), 'double', '3/2-rule', 'VV'), ((32, 32, 32), 'single', '3/2-rule', 'MHD'),
+             # extents the rank count does not divide (N // P per rank, the first N % P ranks one more): axis 1 on 8 ranks;
+             # axis 0 on 4 ranks and both on 8
+             ((24, 12, 16), 'double', '2/3-rule', 'NS'), ((90, 60, 16), 'double', '2/3-rule', 'NS')]
     if os.environ.get('SLAB_CASES'):            # a subset, by index (the 8-GPU box is paid by the second)
         cases = [cases[int(i)] for i in os.environ['SLAB_CASES'].split(',')]
     for case in cases:
@@ -43,15 +46,19 @@ def main():
         kcut = case[4] if len(case) > 4 else None
         conv = case[5] if len(case) > 5 else None
         tol = 1e-11 if prec == 'double' else 1e-4
+        if layout == 'cyclic' and N[1] % world:
+            continue                                    # the cyclic ownership needs N[1] divisible by the ranks
         o = so.Oracle(N, precision=prec, dealias=dealias, kcut=kcut)
         p = Plan(N, precision=prec, dealias=dealias, solver=solver, device=local, rank=rank, nranks=world, kcut=kcut,
                  convection=conv, k1_layout=layout)
         N1l = N[1]//world
         k1s = p.k1_slice
-        assert k1s == (slice(rank, N[1], world) if layout == 'cyclic' else slice(rank*N1l, (rank+1)*N1l)), k1s
-        M0l, Mp0l = N[0]//world, o.M[0]//world
-        x0s, x0ps = slice(rank*M0l, (rank+1)*M0l), slice(rank*Mp0l, (rank+1)*Mp0l)
-        assert p.spectral_shape == (N[0], N1l, N[2]//2+1), p.spectral_shape
+        if N[1] % world == 0:
+            assert k1s == (slice(rank, N[1], world) if layout == 'cyclic' else slice(rank*N1l, (rank+1)*N1l)), k1s
+        x0s, x0ps = p.x0_slice, p.x0p_slice
+        M0l, Mp0l = x0s.stop - x0s.start, x0ps.stop - x0ps.start
+        if N[1] % world == 0:
+            assert p.spectral_shape == (N[0], N1l, N[2]//2+1), p.spectral_shape
         assert p.physical_shape == (M0l, N[1], N[2]) and p.padded_shape == (Mp0l, o.M[1], o.M[2])
         nc = 6 if solver == 'MHD' else 3
         rng = np.random.RandomState(11)

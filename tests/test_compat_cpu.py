@@ -238,7 +238,9 @@ def test_c_abi_error_behaviour():
 
 
 def test_slab_and_plan_size_rules_agree():
-    """spectraldns_b200.slab (host mirror) rejects exactly what sdns_plan_create rejects for sharding."""
+    """spectraldns_b200.slab, the numpy replay of the exchange that the gloo tests drive, covers the even split only and
+    says so; the library itself also takes extents the rank count does not divide (N // P per rank, the first N % P one
+    more: tests/test_kernels_emulated.py::test_emulated_multi_gpu_uneven_slabs)."""
     from spectraldns_b200.slab import SlabLayout
     for N, P, ok in (((64, 64, 64), 8, True), ((64, 36, 64), 8, False), ((36, 64, 64), 8, False),
                      ((48, 48, 48), 3, True), ((32, 32, 32), 5, False)):

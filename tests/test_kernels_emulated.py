@@ -105,9 +105,10 @@ def _multi_case(emu, world, exchange, case, chunks='4', skew=None, k1_layout='bl
         p = ep.EmuPlan(L, N, precision=prec, dealias=dealias, solver=solver, convection=conv, kcut=kcut, rank=rank, nranks=world,
                        k1_layout=k1_layout)
         p.open_peers(sync(p.handle()))
-        N1l, M0l = N[1]//world, N[0]//world
-        k1s, x0s = p.k1_slice, slice(rank*M0l, (rank+1)*M0l)
-        assert k1s == (slice(rank, N[1], world) if k1_layout == 'cyclic' else slice(rank*N1l, (rank+1)*N1l))
+        N1l = N[1]//world
+        k1s, x0s = p.k1_slice, p.x0_slice
+        if N[1] % world == 0:
+            assert k1s == (slice(rank, N[1], world) if k1_layout == 'cyclic' else slice(rank*N1l, (rank+1)*N1l))
         # the sequence visits every transition between operations that store into the peers
         e = [rel_l2(p.forward(u[:, x0s]), uh_ref[:, :, k1s]),
              rel_l2(p.backward(uh_ref[:, :, k1s].astype(o.complex)), u[:, x0s]),
@@ -165,6 +166,25 @@ def test_emulated_multi_gpu_cyclic_k1(emu, world):
         _multi_case(emu, 8, 'tma', ((16, 64, 8), 'double', '2/3-rule', 'NS'), chunks='3', k1_layout='cyclic')
     if world == 4:
         _multi_case(emu, 4, 'tma', ((16, 32, 8), 'double', '3/2-rule', 'NS'), chunks='3', k1_layout='cyclic')
+
+
+@pytest.mark.parametrize('exchange', ['tma', 'ce', 'store'])
+def test_emulated_multi_gpu_uneven_slabs(emu, exchange):
+    """Grid extents the rank count does not divide: N // P entries per rank and one more on the first N % P ranks
+    (mpi4py-fft's slabs), for the spectral axis 1, the physical axis 0 and its 3/2-padded length."""
+    if not FULL and exchange == 'ce':
+        pytest.skip('default run: the transfer role and the fused peer stores')
+    chunks = '3' if exchange == 'tma' else '2'
+    # 3 ranks: 16 = 6 + 5 + 5 on both axes, kept axis-1 modes 0..5 | 11..15;  padded 24 = 8 + 8 + 8 with N1 uneven
+    _multi_case(emu, 3, exchange, ((16, 16, 8), 'double', '2/3-rule', 'NS'), chunks=chunks)
+    _multi_case(emu, 3, exchange, ((16, 16, 8), 'double', '3/2-rule', 'NS'), chunks=chunks)
+    # 8 ranks: 12 = 2,2,2,2,1,1,1,1 on both axes; and the padded axis 0 alone uneven (8 -> 12 planes)
+    _multi_case(emu, 8, exchange, ((12, 12, 8), 'double', '2/3-rule', 'NS'), chunks=chunks)
+    if FULL or exchange == 'tma':
+        _multi_case(emu, 8, exchange, ((8, 16, 8), 'double', '3/2-rule', 'NS'), chunks=chunks)
+    if FULL:
+        _multi_case(emu, 5, exchange, ((16, 24, 8), 'single', '2/3-rule', 'MHD'), chunks=chunks)
+        _multi_case(emu, 3, exchange, ((16, 16, 8), 'double', 'None', 'NS', None, 'Skewed'), chunks=chunks)
 
 
 def test_emulated_multi_gpu_transfer_role_variants(emu):
