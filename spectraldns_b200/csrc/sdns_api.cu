@@ -62,8 +62,9 @@ struct Space {
     int col_nlo, col_gap;  // compact axis-1 index -> memory index
     int K2n, K2p;          // axis-2 modes entering the backward transform, padded pitch
     double scale;          // 1/prod(M)
-    // slab decomposition: this rank owns spectral k1 in [rank*N1l, (rank+1)*N1l) (SDNS_K1_BLOCKS) or the modes
-    // rank, rank + P, ... (SDNS_K1_CYCLIC) and physical x0 in [rank*M0l, (rank+1)*M0l)  (spectralDNS3D_short.py:28-29)
+    // slab decomposition: this rank owns the spectral k1 in [s1, s1 + N1l) (SDNS_K1_BLOCKS) or the modes rank, rank + P,
+    // ... (SDNS_K1_CYCLIC) and the physical x0 in [s0, s0 + M0l)  (spectralDNS3D_short.py:28-29); s = rank * share when
+    // the rank count divides the extent, else mpi4py-fft's uneven shares (share_count / share_start)
     int M0l;               // local physical planes (this rank's share of M[0]: M0/P + (rank < M0 % P), spectralinit's split)
     int M0p, s0;           // ceil(M0/P): the plane pitch of every rank's W0 and send slots; first plane of this rank
     size_t xtab_off;       // uneven split of M[0]: B0 store table, x0 -> (owner << 24 | local plane)
