@@ -230,6 +230,21 @@ def test_full_size_properties(cfg):
     assert float(div.abs().max()) < (1e-12 if prec == 'double' else 1e-5)
 
 
+def test_field_parity_at_baseline_size():
+    """BASELINE configs[1]'s grid (256^3 fp64, 2/3-rule): right-hand side and one RK4 step of a seeded broadband field
+    against the oracle, field level (the oracle needs about half a minute of host time at this size)."""
+    N = (256, 256, 256)
+    o = so.Oracle(N)
+    p = make_plan(N)
+    f0 = so.isotropic_field(o, seed=3)
+    d_u = p.to_device(f0)
+    rhs = p.to_host(p.compute_rhs(p.empty_spectral(), d_u, 0.005))
+    assert rel_l2(rhs, o.ns_rhs(f0, 0.005)) < 1e-11
+    u1, u2 = p.empty_spectral(), p.empty_spectral()
+    p.rk4_step(d_u, u1, u2, 0.002, 0.005)
+    assert rel_l2(p.to_host(d_u), o.solve(f0, 'NS', 1, 0.002, 0.005)) < 1e-11
+
+
 @pytest.mark.parametrize('cfg', [((16, 16, 512), 'double', '2/3-rule'), ((16, 16, 512), 'double', '3/2-rule'),
                                  ((16, 16, 1024), 'double', '2/3-rule'), ((16, 16, 2048), 'single', '2/3-rule'),
                                  ((16, 16, 1024), 'single', '3/2-rule'), ((512, 16, 16), 'double', '2/3-rule'),
