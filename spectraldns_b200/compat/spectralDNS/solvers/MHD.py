@@ -56,6 +56,26 @@ def get_divergence(T, K, U_hat, **context):
     return T.backward(1j*(K[0]*U_hat[0]+K[1]*U_hat[1]+K[2]*U_hat[2]), div_u)
 
 
+# Building blocks of the reference's MHD convection (MHD.py:89-110); the fused CUDA right-hand side (kernel families
+# z_mhd / mhd_f0) does not call them.  Host arrays, any space with forward().
+def set_Elsasser(c, ZZ, K):
+    """c[:3] = -i/2 K_j (ZZ_ij + ZZ_ji),  c[3:] = i/2 K_j (ZZ_ji - ZZ_ij)   (MHD.py:89-97)"""
+    for i in range(3):
+        sym = sum(K[j]*(ZZ[i, j] + ZZ[j, i]) for j in range(3))
+        asym = sum(K[j]*(ZZ[j, i] - ZZ[i, j]) for j in range(3))
+        c[i] = -0.5j*sym
+        c[3 + i] = 0.5j*asym
+    return c
+
+
+def divergenceConvection(c, z0, z1, Tp, K, ZZ_hat):
+    """Elsasser products z0 = u + b, z1 = u - b: ZZ_hat[i, j] = forward(z0_i z1_j), then set_Elsasser   (MHD.py:99-110)"""
+    for i in range(3):
+        for j in range(3):
+            ZZ_hat[i, j] = Tp.forward(z0[i]*z1[j], ZZ_hat[i, j])
+    return set_Elsasser(c, ZZ_hat, K)
+
+
 def getConvection(convection):
     if convection in ('Standard', 'Vortex', 'Skewed'):
         raise NotImplementedError

@@ -90,6 +90,44 @@ def compute_curl(c, a, work, T, K):
     return T.backward(curl_hat, c)
 
 
+# The building blocks getConvection's closures are made of in the reference (NS.py:131-162).  The fused CUDA right-hand
+# side does not call them; they are here for user code that does, and work on host arrays with whatever space is
+# passed in (its forward / backward are the B200 transforms for the spaces of get_context()).
+def Cross(c, a, b, work, T):
+    """c = T.forward(a x b)   (NS.py:131-136)"""
+    prod = np.empty_like(a)
+    prod[0] = a[1]*b[2] - a[2]*b[1]
+    prod[1] = a[2]*b[0] - a[0]*b[2]
+    prod[2] = a[0]*b[1] - a[1]*b[0]
+    return T.forward(prod, c)
+
+
+def standard_convection(rhs, u_dealias, U_hat, work, Tp, K):
+    """rhs_i = forward(u_j d u_i / d x_j)   (NS.py:138-145)"""
+    grad = np.empty_like(u_dealias[0])
+    for i in range(3):
+        acc = np.zeros_like(u_dealias[0])
+        for j in range(3):
+            grad = Tp.backward(1j*K[j]*U_hat[i], grad)
+            acc += u_dealias[j]*grad
+        rhs[i] = Tp.forward(acc, rhs[i])
+    return rhs
+
+
+def divergence_convection(rhs, u_dealias, work, Tp, K, add=False):
+    """rhs_i (+)= i K_j forward(u_i u_j), six transforms for the symmetric product   (NS.py:147-162)"""
+    if not add:
+        rhs.fill(0)
+    uu = np.empty_like(rhs[0])
+    for i in range(3):
+        for j in range(i, 3):
+            uu = Tp.forward(u_dealias[i]*u_dealias[j], uu)
+            rhs[i] += 1j*K[j]*uu
+            if j != i:
+                rhs[j] += 1j*K[i]*uu
+    return rhs
+
+
 def getConvection(convection):
     """Nonlinear term selector: 'Vortex' u x curl(u) (default), 'Standard' u_j du_i/dx_j,
     'Divergence' d(u_i u_j)/dx_j, 'Skewed' their mean -- all compiled into the CUDA pipeline

@@ -102,3 +102,27 @@ def reset_profile(prof):
     prof.disable()
     prof.clear()
     prof.enable()
+
+
+def inheritdocstrings(cls):
+    """Class decorator: methods without a docstring take their parent's (utilities/__init__.py:71-80)."""
+    import types
+    for name, fn in vars(cls).items():
+        if isinstance(fn, types.FunctionType) and not fn.__doc__:
+            for base in cls.__mro__[1:]:
+                doc = getattr(getattr(base, name, None), '__doc__', None)
+                if doc:
+                    fn.__doc__ = doc
+                    break
+    return cls
+
+
+def cleanup():
+    """Remove the result files of a run from the working directory (utilities/__init__.py:122-129): the reference's
+    .h5 / .xdmf and this package's .npz archives."""
+    import glob
+    for f in glob.glob('*.h5') + glob.glob('*.xdmf') + glob.glob('*_c*.npz') + glob.glob('*_w*.npz'):
+        try:
+            os.remove(f)
+        except OSError:
+            pass

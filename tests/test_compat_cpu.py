@@ -280,3 +280,106 @@ def test_checkpoint_metadata_carries_the_slice_step(tmp_path, monkeypatch):
         np.savez('blk_c_rank%d.npz' % r, **{'U/3D/0': g[:, :, 3*r:3*r + 3], 'meta__U/3D/0': m})
     fields, _ = read_global('blk_c', 'U/3D/')
     assert np.array_equal(fields['U/3D/0'], g)
+
+
+def test_convection_building_blocks_of_the_solver_modules(compat):
+    """NS.Cross / standard_convection / divergence_convection and MHD.set_Elsasser / divergenceConvection (reference
+    NS.py:131-162, MHD.py:89-110) exist in the host mirror for user code that calls them; on host arrays and a numpy
+    space they reproduce the oracle's restatement of the reference's convection forms."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import sdns_oracle as so
+    from spectralDNS.solvers import NS, MHD
+    N = (12, 8, 16)
+    o = so.Oracle(N, dealias='None')
+
+    class Space(object):                         # T == Tp without dealiasing
+        def forward(self, u, out=None):
+            r = o.forward(u[None])[0]
+            if out is not None:
+                out[...] = r
+                return out
+            return r
+
+        def backward(self, uh, out=None):
+            r = o.backward(np.asarray(uh)[None])[0]
+            if out is not None:
+                out[...] = r
+                return out
+            return r
+
+    class VSpace(Space):
+        def forward(self, u, out=None):
+            r = o.forward(u)
+            if out is not None:
+                out[...] = r
+                return out
+            return r
+    T = Space()
+    u_hat = so.isotropic_field(o, seed=5)
+    u = o.backward(u_hat)
+    K = o.K
+    rel = lambda a, b: np.linalg.norm((a - b).ravel())/np.linalg.norm(b.ravel())
+    got = NS.standard_convection(np.zeros_like(u_hat), u, u_hat, None, T, K)
+    assert rel(-got, o.ns_conv(u_hat, 'Standard')) < 1e-12
+    got = NS.divergence_convection(np.zeros_like(u_hat), u, None, T, K)
+    assert rel(-got, o.ns_conv(u_hat, 'Divergence')) < 1e-12
+    skew = NS.divergence_convection(NS.standard_convection(np.zeros_like(u_hat), u, u_hat, None, T, K), u, None, T, K, add=True)
+    assert rel(-0.5*skew, o.ns_conv(u_hat, 'Skewed')) < 1e-12
+    curl = o.backward(o.cross2(K, u_hat))
+    assert rel(NS.Cross(np.zeros_like(u_hat), u, curl, None, VSpace()), o.ns_conv(u_hat, 'Vortex')) < 1e-12
+    # MHD: the convection part of the oracle's right-hand side (no Nyquist mask, nu = eta = 0, pressure projected out)
+    ub_hat = so.isotropic_field(o, seed=6, ncomp=6)
+    ub = o.backward(ub_hat)
+    c = MHD.divergenceConvection(np.zeros_like(ub_hat), ub[:3] + ub[3:], ub[:3] - ub[3:], T, K,
+                                 np.zeros((3, 3) + u_hat.shape[1:], dtype=complex))
+    P_hat = np.sum(c[:3]*o.K_over_K2, 0)
+    for i in range(3):
+        c[i] -= P_hat*K[i]
+    o.mask = None
+    assert rel(c, o.mhd_rhs(ub_hat, 0.0, 0.0)) < 1e-12
+
+
+def test_integrator_functions_and_submodule_paths(compat):
+    """spectralDNS.maths.integrators.RK4 / ForwardEuler / AB2 (reference maths/integrators.py:150-175) on host arrays with
+    a solver object whose ComputeRHS is a numpy function, against the oracle's restatement; the submodule import paths
+    of the reference (maths.cross, maths.maths, maths.integrators) and utilities.cleanup / inheritdocstrings exist."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import sdns_oracle as so
+    from spectralDNS.maths.integrators import RK4, ForwardEuler, AB2, getintegrator          # noqa: F401
+    from spectralDNS.maths.cross import cross1, cross2                                       # noqa: F401
+    from spectralDNS.maths.maths import project                                              # noqa: F401
+    from spectralDNS.utilities import cleanup, inheritdocstrings
+    o = so.Oracle((8, 8, 8))
+    lam = -0.7 + 0.3j
+
+    class Solver(object):
+        @staticmethod
+        def ComputeRHS(rhs, u, solver, **ctx):
+            rhs[...] = lam*u + 0.1*u*u
+            return rhs
+    fn = lambda u: lam*u + 0.1*u*u
+    rng = np.random.RandomState(2)
+    u0 = (rng.standard_normal((3, 4, 4, 3)) + 1j*rng.standard_normal((3, 4, 4, 3)))
+    a, b, dt = np.array([1./6., 1./3., 1./3., 1./6.]), np.array([0.5, 0.5, 1.]), 0.05
+    u = u0.copy()
+    got, _, _ = RK4(u, np.zeros_like(u), np.zeros_like(u), np.zeros_like(u), a, b, dt, Solver, {})
+    assert np.allclose(got, o.rk4_step(u0.copy(), fn, dt), rtol=1e-14, atol=0)
+    u = u0.copy()
+    got, _, _ = ForwardEuler(u, np.zeros_like(u), dt, Solver, {})
+    assert np.allclose(got, o.forward_euler_step(u0.copy(), fn, dt), rtol=1e-14, atol=0)
+    u, u1 = u0.copy(), np.zeros_like(u0)
+    ref, r1 = u0.copy(), np.zeros_like(u0)
+    for tstep in range(3):
+        u, _, _ = AB2(u, u1, np.zeros_like(u), dt, tstep, Solver, {})
+        ref, r1 = o.ab2_step(ref, r1, fn, dt, tstep)
+    assert np.allclose(u, ref, rtol=1e-13, atol=0)
+
+    class A(object):
+        def f(self):
+            """doc of A.f"""
+
+    @inheritdocstrings
+    class B(A):
+        def f(self):
+            pass
+    assert B.f.__doc__ == 'doc of A.f' and callable(cleanup)
