@@ -95,6 +95,9 @@ class _PlanAction(argparse.Action):
         setattr(namespace, self.dest, fft_plans)
 
 
+PlanAction = _PlanAction           # the reference's public name (config.py:153-158)
+
+
 params = Params()
 solver = None           # set by get_solver (reference __init__.py:63-64)
 mesh = 'triplyperiodic'
